@@ -1,0 +1,85 @@
+"""Host-side mirror of apply_r.lua's four analysis modes and helpers.  Same names and argument
+meaning as the reference; the inner loops are single calls into libganrev_cuda.so.  JPEG grid
+writing (image.toDisplayTensor / image.save) is presentation and out of scope (SURVEY.md
+section 8f): each function returns the data the reference would have drawn.
+"""
+import math
+
+import numpy as np
+
+from . import nn_utils
+
+
+def cosineSimilarity(v1, v2, ctx=None):
+    """apply_r.lua:396-400."""
+    from .models import default_context
+    return (ctx or default_context()).cosine(v1, v2)
+
+
+def unsup_kmeans(x, k, niter, init=None, rng=None, ctx=None):
+    """unsup.kmeans(x, k, niter) as called at apply_r.lua:198.  unsup draws N(0,1) centroids and
+    divides each row by its norm; that draw happens here (seeded numpy) unless `init` is given.
+    Returns centroids [k x d], totalcounts [k]."""
+    from .models import default_context
+    ctx = ctx or default_context()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if init is None:
+        rng = rng if rng is not None else np.random.default_rng(6)
+        init = rng.normal(size=(k, x.shape[1])).astype(np.float32)
+        init /= np.linalg.norm(init, axis=1, keepdims=True).astype(np.float32)
+    ctx.db_set(x)
+    cen, tot, _ = ctx.kmeans(k, niter, init, want_labels=False)
+    return cen, tot
+
+
+def createClusterImages(nbClusters, nbIterations, nbMaxPerCluster, images, attributes, init=None, ctx=None):
+    """apply_r.lua:197-260.  Returns dict(centroids, counts, img2cluster (0-based), cos,
+    member_ids [k x m] (-1 padded), member_counts, average_faces [k x C x H x W])."""
+    from .models import default_context
+    ctx = ctx or default_context()
+    attributes = np.ascontiguousarray(attributes, dtype=np.float32)
+    images = np.ascontiguousarray(images, dtype=np.float32)
+    centroids, counts = unsup_kmeans(attributes, nbClusters, nbIterations, init=init, ctx=ctx)   # :198
+    img2cluster, cos = ctx.assign_cosine_min(centroids)                                          # :206-218
+    ids, cnt, mean = ctx.cluster_members(nbClusters, nbMaxPerCluster, images)                   # :222-243
+    return {"centroids": centroids, "counts": counts, "img2cluster": img2cluster, "cos": cos,
+            "member_ids": ids, "member_counts": cnt, "average_faces": mean.reshape((nbClusters,) + images.shape[1:])}
+
+
+def createSimilaritySearchImages(nbSimilarNeedles, nbShowMax, images, attributes, ctx=None):
+    """apply_r.lua:265-318.  Needle i (1-based) is row i*100 (:268), i.e. 0-based row i*100-1.
+    Returns {"attributes": (ids, scores), "pixelwise": (ids, scores)}, ids 0-based [needles x n]."""
+    from .models import default_context
+    ctx = ctx or default_context()
+    attributes = np.ascontiguousarray(attributes, dtype=np.float32)
+    images = np.ascontiguousarray(images, dtype=np.float32)
+    N = attributes.shape[0]
+    n = min(nbShowMax, N)                                        # :281
+    needles = np.array([i * 100 - 1 for i in range(1, nbSimilarNeedles + 1)])
+    out = {}
+    ctx.db_set(attributes)                                       # similarityMeasureAttributes :303-305
+    out["attributes"] = ctx.search_cosine(attributes[needles], n)
+    flat = images.reshape(N, -1)                                 # similarityMeasurePixelwise :308-314
+    ctx.db_set(flat)
+    out["pixelwise"] = ctx.search_cosine(flat[needles], n)
+    return out
+
+
+def fixFaces(nbPairs, nbFixedImages, images, attributesFixer, model_G):
+    """apply_r.lua:324-352: G over the fixer's recovered vectors (pairs, then the first N)."""
+    pairs_fixed = nn_utils.forwardBatched(model_G, attributesFixer[:nbPairs])                    # :328-332
+    fixed = nn_utils.forwardBatched(model_G, attributesFixer[:nbFixedImages])                   # :349
+    return {"pairs": (np.asarray(images[:nbPairs]), pairs_fixed), "unfixed": np.asarray(images[:nbFixedImages]),
+            "fixed": fixed}
+
+
+def detectAnomalies(nbImagesCalculations, nbImagesShow, threshold, images, noise, attributesFixer, model_G):
+    """apply_r.lua:355-390.  `noise` is unused, as in the reference.  Returns (flags [nbImagesShow],
+    similarities = 1 - dist [nbImagesCalculations], anomalyBelow)."""
+    ctx = model_G.ctx
+    fixed = nn_utils.forwardBatched(model_G, attributesFixer[:nbImagesCalculations])             # :361-363
+    l2 = ctx.l2(np.asarray(images[:nbImagesCalculations]), fixed)                                # :366
+    if math.floor(nbImagesCalculations * threshold) < 1:
+        raise ValueError("floor(nbImagesCalculations*threshold) must be >= 1 (Lua would index nil)")
+    flags, thr = ctx.anomaly_flags(l2, nbImagesCalculations, nbImagesShow, threshold)            # :370-378
+    return flags.astype(bool), 1.0 - l2, thr

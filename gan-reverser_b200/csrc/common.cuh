@@ -1,0 +1,74 @@
+// common.cuh -- shared declarations for libganrev_cuda.so (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ganrev.h"
+
+namespace ganrev {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------
+// Per-kernel profiling record (ganrev_profile_*): CUDA events on the library stream.
+// ---------------------------------------------------------------------------------
+struct ProfEntry {
+    std::string name;
+    uint64_t launches = 0;
+    double total_ms = 0.0;
+    double flops = 0.0;   // algorithmic-executed FLOPs summed over launches
+    double bytes = 0.0;   // algorithmic bytes summed over launches
+};
+struct ProfPending {
+    int entry;
+    cudaEvent_t e0, e1;
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;  // bytes
+};
+
+// conv-as-GEMM layer description, shared by the tcgen05 kernel and the CUDA-core kernel.
+struct ConvGemm {
+    // A operand: NHWC bf16 activation [n_cap][Hin][Win][Cin]; M tile = box (64ch, BW, BH, BN)
+    int Hin, Win, Cin;
+    int lgBW, lgBH, lgBN;      // log2 of the box extents, BW*BH*BN == 128
+    int tiles_w, tiles_h;      // tiles per image
+    int n_img;                 // valid images in this launch
+    int nphase, ntaps;         // phase-decomposed upsample: 4 phases x 4 taps; else 1 x {9,1}
+    int8_t dy[4][9], dx[4][9];
+    // B operand: bf16 weights [nphase*cout_pad][ntaps*Cin], K index = tap*Cin + ci
+    int cout_pad, n_tiles;     // cout_pad = n_tiles*NT
+    int cout_real;             // channels actually stored
+    int out_cstride;           // channel stride of one output pixel
+    // output
+    int Hout, Wout, up, pool, act, out_fp32;
+    float post_scale;
+    void* out;
+    const float* scale;        // [cout_pad] folded BN scale
+    const float* shift;        // [cout_pad] folded BN shift (+ conv bias)
+    const bf16* A;             // raw pointers (CUDA-core kernel)
+    const bf16* B;
+    int* err_flag;
+};
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2, ACT_TANH = 3 };
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == ACT_RELU) return v > 0.0f ? v : 0.0f;
+    if (act == ACT_ELU) return v > 0.0f ? v : expm1f(v);
+    if (act == ACT_TANH) return tanhf(v);
+    return v;
+}
+
+}  // namespace ganrev

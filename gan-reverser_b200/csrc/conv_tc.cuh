@@ -1,0 +1,358 @@
+// conv_tc.cuh -- implicit-GEMM convolution / linear layer on the 5th-gen tensor cores.
+//
+// One persistent kernel serves every "real contraction" layer of G3 and R_default
+// (models.lua:115-130, 414-451; SURVEY.md section 8a table "Implicit-GEMM view"):
+//   D[128 pixels x NT channels] = sum over (tap, 64-channel chunk) A_tap[128 x 64] * W[NT x 64]^T
+//  * A tiles are boxes (64 ch, BW, BH, BN) of the NHWC bf16 activation, fetched by TMA with
+//    the tap offset added to the (w, h) coordinates; out-of-bounds rows are zero-filled by
+//    the TMA unit, which *is* the conv's zero padding.  128B swizzle, K-major.
+//  * nearest-upsample + 3x3 conv (models.lua:121-122, 127-128) runs as four 2x2 phase
+//    convolutions on the low-res input (weights pre-summed per phase at load time).
+//  * tcgen05.mma (cta_group::1, kind::f16, bf16 x bf16 -> fp32) is issued by one thread;
+//    the accumulator lives in TMEM, double-buffered so the epilogue of tile i overlaps
+//    the MMAs of tile i+1.
+//  * epilogue: tcgen05.ld -> folded BatchNorm affine -> ReLU/ELU/tanh -> optional 2x2
+//    max-pool (warp shuffles) and x0.75 (SpatialDropout in eval) -> bf16 NHWC / fp32 store.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer,
+// warps 2..5 = epilogue (warp 2 also owns the TMEM allocation).
+#pragma once
+#include "common.cuh"
+
+namespace ganrev {
+namespace tc {
+
+constexpr int kThreads = 192;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;               // bf16 elements = 128 bytes = one swizzle span
+constexpr int kABytes = kBlockM * kBlockK * 2;
+constexpr unsigned long long kSpinLimitCycles = 4000000000ull;  // ~2 s: turn a hang into a trap
+
+template <int NT> struct Cfg {
+    static constexpr int kBBytes = NT * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (NT >= 256) ? 4 : (NT >= 128 ? 6 : 8);
+    static constexpr int kTmemCols = (2 * NT <= 32) ? 32 : (2 * NT <= 64 ? 64 : (2 * NT <= 128 ? 128 : (2 * NT <= 256 ? 256 : 512)));
+    // stages + (2*stages + 4) mbarriers + tmem ptr, plus 1024 B alignment slack
+    static constexpr int kSmemBytes = kStages * kStageBytes + (2 * kStages + 4) * 8 + 16 + 1024;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as an error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > kSpinLimitCycles) {
+            if (err_flag) atomicExch(err_flag, code);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+template <int COLS> __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS> __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]; one elected thread issues this for the whole CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives once every previously issued tcgen05 op of this thread has completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i = lane base+i).
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B (SBO), sm_100
+// descriptor version 1.  (cute/arch/mma_sm100_desc.hpp SmemDescriptor bit layout.)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);        // [0,14)  start address >> 4
+    d |= static_cast<uint64_t>(0) << 16;                         // [16,30) LBO (unused for swizzled K-major)
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;                 // [32,46) SBO = 1024 B
+    d |= static_cast<uint64_t>(1) << 46;                         // [46,48) version = 1 (sm_100)
+    d |= static_cast<uint64_t>(2) << 61;                         // [61,64) SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=NT.
+template <int NT> __device__ __forceinline__ constexpr uint32_t make_idesc() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) |
+           (static_cast<uint32_t>(kBlockM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+struct ItemCoord {
+    int n0, h0, w0, phase, ntile;
+};
+__device__ __forceinline__ ItemCoord decode_item(const ConvGemm& p, int item) {
+    ItemCoord c;
+    c.ntile = item % p.n_tiles;
+    int t = item / p.n_tiles;
+    c.phase = t % p.nphase;
+    t /= p.nphase;
+    c.w0 = (t % p.tiles_w) << p.lgBW;
+    t /= p.tiles_w;
+    c.h0 = (t % p.tiles_h) << p.lgBH;
+    t /= p.tiles_h;
+    c.n0 = t << p.lgBN;
+    return c;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ ConvGemm p, const int n_items) {
+    using C = Cfg<NT>;
+    constexpr int S = C::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    // 128B swizzle needs 1024 B alignment of every operand tile
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bar_base = smem_base + S * C::kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + S * C::kStageBytes + 8 * (2 * S + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int kblocks = p.ntaps * (p.Cin / kBlockK);
+    const int cin_chunks = p.Cin / kBlockK;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const ItemCoord c = decode_item(p, item);
+                const int brow = c.phase * p.cout_pad + c.ntile * NT;
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    const int dy = p.dy[c.phase][tap], dx = p.dx[c.phase][tap];
+                    for (int cc = 0; cc < cin_chunks; ++cc) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 101);
+                        const uint32_t a_dst = smem_base + stage * C::kStageBytes;
+                        const uint32_t b_dst = a_dst + kABytes;
+                        mbar_expect_tx(full_bar(stage), C::kStageBytes);
+                        tma_load_4d(a_dst, &tmA, full_bar(stage), cc * kBlockK, c.w0 + dx, c.h0 + dy, c.n0);
+                        tma_load_2d(b_dst, &tmB, full_bar(stage), (tap * cin_chunks + cc) * kBlockK, brow);
+                        if (++stage == S) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc<NT>();
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1u;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 102);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * NT);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase, p.err_flag, 103);
+                    tcgen05_fence_after();
+                    const uint32_t a_addr = smem_base + stage * C::kStageBytes;
+                    const uint64_t adesc = make_smem_desc(a_addr);
+                    const uint64_t bdesc = make_smem_desc(a_addr + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        // +32 B per K=16 step inside the 128 B swizzle span (>>4 -> +2)
+                        umma_bf16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));           // frees the smem slot when the MMAs retire
+                    if (kb == kblocks - 1) umma_commit(tfull_bar(acc));  // accumulator complete
+                    if (++stage == S) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;            // tile row = pixel
+        const int BW = 1 << p.lgBW;
+        const int w_l = m & (BW - 1);
+        const int h_l = (m >> p.lgBW) & ((1 << p.lgBH) - 1);
+        const int n_l = m >> (p.lgBW + p.lgBH);
+        int it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const ItemCoord c = decode_item(p, item);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1u;
+            const int n = c.n0 + n_l, h = c.h0 + h_l, w = c.w0 + w_l;
+            int oh = h, ow = w;
+            bool writer = n < p.n_img;
+            if (p.pool) {
+                oh = h >> 1; ow = w >> 1;
+                writer = writer && !(h & 1) && !(w & 1);
+            } else if (p.up == 2) {
+                oh = 2 * h + (c.phase >> 1); ow = 2 * w + (c.phase & 1);
+            }
+            const size_t pix_off = ((static_cast<size_t>(n) * p.Hout + oh) * p.Wout + ow) * static_cast<size_t>(p.out_cstride);
+            const int cbase = c.ntile * NT;
+
+            mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 104);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * NT);
+#pragma unroll 1
+            for (int c0 = 0; c0 < NT; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c0, r);
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + cbase + c0 + j));
+                    const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + cbase + c0 + j));
+                    v[j + 0] = fmaf(__uint_as_float(r[j + 0]), sc.x, sh.x);
+                    v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y);
+                    v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z);
+                    v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
+                }
+                if (p.pool) {
+                    // 2x2 max: w-neighbour is lane^1, h-neighbour is lane^BW (BW <= 16)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], BW));
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act) * p.post_scale;
+                if (writer) {
+                    if (p.out_fp32) {
+                        float* o = reinterpret_cast<float*>(p.out) + pix_off + cbase + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (cbase + c0 + j < p.cout_real) o[j] = v[j];
+                    } else {
+                        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + pix_off + cbase + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 pk;
+                            pk.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                            pk.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                            pk.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                            pk.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                            o[j] = pk;
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive(tempty_bar(acc));
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc<C::kTmemCols>(tmem_base);
+    }
+}
+
+}  // namespace tc
+}  // namespace ganrev

@@ -1,0 +1,1201 @@
+// ganrev.cu -- C ABI of libganrev_cuda.so (include/ganrev.h): context, weight preparation,
+// chunked G / R pipelines, database ops, NCCL plumbing.  sm_100a only, no CPU fallback.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <memory>
+
+#include "common.cuh"
+#include "conv_simt.cuh"
+#include "conv_tc.cuh"
+#include "layers.cuh"
+#include "scan.cuh"
+
+using namespace ganrev;
+
+// =================================================================================
+// context
+// =================================================================================
+struct TcLayer {
+    std::string name;
+    ConvGemm g{};
+    int NT = 0, Ktot = 0;
+    DevBuf w, scale, shift;
+    CUtensorMap tmB{};
+    double flops_per_img = 0.0;   // executed MAC*2 per image (phase form counts the folded work)
+    double bytes_per_img = 0.0;   // activation in + out (bf16) per image
+};
+
+struct GModel {
+    bool loaded = false;
+    int C = 0, H = 0, W = 0, nd = 0, kpad = 0, F = 0;
+    TcLayer lin, c1, c2;
+    DevBuf w3, b3;
+};
+struct RModel {
+    bool loaded = false;
+    int C = 0, H = 0, W = 0, nd = 0, tanh_out = 0;
+    DevBuf c1pack;
+    TcLayer c2, c3, c4, c5, c6, l1, l2;
+};
+
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct ganrev_ctx {
+    int device = 0, num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t chunk = 2048;
+    int conv_impl = 0;
+    uint64_t launches = 0;
+    int* d_err_flag = nullptr;
+    EncodeTiledFn encode = nullptr;
+    // profiling
+    bool prof_on = false;
+    std::vector<ProfEntry> prof;
+    std::map<std::string, int> prof_idx;
+    std::vector<ProfPending> pending;
+    std::vector<cudaEvent_t> ev_pool;
+    // models
+    GModel G;
+    RModel R[2];
+    // resident buffers + activation arena
+    DevBuf buf[GANREV_BUF_COUNT];
+    int64_t buf_rows[GANREV_BUF_COUNT] = {0, 0, 0, 0, 0, 0};
+    DevBuf arena[2], noise_bf16, stage_a, stage_b, l2buf, thr, flags;
+    // database
+    DevBuf db, rdb, maxabs;
+    int64_t db_n = 0, db_offset = 0, db_total = 0;
+    int db_d = 0;
+    float db_maxabs = 0.0f;
+    DevBuf q, rq, c2, partial, keys, keys_all, ids, scores;
+    DevBuf cen, acc, cnt, total, labels, cosv, tcounts, mids, mcnt, mmean;
+    bool assigned = false;
+    int assigned_k = 0;
+    // nccl
+    NcclApi nccl;
+    ncclComm_t comm = nullptr;
+    int world = 1, rank = 0;
+};
+
+static int fail(ganrev_ctx* c, int code, const char* fmt, ...) {
+    char tmp[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tmp, sizeof(tmp), fmt, ap);
+    va_end(ap);
+    if (c) c->err = tmp;
+    return code;
+}
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess) return fail(ctx, GANREV_ECUDA, "%s failed: %s (%s:%d)", #expr,     \
+                                           cudaGetErrorString(e_), __FILE__, __LINE__);           \
+    } while (0)
+#define RC_TRY(expr)            \
+    do {                        \
+        int rc_ = (expr);       \
+        if (rc_ != GANREV_OK) return rc_; \
+    } while (0)
+
+static int ensure(ganrev_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return GANREV_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    if (bytes == 0) bytes = 256;
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) return fail(ctx, GANREV_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    b.cap = bytes;
+    return GANREV_OK;
+}
+static void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+}
+
+// ---- profiling helpers -------------------------------------------------------------
+struct ProfScope {
+    ganrev_ctx* ctx;
+    ProfPending pp{};
+    bool on;
+    ProfScope(ganrev_ctx* c, const std::string& name, double flops, double bytes) : ctx(c), on(c->prof_on) {
+        ctx->launches++;
+        if (!on) return;
+        auto it = ctx->prof_idx.find(name);
+        int idx;
+        if (it == ctx->prof_idx.end()) {
+            idx = static_cast<int>(ctx->prof.size());
+            ProfEntry e; e.name = name;
+            ctx->prof.push_back(e);
+            ctx->prof_idx[name] = idx;
+        } else idx = it->second;
+        ctx->prof[idx].launches++;
+        ctx->prof[idx].flops += flops;
+        ctx->prof[idx].bytes += bytes;
+        pp.entry = idx;
+        pp.e0 = take(); pp.e1 = take();
+        cudaEventRecord(pp.e0, ctx->stream);
+    }
+    cudaEvent_t take() {
+        if (!ctx->ev_pool.empty()) { cudaEvent_t e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(pp.e1, ctx->stream);
+        ctx->pending.push_back(pp);
+    }
+};
+static void prof_resolve(ganrev_ctx* ctx) {
+    for (auto& pp : ctx->pending) {
+        float ms = 0.0f;
+        if (cudaEventSynchronize(pp.e1) == cudaSuccess && cudaEventElapsedTime(&ms, pp.e0, pp.e1) == cudaSuccess)
+            ctx->prof[pp.entry].total_ms += ms;
+        ctx->ev_pool.push_back(pp.e0);
+        ctx->ev_pool.push_back(pp.e1);
+    }
+    ctx->pending.clear();
+}
+
+static int finish(ganrev_ctx* ctx) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        int flag = 0;
+        return fail(ctx, GANREV_ECUDA, "device error: %s (pipeline watchdog flag unreadable=%d)", cudaGetErrorString(e), flag);
+    }
+    int flag = 0;
+    cudaMemcpy(&flag, ctx->d_err_flag, sizeof(int), cudaMemcpyDeviceToHost);
+    if (flag != 0) return fail(ctx, GANREV_ECUDA, "tcgen05 pipeline watchdog fired (code %d)", flag);
+    return GANREV_OK;
+}
+
+// =================================================================================
+// host-side weight preparation
+// =================================================================================
+static inline uint16_t f2bf(float f) {   // round-to-nearest-even, NaN preserved
+    uint32_t u; memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40u);
+    const uint32_t r = 0x7fffu + ((u >> 16) & 1u);
+    return static_cast<uint16_t>((u + r) >> 16);
+}
+struct BnFold {
+    std::vector<float> scale, shift;
+};
+// eval-mode BatchNorm after a layer with bias b:  y = (x + b - mean) * g/sqrt(var+eps) + beta
+static BnFold fold_bn(const float* bias, const float* g, const float* beta, const float* mean, const float* var, int n, int pad) {
+    BnFold f;
+    f.scale.assign(pad, 0.0f); f.shift.assign(pad, 0.0f);
+    for (int i = 0; i < n; ++i) {
+        const float s = g[i] / std::sqrt(var[i] + 1e-5f);
+        f.scale[i] = s;
+        f.shift[i] = beta[i] + (bias[i] - mean[i]) * s;
+    }
+    return f;
+}
+static int upload(ganrev_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
+    RC_TRY(ensure(ctx, b, bytes));
+    CU_TRY(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
+    return GANREV_OK;
+}
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+static void pick_box(ConvGemm& g, bool pool) {
+    const int BW = std::min(g.Win, pool ? 16 : 128);
+    const int BH = std::min(g.Hin, 128 / BW);
+    const int BN = 128 / (BW * BH);
+    g.lgBW = ilog2(BW); g.lgBH = ilog2(BH); g.lgBN = ilog2(BN);
+    g.tiles_w = g.Win / BW; g.tiles_h = g.Hin / BH;
+}
+
+static int make_tmB(ganrev_ctx* ctx, TcLayer& L) {
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(L.Ktot), static_cast<cuuint64_t>(L.g.nphase) * L.g.cout_pad};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(L.Ktot) * 2};
+    const cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(L.NT)};
+    const cuuint32_t es[2] = {1u, 1u};
+    CUresult r = ctx->encode(&L.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, L.w.p, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, GANREV_ECUDA, "cuTensorMapEncodeTiled(B, %s) failed: %d", L.name.c_str(), (int)r);
+    return GANREV_OK;
+}
+
+// Generic layer builder.  wmat: [nphase*cout_pad][Ktot] fp32 (K index = tap*Cin + ci).
+static int build_tc_layer(ganrev_ctx* ctx, TcLayer& L, const char* name, int NT, int Hin, int Win, int Cin, int nphase, int ntaps,
+                          const int8_t (*dy)[9], const int8_t (*dx)[9], int cout_real, int n_tiles,
+                          const std::vector<float>& wmat, const BnFold& bn, int Hout, int Wout, int out_cstride, int up, int pool,
+                          int act, float post_scale, int out_fp32) {
+    L.name = name;
+    L.NT = NT;
+    ConvGemm& g = L.g;
+    g = ConvGemm{};
+    g.Hin = Hin; g.Win = Win; g.Cin = Cin;
+    g.nphase = nphase; g.ntaps = ntaps;
+    for (int p = 0; p < nphase; ++p)
+        for (int t = 0; t < ntaps; ++t) { g.dy[p][t] = dy[p][t]; g.dx[p][t] = dx[p][t]; }
+    g.n_tiles = n_tiles; g.cout_pad = n_tiles * NT; g.cout_real = cout_real; g.out_cstride = out_cstride;
+    g.Hout = Hout; g.Wout = Wout; g.up = up; g.pool = pool; g.act = act; g.post_scale = post_scale; g.out_fp32 = out_fp32;
+    g.err_flag = ctx->d_err_flag;
+    pick_box(g, pool != 0);
+    L.Ktot = ntaps * Cin;
+    if (Cin % 64 != 0) return fail(ctx, GANREV_EINVAL, "layer %s: Cin=%d not a multiple of 64", name, Cin);
+    if (wmat.size() != static_cast<size_t>(nphase) * g.cout_pad * L.Ktot) return fail(ctx, GANREV_EINVAL, "layer %s: bad weight matrix", name);
+    std::vector<uint16_t> wb(wmat.size());
+    for (size_t i = 0; i < wmat.size(); ++i) wb[i] = f2bf(wmat[i]);
+    RC_TRY(upload(ctx, L.w, wb.data(), wb.size() * 2));
+    RC_TRY(upload(ctx, L.scale, bn.scale.data(), bn.scale.size() * 4));
+    RC_TRY(upload(ctx, L.shift, bn.shift.data(), bn.shift.size() * 4));
+    g.B = reinterpret_cast<const bf16*>(L.w.p);
+    g.scale = reinterpret_cast<const float*>(L.scale.p);
+    g.shift = reinterpret_cast<const float*>(L.shift.p);
+    RC_TRY(make_tmB(ctx, L));
+    const double px_in = static_cast<double>(Hin) * Win;
+    L.flops_per_img = 2.0 * px_in * nphase * g.cout_pad * L.Ktot;
+    L.bytes_per_img = 2.0 * px_in * Cin + (out_fp32 ? 4.0 : 2.0) * Hout * Wout * cout_real;
+    return GANREV_OK;
+}
+
+static const int8_t kTaps9Y[1][9] = {{-1, -1, -1, 0, 0, 0, 1, 1, 1}};
+static const int8_t kTaps9X[1][9] = {{-1, 0, 1, -1, 0, 1, -1, 0, 1}};
+static const int8_t kTap1[1][9] = {{0, 0, 0, 0, 0, 0, 0, 0, 0}};
+// phase p = a*2 + b, tap t = ty*2 + tx: low-res offset (a-1+ty, b-1+tx)
+static const int8_t kPhaseY[4][9] = {{-1, -1, 0, 0}, {-1, -1, 0, 0}, {0, 0, 1, 1}, {0, 0, 1, 1}};
+static const int8_t kPhaseX[4][9] = {{-1, 0, -1, 0}, {0, 1, 0, 1}, {-1, 0, -1, 0}, {0, 1, 0, 1}};
+
+// [Cout][Cin][3][3] -> [Cout_pad][9*Cin], K = tap*Cin + ci
+static std::vector<float> conv_w_direct(const float* w, int Cout, int Cin, int cout_pad) {
+    std::vector<float> m(static_cast<size_t>(cout_pad) * 9 * Cin, 0.0f);
+    for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int t = 0; t < 9; ++t) m[(static_cast<size_t>(co) * 9 + t) * Cin + ci] = w[(static_cast<size_t>(co) * Cin + ci) * 9 + t];
+    return m;
+}
+// nearest-upsample x2 followed by 3x3/pad1 == four 2x2 convolutions on the low-res input:
+// output row 2y+a reads low-res rows {y-1: ky=0 | y: ky=1,2} (a=0) or {y: ky=0,1 | y+1: ky=2} (a=1).
+static std::vector<float> conv_w_phase(const float* w, int Cout, int Cin) {
+    static const int S[2][2][2] = {{{0, 0}, {1, 2}}, {{0, 1}, {2, 2}}};   // S[a][t] = {first, last} ky
+    std::vector<float> m(static_cast<size_t>(4) * Cout * 4 * Cin, 0.0f);
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b)
+            for (int co = 0; co < Cout; ++co)
+                for (int ty = 0; ty < 2; ++ty)
+                    for (int tx = 0; tx < 2; ++tx)
+                        for (int ci = 0; ci < Cin; ++ci) {
+                            double s = 0.0;
+                            for (int ky = S[a][ty][0]; ky <= S[a][ty][1]; ++ky)
+                                for (int kx = S[b][tx][0]; kx <= S[b][tx][1]; ++kx)
+                                    s += w[((static_cast<size_t>(co) * Cin + ci) * 3 + ky) * 3 + kx];
+                            m[((static_cast<size_t>(a * 2 + b) * Cout + co) * 4 + (ty * 2 + tx)) * Cin + ci] = static_cast<float>(s);
+                        }
+    return m;
+}
+
+static int check_geom(ganrev_ctx* ctx, int C, int H, int W, int nd) {
+    if (!(C == 1 || C == 3)) return fail(ctx, GANREV_EINVAL, "C must be 1 or 3 (got %d)", C);
+    if (!is_pow2(H) || !is_pow2(W) || H < 16 || W < 16 || H > 256 || W > 256)
+        return fail(ctx, GANREV_EINVAL, "H, W must be powers of two in [16,256] (got %dx%d)", H, W);
+    if (nd < 1 || nd > 4096) return fail(ctx, GANREV_EINVAL, "noise_dim out of range: %d", nd);
+    return GANREV_OK;
+}
+
+// =================================================================================
+// layer launches
+// =================================================================================
+template <int NT>
+static int launch_tc(ganrev_ctx* ctx, const TcLayer& L, const CUtensorMap& tmA, const ConvGemm& g, int n_items) {
+    using C = tc::Cfg<NT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU_TRY(cudaFuncSetAttribute(tc::conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+        attr_set = true;
+    }
+    const int grid = std::min(n_items, ctx->num_sms);
+    tc::conv_tc_kernel<NT><<<grid, tc::kThreads, C::kSmemBytes, ctx->stream>>>(tmA, L.tmB, g, n_items);
+    CU_TRY(cudaGetLastError());
+    return GANREV_OK;
+}
+
+static int run_layer(ganrev_ctx* ctx, TcLayer& L, const void* in, void* out, int n_img, int64_t n_cap) {
+    ConvGemm g = L.g;
+    g.A = reinterpret_cast<const bf16*>(in);
+    g.out = out;
+    g.n_img = n_img;
+    const int BN = 1 << g.lgBN;
+    const int tiles_n = (n_img + BN - 1) / BN;
+    const int n_items = tiles_n * g.tiles_h * g.tiles_w * g.nphase * g.n_tiles;
+    ProfScope ps(ctx, L.name, L.flops_per_img * n_img, L.bytes_per_img * n_img);
+    if (ctx->conv_impl == 1) {
+        const long long total = static_cast<long long>(n_img) * g.Hout * g.Wout * g.cout_real;
+        conv_simt_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, ctx->stream>>>(g, total);
+        CU_TRY(cudaGetLastError());
+        return GANREV_OK;
+    }
+    CUtensorMap tmA;
+    const cuuint64_t dims[4] = {static_cast<cuuint64_t>(g.Cin), static_cast<cuuint64_t>(g.Win), static_cast<cuuint64_t>(g.Hin),
+                                static_cast<cuuint64_t>(n_cap)};
+    const cuuint64_t strides[3] = {static_cast<cuuint64_t>(g.Cin) * 2, static_cast<cuuint64_t>(g.Win) * g.Cin * 2,
+                                   static_cast<cuuint64_t>(g.Hin) * g.Win * g.Cin * 2};
+    const cuuint32_t box[4] = {64u, 1u << g.lgBW, 1u << g.lgBH, 1u << g.lgBN};
+    const cuuint32_t es[4] = {1u, 1u, 1u, 1u};
+    CUresult r = ctx->encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, GANREV_ECUDA, "cuTensorMapEncodeTiled(A, %s) failed: %d", L.name.c_str(), (int)r);
+    switch (L.NT) {
+        case 32: return launch_tc<32>(ctx, L, tmA, g, n_items);
+        case 64: return launch_tc<64>(ctx, L, tmA, g, n_items);
+        case 128: return launch_tc<128>(ctx, L, tmA, g, n_items);
+        case 256: return launch_tc<256>(ctx, L, tmA, g, n_items);
+    }
+    return fail(ctx, GANREV_EINVAL, "unsupported NT=%d", L.NT);
+}
+
+// =================================================================================
+// model loading
+// =================================================================================
+static void release_layer(TcLayer& L) { release(L.w); release(L.scale); release(L.shift); }
+
+static int load_G_impl(ganrev_ctx* ctx, int C, int H, int W, int nd, const float* blob, size_t n_floats) {
+    RC_TRY(check_geom(ctx, C, H, W, nd));
+    const int sH = H / 4, sW = W / 4, HW0 = sH * sW, F = 512 * HW0;
+    const size_t need = static_cast<size_t>(F) * nd + 5 * static_cast<size_t>(F) + 256u * 512 * 9 + 5 * 256 + 128u * 256 * 9 + 5 * 128 +
+                        static_cast<size_t>(C) * 128 * 9 + C;
+    if (n_floats != need) return fail(ctx, GANREV_EINVAL, "G blob has %zu floats, expected %zu", n_floats, need);
+    GModel& G = ctx->G;
+    G.loaded = false;
+    const float* p = blob;
+    const float* lw = p; p += static_cast<size_t>(F) * nd;
+    const float* lb = p; p += F;
+    const float *g0 = p, *be0 = p + F, *m0 = p + 2 * static_cast<size_t>(F), *v0 = p + 3 * static_cast<size_t>(F); p += 4 * static_cast<size_t>(F);
+    const float* w1 = p; p += 256u * 512 * 9;
+    const float* b1 = p; p += 256;
+    const float *g1 = p, *be1 = p + 256, *m1 = p + 512, *v1 = p + 768; p += 1024;
+    const float* w2 = p; p += 128u * 256 * 9;
+    const float* b2 = p; p += 128;
+    const float *g2 = p, *be2 = p + 128, *m2 = p + 256, *v2 = p + 384; p += 512;
+    const float* w3 = p; p += static_cast<size_t>(C) * 128 * 9;
+    const float* b3 = p;
+
+    G.C = C; G.H = H; G.W = W; G.nd = nd; G.F = F;
+    G.kpad = (nd + 63) / 64 * 64;
+    {   // Linear + BN1d + ReLU; output features re-ordered from View(512,sH,sW) (NCHW, models.lua:118) to NHWC
+        std::vector<float> wm(static_cast<size_t>(F) * G.kpad, 0.0f);
+        std::vector<float> bb(F), gg(F), be(F), mm(F), vv(F);
+        for (int c = 0; c < 512; ++c)
+            for (int s = 0; s < HW0; ++s) {
+                const int fo = c * HW0 + s, fn = s * 512 + c;
+                memcpy(&wm[static_cast<size_t>(fn) * G.kpad], lw + static_cast<size_t>(fo) * nd, sizeof(float) * nd);
+                bb[fn] = lb[fo]; gg[fn] = g0[fo]; be[fn] = be0[fo]; mm[fn] = m0[fo]; vv[fn] = v0[fo];
+            }
+        BnFold bn = fold_bn(bb.data(), gg.data(), be.data(), mm.data(), vv.data(), F, F);
+        RC_TRY(build_tc_layer(ctx, G.lin, "g_linear", 256, 1, 1, G.kpad, 1, 1, kTap1, kTap1, F, F / 256, wm, bn, 1, 1, F, 1, 0, ACT_RELU, 1.0f, 0));
+    }
+    {
+        BnFold bn = fold_bn(b1, g1, be1, m1, v1, 256, 256);
+        RC_TRY(build_tc_layer(ctx, G.c1, "g_conv1_up", 256, sH, sW, 512, 4, 4, kPhaseY, kPhaseX, 256, 1, conv_w_phase(w1, 256, 512), bn,
+                              2 * sH, 2 * sW, 256, 2, 0, ACT_RELU, 1.0f, 0));
+    }
+    {
+        BnFold bn = fold_bn(b2, g2, be2, m2, v2, 128, 128);
+        RC_TRY(build_tc_layer(ctx, G.c2, "g_conv2_up", 128, 2 * sH, 2 * sW, 256, 4, 4, kPhaseY, kPhaseX, 128, 1, conv_w_phase(w2, 128, 256), bn,
+                              H, W, 128, 2, 0, ACT_RELU, 1.0f, 0));
+    }
+    {   // conv3 weights fp32 [C][9][128]
+        std::vector<float> w3p(static_cast<size_t>(C) * 9 * 128);
+        for (int co = 0; co < C; ++co)
+            for (int ci = 0; ci < 128; ++ci)
+                for (int t = 0; t < 9; ++t) w3p[(static_cast<size_t>(co) * 9 + t) * 128 + ci] = w3[(static_cast<size_t>(co) * 128 + ci) * 9 + t];
+        RC_TRY(upload(ctx, G.w3, w3p.data(), w3p.size() * 4));
+        RC_TRY(upload(ctx, G.b3, b3, sizeof(float) * C));
+    }
+    G.loaded = true;
+    return GANREV_OK;
+}
+
+static int load_R_impl(ganrev_ctx* ctx, int slot, int C, int H, int W, int nd, int tanh_out, const float* blob, size_t n_floats) {
+    RC_TRY(check_geom(ctx, C, H, W, nd));
+    if (slot < 0 || slot > 1) return fail(ctx, GANREV_EINVAL, "slot must be 0 or 1");
+    const int Hh = H / 2, Wh = W / 2, Hq = H / 4, Wq = W / 4, HWq = Hq * Wq, F = 128 * HWq;
+    const size_t need = static_cast<size_t>(64) * C * 9 + 5 * 64 + 2 * (64u * 64 * 9 + 5 * 64) + (128u * 64 * 9 + 5 * 128) +
+                        2 * (128u * 128 * 9 + 5 * 128) + 512 * static_cast<size_t>(F) + 5 * 512 + static_cast<size_t>(nd) * 512 + nd;
+    if (n_floats != need) return fail(ctx, GANREV_EINVAL, "R blob has %zu floats, expected %zu", n_floats, need);
+    RModel& R = ctx->R[slot];
+    R.loaded = false;
+    R.C = C; R.H = H; R.W = W; R.nd = nd; R.tanh_out = tanh_out;
+    const float* p = blob;
+    struct CB { const float *w, *b, *g, *be, *m, *v; };
+    auto take_cb = [&](int co, int ci) {
+        CB c;
+        c.w = p; p += static_cast<size_t>(co) * ci * 9;
+        c.b = p; p += co;
+        c.g = p; c.be = p + co; c.m = p + 2 * co; c.v = p + 3 * co; p += 4 * co;
+        return c;
+    };
+    const CB c1 = take_cb(64, C), c2 = take_cb(64, 64), c3 = take_cb(64, 64), c4 = take_cb(128, 64), c5 = take_cb(128, 128), c6 = take_cb(128, 128);
+    const float* l1w = p; p += 512 * static_cast<size_t>(F);
+    const float* l1b = p; p += 512;
+    const float *g7 = p, *be7 = p + 512, *m7 = p + 1024, *v7 = p + 1536; p += 2048;
+    const float* l2w = p; p += static_cast<size_t>(nd) * 512;
+    const float* l2b = p;
+
+    {   // conv1 pack: [k=(ci*3+ky)*3+kx][64] + scale[64] + shift[64]
+        const int K = C * 9;
+        std::vector<float> pack(static_cast<size_t>(K) * 64 + 128);
+        for (int co = 0; co < 64; ++co)
+            for (int k = 0; k < K; ++k) pack[static_cast<size_t>(k) * 64 + co] = c1.w[static_cast<size_t>(co) * K + k];
+        BnFold bn = fold_bn(c1.b, c1.g, c1.be, c1.m, c1.v, 64, 64);
+        memcpy(&pack[static_cast<size_t>(K) * 64], bn.scale.data(), 64 * 4);
+        memcpy(&pack[static_cast<size_t>(K) * 64 + 64], bn.shift.data(), 64 * 4);
+        RC_TRY(upload(ctx, R.c1pack, pack.data(), pack.size() * 4));
+    }
+    auto conv_layer = [&](TcLayer& L, const char* name, const CB& c, int co, int ci, int Hin, int Win, int pool, float post) {
+        BnFold bn = fold_bn(c.b, c.g, c.be, c.m, c.v, co, co);
+        const int Ho = pool ? Hin / 2 : Hin, Wo = pool ? Win / 2 : Win;
+        return build_tc_layer(ctx, L, name, co, Hin, Win, ci, 1, 9, kTaps9Y, kTaps9X, co, 1, conv_w_direct(c.w, co, ci, co), bn, Ho, Wo, co, 1,
+                              pool, ACT_ELU, post, 0);
+    };
+    RC_TRY(conv_layer(R.c2, "r_conv2", c2, 64, 64, H, W, 0, 1.0f));
+    RC_TRY(conv_layer(R.c3, "r_conv3_pool", c3, 64, 64, H, W, 1, 1.0f));
+    RC_TRY(conv_layer(R.c4, "r_conv4", c4, 128, 64, Hh, Wh, 0, 1.0f));
+    RC_TRY(conv_layer(R.c5, "r_conv5", c5, 128, 128, Hh, Wh, 0, 1.0f));
+    RC_TRY(conv_layer(R.c6, "r_conv6_pool", c6, 128, 128, Hh, Wh, 1, 0.75f));   // SpatialDropout(0.25) in eval: x0.75
+    {   // Linear(F -> 512) + BN1d + ELU; input columns re-ordered from View (NCHW flatten, models.lua:446) to NHWC
+        std::vector<float> wm(static_cast<size_t>(512) * F);
+        for (int o = 0; o < 512; ++o)
+            for (int c = 0; c < 128; ++c)
+                for (int s = 0; s < HWq; ++s) wm[static_cast<size_t>(o) * F + s * 128 + c] = l1w[static_cast<size_t>(o) * F + c * HWq + s];
+        BnFold bn = fold_bn(l1b, g7, be7, m7, v7, 512, 512);
+        RC_TRY(build_tc_layer(ctx, R.l1, "r_linear1", 64, 1, 1, F, 1, 1, kTap1, kTap1, 512, 8, wm, bn, 1, 1, 512, 1, 0, ACT_ELU, 1.0f, 0));
+    }
+    {   // Linear(512 -> nd) [+ Tanh], fp32 output
+        const int NT = nd <= 32 ? 32 : (nd <= 64 ? 64 : (nd <= 128 ? 128 : 256));
+        const int n_tiles = (nd + NT - 1) / NT, cp = n_tiles * NT;
+        std::vector<float> wm(static_cast<size_t>(cp) * 512, 0.0f);
+        memcpy(wm.data(), l2w, sizeof(float) * static_cast<size_t>(nd) * 512);
+        BnFold bn;
+        bn.scale.assign(cp, 0.0f); bn.shift.assign(cp, 0.0f);
+        for (int i = 0; i < nd; ++i) { bn.scale[i] = 1.0f; bn.shift[i] = l2b[i]; }
+        RC_TRY(build_tc_layer(ctx, R.l2, "r_linear2", NT, 1, 1, 512, 1, 1, kTap1, kTap1, nd, n_tiles, wm, bn, 1, 1, nd, 1, 0,
+                              tanh_out ? ACT_TANH : ACT_NONE, 1.0f, 1));
+    }
+    R.loaded = true;
+    return GANREV_OK;
+}
+
+// =================================================================================
+// pipelines (device pointers in, device pointers out)
+// =================================================================================
+static int ensure_arena(ganrev_ctx* ctx, size_t per_img_bytes, int64_t chunk) {
+    RC_TRY(ensure(ctx, ctx->arena[0], per_img_bytes * chunk));
+    RC_TRY(ensure(ctx, ctx->arena[1], per_img_bytes * chunk));
+    return GANREV_OK;
+}
+
+static int forward_G_dev(ganrev_ctx* ctx, const float* d_noise, int64_t N, float* d_images) {
+    GModel& G = ctx->G;
+    if (!G.loaded) return fail(ctx, GANREV_ESTATE, "G not loaded");
+    const int64_t CH = std::min<int64_t>(ctx->chunk, std::max<int64_t>(N, 1));
+    const size_t per_img = static_cast<size_t>(G.H) * G.W * 128 * 2;   // largest activation (conv2 out); a0/a1 are smaller
+    RC_TRY(ensure_arena(ctx, per_img, CH));
+    RC_TRY(ensure(ctx, ctx->noise_bf16, static_cast<size_t>(CH) * G.kpad * 2));
+    for (int64_t n0 = 0; n0 < N; n0 += CH) {
+        const int n = static_cast<int>(std::min<int64_t>(CH, N - n0));
+        {
+            ProfScope ps(ctx, "g_noise_to_bf16", 0.0, static_cast<double>(n) * (G.nd * 4.0 + G.kpad * 2.0));
+            const long long tot = static_cast<long long>(n) * G.kpad;
+            noise_to_bf16_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ctx->stream>>>(
+                d_noise + n0 * G.nd, G.nd, G.kpad, reinterpret_cast<bf16*>(ctx->noise_bf16.p), n);
+            CU_TRY(cudaGetLastError());
+        }
+        RC_TRY(run_layer(ctx, G.lin, ctx->noise_bf16.p, ctx->arena[0].p, n, CH));   // [n][sH][sW][512]
+        RC_TRY(run_layer(ctx, G.c1, ctx->arena[0].p, ctx->arena[1].p, n, CH));      // [n][2sH][2sW][256]
+        RC_TRY(run_layer(ctx, G.c2, ctx->arena[1].p, ctx->arena[0].p, n, CH));      // [n][H][W][128]
+        {
+            const double px = static_cast<double>(n) * G.H * G.W;
+            ProfScope ps(ctx, "g_conv3_sigmoid", 2.0 * px * 1152 * G.C, px * (128 * 2.0 + 4.0 * G.C));
+            const long long warps = static_cast<long long>(n) * (G.H * G.W / 32);
+            const unsigned blocks = static_cast<unsigned>((warps * 32 + 255) / 256);
+            float* o = d_images + n0 * G.C * G.H * G.W;
+            if (G.C == 1)
+                g_conv3_kernel<1><<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const bf16*>(ctx->arena[0].p), (const float*)G.w3.p, (const float*)G.b3.p, o, G.H, G.W, n);
+            else
+                g_conv3_kernel<3><<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const bf16*>(ctx->arena[0].p), (const float*)G.w3.p, (const float*)G.b3.p, o, G.H, G.W, n);
+            CU_TRY(cudaGetLastError());
+        }
+    }
+    return GANREV_OK;
+}
+
+static int forward_R_dev(ganrev_ctx* ctx, int slot, const float* d_images, const uint8_t* d_mask, int64_t N, float* d_attrs) {
+    if (slot < 0 || slot > 1) return fail(ctx, GANREV_EINVAL, "slot must be 0 or 1");
+    RModel& R = ctx->R[slot];
+    if (!R.loaded) return fail(ctx, GANREV_ESTATE, "R slot %d not loaded", slot);
+    const int64_t CH = std::min<int64_t>(ctx->chunk, std::max<int64_t>(N, 1));
+    const size_t per_img = static_cast<size_t>(R.H) * R.W * 64 * 2;   // conv1/conv2 outputs are the largest
+    RC_TRY(ensure_arena(ctx, per_img, CH));
+    const long long img_elems = static_cast<long long>(R.C) * R.H * R.W;
+    for (int64_t n0 = 0; n0 < N; n0 += CH) {
+        const int n = static_cast<int>(std::min<int64_t>(CH, N - n0));
+        {
+            const long long npix = static_cast<long long>(n) * R.H * R.W;
+            ProfScope ps(ctx, "r_conv1", 2.0 * npix * 64 * 9 * R.C, npix * (R.C * (4.0 + (d_mask ? 1.0 : 0.0)) + 128.0));
+            const unsigned blocks = static_cast<unsigned>((npix + 127) / 128);
+            const float* in = d_images + n0 * img_elems;
+            const uint8_t* mk = d_mask ? d_mask + n0 * img_elems : nullptr;
+            if (R.C == 1)
+                r_conv1_kernel<1><<<blocks, 128, 0, ctx->stream>>>(in, mk, (const float*)R.c1pack.p, reinterpret_cast<bf16*>(ctx->arena[0].p), R.H, R.W, npix);
+            else
+                r_conv1_kernel<3><<<blocks, 128, 0, ctx->stream>>>(in, mk, (const float*)R.c1pack.p, reinterpret_cast<bf16*>(ctx->arena[0].p), R.H, R.W, npix);
+            CU_TRY(cudaGetLastError());
+        }
+        RC_TRY(run_layer(ctx, R.c2, ctx->arena[0].p, ctx->arena[1].p, n, CH));
+        RC_TRY(run_layer(ctx, R.c3, ctx->arena[1].p, ctx->arena[0].p, n, CH));
+        RC_TRY(run_layer(ctx, R.c4, ctx->arena[0].p, ctx->arena[1].p, n, CH));
+        RC_TRY(run_layer(ctx, R.c5, ctx->arena[1].p, ctx->arena[0].p, n, CH));
+        RC_TRY(run_layer(ctx, R.c6, ctx->arena[0].p, ctx->arena[1].p, n, CH));
+        RC_TRY(run_layer(ctx, R.l1, ctx->arena[1].p, ctx->arena[0].p, n, CH));
+        RC_TRY(run_layer(ctx, R.l2, ctx->arena[0].p, d_attrs + n0 * R.nd, n, CH));
+    }
+    return GANREV_OK;
+}
+
+static int l2_dev(ganrev_ctx* ctx, const float* a, const float* b, int64_t N, int px, double* out) {
+    ProfScope ps(ctx, "l2_pairs", 3.0 * N * px, 8.0 * N * px + 8.0 * N);
+    const unsigned blocks = static_cast<unsigned>((N * 32 + 255) / 256);
+    if (N > 0) l2_pairs_kernel<<<blocks, 256, 0, ctx->stream>>>(a, b, N, px, out);
+    CU_TRY(cudaGetLastError());
+    return GANREV_OK;
+}
+
+// =================================================================================
+// C ABI
+// =================================================================================
+extern "C" {
+
+int ganrev_version(void) { return 100; }
+
+int ganrev_create(ganrev_ctx** out, int device) {
+    if (!out) return GANREV_EINVAL;
+    *out = nullptr;
+    std::unique_ptr<ganrev_ctx> c(new ganrev_ctx());
+    ganrev_ctx* ctx = c.get();
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return GANREV_ENODEV;
+    if (device < 0 || device >= count) return GANREV_ENODEV;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GANREV_ENODEV;
+    if (prop.major != 10) return GANREV_ENODEV;   // tcgen05 / TMEM kernels are sm_100a only; there is no fallback
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess) return GANREV_ECUDA;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return GANREV_ECUDA;
+    if (cudaMalloc(&ctx->d_err_flag, sizeof(int)) != cudaSuccess) return GANREV_ENOMEM;
+    cudaMemset(ctx->d_err_flag, 0, sizeof(int));
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return GANREV_ECUDA;
+    ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    *out = c.release();
+    return GANREV_OK;
+}
+
+void ganrev_destroy(ganrev_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    prof_resolve(ctx);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
+    for (TcLayer* L : {&ctx->G.lin, &ctx->G.c1, &ctx->G.c2}) release_layer(*L);
+    release(ctx->G.w3); release(ctx->G.b3);
+    for (int s = 0; s < 2; ++s) {
+        RModel& R = ctx->R[s];
+        release(R.c1pack);
+        for (TcLayer* L : {&R.c2, &R.c3, &R.c4, &R.c5, &R.c6, &R.l1, &R.l2}) release_layer(*L);
+    }
+    for (auto& b : ctx->buf) release(b);
+    for (DevBuf* b : {&ctx->arena[0], &ctx->arena[1], &ctx->noise_bf16, &ctx->stage_a, &ctx->stage_b, &ctx->l2buf, &ctx->thr, &ctx->flags,
+                      &ctx->db, &ctx->rdb, &ctx->maxabs, &ctx->q, &ctx->rq, &ctx->c2, &ctx->partial, &ctx->keys, &ctx->keys_all, &ctx->ids,
+                      &ctx->scores, &ctx->cen, &ctx->acc, &ctx->cnt, &ctx->total, &ctx->labels, &ctx->cosv, &ctx->tcounts, &ctx->mids,
+                      &ctx->mcnt, &ctx->mmean})
+        release(*b);
+    if (ctx->d_err_flag) cudaFree(ctx->d_err_flag);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* ganrev_last_error(const ganrev_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+// ---------------------------------------------------------------- NCCL (dlopen)
+static int nccl_load(ganrev_ctx* ctx) {
+    NcclApi& a = ctx->nccl;
+    if (a.h) return GANREV_OK;
+    a.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!a.h) a.h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!a.h) return fail(ctx, GANREV_ENCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define NCCL_SYM(field, sym)                                                     \
+    a.field = reinterpret_cast<decltype(a.field)>(dlsym(a.h, sym));              \
+    if (!a.field) return fail(ctx, GANREV_ENCCL, "libnccl lacks %s", sym);
+    NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    NCCL_SYM(AllGather, "ncclAllGather")
+    NCCL_SYM(AllReduce, "ncclAllReduce")
+    NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef NCCL_SYM
+    return GANREV_OK;
+}
+#define NCCL_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        ncclResult_t r_ = (expr);                                                                        \
+        if (r_ != ncclSuccess) return fail(ctx, GANREV_ENCCL, "%s failed: %s", #expr, ctx->nccl.GetErrorString(r_)); \
+    } while (0)
+
+int ganrev_comm_unique_id(ganrev_ctx* ctx, void* out, size_t cap, size_t* len) {
+    if (!ctx || !out) return GANREV_EINVAL;
+    if (cap < sizeof(ncclUniqueId)) return fail(ctx, GANREV_EINVAL, "unique id needs %zu bytes", sizeof(ncclUniqueId));
+    RC_TRY(nccl_load(ctx));
+    ncclUniqueId id;
+    NCCL_TRY(ctx->nccl.GetUniqueId(&id));
+    memcpy(out, &id, sizeof(id));
+    if (len) *len = sizeof(id);
+    return GANREV_OK;
+}
+
+int ganrev_comm_init(ganrev_ctx* ctx, int world, int rank, const void* uid, size_t len) {
+    if (!ctx || !uid || world < 1 || rank < 0 || rank >= world) return ctx ? fail(ctx, GANREV_EINVAL, "bad comm arguments") : GANREV_EINVAL;
+    if (len != sizeof(ncclUniqueId)) return fail(ctx, GANREV_EINVAL, "unique id must be %zu bytes", sizeof(ncclUniqueId));
+    CU_TRY(cudaSetDevice(ctx->device));
+    RC_TRY(nccl_load(ctx));
+    ncclUniqueId id;
+    memcpy(&id, uid, sizeof(id));
+    NCCL_TRY(ctx->nccl.CommInitRank(&ctx->comm, world, id, rank));
+    ctx->world = world; ctx->rank = rank;
+    return GANREV_OK;
+}
+
+// ---------------------------------------------------------------- models
+int ganrev_load_G(ganrev_ctx* ctx, int C, int H, int W, int noise_dim, const float* blob, size_t n_floats) {
+    if (!ctx || !blob) return GANREV_EINVAL;
+    CU_TRY(cudaSetDevice(ctx->device));
+    return load_G_impl(ctx, C, H, W, noise_dim, blob, n_floats);
+}
+int ganrev_load_R(ganrev_ctx* ctx, int slot, int C, int H, int W, int noise_dim, int tanh_out, const float* blob, size_t n_floats) {
+    if (!ctx || !blob) return GANREV_EINVAL;
+    CU_TRY(cudaSetDevice(ctx->device));
+    return load_R_impl(ctx, slot, C, H, W, noise_dim, tanh_out, blob, n_floats);
+}
+
+// ---------------------------------------------------------------- resident buffers
+static size_t buf_row_bytes(ganrev_ctx* ctx, int which) {
+    int C = 0, H = 0, W = 0, nd = 0;
+    if (ctx->G.loaded) { C = ctx->G.C; H = ctx->G.H; W = ctx->G.W; nd = ctx->G.nd; }
+    else for (int s = 0; s < 2; ++s) if (ctx->R[s].loaded) { C = ctx->R[s].C; H = ctx->R[s].H; W = ctx->R[s].W; nd = ctx->R[s].nd; break; }
+    switch (which) {
+        case GANREV_BUF_NOISE: case GANREV_BUF_ATTRS0: case GANREV_BUF_ATTRS1: return static_cast<size_t>(nd) * 4;
+        case GANREV_BUF_IMAGES: case GANREV_BUF_FIXED: return static_cast<size_t>(C) * H * W * 4;
+        case GANREV_BUF_MASK: return static_cast<size_t>(C) * H * W;
+    }
+    return 0;
+}
+static int buf_reserve(ganrev_ctx* ctx, int which, int64_t rows) {
+    const size_t rb = buf_row_bytes(ctx, which);
+    if (rb == 0) return fail(ctx, GANREV_ESTATE, "load a model before using resident buffers");
+    RC_TRY(ensure(ctx, ctx->buf[which], rb * static_cast<size_t>(std::max<int64_t>(rows, 1))));
+    return GANREV_OK;
+}
+int ganrev_buffer_put(ganrev_ctx* ctx, int which, const void* host, int64_t rows) {
+    if (!ctx || !host || which < 0 || which >= GANREV_BUF_COUNT || rows < 0) return ctx ? fail(ctx, GANREV_EINVAL, "bad buffer_put arguments") : GANREV_EINVAL;
+    CU_TRY(cudaSetDevice(ctx->device));
+    RC_TRY(buf_reserve(ctx, which, rows));
+    CU_TRY(cudaMemcpyAsync(ctx->buf[which].p, host, buf_row_bytes(ctx, which) * rows, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->buf_rows[which] = rows;
+    return finish(ctx);
+}
+int ganrev_buffer_get(ganrev_ctx* ctx, int which, void* host, int64_t row0, int64_t rows) {
+    if (!ctx || !host || which < 0 || which >= GANREV_BUF_COUNT || rows < 0 || row0 < 0) return ctx ? fail(ctx, GANREV_EINVAL, "bad buffer_get arguments") : GANREV_EINVAL;
+    if (row0 + rows > ctx->buf_rows[which]) return fail(ctx, GANREV_ESTATE, "buffer %d holds %lld rows", which, (long long)ctx->buf_rows[which]);
+    CU_TRY(cudaSetDevice(ctx->device));
+    const size_t rb = buf_row_bytes(ctx, which);
+    CU_TRY(cudaMemcpyAsync(host, static_cast<const uint8_t*>(ctx->buf[which].p) + rb * row0, rb * rows, cudaMemcpyDeviceToHost, ctx->stream));
+    return finish(ctx);
+}
+
+// input helper: host pointer -> upload into resident buffer; NULL -> resident buffer must hold >= N rows
+static int stage_input(ganrev_ctx* ctx, int which, const void* host, int64_t N) {
+    if (host) {
+        RC_TRY(buf_reserve(ctx, which, N));
+        CU_TRY(cudaMemcpyAsync(ctx->buf[which].p, host, buf_row_bytes(ctx, which) * N, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->buf_rows[which] = N;
+    } else if (ctx->buf_rows[which] < N || !ctx->buf[which].p) {
+        return fail(ctx, GANREV_ESTATE, "resident buffer %d holds %lld rows, need %lld", which, (long long)ctx->buf_rows[which], (long long)N);
+    }
+    return GANREV_OK;
+}
+static int fetch_output(ganrev_ctx* ctx, int which, void* host, int64_t N) {
+    if (host) CU_TRY(cudaMemcpyAsync(host, ctx->buf[which].p, buf_row_bytes(ctx, which) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    return GANREV_OK;
+}
+
+// ---------------------------------------------------------------- forward passes
+int ganrev_forward_G(ganrev_ctx* ctx, const float* noise, int64_t N, float* images) {
+    if (!ctx || N < 0) return ctx ? fail(ctx, GANREV_EINVAL, "bad forward_G arguments") : GANREV_EINVAL;
+    if (!ctx->G.loaded) return fail(ctx, GANREV_ESTATE, "G not loaded");
+    CU_TRY(cudaSetDevice(ctx->device));
+    RC_TRY(stage_input(ctx, GANREV_BUF_NOISE, noise, N));
+    RC_TRY(buf_reserve(ctx, GANREV_BUF_IMAGES, N));
+    RC_TRY(forward_G_dev(ctx, static_cast<const float*>(ctx->buf[GANREV_BUF_NOISE].p), N, static_cast<float*>(ctx->buf[GANREV_BUF_IMAGES].p)));
+    ctx->buf_rows[GANREV_BUF_IMAGES] = N;
+    RC_TRY(fetch_output(ctx, GANREV_BUF_IMAGES, images, N));
+    return finish(ctx);
+}
+
+int ganrev_forward_R(ganrev_ctx* ctx, int slot, const float* images, const uint8_t* mask, int64_t N, float* attrs) {
+    if (!ctx || N < 0 || slot < 0 || slot > 1) return ctx ? fail(ctx, GANREV_EINVAL, "bad forward_R arguments") : GANREV_EINVAL;
+    if (!ctx->R[slot].loaded) return fail(ctx, GANREV_ESTATE, "R slot %d not loaded", slot);
+    CU_TRY(cudaSetDevice(ctx->device));
+    RC_TRY(stage_input(ctx, GANREV_BUF_IMAGES, images, N));
+    const uint8_t* d_mask = nullptr;
+    if (mask) {
+        RC_TRY(stage_input(ctx, GANREV_BUF_MASK, mask, N));
+        d_mask = static_cast<const uint8_t*>(ctx->buf[GANREV_BUF_MASK].p);
+    }
+    const int ob = slot == 0 ? GANREV_BUF_ATTRS0 : GANREV_BUF_ATTRS1;
+    RC_TRY(buf_reserve(ctx, ob, N));
+    RC_TRY(forward_R_dev(ctx, slot, static_cast<const float*>(ctx->buf[GANREV_BUF_IMAGES].p), d_mask, N, static_cast<float*>(ctx->buf[ob].p)));
+    ctx->buf_rows[ob] = N;
+    RC_TRY(fetch_output(ctx, ob, attrs, N));
+    return finish(ctx);
+}
+
+int ganrev_fix_l2(ganrev_ctx* ctx, int slot, const float* images, const uint8_t* mask, int64_t N, float* attrs, float* fixed, double* l2) {
+    if (!ctx || N < 0 || slot < 0 || slot > 1) return ctx ? fail(ctx, GANREV_EINVAL, "bad fix_l2 arguments") : GANREV_EINVAL;
+    if (!ctx->R[slot].loaded || !ctx->G.loaded) return fail(ctx, GANREV_ESTATE, "fix_l2 needs G and R slot %d", slot);
+    if (ctx->G.nd != ctx->R[slot].nd || ctx->G.C != ctx->R[slot].C || ctx->G.H != ctx->R[slot].H || ctx->G.W != ctx->R[slot].W)
+        return fail(ctx, GANREV_ESTATE, "G and R geometries differ");
+    CU_TRY(cudaSetDevice(ctx->device));
+    RC_TRY(stage_input(ctx, GANREV_BUF_IMAGES, images, N));
+    const uint8_t* d_mask = nullptr;
+    if (mask) {
+        RC_TRY(stage_input(ctx, GANREV_BUF_MASK, mask, N));
+        d_mask = static_cast<const uint8_t*>(ctx->buf[GANREV_BUF_MASK].p);
+    }
+    const int ob = slot == 0 ? GANREV_BUF_ATTRS0 : GANREV_BUF_ATTRS1;
+    RC_TRY(buf_reserve(ctx, ob, N));
+    RC_TRY(buf_reserve(ctx, GANREV_BUF_FIXED, N));
+    RC_TRY(ensure(ctx, ctx->l2buf, sizeof(double) * static_cast<size_t>(std::max<int64_t>(N, 1))));
+    const float* d_img = static_cast<const float*>(ctx->buf[GANREV_BUF_IMAGES].p);
+    float* d_att = static_cast<float*>(ctx->buf[ob].p);
+    float* d_fix = static_cast<float*>(ctx->buf[GANREV_BUF_FIXED].p);
+    RC_TRY(forward_R_dev(ctx, slot, d_img, d_mask, N, d_att));
+    ctx->buf_rows[ob] = N;
+    RC_TRY(forward_G_dev(ctx, d_att, N, d_fix));
+    ctx->buf_rows[GANREV_BUF_FIXED] = N;
+    RC_TRY(l2_dev(ctx, d_img, d_fix, N, ctx->G.C * ctx->G.H * ctx->G.W, static_cast<double*>(ctx->l2buf.p)));
+    RC_TRY(fetch_output(ctx, ob, attrs, N));
+    RC_TRY(fetch_output(ctx, GANREV_BUF_FIXED, fixed, N));
+    if (l2) CU_TRY(cudaMemcpyAsync(l2, ctx->l2buf.p, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    return finish(ctx);
+}
+
+int ganrev_l2(ganrev_ctx* ctx, const float* a, const float* b, int64_t N, int px, double* l2) {
+    if (!ctx || !a || !b || !l2 || N < 0 || px < 1) return ctx ? fail(ctx, GANREV_EINVAL, "bad l2 arguments") : GANREV_EINVAL;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const size_t bytes = sizeof(float) * static_cast<size_t>(N) * px;
+    RC_TRY(ensure(ctx, ctx->stage_a, bytes));
+    RC_TRY(ensure(ctx, ctx->stage_b, bytes));
+    RC_TRY(ensure(ctx, ctx->l2buf, sizeof(double) * static_cast<size_t>(std::max<int64_t>(N, 1))));
+    CU_TRY(cudaMemcpyAsync(ctx->stage_a.p, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(ctx->stage_b.p, b, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    RC_TRY(l2_dev(ctx, static_cast<const float*>(ctx->stage_a.p), static_cast<const float*>(ctx->stage_b.p), N, px, static_cast<double*>(ctx->l2buf.p)));
+    CU_TRY(cudaMemcpyAsync(l2, ctx->l2buf.p, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    return finish(ctx);
+}
+
+int ganrev_anomaly_flags(ganrev_ctx* ctx, const double* l2, int64_t n_calc, int64_t n_show, double quantile, uint8_t* flags, double* thr) {
+    if (!ctx || n_calc < 1 || n_show < 0 || n_show > n_calc || !flags) return ctx ? fail(ctx, GANREV_EINVAL, "bad anomaly_flags arguments") : GANREV_EINVAL;
+    const int64_t r = static_cast<int64_t>(std::floor(static_cast<double>(n_calc) * quantile));   // math.floor(#distancesForSort*threshold)
+    if (r < 1 || r > n_calc) return fail(ctx, GANREV_EINVAL, "floor(n_calc*quantile)=%lld is not a valid 1-based index", (long long)r);
+    CU_TRY(cudaSetDevice(ctx->device));
+    RC_TRY(ensure(ctx, ctx->l2buf, sizeof(double) * static_cast<size_t>(n_calc)));
+    RC_TRY(ensure(ctx, ctx->thr, sizeof(double)));
+    RC_TRY(ensure(ctx, ctx->flags, static_cast<size_t>(std::max<int64_t>(n_show, 1))));
+    if (l2) CU_TRY(cudaMemcpyAsync(ctx->l2buf.p, l2, sizeof(double) * n_calc, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        ProfScope ps(ctx, "quantile_select", 0.0, 8.0 * 8.0 * n_calc);
+        quantile_select_kernel<<<1, 1024, 0, ctx->stream>>>(static_cast<const double*>(ctx->l2buf.p), n_calc, r - 1, static_cast<double*>(ctx->thr.p));
+        CU_TRY(cudaGetLastError());
+    }
+    if (n_show > 0) {
+        ProfScope ps(ctx, "anomaly_flags", 0.0, 9.0 * n_show);
+        anomaly_flags_kernel<<<static_cast<unsigned>((n_show + 255) / 256), 256, 0, ctx->stream>>>(
+            static_cast<const double*>(ctx->l2buf.p), n_show, static_cast<const double*>(ctx->thr.p), static_cast<uint8_t*>(ctx->flags.p));
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(flags, ctx->flags.p, n_show, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (thr) CU_TRY(cudaMemcpyAsync(thr, ctx->thr.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return finish(ctx);
+}
+
+// ---------------------------------------------------------------- database
+static int vec_prep(ganrev_ctx* ctx, const float* x, int64_t n, int d, float* rn, float* halfsq, unsigned int* maxabs) {
+    ProfScope ps(ctx, "vec_prep", 2.0 * n * d, 4.0 * n * d);
+    if (n > 0) scan::vec_prep_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, ctx->stream>>>(x, n, d, rn, halfsq, maxabs);
+    CU_TRY(cudaGetLastError());
+    return GANREV_OK;
+}
+
+int ganrev_db_set(ganrev_ctx* ctx, const float* vecs, int64_t N, int d) {
+    if (!ctx || N < 0 || d < 1 || N > 0xFFFFFFF0ll) return ctx ? fail(ctx, GANREV_EINVAL, "bad db_set arguments") : GANREV_EINVAL;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const size_t bytes = sizeof(float) * static_cast<size_t>(N) * d;
+    RC_TRY(ensure(ctx, ctx->db, bytes));
+    RC_TRY(ensure(ctx, ctx->rdb, sizeof(float) * static_cast<size_t>(std::max<int64_t>(N, 1))));
+    RC_TRY(ensure(ctx, ctx->maxabs, 3 * sizeof(long long)));
+    if (vecs) {
+        CU_TRY(cudaMemcpyAsync(ctx->db.p, vecs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        if (ctx->buf_rows[GANREV_BUF_ATTRS0] < N || buf_row_bytes(ctx, GANREV_BUF_ATTRS0) != sizeof(float) * static_cast<size_t>(d))
+            return fail(ctx, GANREV_ESTATE, "resident ATTRS0 does not hold %lld x %d", (long long)N, d);
+        CU_TRY(cudaMemcpyAsync(ctx->db.p, ctx->buf[GANREV_BUF_ATTRS0].p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CU_TRY(cudaMemsetAsync(ctx->maxabs.p, 0, 3 * sizeof(long long), ctx->stream));
+    RC_TRY(vec_prep(ctx, static_cast<const float*>(ctx->db.p), N, d, static_cast<float*>(ctx->rdb.p), nullptr, static_cast<unsigned int*>(ctx->maxabs.p)));
+    ctx->db_n = N; ctx->db_d = d; ctx->assigned = false;
+    unsigned int mb = 0;
+    CU_TRY(cudaMemcpyAsync(&mb, ctx->maxabs.p, sizeof(mb), cudaMemcpyDeviceToHost, ctx->stream));
+    RC_TRY(finish(ctx));
+    memcpy(&ctx->db_maxabs, &mb, 4);
+    ctx->db_offset = 0; ctx->db_total = N;
+    if (ctx->world > 1) {
+        // row-shard bookkeeping: global offset = sum of the lower ranks' N; global max|x|
+        std::vector<long long> all(ctx->world);
+        long long* d_all = nullptr;
+        CU_TRY(cudaMalloc(&d_all, sizeof(long long) * (ctx->world + 1)));
+        long long mine = N;
+        CU_TRY(cudaMemcpyAsync(d_all + ctx->world, &mine, sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        NCCL_TRY(ctx->nccl.AllGather(d_all + ctx->world, d_all, 1, ncclInt64, ctx->comm, ctx->stream));
+        NCCL_TRY(ctx->nccl.AllReduce(ctx->maxabs.p, ctx->maxabs.p, 1, ncclUint32, ncclMax, ctx->comm, ctx->stream));
+        CU_TRY(cudaMemcpyAsync(all.data(), d_all, sizeof(long long) * ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(cudaMemcpyAsync(&mb, ctx->maxabs.p, sizeof(mb), cudaMemcpyDeviceToHost, ctx->stream));
+        int rc = finish(ctx);
+        cudaFree(d_all);
+        RC_TRY(rc);
+        memcpy(&ctx->db_maxabs, &mb, 4);
+        ctx->db_offset = 0; ctx->db_total = 0;
+        for (int r = 0; r < ctx->world; ++r) { if (r < ctx->rank) ctx->db_offset += all[r]; ctx->db_total += all[r]; }
+        if (ctx->db_total > 0xFFFFFFF0ll) return fail(ctx, GANREV_EINVAL, "global database exceeds 2^32 rows");
+    }
+    return GANREV_OK;
+}
+
+int ganrev_cosine(ganrev_ctx* ctx, const float* a, const float* b, int d, float* out) {
+    if (!ctx || !a || !b || !out || d < 1) return ctx ? fail(ctx, GANREV_EINVAL, "bad cosine arguments") : GANREV_EINVAL;
+    CU_TRY(cudaSetDevice(ctx->device));
+    RC_TRY(ensure(ctx, ctx->stage_a, sizeof(float) * (2 * static_cast<size_t>(d) + 1)));
+    float* da = static_cast<float*>(ctx->stage_a.p);
+    CU_TRY(cudaMemcpyAsync(da, a, sizeof(float) * d, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(da + d, b, sizeof(float) * d, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        ProfScope ps(ctx, "cosine_pair", 6.0 * d, 8.0 * d);
+        scan::cosine_pair_kernel<<<1, 32, 0, ctx->stream>>>(da, da + d, d, da + 2 * d);
+        CU_TRY(cudaGetLastError());
+    }
+    CU_TRY(cudaMemcpyAsync(out, da + 2 * d, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    return finish(ctx);
+}
+
+}  // extern "C"
+template <int TQ, int E>
+static int launch_search(ganrev_ctx* ctx, const scan::ScanParams& p, int splits) {
+    constexpr int QT = 16 * TQ, K2 = 32 * E;
+    const size_t smem = sizeof(float) * (scan::DK * scan::XS + scan::DK * QT) + sizeof(unsigned long long) * (QT * K2 + QT * scan::CAP + QT) + sizeof(int) * QT;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU_TRY(cudaFuncSetAttribute(scan::search_kernel<TQ, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr_set = true;
+    }
+    dim3 grid(splits, (p.nq + QT - 1) / QT);
+    scan::search_kernel<TQ, E><<<grid, scan::kThreads, smem, ctx->stream>>>(p);
+    CU_TRY(cudaGetLastError());
+    return GANREV_OK;
+}
+
+extern "C" {
+int ganrev_search_cosine(ganrev_ctx* ctx, const float* queries, int Q, int k, int64_t* ids, float* scores) {
+    if (!ctx || !queries || Q < 0 || k < 1 || k > 128 || !ids || !scores) return ctx ? fail(ctx, GANREV_EINVAL, "bad search arguments (k must be 1..128)") : GANREV_EINVAL;
+    if (!ctx->db.p) return fail(ctx, GANREV_ESTATE, "database not set");
+    if (Q == 0) return GANREV_OK;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const int d = ctx->db_d;
+    const int64_t N = ctx->db_n;
+    RC_TRY(ensure(ctx, ctx->q, sizeof(float) * static_cast<size_t>(Q) * d));
+    RC_TRY(ensure(ctx, ctx->rq, sizeof(float) * Q));
+    CU_TRY(cudaMemcpyAsync(ctx->q.p, queries, sizeof(float) * static_cast<size_t>(Q) * d, cudaMemcpyHostToDevice, ctx->stream));
+    RC_TRY(vec_prep(ctx, static_cast<const float*>(ctx->q.p), Q, d, static_cast<float*>(ctx->rq.p), nullptr, nullptr));
+    const int TQ = Q <= 16 ? 1 : 4;
+    const int QT = 16 * TQ;
+    const int qtiles = (Q + QT - 1) / QT;
+    // row splits: fill the machine about 4 blocks per SM deep, at least one 128-row tile each
+    const int64_t row_tiles = std::max<int64_t>(1, (N + scan::RT - 1) / scan::RT);
+    int splits = static_cast<int>(std::min<int64_t>(row_tiles, std::max<int64_t>(1, (4LL * ctx->num_sms + qtiles - 1) / qtiles)));
+    const int64_t rows_per_split = ((row_tiles + splits - 1) / splits) * scan::RT;
+    splits = static_cast<int>(std::max<int64_t>(1, (N + rows_per_split - 1) / rows_per_split));
+    RC_TRY(ensure(ctx, ctx->partial, sizeof(unsigned long long) * static_cast<size_t>(splits) * Q * k));
+    RC_TRY(ensure(ctx, ctx->ids, sizeof(long long) * static_cast<size_t>(Q) * k));
+    RC_TRY(ensure(ctx, ctx->scores, sizeof(float) * static_cast<size_t>(Q) * k));
+    scan::ScanParams p{};
+    p.db = static_cast<const float*>(ctx->db.p); p.rdb = static_cast<const float*>(ctx->rdb.p); p.n_rows = N; p.d = d;
+    p.q = static_cast<const float*>(ctx->q.p); p.rq = static_cast<const float*>(ctx->rq.p); p.nq = Q; p.k = k;
+    p.partial = static_cast<unsigned long long*>(ctx->partial.p); p.rows_per_split = rows_per_split;
+    {
+        ProfScope ps(ctx, "search_scan", 2.0 * N * Q * d, 4.0 * N * d + 4.0 * Q * d + 8.0 * splits * Q * k);
+        if (TQ == 1) { if (k <= 32) RC_TRY((launch_search<1, 1>(ctx, p, splits))); else RC_TRY((launch_search<1, 4>(ctx, p, splits))); }
+        else         { if (k <= 32) RC_TRY((launch_search<4, 1>(ctx, p, splits))); else RC_TRY((launch_search<4, 4>(ctx, p, splits))); }
+    }
+    const unsigned mblocks = static_cast<unsigned>((static_cast<long long>(Q) * 32 + scan::kThreads - 1) / scan::kThreads);
+    const bool multi = ctx->world > 1;
+    if (multi) {
+        RC_TRY(ensure(ctx, ctx->keys, sizeof(unsigned long long) * static_cast<size_t>(Q) * k));
+        RC_TRY(ensure(ctx, ctx->keys_all, sizeof(unsigned long long) * static_cast<size_t>(Q) * k * ctx->world));
+    }
+    {
+        ProfScope ps(ctx, "search_merge", 0.0, 8.0 * splits * Q * k + 12.0 * Q * k);
+        if (k <= 32)
+            scan::merge_kernel<1><<<mblocks, scan::kThreads, 0, ctx->stream>>>(p.partial, splits, Q, k, ctx->db_offset, multi ? 1 : 0,
+                static_cast<long long*>(ctx->ids.p), static_cast<float*>(ctx->scores.p), static_cast<unsigned long long*>(ctx->keys.p));
+        else
+            scan::merge_kernel<4><<<mblocks, scan::kThreads, 0, ctx->stream>>>(p.partial, splits, Q, k, ctx->db_offset, multi ? 1 : 0,
+                static_cast<long long*>(ctx->ids.p), static_cast<float*>(ctx->scores.p), static_cast<unsigned long long*>(ctx->keys.p));
+        CU_TRY(cudaGetLastError());
+    }
+    if (multi) {
+        // per-query top-k allgather (Q*k*8 B per rank), then the same merge over `world` partial lists
+        NCCL_TRY(ctx->nccl.AllGather(ctx->keys.p, ctx->keys_all.p, static_cast<size_t>(Q) * k, ncclUint64, ctx->comm, ctx->stream));
+        ProfScope ps(ctx, "search_merge_global", 0.0, 8.0 * ctx->world * Q * k + 12.0 * Q * k);
+        if (k <= 32)
+            scan::merge_kernel<1><<<mblocks, scan::kThreads, 0, ctx->stream>>>(static_cast<const unsigned long long*>(ctx->keys_all.p), ctx->world, Q, k, 0, 0,
+                static_cast<long long*>(ctx->ids.p), static_cast<float*>(ctx->scores.p), nullptr);
+        else
+            scan::merge_kernel<4><<<mblocks, scan::kThreads, 0, ctx->stream>>>(static_cast<const unsigned long long*>(ctx->keys_all.p), ctx->world, Q, k, 0, 0,
+                static_cast<long long*>(ctx->ids.p), static_cast<float*>(ctx->scores.p), nullptr);
+        CU_TRY(cudaGetLastError());
+    }
+    CU_TRY(cudaMemcpyAsync(ids, ctx->ids.p, sizeof(long long) * static_cast<size_t>(Q) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(scores, ctx->scores.p, sizeof(float) * static_cast<size_t>(Q) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    return finish(ctx);
+}
+
+}  // extern "C"
+template <int TQ, int MODE>
+static int launch_assign(ganrev_ctx* ctx, const scan::ScanParams& p) {
+    constexpr int QT = 16 * TQ;
+    size_t smem = sizeof(float) * (scan::DK * scan::XS + scan::DK * QT + 16 * scan::RT) + sizeof(int) * (16 * scan::RT + scan::RT);
+    if (MODE == 1 && p.smem_acc) smem += sizeof(unsigned long long) * (static_cast<size_t>(p.nq) * p.d + p.nq);
+    static size_t attr_max = 0;
+    if (smem > attr_max) {
+        CU_TRY(cudaFuncSetAttribute(scan::assign_kernel<TQ, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr_max = smem;
+    }
+    const long long n_tiles = (p.n_rows + scan::RT - 1) / scan::RT;
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(n_tiles, 4LL * ctx->num_sms)));
+    scan::assign_kernel<TQ, MODE><<<grid, scan::kThreads, smem, ctx->stream>>>(p, n_tiles);
+    CU_TRY(cudaGetLastError());
+    return GANREV_OK;
+}
+
+extern "C" {
+static int kmeans_shift_of(float maxabs, int64_t n_total) {
+    if (!(maxabs <= 3.0e38f)) return -1;
+    int e = 0;
+    if (maxabs > 0.0f) (void)std::frexp(maxabs, &e);
+    int n = 0;
+    while ((static_cast<int64_t>(1) << n) < n_total) ++n;
+    int s = 62 - n - e;
+    return std::max(0, std::min(60, s));
+}
+
+int ganrev_kmeans(ganrev_ctx* ctx, int k, int niter, const float* init_centroids, float* centroids, float* total_counts, int32_t* last_labels) {
+    if (!ctx || k < 1 || niter < 0 || !init_centroids || !centroids || !total_counts) return ctx ? fail(ctx, GANREV_EINVAL, "bad kmeans arguments") : GANREV_EINVAL;
+    if (!ctx->db.p) return fail(ctx, GANREV_ESTATE, "database not set");
+    CU_TRY(cudaSetDevice(ctx->device));
+    const int d = ctx->db_d;
+    const int64_t N = ctx->db_n;
+    const int shift = kmeans_shift_of(ctx->db_maxabs, ctx->db_total);
+    if (shift < 0) return fail(ctx, GANREV_EINVAL, "database contains non-finite values");
+    const double sc = std::ldexp(1.0, shift);
+    const size_t kd = static_cast<size_t>(k) * d;
+    RC_TRY(ensure(ctx, ctx->cen, sizeof(float) * kd));
+    RC_TRY(ensure(ctx, ctx->c2, sizeof(float) * k));
+    RC_TRY(ensure(ctx, ctx->acc, sizeof(unsigned long long) * (kd + k)));   // acc followed by cnt: one allreduce
+    RC_TRY(ensure(ctx, ctx->total, sizeof(unsigned long long) * k));
+    RC_TRY(ensure(ctx, ctx->labels, sizeof(int) * static_cast<size_t>(std::max<int64_t>(N, 1))));
+    RC_TRY(ensure(ctx, ctx->tcounts, sizeof(float) * k));
+    unsigned long long* d_acc = static_cast<unsigned long long*>(ctx->acc.p);
+    unsigned long long* d_cnt = d_acc + kd;
+    CU_TRY(cudaMemcpyAsync(ctx->cen.p, init_centroids, sizeof(float) * kd, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemsetAsync(ctx->acc.p, 0, sizeof(unsigned long long) * (kd + k), ctx->stream));
+    CU_TRY(cudaMemsetAsync(ctx->total.p, 0, sizeof(unsigned long long) * k, ctx->stream));
+    if (niter == 0) CU_TRY(cudaMemsetAsync(ctx->labels.p, 0xFF, sizeof(int) * static_cast<size_t>(std::max<int64_t>(N, 1)), ctx->stream));
+    scan::ScanParams p{};
+    p.db = static_cast<const float*>(ctx->db.p); p.rdb = static_cast<const float*>(ctx->rdb.p); p.n_rows = N; p.d = d;
+    p.q = static_cast<const float*>(ctx->cen.p); p.c2 = static_cast<const float*>(ctx->c2.p); p.rq = nullptr; p.nq = k;
+    p.labels = static_cast<int*>(ctx->labels.p); p.acc = d_acc; p.cnt = d_cnt; p.sc = sc;
+    p.smem_acc = (kd + k) * sizeof(unsigned long long) <= 96 * 1024 ? 1 : 0;
+    for (int it = 0; it < niter; ++it) {
+        RC_TRY(vec_prep(ctx, static_cast<const float*>(ctx->cen.p), k, d, nullptr, static_cast<float*>(ctx->c2.p), nullptr));
+        {
+            ProfScope ps(ctx, "kmeans_assign", 2.0 * N * k * d + 1.0 * N * d, 8.0 * N * d + 4.0 * N + 4.0 * kd);
+            if (k <= 16) RC_TRY((launch_assign<1, 1>(ctx, p))); else RC_TRY((launch_assign<4, 1>(ctx, p)));
+        }
+        if (ctx->world > 1)   // centroid sums + counts: one order-free int64 allreduce per iteration
+            NCCL_TRY(ctx->nccl.AllReduce(ctx->acc.p, ctx->acc.p, kd + k, ncclUint64, ncclSum, ctx->comm, ctx->stream));
+        {
+            ProfScope ps(ctx, "kmeans_finalize", 0.0, 12.0 * kd);
+            scan::kmeans_finalize_kernel<<<k, 128, 0, ctx->stream>>>(static_cast<float*>(ctx->cen.p), d_acc, d_cnt,
+                                                                      static_cast<unsigned long long*>(ctx->total.p), k, d, sc);
+            CU_TRY(cudaGetLastError());
+        }
+    }
+    scan::counts_to_float_kernel<<<(k + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const unsigned long long*>(ctx->total.p), static_cast<float*>(ctx->tcounts.p), k);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(centroids, ctx->cen.p, sizeof(float) * kd, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(total_counts, ctx->tcounts.p, sizeof(float) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    if (last_labels && N > 0) CU_TRY(cudaMemcpyAsync(last_labels, ctx->labels.p, sizeof(int) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    return finish(ctx);
+}
+
+int ganrev_assign_cosine_min(ganrev_ctx* ctx, const float* centroids, int k, int32_t* cluster, float* cosv) {
+    if (!ctx || !centroids || k < 1) return ctx ? fail(ctx, GANREV_EINVAL, "bad assign arguments") : GANREV_EINVAL;
+    if (!ctx->db.p) return fail(ctx, GANREV_ESTATE, "database not set");
+    CU_TRY(cudaSetDevice(ctx->device));
+    const int d = ctx->db_d;
+    const int64_t N = ctx->db_n;
+    const size_t kd = static_cast<size_t>(k) * d;
+    RC_TRY(ensure(ctx, ctx->q, sizeof(float) * kd));
+    RC_TRY(ensure(ctx, ctx->rq, sizeof(float) * k));
+    RC_TRY(ensure(ctx, ctx->labels, sizeof(int) * static_cast<size_t>(std::max<int64_t>(N, 1))));
+    RC_TRY(ensure(ctx, ctx->cosv, sizeof(float) * static_cast<size_t>(std::max<int64_t>(N, 1))));
+    CU_TRY(cudaMemcpyAsync(ctx->q.p, centroids, sizeof(float) * kd, cudaMemcpyHostToDevice, ctx->stream));
+    RC_TRY(vec_prep(ctx, static_cast<const float*>(ctx->q.p), k, d, static_cast<float*>(ctx->rq.p), nullptr, nullptr));
+    scan::ScanParams p{};
+    p.db = static_cast<const float*>(ctx->db.p); p.rdb = static_cast<const float*>(ctx->rdb.p); p.n_rows = N; p.d = d;
+    p.q = static_cast<const float*>(ctx->q.p); p.rq = static_cast<const float*>(ctx->rq.p); p.nq = k;
+    p.labels = static_cast<int*>(ctx->labels.p); p.cosv = static_cast<float*>(ctx->cosv.p);
+    {
+        ProfScope ps(ctx, "assign_cosine_min", 2.0 * N * k * d, 4.0 * N * d + 8.0 * N + 4.0 * kd);
+        if (k <= 16) RC_TRY((launch_assign<1, 2>(ctx, p))); else RC_TRY((launch_assign<4, 2>(ctx, p)));
+    }
+    ctx->assigned = true; ctx->assigned_k = k;
+    if (cluster && N > 0) CU_TRY(cudaMemcpyAsync(cluster, ctx->labels.p, sizeof(int) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cosv && N > 0) CU_TRY(cudaMemcpyAsync(cosv, ctx->cosv.p, sizeof(float) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    return finish(ctx);
+}
+
+int ganrev_cluster_members(ganrev_ctx* ctx, int k, int m, const float* images, int px, int64_t* member_ids, int32_t* member_counts, float* mean_images) {
+    if (!ctx || k < 1 || m < 1 || m > 128 || !member_ids || !member_counts) return ctx ? fail(ctx, GANREV_EINVAL, "bad cluster_members arguments (m must be 1..128)") : GANREV_EINVAL;
+    if (!ctx->assigned || ctx->assigned_k != k) return fail(ctx, GANREV_ESTATE, "call ganrev_assign_cosine_min with k=%d first", k);
+    if (ctx->world > 1) return fail(ctx, GANREV_ESTATE, "cluster_members is single-rank");
+    CU_TRY(cudaSetDevice(ctx->device));
+    const int64_t N = ctx->db_n;
+    RC_TRY(ensure(ctx, ctx->mids, sizeof(long long) * static_cast<size_t>(k) * m));
+    RC_TRY(ensure(ctx, ctx->mcnt, sizeof(int) * k));
+    {
+        ProfScope ps(ctx, "cluster_members", 0.0, 8.0 * N * k);
+        scan::cluster_members_kernel<<<k, 32, 0, ctx->stream>>>(static_cast<const int*>(ctx->labels.p), static_cast<const float*>(ctx->cosv.p), N, m,
+                                                               static_cast<long long*>(ctx->mids.p), static_cast<int*>(ctx->mcnt.p));
+        CU_TRY(cudaGetLastError());
+    }
+    if (mean_images) {
+        if (px < 1) return fail(ctx, GANREV_EINVAL, "px must be positive");
+        const float* d_img = nullptr;
+        if (images) {
+            RC_TRY(ensure(ctx, ctx->stage_a, sizeof(float) * static_cast<size_t>(N) * px));
+            CU_TRY(cudaMemcpyAsync(ctx->stage_a.p, images, sizeof(float) * static_cast<size_t>(N) * px, cudaMemcpyHostToDevice, ctx->stream));
+            d_img = static_cast<const float*>(ctx->stage_a.p);
+        } else {
+            if (ctx->buf_rows[GANREV_BUF_IMAGES] < N || buf_row_bytes(ctx, GANREV_BUF_IMAGES) != sizeof(float) * static_cast<size_t>(px))
+                return fail(ctx, GANREV_ESTATE, "resident IMAGES does not hold %lld x %d", (long long)N, px);
+            d_img = static_cast<const float*>(ctx->buf[GANREV_BUF_IMAGES].p);
+        }
+        RC_TRY(ensure(ctx, ctx->mmean, sizeof(float) * static_cast<size_t>(k) * px));
+        ProfScope ps(ctx, "cluster_mean", 1.0 * k * m * px, 4.0 * k * m * px);
+        dim3 grid((px + 255) / 256, k);
+        scan::cluster_mean_kernel<<<grid, 256, 0, ctx->stream>>>(d_img, px, static_cast<const long long*>(ctx->mids.p), static_cast<const int*>(ctx->mcnt.p), m,
+                                                                static_cast<float*>(ctx->mmean.p));
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(mean_images, ctx->mmean.p, sizeof(float) * static_cast<size_t>(k) * px, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU_TRY(cudaMemcpyAsync(member_ids, ctx->mids.p, sizeof(long long) * static_cast<size_t>(k) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(member_counts, ctx->mcnt.p, sizeof(int) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    return finish(ctx);
+}
+
+// ---------------------------------------------------------------- measurement hooks
+void* ganrev_stream(ganrev_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
+int ganrev_sync(ganrev_ctx* ctx) {
+    if (!ctx) return GANREV_EINVAL;
+    CU_TRY(cudaSetDevice(ctx->device));
+    return finish(ctx);
+}
+uint64_t ganrev_launch_count(const ganrev_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int ganrev_profile_enable(ganrev_ctx* ctx, int on) {
+    if (!ctx) return GANREV_EINVAL;
+    ctx->prof_on = on != 0;
+    return GANREV_OK;
+}
+int ganrev_profile_reset(ganrev_ctx* ctx) {
+    if (!ctx) return GANREV_EINVAL;
+    cudaStreamSynchronize(ctx->stream);
+    prof_resolve(ctx);
+    ctx->prof.clear(); ctx->prof_idx.clear();
+    return GANREV_OK;
+}
+int ganrev_profile_count(ganrev_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaStreamSynchronize(ctx->stream);
+    prof_resolve(ctx);
+    return static_cast<int>(ctx->prof.size());
+}
+int ganrev_profile_get(ganrev_ctx* ctx, int idx, const char** name, uint64_t* launches, double* total_ms, double* flops, double* bytes) {
+    if (!ctx || idx < 0 || idx >= static_cast<int>(ctx->prof.size())) return GANREV_EINVAL;
+    const ProfEntry& e = ctx->prof[idx];
+    if (name) *name = e.name.c_str();
+    if (launches) *launches = e.launches;
+    if (total_ms) *total_ms = e.total_ms;
+    if (flops) *flops = e.flops;
+    if (bytes) *bytes = e.bytes;
+    return GANREV_OK;
+}
+int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value) {
+    if (!ctx || !name) return GANREV_EINVAL;
+    if (!strcmp(name, "chunk")) {
+        if (value < 1 || value > (1 << 20)) return fail(ctx, GANREV_EINVAL, "chunk out of range");
+        ctx->chunk = value;
+        return GANREV_OK;
+    }
+    if (!strcmp(name, "conv_impl")) {
+        if (value != 0 && value != 1) return fail(ctx, GANREV_EINVAL, "conv_impl must be 0 or 1");
+        ctx->conv_impl = static_cast<int>(value);
+        return GANREV_OK;
+    }
+    return fail(ctx, GANREV_EINVAL, "unknown option %s", name);
+}
+
+}  // extern "C"

@@ -1,0 +1,255 @@
+// layers.cuh -- the shallow / narrow layers that stay on CUDA cores:
+//   * noise fp32 -> bf16 K-padded rows (A operand of G's Linear, models.lua:115)
+//   * R conv1  C->64, K = 9*C      (models.lua:399-411) fp32 NCHW in (+ explicit dropout
+//     mask fused into the loader), folded BN + ELU, bf16 NHWC out
+//   * G conv3  128->C, N = 1 or 3  (models.lua:132-133) bf16 NHWC in, fp32 NCHW out, sigmoid
+//   * torch.dist over image pairs  (apply_r.lua:366) in the canonical lane-tree order
+//   * the 15%-quantile threshold + flags (apply_r.lua:370-378) as a device radix select
+#pragma once
+#include "common.cuh"
+
+namespace ganrev {
+
+// ------------------------------------------------------------------ noise -> bf16 [n][kpad]
+__global__ void noise_to_bf16_kernel(const float* __restrict__ in, int nd, int kpad, bf16* __restrict__ out, long long n) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= n * kpad) return;
+    const long long r = idx / kpad;
+    const int c = static_cast<int>(idx - r * kpad);
+    out[idx] = __float2bfloat16_rn(c < nd ? in[r * nd + c] : 0.0f);
+}
+
+// ------------------------------------------------------------------ R conv1
+// wsm layout: [k = (ci*3+ky)*3+kx][64] fp32, then scale[64], shift[64].
+template <int CIN>
+__global__ void __launch_bounds__(128)
+r_conv1_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mask, const float* __restrict__ wpack,
+               bf16* __restrict__ out, int H, int W, long long npix_total) {
+    constexpr int K = CIN * 9;
+    __shared__ __align__(16) float wsm[K * 64 + 128];
+    for (int i = threadIdx.x; i < K * 64 + 128; i += blockDim.x) wsm[i] = wpack[i];
+    __syncthreads();
+    const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (pix >= npix_total) return;
+    const int w = static_cast<int>(pix % W);
+    const int h = static_cast<int>((pix / W) % H);
+    const long long n = pix / (static_cast<long long>(W) * H);
+    float acc[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) acc[c] = 0.0f;
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+        const long long plane = (n * CIN + ci) * static_cast<long long>(H) * W;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int hh = h + ky - 1;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ww = w + kx - 1;
+                float x = 0.0f;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                    const long long off = plane + static_cast<long long>(hh) * W + ww;
+                    x = img[off];
+                    if (mask != nullptr && mask[off] == 0) x = 0.0f;   // v1 dropout: x*mask, no rescale
+                }
+                const float4* wr = reinterpret_cast<const float4*>(wsm + ((ci * 3 + ky) * 3 + kx) * 64);
+#pragma unroll
+                for (int c4 = 0; c4 < 16; ++c4) {
+                    const float4 wv = wr[c4];
+                    acc[4 * c4 + 0] = fmaf(x, wv.x, acc[4 * c4 + 0]);
+                    acc[4 * c4 + 1] = fmaf(x, wv.y, acc[4 * c4 + 1]);
+                    acc[4 * c4 + 2] = fmaf(x, wv.z, acc[4 * c4 + 2]);
+                    acc[4 * c4 + 3] = fmaf(x, wv.w, acc[4 * c4 + 3]);
+                }
+            }
+        }
+    }
+    const float* sc = wsm + K * 64;
+    const float* sh = sc + 64;
+    uint4* o = reinterpret_cast<uint4*>(out + pix * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[t] = apply_act(fmaf(acc[8 * j + t], sc[8 * j + t], sh[8 * j + t]), ACT_ELU);
+        uint4 pk;
+        __nv_bfloat162 b0 = __floats2bfloat162_rn(v[0], v[1]), b1 = __floats2bfloat162_rn(v[2], v[3]);
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(v[4], v[5]), b3 = __floats2bfloat162_rn(v[6], v[7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+        pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+        o[j] = pk;
+    }
+}
+
+// ------------------------------------------------------------------ G conv3 + sigmoid
+// act: NHWC bf16 [n][H][W][128]; w3: fp32 [C][9][128]; out: fp32 NCHW [n][C][H][W].
+// One warp produces 32 consecutive pixels (row-major) of an image; lane l owns channels 4l..4l+3 of every
+// tap, partial sums are reduced by shuffles and lane j keeps pixel j for a coalesced store.
+template <int COUT>
+__global__ void __launch_bounds__(256)
+g_conv3_kernel(const bf16* __restrict__ act, const float* __restrict__ w3, const float* __restrict__ b3,
+               float* __restrict__ out, int H, int W, long long n_img) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int segs_per_img = (H * W) / 32;           // H*W is a multiple of 32 (H, W >= 16, powers of two)
+    const long long total_segs = n_img * segs_per_img;
+    if (warp_global >= total_segs) return;
+    const int seg = static_cast<int>(warp_global % segs_per_img);
+    const long long n = warp_global / segs_per_img;
+
+    float wreg[COUT][9][4];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co)
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(w3 + (co * 9 + t) * 128 + lane * 4));
+            wreg[co][t][0] = wv.x; wreg[co][t][1] = wv.y; wreg[co][t][2] = wv.z; wreg[co][t][3] = wv.w;
+        }
+    float keep[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) keep[co] = 0.0f;
+
+    for (int j = 0; j < 32; ++j) {
+        const int pj = seg * 32 + j;
+        const int h = pj / W, w = pj - h * W;
+        float part[COUT];
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) part[co] = 0.0f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int hh = h + ky - 1;
+            if (hh < 0 || hh >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ww = w + kx - 1;
+                if (ww < 0 || ww >= W) continue;
+                const uint2 raw = __ldg(reinterpret_cast<const uint2*>(act + ((n * H + hh) * W + ww) * 128 + lane * 4));
+                const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+                const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+                const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) {
+                    const float* wt = wreg[co][ky * 3 + kx];
+                    part[co] = fmaf(f0.x, wt[0], part[co]);
+                    part[co] = fmaf(f0.y, wt[1], part[co]);
+                    part[co] = fmaf(f1.x, wt[2], part[co]);
+                    part[co] = fmaf(f1.y, wt[3], part[co]);
+                }
+            }
+        }
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+            float s = part[co];
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == j) keep[co] = s;
+        }
+    }
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+        const float v = keep[co] + __ldg(b3 + co);
+        out[(n * COUT + co) * static_cast<long long>(H) * W + seg * 32 + lane] = 1.0f / (1.0f + expf(-v));   // nn.Sigmoid
+    }
+}
+
+// ------------------------------------------------------------------ torch.dist, batched
+// Canonical order (mirrored by oracle orc_l2): element i belongs to lane (i/4)%32, each lane
+// adds its fp32 squares in ascending i into a double, then an xor-butterfly over the lanes.
+__global__ void __launch_bounds__(256)
+l2_pairs_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, int px, double* __restrict__ l2) {
+    const int lane = threadIdx.x & 31;
+    const long long pair = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (pair >= n) return;
+    const float* x = a + pair * px;
+    const float* y = b + pair * px;
+    double s = 0.0;
+    const bool vec = ((px & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    if (vec) {
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        const float4* y4 = reinterpret_cast<const float4*>(y);
+        const int n4 = px >> 2;
+        int i = lane;
+        // 4 independent 128-bit loads per operand in flight
+        for (; i + 96 < n4; i += 128) {
+            float4 xa[4], ya[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { xa[u] = __ldcs(x4 + i + 32 * u); ya[u] = __ldcs(y4 + i + 32 * u); }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float d0 = __fsub_rn(xa[u].x, ya[u].x), d1 = __fsub_rn(xa[u].y, ya[u].y);
+                float d2 = __fsub_rn(xa[u].z, ya[u].z), d3 = __fsub_rn(xa[u].w, ya[u].w);
+                s += static_cast<double>(__fmul_rn(d0, d0));
+                s += static_cast<double>(__fmul_rn(d1, d1));
+                s += static_cast<double>(__fmul_rn(d2, d2));
+                s += static_cast<double>(__fmul_rn(d3, d3));
+            }
+        }
+        for (; i < n4; i += 32) {
+            const float4 xv = __ldcs(x4 + i), yv = __ldcs(y4 + i);
+            float d0 = __fsub_rn(xv.x, yv.x), d1 = __fsub_rn(xv.y, yv.y);
+            float d2 = __fsub_rn(xv.z, yv.z), d3 = __fsub_rn(xv.w, yv.w);
+            s += static_cast<double>(__fmul_rn(d0, d0));
+            s += static_cast<double>(__fmul_rn(d1, d1));
+            s += static_cast<double>(__fmul_rn(d2, d2));
+            s += static_cast<double>(__fmul_rn(d3, d3));
+        }
+    } else {
+        for (int base = lane * 4; base < px; base += 128)
+            for (int j = 0; j < 4 && base + j < px; ++j) {
+                const float d = __fsub_rn(x[base + j], y[base + j]);
+                s += static_cast<double>(__fmul_rn(d, d));
+            }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) l2[pair] = __dsqrt_rn(s);
+}
+
+// ------------------------------------------------------------------ quantile threshold + flags
+__device__ __forceinline__ unsigned long long f64_key(double v) {   // ascending order-preserving
+    const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double f64_unkey(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    return __longlong_as_double(static_cast<long long>(b));
+}
+// Single-block MSB radix select of the rank-th smallest (0-based) of sims = 1 - l2.
+__global__ void __launch_bounds__(1024)
+quantile_select_kernel(const double* __restrict__ l2, long long n, long long rank, double* __restrict__ thr_out) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ long long s_rank;
+    if (threadIdx.x == 0) { s_prefix = 0ull; s_rank = rank; }
+    __syncthreads();
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        const unsigned long long himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned long long k = f64_key(1.0 - l2[i]);
+            if ((k & himask) == prefix) atomicAdd(&hist[(k >> shift) & 0xFF], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long r = s_rank;
+            int bin = 0;
+            for (; bin < 256; ++bin) {
+                if (r < static_cast<long long>(hist[bin])) break;
+                r -= hist[bin];
+            }
+            s_rank = r;
+            s_prefix = prefix | (static_cast<unsigned long long>(bin) << shift);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *thr_out = f64_unkey(s_prefix);
+}
+__global__ void anomaly_flags_kernel(const double* __restrict__ l2, long long n_show, const double* __restrict__ thr, uint8_t* __restrict__ flags) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n_show) flags[i] = ((1.0 - l2[i]) <= *thr) ? 1 : 0;
+}
+
+}  // namespace ganrev

@@ -1,0 +1,537 @@
+// scan.cuh -- database kernels over the recovered noise vectors: cosine top-k search
+// (apply_r.lua:265-282), kmeans assignment + centroid sums (unsup.kmeans at apply_r.lua:198),
+// cosine-min cluster assignment (apply_r.lua:206-218), per-cluster members + mean image
+// (apply_r.lua:222-243).
+//
+// Exactness contract (mirrored by oracle/ganrev_oracle.c): every (query,row)
+// dot product is ONE thread's sequential fp32 fmaf chain over d in index order, norms the
+// same, IEEE div/sqrt, no fast-math; selections use a total order (score, lowest id), so the
+// result does not depend on tiling, split count or GPU count.  Centroid sums are int64
+// fixed-point (associative), so any partition of the rows gives identical centroids.
+//
+// Tiling: a 256-thread block holds a [16*TQ queries] x [128 rows] score tile in registers
+// (TQ x 8 per thread); rows and queries are staged through shared memory in 32-wide d-chunks
+// with coalesced global loads.
+#pragma once
+#include "common.cuh"
+
+namespace ganrev {
+namespace scan {
+
+constexpr int kThreads = 256;
+constexpr int RT = 128;        // rows per tile
+constexpr int DK = 32;         // d-chunk staged in smem
+constexpr int XS = RT + 4;     // smem stride of one d-row of the row tile (keeps float4 alignment)
+constexpr int CAP = 32;        // candidate buffer entries per query
+
+// ---- total-order keys: larger key = better ("score desc, NaN last, -0 == +0, lowest id")
+__device__ __forceinline__ uint32_t score_key32(float s) {
+    if (s != s) return 0u;
+    s = __fadd_rn(s, 0.0f);   // -0 -> +0
+    const uint32_t b = __float_as_uint(s);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float score_unkey32(uint32_t k) {
+    if (k == 0u) return __uint_as_float(0x7fc00000u);
+    return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+__device__ __forceinline__ unsigned long long make_key(float s, uint32_t id) {
+    return (static_cast<unsigned long long>(score_key32(s)) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - id);
+}
+
+// Sorted (descending) list of 32*E keys held by one warp, blocked layout idx = lane*E + j.
+template <int E>
+__device__ __forceinline__ void list_insert(unsigned long long (&L)[E], unsigned long long c, int lane) {
+    int pos = 0;
+#pragma unroll
+    for (int j = 0; j < E; ++j) pos += (L[j] > c) ? 1 : 0;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) pos += __shfl_xor_sync(0xffffffffu, pos, off);
+    const unsigned long long carry = __shfl_up_sync(0xffffffffu, L[E - 1], 1);
+    if (pos >= 32 * E) return;
+#pragma unroll
+    for (int j = E - 1; j >= 0; --j) {
+        const int g = lane * E + j;
+        const unsigned long long prev = (j > 0) ? L[j - 1] : carry;
+        if (g > pos) L[j] = prev;
+        else if (g == pos) L[j] = c;
+    }
+}
+template <int E>
+__device__ __forceinline__ unsigned long long list_kth(const unsigned long long (&L)[E], int k) {
+    unsigned long long mine = 0ull;
+#pragma unroll
+    for (int j = 0; j < E; ++j)
+        if (j == ((k - 1) % E)) mine = L[j];
+    return __shfl_sync(0xffffffffu, mine, (k - 1) / E);
+}
+
+struct ScanParams {
+    const float* db;        // [n_rows][d]
+    const float* rdb;       // [n_rows] 1/(|x|^2 + 1e-12)
+    long long n_rows;
+    int d;
+    const float* q;         // [nq][d] queries or centroids
+    const float* rq;        // [nq] 1/(|q|^2 + 1e-12)
+    const float* c2;        // [nq] 0.5*|c|^2 (kmeans)
+    int nq;
+    // search
+    int k;
+    unsigned long long* partial;   // [splits][nq][k]
+    long long rows_per_split;
+    // kmeans / cosmin
+    int* labels;
+    float* cosv;
+    unsigned long long* acc;       // [nq][d] int64 fixed-point sums
+    unsigned long long* cnt;       // [nq]
+    double sc;
+    int smem_acc;
+};
+
+// Stage one d-chunk of the row tile and of the query tile (transposed: [i][row]).
+template <int TQ>
+__device__ __forceinline__ void stage_chunk(const ScanParams& p, float* xs, float* qs, long long row0, long long row_end,
+                                            int qbase, int i0) {
+    constexpr int QT = 16 * TQ;
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int t = 0; t < RT * DK / kThreads; ++t) {
+        const int e = tid + kThreads * t;
+        const int r = e >> 5, c = e & 31;
+        const long long row = row0 + r;
+        float v = 0.0f;
+        if (row < row_end && i0 + c < p.d) v = __ldg(p.db + row * p.d + i0 + c);
+        xs[c * XS + r] = v;
+    }
+#pragma unroll
+    for (int t = 0; t < QT * DK / kThreads; ++t) {
+        const int e = tid + kThreads * t;
+        const int r = e >> 5, c = e & 31;
+        float v = 0.0f;
+        if (qbase + r < p.nq && i0 + c < p.d) v = __ldg(p.q + static_cast<long long>(qbase + r) * p.d + i0 + c);
+        qs[c * QT + r] = v;
+    }
+}
+
+// acc[v][u] = fmaf chain over the whole d for query tq*TQ+v and row r(u).
+template <int TQ>
+__device__ __forceinline__ void dot_tile(const ScanParams& p, float* xs, float* qs, long long row0, long long row_end,
+                                         int qbase, float (&acc)[TQ][8]) {
+    constexpr int QT = 16 * TQ;
+    const int tq = threadIdx.x >> 4, tr = threadIdx.x & 15;
+#pragma unroll
+    for (int v = 0; v < TQ; ++v)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[v][u] = 0.0f;
+    for (int i0 = 0; i0 < p.d; i0 += DK) {
+        __syncthreads();
+        stage_chunk<TQ>(p, xs, qs, row0, row_end, qbase, i0);
+        __syncthreads();
+        const int kk = min(DK, p.d - i0);
+        for (int i = 0; i < kk; ++i) {
+            float qv[TQ];
+            if (TQ == 4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(qs + i * QT + tq * 4);
+                qv[0] = t4.x; qv[1 % TQ] = t4.y; qv[2 % TQ] = t4.z; qv[3 % TQ] = t4.w;
+            } else {
+#pragma unroll
+                for (int v = 0; v < TQ; ++v) qv[v] = qs[i * QT + tq * TQ + v];
+            }
+            const float4 xa = *reinterpret_cast<const float4*>(xs + i * XS + tr * 4);
+            const float4 xb = *reinterpret_cast<const float4*>(xs + i * XS + 64 + tr * 4);
+            const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+            for (int v = 0; v < TQ; ++v)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc[v][u] = __fmaf_rn(qv[v], xv[u], acc[v][u]);
+        }
+    }
+}
+__device__ __forceinline__ int row_of(int tr, int u) { return tr * 4 + (u & 3) + ((u >> 2) << 6); }
+__device__ __forceinline__ float cos_from(float dot, float ra, float rb) {
+    return __fmul_rn(dot, __fsqrt_rn(__fmul_rn(ra, rb)));
+}
+
+// ------------------------------------------------------------------ search
+// grid = (splits, ceil(nq / (16*TQ))).  K2 = 32*E >= k.
+template <int TQ, int E>
+__global__ void __launch_bounds__(kThreads)
+search_kernel(const ScanParams p) {
+    constexpr int QT = 16 * TQ;
+    constexpr int K2 = 32 * E;
+    extern __shared__ __align__(16) uint8_t sm[];
+    float* xs = reinterpret_cast<float*>(sm);
+    float* qs = xs + DK * XS;
+    unsigned long long* lists = reinterpret_cast<unsigned long long*>(qs + DK * QT);
+    unsigned long long* cand = lists + QT * K2;
+    unsigned long long* tau = cand + QT * CAP;
+    int* ccount = reinterpret_cast<int*>(tau + QT);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tq = tid >> 4, tr = tid & 15;
+    const int qbase = blockIdx.y * QT;
+    for (int i = tid; i < QT * K2; i += kThreads) lists[i] = 0ull;
+    for (int i = tid; i < QT; i += kThreads) { tau[i] = 0ull; ccount[i] = 0; }
+    __syncthreads();
+
+    const long long r_begin = static_cast<long long>(blockIdx.x) * p.rows_per_split;
+    const long long r_end = min(p.n_rows, r_begin + p.rows_per_split);
+    for (long long row0 = r_begin; row0 < r_end; row0 += RT) {
+        float acc[TQ][8];
+        dot_tile<TQ>(p, xs, qs, row0, r_end, qbase, acc);
+        // scores in place
+        float rxv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const long long row = row0 + row_of(tr, u);
+            rxv[u] = row < r_end ? __ldg(p.rdb + row) : 0.0f;
+        }
+        unsigned pend = 0u;
+#pragma unroll
+        for (int v = 0; v < TQ; ++v) {
+            const int ql = tq * TQ + v;
+            const bool qok = qbase + ql < p.nq;
+            const float rqv = qok ? __ldg(p.rq + qbase + ql) : 0.0f;
+            const unsigned long long t = tau[ql];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const long long row = row0 + row_of(tr, u);
+                acc[v][u] = cos_from(acc[v][u], rqv, rxv[u]);
+                if (qok && row < r_end && make_key(acc[v][u], static_cast<uint32_t>(row)) > t) pend |= 1u << (v * 8 + u);
+            }
+        }
+        while (__syncthreads_or(pend != 0u)) {
+            // append candidates that still beat the current k-th best
+#pragma unroll
+            for (int v = 0; v < TQ; ++v) {
+                const int ql = tq * TQ + v;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const unsigned bit = 1u << (v * 8 + u);
+                    if (pend & bit) {
+                        const unsigned long long key = make_key(acc[v][u], static_cast<uint32_t>(row0 + row_of(tr, u)));
+                        if (key > tau[ql]) {
+                            const int slot = atomicAdd(&ccount[ql], 1);
+                            if (slot < CAP) { cand[ql * CAP + slot] = key; pend &= ~bit; }
+                        } else {
+                            pend &= ~bit;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // merge: one warp per query, sequential insertion into the sorted list
+            for (int ql = warp; ql < QT; ql += kThreads / 32) {
+                const int n = min(ccount[ql], CAP);
+                if (n > 0) {
+                    unsigned long long L[E];
+#pragma unroll
+                    for (int j = 0; j < E; ++j) L[j] = lists[ql * K2 + lane * E + j];
+                    for (int t = 0; t < n; ++t) list_insert<E>(L, cand[ql * CAP + t], lane);
+#pragma unroll
+                    for (int j = 0; j < E; ++j) lists[ql * K2 + lane * E + j] = L[j];
+                    const unsigned long long kth = list_kth<E>(L, p.k);
+                    __syncwarp();
+                    if (lane == 0) { tau[ql] = kth; ccount[ql] = 0; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < QT * p.k; i += kThreads) {
+        const int ql = i / p.k, t = i - ql * p.k;
+        if (qbase + ql < p.nq)
+            p.partial[(static_cast<long long>(blockIdx.x) * p.nq + qbase + ql) * p.k + t] = lists[ql * K2 + t];
+    }
+}
+
+// Merge [parts][nq][k] partial lists per query (one warp per query).
+//   mode 0: write ids (int64, + id_offset) and scores
+//   mode 1: write keys re-based to global ids (for the NCCL allgather)
+template <int E>
+__global__ void __launch_bounds__(kThreads)
+merge_kernel(const unsigned long long* __restrict__ partial, int parts, int nq, int k, long long id_offset, int mode,
+             long long* __restrict__ ids, float* __restrict__ scores, unsigned long long* __restrict__ keys_out) {
+    const int lane = threadIdx.x & 31;
+    const int q = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+    if (q >= nq) return;
+    unsigned long long L[E];
+#pragma unroll
+    for (int j = 0; j < E; ++j) L[j] = 0ull;
+    unsigned long long kth = 0ull;
+    const int total = parts * k;
+    for (int base = 0; base < total; base += 32) {
+        const int e = base + lane;
+        unsigned long long c = 0ull;
+        if (e < total) {
+            const int part = e / k, t = e - part * k;
+            c = partial[(static_cast<long long>(part) * nq + q) * k + t];
+        }
+        for (int t = 0; t < 32; ++t) {
+            const unsigned long long cc = __shfl_sync(0xffffffffu, c, t);
+            if (cc > kth) {   // warp-uniform
+                list_insert<E>(L, cc, lane);
+                kth = list_kth<E>(L, k);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+        const int t = lane * E + j;
+        if (t < k) {
+            const unsigned long long key = L[j];
+            const long long o = static_cast<long long>(q) * k + t;
+            if (mode == 0) {
+                if (key == 0ull) { ids[o] = -1; scores[o] = 0.0f; }
+                else {
+                    ids[o] = id_offset + static_cast<long long>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull));
+                    scores[o] = score_unkey32(static_cast<uint32_t>(key >> 32));
+                }
+            } else {
+                if (key == 0ull) keys_out[o] = 0ull;
+                else {
+                    const uint32_t lid = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
+                    const uint32_t gid = static_cast<uint32_t>(id_offset) + lid;
+                    keys_out[o] = (key & 0xFFFFFFFF00000000ull) | static_cast<unsigned long long>(0xFFFFFFFFu - gid);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ kmeans label / cosine-min assign
+struct Best {
+    float v;
+    int j;
+};
+// MODE 1 (unsup.kmeans, TH max scan "!(v <= best)", break on NaN): first NaN wins, else the
+// largest value, lowest index on ties.
+// MODE 2 (apply_r.lua:206-218 "dist < minDist"): a NaN at j == 0 sticks, otherwise NaNs never
+// win; smallest value, lowest index on ties.
+template <int MODE>
+__device__ __forceinline__ bool better(const Best a, const Best b) {   // is a strictly preferable to b?
+    if (b.j < 0) return a.j >= 0;
+    if (a.j < 0) return false;
+    const bool an = a.v != a.v, bn = b.v != b.v;
+    if (MODE == 1) {
+        if (an || bn) return an && (!bn || a.j < b.j);
+        return a.v > b.v || (a.v == b.v && a.j < b.j);
+    } else {
+        const bool a0 = an && a.j == 0, b0 = bn && b.j == 0;
+        if (a0 || b0) return a0;
+        if (an || bn) return !an && bn ? true : (an && bn ? a.j < b.j : false);
+        return a.v < b.v || (a.v == b.v && a.j < b.j);
+    }
+}
+
+template <int TQ, int MODE>
+__global__ void __launch_bounds__(kThreads)
+assign_kernel(const ScanParams p, const long long n_tiles) {
+    constexpr int QT = 16 * TQ;
+    extern __shared__ __align__(16) uint8_t sm[];
+    float* xs = reinterpret_cast<float*>(sm);
+    float* qs = xs + DK * XS;
+    float* redv = qs + DK * QT;                         // [16][RT]
+    int* redj = reinterpret_cast<int*>(redv + 16 * RT);  // [16][RT]
+    int* slab = redj + 16 * RT;                          // [RT]
+    unsigned long long* sacc = reinterpret_cast<unsigned long long*>(slab + RT);   // [nq*d] + [nq] when smem_acc
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tq = tid >> 4, tr = tid & 15;
+    const int nacc = p.nq * p.d;
+    if (MODE == 1 && p.smem_acc) {
+        for (int i = tid; i < nacc + p.nq; i += kThreads) sacc[i] = 0ull;
+    }
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long row0 = tile * RT;
+        Best best[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { best[u].v = 0.0f; best[u].j = -1; }
+        float rxv[8];
+        if (MODE == 2) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const long long row = row0 + row_of(tr, u);
+                rxv[u] = row < p.n_rows ? __ldg(p.rdb + row) : 0.0f;
+            }
+        }
+        for (int qbase = 0; qbase < p.nq; qbase += QT) {
+            float acc[TQ][8];
+            dot_tile<TQ>(p, xs, qs, row0, p.n_rows, qbase, acc);
+#pragma unroll
+            for (int v = 0; v < TQ; ++v) {
+                const int jg = qbase + tq * TQ + v;
+                if (jg < p.nq) {
+                    const float aux = MODE == 1 ? __ldg(p.c2 + jg) : __ldg(p.rq + jg);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        Best c;
+                        c.j = jg;
+                        c.v = MODE == 1 ? __fsub_rn(acc[v][u], aux) : cos_from(acc[v][u], rxv[u], aux);
+                        if (better<MODE>(c, best[u])) best[u] = c;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            redv[tq * RT + row_of(tr, u)] = best[u].v;
+            redj[tq * RT + row_of(tr, u)] = best[u].j;
+        }
+        __syncthreads();
+        if (tid < RT) {
+            Best b;
+            b.v = redv[tid]; b.j = redj[tid];
+            for (int t = 1; t < 16; ++t) {
+                Best c;
+                c.v = redv[t * RT + tid]; c.j = redj[t * RT + tid];
+                if (better<MODE>(c, b)) b = c;
+            }
+            slab[tid] = b.j;
+            const long long row = row0 + tid;
+            if (row < p.n_rows) {
+                p.labels[row] = b.j;
+                if (MODE == 2) p.cosv[row] = b.v;
+            }
+        }
+        __syncthreads();
+        if (MODE == 1) {
+            const int rows_here = static_cast<int>(min(static_cast<long long>(RT), p.n_rows - row0));
+            for (int rr = warp; rr < rows_here; rr += kThreads / 32) {
+                const int j = slab[rr];
+                const float* xrow = p.db + (row0 + rr) * p.d;
+                for (int c = lane; c < p.d; c += 32) {
+                    const long long qv = __double2ll_rn(static_cast<double>(__ldg(xrow + c)) * p.sc);
+                    if (p.smem_acc) atomicAdd(&sacc[j * p.d + c], static_cast<unsigned long long>(qv));
+                    else atomicAdd(&p.acc[static_cast<long long>(j) * p.d + c], static_cast<unsigned long long>(qv));
+                }
+                if (lane == 0) {
+                    if (p.smem_acc) atomicAdd(&sacc[nacc + j], 1ull);
+                    else atomicAdd(&p.cnt[j], 1ull);
+                }
+            }
+        }
+    }
+    if (MODE == 1 && p.smem_acc) {
+        __syncthreads();
+        for (int i = tid; i < nacc; i += kThreads)
+            if (sacc[i] != 0ull) atomicAdd(&p.acc[i], sacc[i]);
+        for (int i = tid; i < p.nq; i += kThreads)
+            if (sacc[nacc + i] != 0ull) atomicAdd(&p.cnt[i], sacc[nacc + i]);
+    }
+}
+
+// centroid = sum / count for non-empty clusters (empty keep the old centroid); add counts to the
+// running totals; clear the accumulators for the next iteration.
+__global__ void kmeans_finalize_kernel(float* __restrict__ cen, unsigned long long* __restrict__ acc,
+                                       unsigned long long* __restrict__ cnt, unsigned long long* __restrict__ total,
+                                       int k, int d, double sc) {
+    const int j = blockIdx.x;
+    const long long c = static_cast<long long>(cnt[j]);
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+        if (c != 0) {
+            const long long a = static_cast<long long>(acc[static_cast<long long>(j) * d + i]);
+            cen[static_cast<long long>(j) * d + i] = static_cast<float>(static_cast<double>(a) / (static_cast<double>(c) * sc));
+        }
+        acc[static_cast<long long>(j) * d + i] = 0ull;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { total[j] += static_cast<unsigned long long>(c); cnt[j] = 0ull; }
+}
+__global__ void counts_to_float_kernel(const unsigned long long* __restrict__ total, float* __restrict__ out, int k) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < k) out[j] = static_cast<float>(static_cast<long long>(total[j]));
+}
+
+// ------------------------------------------------------------------ per-vector prep
+// rn[r] = 1/(|x_r|^2 + 1e-12) (fmaf chain), optional half-sq (0.5*|x|^2), optional max|x| (as uint bits).
+__global__ void vec_prep_kernel(const float* __restrict__ x, long long n, int d, float* __restrict__ rn,
+                                float* __restrict__ halfsq, unsigned int* __restrict__ maxabs_bits) {
+    const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    float mx = 0.0f;
+    if (r < n) {
+        const float* xr = x + r * d;
+        float s = 0.0f;
+        for (int i = 0; i < d; ++i) {
+            const float v = xr[i];
+            s = __fmaf_rn(v, v, s);
+            const float a = fabsf(v);
+            if (!(a <= mx)) mx = a;
+        }
+        if (rn) rn[r] = __fdiv_rn(1.0f, __fadd_rn(s, 1e-12f));
+        if (halfsq) halfsq[r] = __fmul_rn(0.5f, s);
+    }
+    if (maxabs_bits) {
+        unsigned int b = __float_as_uint(mx);   // non-negative floats and NaN order as unsigned ints
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, off));
+        if ((threadIdx.x & 31) == 0 && b != 0u) atomicMax(maxabs_bits, b);
+    }
+}
+// cosineSimilarity(v1, v2), apply_r.lua:396-400
+__global__ void cosine_pair_kernel(const float* __restrict__ a, const float* __restrict__ b, int d, float* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float dot = 0.0f, na = 0.0f, nb = 0.0f;
+    for (int i = 0; i < d; ++i) {
+        dot = __fmaf_rn(a[i], b[i], dot);
+        na = __fmaf_rn(a[i], a[i], na);
+        nb = __fmaf_rn(b[i], b[i], nb);
+    }
+    const float ra = __fdiv_rn(1.0f, __fadd_rn(na, 1e-12f)), rb = __fdiv_rn(1.0f, __fadd_rn(nb, 1e-12f));
+    *out = cos_from(dot, ra, rb);
+}
+
+// ------------------------------------------------------------------ cluster members + mean image
+// One warp per cluster scans all rows; keeps the best m by (cos desc, id asc).  K2 = 128.
+__global__ void __launch_bounds__(32)
+cluster_members_kernel(const int* __restrict__ cluster, const float* __restrict__ cosv, long long n, int m,
+                       long long* __restrict__ member_ids, int* __restrict__ member_counts) {
+    constexpr int E = 4;
+    const int j = blockIdx.x, lane = threadIdx.x;
+    unsigned long long L[E];
+#pragma unroll
+    for (int t = 0; t < E; ++t) L[t] = 0ull;
+    unsigned long long kth = 0ull;
+    int count = 0;
+    for (long long base = 0; base < n; base += 32) {
+        const long long i = base + lane;
+        unsigned long long c = 0ull;
+        if (i < n && cluster[i] == j) c = make_key(cosv[i], static_cast<uint32_t>(i));
+        unsigned hit = __ballot_sync(0xffffffffu, c != 0ull);
+        count += __popc(hit);
+        while (hit) {
+            const int t = __ffs(hit) - 1;
+            hit &= hit - 1;
+            const unsigned long long cc = __shfl_sync(0xffffffffu, c, t);
+            if (cc > kth) {
+                list_insert<E>(L, cc, lane);
+                kth = list_kth<E>(L, m);
+            }
+        }
+    }
+    const int keep = min(count, m);
+    if (lane == 0) member_counts[j] = keep;
+#pragma unroll
+    for (int t = 0; t < E; ++t) {
+        const int r = lane * E + t;
+        if (r < m) {
+            const unsigned long long key = L[t];
+            member_ids[static_cast<long long>(j) * m + r] =
+                (r < keep) ? static_cast<long long>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull)) : -1;
+        }
+    }
+}
+// face = zeros; face:add(img) in member order; face:div(count)   (apply_r.lua:236-242)
+__global__ void cluster_mean_kernel(const float* __restrict__ images, int px, const long long* __restrict__ member_ids,
+                                    const int* __restrict__ member_counts, int m, float* __restrict__ mean) {
+    const int j = blockIdx.y;
+    const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pidx >= px) return;
+    const int keep = member_counts[j];
+    float s = 0.0f;
+    for (int r = 0; r < keep; ++r) s = __fadd_rn(s, images[member_ids[static_cast<long long>(j) * m + r] * px + pidx]);
+    mean[static_cast<long long>(j) * px + pidx] = __fdiv_rn(s, static_cast<float>(keep));
+}
+
+}  // namespace scan
+}  // namespace ganrev

@@ -1,0 +1,156 @@
+/*
+ * ganrev.h -- C ABI of libganrev_cuda.so, the B200-native (sm_100a) replacement for
+ * the arithmetic under aleju/gan-reverser's apply_r.lua.
+ *
+ * The reference has no plugin / FFI interface of its own: apply_r.lua calls Torch7
+ * objects directly.  The boundary is therefore the set of Lua calls apply_r.lua makes;
+ * each entry point below names the reference call site (file:line in
+ * aleju/gan-reverser) it stands behind.  INTEGRATION.md shows the LuaJIT-FFI binding.
+ *
+ * Conventions
+ *  - All host tensors are contiguous row-major; float32 unless stated; images NCHW
+ *    (exactly what FloatTensor:data() yields).  Ids are 0-based (the Lua shim adds 1).
+ *  - Every call returns GANREV_OK (0) or an error code; ganrev_last_error() gives the
+ *    message.  No exceptions, no abort(), and NO CPU FALLBACK: without an sm_100
+ *    device ganrev_create() fails.
+ *  - The caller owns every host buffer; the library owns all device memory.  Calls are
+ *    synchronous: outputs are valid on return.  A ctx is driven by one host thread.
+ *  - Dropout is never drawn inside the library: R's input mask is an explicit argument
+ *    (uint8, 1 = keep) with the reference's semantics x*mask, no 1/(1-p) rescale
+ *    (models.lua:399-406).
+ *  - Resident buffers: every forward leaves its result on the device (G -> IMAGES,
+ *    R slot s -> ATTRS_s, fix -> FIXED).  A NULL *input* pointer means "use the
+ *    resident buffer"; a NULL *output* pointer means "keep it resident, do not copy
+ *    back" (1M 32x32 fp32 faces are 4.1 GB; returning them costs more than making them).
+ *
+ * Weight blob (ganrev_load_G / ganrev_load_R): every parameter, float32, concatenated in
+ * models.lua module order.  Conv weight [Cout][Cin][3][3] then bias [Cout]; Linear weight
+ * [out][in] then bias [out]; each BatchNorm as gamma, beta, running_mean, running_var
+ * ([C] each), eps = 1e-5.
+ *   G (models.lua:115-132): Linear(nd -> 512*H/4*W/4), BN, Conv 512->256, BN,
+ *                           Conv 256->128, BN, Conv 128->C.
+ *   R (models.lua:409-451): 6 x (Conv, BN) with channels C->64->64->64->128->128->128,
+ *                           Linear(128*H/4*W/4 -> 512), BN, Linear(512 -> nd).
+ */
+#ifndef GANREV_H
+#define GANREV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GANREV_OK      0
+#define GANREV_EINVAL  1   /* bad argument / unsupported geometry */
+#define GANREV_ECUDA   2   /* CUDA runtime or kernel error */
+#define GANREV_ENODEV  3   /* no sm_100 device */
+#define GANREV_ESTATE  4   /* model / db / buffer not loaded */
+#define GANREV_ENCCL   5   /* NCCL unavailable or failed */
+#define GANREV_ENOMEM  6
+
+/* resident device buffers (see "Resident buffers" above) */
+#define GANREV_BUF_NOISE   0   /* [rows x nd]        float32 */
+#define GANREV_BUF_IMAGES  1   /* [rows x C x H x W] float32 */
+#define GANREV_BUF_ATTRS0  2   /* [rows x nd]        float32, output of R slot 0 */
+#define GANREV_BUF_ATTRS1  3   /* [rows x nd]        float32, output of R slot 1 (fixer) */
+#define GANREV_BUF_FIXED   4   /* [rows x C x H x W] float32, G(R_fixer(images)) */
+#define GANREV_BUF_MASK    5   /* [rows x C x H x W] uint8 */
+#define GANREV_BUF_COUNT   6
+
+typedef struct ganrev_ctx ganrev_ctx;
+
+int         ganrev_version(void);
+/* One context = one GPU (one process per GPU under torchrun / one Lua state per GPU).
+ * Replaces cutorch.setDevice (apply_r.lua:52-56). */
+int         ganrev_create(ganrev_ctx** out, int device);
+void        ganrev_destroy(ganrev_ctx* ctx);
+const char* ganrev_last_error(const ganrev_ctx* ctx);   /* valid until the next call on ctx */
+
+/* ---- multi-GPU (new work; the reference is single-device) ------------------------
+ * Rank 0 makes a unique id, the launcher (torch.distributed / MPI / a file) hands it
+ * to every rank, every rank calls ganrev_comm_init.  NCCL is dlopen()ed on first use.
+ * After init the database of ganrev_db_set is one row-shard of a global database:
+ * search merges per-rank top-k with one allgather, kmeans sums centroid accumulators
+ * with one allreduce per iteration.  G / R need no communication. */
+int ganrev_comm_unique_id(ganrev_ctx* ctx, void* out, size_t cap, size_t* len);
+int ganrev_comm_init(ganrev_ctx* ctx, int world, int rank, const void* uid, size_t len);
+
+/* ---- models ---------------------------------------------------------------------
+ * MODELS.create_G(dimensions, noiseDim, cuda)   models.lua:201-203 -> create_G3 :104-143
+ * MODELS.create_R(dimensions, noiseDim, noiseMethod, fixer, cuda)  models.lua:385-464
+ * slot 0 = R (apply_r.lua:92-94), slot 1 = R_fixer (apply_r.lua:97-104).
+ * tanh_out = (noiseMethod ~= "normal")  models.lua:452-454. */
+int ganrev_load_G(ganrev_ctx* ctx, int C, int H, int W, int noise_dim,
+                  const float* blob, size_t n_floats);
+int ganrev_load_R(ganrev_ctx* ctx, int slot, int C, int H, int W, int noise_dim, int tanh_out,
+                  const float* blob, size_t n_floats);
+
+/* NN_UTILS.forwardBatched(MODEL_G, noise, batchSize)   utils/nn_utils.lua:5-33,
+ * apply_r.lua:136,146,349.  noise [N x nd] -> images [N x C x H x W] in [0,1]. */
+int ganrev_forward_G(ganrev_ctx* ctx, const float* noise, int64_t N, float* images);
+/* NN_UTILS.forwardBatched(MODEL_R / MODEL_R_FIXER, images, batchSize)  apply_r.lua:152-153.
+ * mask may be NULL (no input dropout).  images [N x C x H x W] -> attrs [N x nd]. */
+int ganrev_forward_R(ganrev_ctx* ctx, int slot, const float* images, const uint8_t* mask,
+                     int64_t N, float* attrs);
+/* fixFaces / detectAnomalies inner loop, batched: attrs = R_slot(images, mask);
+ * fixed = G(attrs); l2[i] = torch.dist(images[i], fixed[i]).  apply_r.lua:328-332,349,361-366.
+ * attrs, fixed, l2 may each be NULL. */
+int ganrev_fix_l2(ganrev_ctx* ctx, int slot, const float* images, const uint8_t* mask, int64_t N,
+                  float* attrs, float* fixed, double* l2);
+/* torch.dist(a[i], b[i]) for N pairs of px-element vectors (apply_r.lua:366). */
+int ganrev_l2(ganrev_ctx* ctx, const float* a, const float* b, int64_t N, int px, double* l2);
+/* apply_r.lua:370-378: sims = 1 - l2; thr = ascending sims[floor(n_calc*quantile)] (1-based);
+ * flags[i] = sims[i] <= thr, i < n_show.  thr may be NULL. */
+int ganrev_anomaly_flags(ganrev_ctx* ctx, const double* l2, int64_t n_calc, int64_t n_show,
+                         double quantile, uint8_t* flags, double* thr);
+
+/* ---- resident buffers ----------------------------------------------------------- */
+int ganrev_buffer_put(ganrev_ctx* ctx, int which, const void* host, int64_t rows);
+int ganrev_buffer_get(ganrev_ctx* ctx, int which, void* host, int64_t row0, int64_t rows);
+
+/* ---- recovered-vector database --------------------------------------------------
+ * vecs [N x d] (NULL = copy the resident ATTRS0 rows) becomes this rank's row shard. */
+int ganrev_db_set(ganrev_ctx* ctx, const float* vecs, int64_t N, int d);
+/* cosineSimilarity(v1, v2)   apply_r.lua:396-400 (nn.CosineDistance). */
+int ganrev_cosine(ganrev_ctx* ctx, const float* a, const float* b, int d, float* out);
+/* createSimilaritySearchImages inner loops   apply_r.lua:267-282: for each query the k
+ * best rows by (cosine desc, id asc), NaN last.  ids [Q x k] global 0-based row ids
+ * (-1 past the end of the database), scores [Q x k].  k <= 128. */
+int ganrev_search_cosine(ganrev_ctx* ctx, const float* queries, int Q, int k,
+                         int64_t* ids, float* scores);
+/* unsup.kmeans(x, k, niter)   apply_r.lua:198.  init_centroids [k x d] is explicit
+ * (unsup draws N(0,1) rows and normalises them; the shim does that and passes them in).
+ * total_counts [k] = counts summed over iterations; last_labels [N local rows] or NULL. */
+int ganrev_kmeans(ganrev_ctx* ctx, int k, int niter, const float* init_centroids,
+                  float* centroids, float* total_counts, int32_t* last_labels);
+/* createClusterImages assignment loop   apply_r.lua:206-218: per row the cluster with the
+ * MINIMUM cosine (strict <, lowest index on ties) and that cosine. */
+int ganrev_assign_cosine_min(ganrev_ctx* ctx, const float* centroids, int k,
+                             int32_t* cluster, float* cosv);
+/* apply_r.lua:222-243: per cluster keep <= m members by (cos desc, id asc) and average
+ * their images (images NULL = resident IMAGES; px = C*H*W).  member_ids [k x m] (-1
+ * padded), member_counts [k], mean_images [k x px] (NULL to skip).  m <= 128.
+ * Uses the result of the last ganrev_assign_cosine_min.  Single-rank only. */
+int ganrev_cluster_members(ganrev_ctx* ctx, int k, int m, const float* images, int px,
+                           int64_t* member_ids, int32_t* member_counts, float* mean_images);
+
+/* ---- measurement hooks (bench.py) ----------------------------------------------- */
+void*    ganrev_stream(ganrev_ctx* ctx);                 /* cudaStream_t all work runs on */
+int      ganrev_sync(ganrev_ctx* ctx);
+uint64_t ganrev_launch_count(const ganrev_ctx* ctx);     /* kernels launched so far */
+/* Per-kernel CUDA-event timing on the library's stream. */
+int ganrev_profile_enable(ganrev_ctx* ctx, int on);
+int ganrev_profile_reset(ganrev_ctx* ctx);
+int ganrev_profile_count(ganrev_ctx* ctx);
+int ganrev_profile_get(ganrev_ctx* ctx, int idx, const char** name, uint64_t* launches,
+                       double* total_ms, double* flops, double* bytes);
+/* Tuning / debugging knobs: "chunk" (images per pipeline chunk), "conv_impl"
+ * (0 = tcgen05 implicit GEMM, 1 = plain CUDA-core kernel kept for A/B debugging). */
+int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,143 @@
+"""GPU parity of the database kernels: cosine top-k (apply_r.lua:265-282), kmeans (unsup.kmeans,
+apply_r.lua:198), cosine-min assignment (:206-218), cluster members + mean image (:222-243).
+Everything here is BIT-EXACT against the oracle: ids, labels, scores, centroids."""
+import numpy as np
+import pytest
+
+from util import assert_bitexact
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(pkg):
+    c = pkg.Context(0)
+    yield c
+    c.close()
+
+
+def _db(N, d, seed=0, scale=1.0):
+    return (np.random.default_rng(seed).normal(size=(N, d)) * scale).astype(np.float32)
+
+
+SEARCH_CASES = [
+    # N, d, Q, k
+    (10000, 32, 5, 100),     # apply_r.lua's own values (5 needles, top-100)
+    (10000, 32, 4, 20),      # BASELINE config 1
+    (2000, 1024, 5, 100),    # pixelwise measure, d = C*H*W
+    (5000, 100, 70, 20),     # 64-wide query tiles, ragged last tile
+    (3000, 30, 33, 128),     # d not a multiple of 4 or 32, max k
+    (777, 7, 17, 5),
+    (50, 32, 3, 100),        # k > N: ids -1 past the end
+    (1, 32, 2, 3),
+]
+
+
+@pytest.mark.parametrize("case", SEARCH_CASES, ids=lambda c: "N%d_d%d_Q%d_k%d" % c)
+def test_search_exact(orc, ctx, case):
+    N, d, Q, k = case
+    db = _db(N, d, 1)
+    q = np.concatenate([db[: min(Q, N) // 2], _db(Q - min(Q, N) // 2, d, 2)])[:Q]   # some queries are db rows
+    want_ids, want_sc = orc.search_cosine(db, q, k)
+    ctx.db_set(db)
+    ids, sc = ctx.search_cosine(q, k)
+    np.testing.assert_array_equal(ids, want_ids)
+    assert_bitexact(sc, want_sc, "scores")
+
+
+def test_search_ties_nan_zero(orc, ctx):
+    """Duplicate rows (exact score ties -> lowest id first), zero rows, NaN rows (sorted last)."""
+    rng = np.random.default_rng(7)
+    base = rng.normal(size=(40, 16)).astype(np.float32)
+    db = base[rng.integers(0, 40, size=4000)]                 # heavy duplication
+    db[5] = 0.0
+    db[100] = np.nan
+    db[101, 3] = np.nan
+    q = np.concatenate([base[:6], np.zeros((1, 16), np.float32)])
+    for k in (1, 20, 128):
+        want_ids, want_sc = orc.search_cosine(db, q, k)
+        ctx.db_set(db)
+        ids, sc = ctx.search_cosine(q, k)
+        np.testing.assert_array_equal(ids, want_ids)
+        assert_bitexact(sc, want_sc, f"scores k={k}")
+    # every NaN row sorts after every finite row when k covers the whole db
+    small = db[:120]
+    want_ids, _ = orc.search_cosine(small, q[:2], 120)
+    ctx.db_set(small)
+    ids, sc = ctx.search_cosine(q[:2], 120)
+    np.testing.assert_array_equal(ids, want_ids)
+    assert set(ids[0, -2:].tolist()) == {100, 101} and np.isnan(sc[0, -2:]).all()
+
+
+def test_cosine_pair(orc, ctx):
+    rng = np.random.default_rng(3)
+    for d in (1, 32, 100, 1024):
+        a, b = rng.normal(size=d).astype(np.float32), rng.normal(size=d).astype(np.float32)
+        assert np.float32(ctx.cosine(a, b)).view(np.uint32) == np.float32(orc.cosine(a, b)).view(np.uint32)
+
+
+KMEANS_CASES = [
+    # N, d, k, niter
+    (10000, 32, 20, 15),     # apply_r.lua:159-161
+    (4000, 100, 70, 4),      # several centroid tiles
+    (3000, 30, 7, 5),        # k <= 16 path, ragged d
+    (129, 8, 3, 3),
+    (6000, 256, 33, 2),      # k*d too big for the shared-memory accumulators
+]
+
+
+def _init(k, d, seed=6):
+    c = np.random.default_rng(seed).normal(size=(k, d)).astype(np.float32)
+    return (c / np.linalg.norm(c, axis=1, keepdims=True)).astype(np.float32)
+
+
+@pytest.mark.parametrize("case", KMEANS_CASES, ids=lambda c: "N%d_d%d_k%d_it%d" % c)
+def test_kmeans_exact(orc, ctx, case):
+    N, d, k, niter = case
+    x = _db(N, d, 11)
+    init = _init(k, d)
+    want_c, want_t, want_l = orc.kmeans(x, k, niter, init)
+    ctx.db_set(x)
+    cen, tot, lab = ctx.kmeans(k, niter, init)
+    np.testing.assert_array_equal(lab, want_l)
+    assert_bitexact(tot, want_t, "total counts")
+    assert_bitexact(cen, want_c, "centroids")
+
+
+def test_kmeans_empty_cluster_and_zero_iters(orc, ctx):
+    x = _db(500, 16, 12)
+    init = _init(5, 16)
+    init[3] = -1000.0 * np.abs(init[3]) - 1000.0     # |c|^2 term makes it lose everywhere: stays empty
+    want_c, want_t, want_l = orc.kmeans(x, 5, 4, init)
+    ctx.db_set(x)
+    cen, tot, lab = ctx.kmeans(5, 4, init)
+    assert want_t[3] == 0 and (want_c[3] == init[3]).all(), "empty clusters keep their centroid"
+    np.testing.assert_array_equal(lab, want_l)
+    assert_bitexact(cen, want_c)
+    assert_bitexact(tot, want_t)
+    cen0, tot0, lab0 = ctx.kmeans(5, 0, init)
+    assert_bitexact(cen0, init)
+    assert (tot0 == 0).all() and (lab0 == -1).all()
+
+
+@pytest.mark.parametrize("case", [(10000, 32, 20), (3000, 100, 70), (500, 30, 3)], ids=lambda c: "N%d_d%d_k%d" % c)
+def test_assign_cosine_min_and_members_exact(orc, ctx, case):
+    N, d, k = case
+    x = _db(N, d, 21)
+    cen = _db(k, d, 22)
+    x[7] = cen[0]                                    # exact duplicates -> ties
+    x[8] = cen[0]
+    images = np.random.default_rng(23).random((N, 48)).astype(np.float32)
+    want_cl, want_cv = orc.assign_cosine_min(x, cen)
+    ctx.db_set(x)
+    cl, cv = ctx.assign_cosine_min(cen)
+    np.testing.assert_array_equal(cl, want_cl)
+    assert_bitexact(cv, want_cv, "cos")
+    m = 71                                            # nbMaxPerCluster = 64+7, apply_r.lua:161
+    want_ids, want_cnt, want_mean = orc.cluster_members(want_cl, want_cv, k, m, images)
+    ids, cnt, mean = ctx.cluster_members(k, m, images)
+    np.testing.assert_array_equal(cnt, want_cnt)
+    np.testing.assert_array_equal(ids, want_ids)
+    ok = want_cnt > 0                                 # empty clusters: 0/0 = NaN on both sides
+    assert_bitexact(mean[ok], want_mean[ok], "mean images")
+    assert np.isnan(mean[~ok]).all()

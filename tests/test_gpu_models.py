@@ -1,0 +1,150 @@
+"""GPU parity of G3 / R_default (models.lua:104-143, 389-464) through the C ABI against the
+CPU oracle.  Tolerances are north_star's: generated pixels within 2e-2 max-abs, recovered
+vectors cosine >= 0.999 -- plus a relative-L2 bound so a constant offset cannot hide errors."""
+import numpy as np
+import pytest
+
+from util import rel_l2, row_cosine
+
+pytestmark = pytest.mark.gpu
+
+PIX_TOL = 2e-2      # north_star: "Generated pixels must be within 2e-2 max-abs"
+COS_TOL = 0.999     # north_star: "Recovered vectors must reach cosine >= 0.999"
+REL_TOL = 3e-2      # our own, stricter companion bound (bf16 operands, fp32 accumulate)
+
+GEOMS = [
+    # C, H, W, nd, N
+    (1, 32, 32, 32, 37),
+    (1, 32, 32, 100, 19),
+    (3, 64, 64, 256, 5),
+    (1, 16, 16, 32, 21),
+    (3, 32, 32, 64, 9),
+]
+
+
+@pytest.fixture(scope="module")
+def ctx(pkg):
+    c = pkg.Context(0)
+    yield c
+    c.close()
+
+
+def _setup(pkg, ctx, geom, stress, impl):
+    C, H, W, nd, N = geom
+    ctx.set_option("conv_impl", impl)
+    ctx.set_option("chunk", 16)        # several chunks, the last one ragged
+    gb = pkg.weights.init_G(C, H, W, nd, seed=1, stress=stress)
+    rb = pkg.weights.init_R(C, H, W, nd, seed=2, stress=stress)
+    rfb = pkg.weights.init_R(C, H, W, nd, seed=4, stress=stress)
+    ctx.load_G(C, H, W, nd, gb)
+    ctx.load_R(0, C, H, W, nd, rb)
+    ctx.load_R(1, C, H, W, nd, rfb)
+    noise = np.random.default_rng(3).normal(size=(N, nd)).astype(np.float32)
+    return gb, rb, rfb, noise
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["cudacore", "tcgen05"])
+@pytest.mark.parametrize("geom", GEOMS, ids=lambda g: "C%dx%dx%d_nd%d_N%d" % g)
+def test_G_matches_oracle(pkg, orc, ctx, geom, impl):
+    C, H, W, nd, N = geom
+    gb, _, _, noise = _setup(pkg, ctx, geom, True, impl)
+    want = orc.forward_G(gb, C, H, W, nd, noise)
+    got = ctx.forward_G(noise)
+    assert got.shape == want.shape
+    err = np.abs(got - want).max()
+    assert want.std() > 0.05, "stress weights should spread pixels over (0,1)"
+    assert err <= PIX_TOL, f"max |pixel diff| {err}"
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["cudacore", "tcgen05"])
+@pytest.mark.parametrize("geom", GEOMS, ids=lambda g: "C%dx%dx%d_nd%d_N%d" % g)
+def test_R_matches_oracle(pkg, orc, ctx, geom, impl):
+    C, H, W, nd, N = geom
+    gb, rb, rfb, noise = _setup(pkg, ctx, geom, True, impl)
+    images = orc.forward_G(gb, C, H, W, nd, noise)          # identical inputs for both sides
+    want = orc.forward_R(rb, C, H, W, nd, images)
+    got = ctx.forward_R(0, images)
+    assert row_cosine(got, want).min() >= COS_TOL
+    assert rel_l2(got, want) <= REL_TOL, rel_l2(got, want)
+    # fixer: explicit 50% input dropout mask, multiply-no-rescale (models.lua:399-406)
+    mask = (np.random.default_rng(5).random(images.shape) >= 0.5).astype(np.uint8)
+    want_f = orc.forward_R(rfb, C, H, W, nd, images, mask)
+    got_f = ctx.forward_R(1, images, mask)
+    assert row_cosine(got_f, want_f).min() >= COS_TOL
+    assert rel_l2(got_f, want_f) <= REL_TOL, rel_l2(got_f, want_f)
+    assert rel_l2(got_f, want) > 10 * REL_TOL, "mask must change the result"
+
+
+def test_tanh_output(pkg, orc, ctx):
+    C, H, W, nd, N = 1, 32, 32, 32, 8
+    ctx.set_option("conv_impl", 0)
+    rb = pkg.weights.init_R(C, H, W, nd, seed=2, stress=True)
+    ctx.load_G(C, H, W, nd, pkg.weights.init_G(C, H, W, nd, seed=1, stress=True))
+    ctx.load_R(0, C, H, W, nd, rb, tanh_out=True)            # noiseMethod ~= "normal", models.lua:452-454
+    images = np.random.default_rng(0).random((N, C, H, W)).astype(np.float32)
+    want = orc.forward_R(rb, C, H, W, nd, images, None, tanh_out=True)
+    got = ctx.forward_R(0, images)
+    assert np.abs(got).max() <= 1.0
+    assert np.abs(got - want).max() <= 3e-2
+
+
+def test_default_init_and_tc_vs_cudacore(pkg, orc, ctx):
+    """The reference's own init (weight-init.lua 'heuristic'): tiny activations, images ~0.5."""
+    geom = (1, 32, 32, 32, 24)
+    C, H, W, nd, N = geom
+    gb, rb, _, noise = _setup(pkg, ctx, geom, False, 0)
+    want_img = orc.forward_G(gb, C, H, W, nd, noise)
+    got_img = ctx.forward_G(noise)
+    assert np.abs(got_img - want_img).max() <= 1e-3
+    # relative accuracy of the (tiny) image-dependent signal around 0.5
+    assert rel_l2(got_img - 0.5, want_img - 0.5) <= REL_TOL
+    got_att = ctx.forward_R(0, want_img)
+    want_att = orc.forward_R(rb, C, H, W, nd, want_img)
+    assert row_cosine(got_att, want_att).min() >= COS_TOL
+    assert rel_l2(got_att, want_att) <= REL_TOL
+    ctx.set_option("conv_impl", 1)
+    cc_img = ctx.forward_G(noise)
+    cc_att = ctx.forward_R(0, want_img)
+    # same bf16 operands, different accumulation order only
+    assert rel_l2(got_img - 0.5, cc_img - 0.5) <= 1e-2
+    assert rel_l2(got_att, cc_att) <= 1e-2
+    ctx.set_option("conv_impl", 0)
+
+
+def test_resident_chain_and_fix_l2(pkg, orc, ctx):
+    """G -> R -> G with device-resident intermediates (NULL pointers) equals the host-pointer
+    path bit for bit, and fix_l2 matches the oracle's G(R_fixer(x)) distance within tolerance."""
+    geom = (1, 32, 32, 32, 50)
+    C, H, W, nd, N = geom
+    gb, rb, rfb, noise = _setup(pkg, ctx, geom, True, 0)
+    img = ctx.forward_G(noise)
+    att = ctx.forward_R(0, img)
+    ctx.buffer_put(pkg._lib.BUF_NOISE, noise)
+    assert ctx.forward_G(None, N=N, want_images=False) is None
+    att2 = ctx.forward_R(0, None, N=N)
+    np.testing.assert_array_equal(att, att2)
+    np.testing.assert_array_equal(ctx.buffer_get(pkg._lib.BUF_IMAGES, 0, N), img)
+    mask = (np.random.default_rng(5).random(img.shape) >= 0.5).astype(np.uint8)
+    a1, fixed, l2 = ctx.fix_l2(1, img, mask)
+    np.testing.assert_array_equal(a1, ctx.forward_R(1, img, mask))
+    np.testing.assert_array_equal(fixed, ctx.forward_G(a1))
+    # exact distance of the library's own pair of image sets
+    from util import assert_bitexact
+    assert_bitexact(l2, orc.l2(img, fixed), "fix_l2 distances")
+    # tolerance check against the all-oracle chain
+    want_fixed = orc.forward_G(gb, C, H, W, nd, orc.forward_R(rfb, C, H, W, nd, img, mask))
+    assert np.abs(fixed - want_fixed).max() <= 2 * PIX_TOL
+
+
+def test_errors(pkg, ctx):
+    with pytest.raises(pkg.GanrevError):
+        ctx.load_G(2, 32, 32, 32, np.zeros(10, np.float32))          # C must be 1 or 3
+    with pytest.raises(pkg.GanrevError):
+        ctx.load_G(1, 48, 48, 32, np.zeros(10, np.float32))          # power-of-two geometry only
+    with pytest.raises(pkg.GanrevError):
+        ctx.load_G(1, 32, 32, 32, np.zeros(10, np.float32))          # wrong blob size
+    c2 = pkg.Context(0)
+    with pytest.raises(pkg.GanrevError):
+        c2.geom = (1, 32, 32, 32)
+        c2.forward_G(np.zeros((2, 32), np.float32))                  # nothing loaded
+    c2.close()
