@@ -50,7 +50,8 @@ struct ConvGemm {
     // B operand: bf16 weights [nphase*cout_pad][ntaps*Cin], K index = tap*Cin + ci
     int cout_pad, n_tiles;     // cout_pad = n_tiles*NT
     int cout_real;             // channels actually stored
-    int out_cstride;           // channel stride of one output pixel
+    long long out_sN;          // output strides (elements): image,
+    int out_sP, out_sC;        //   pixel (row-major oh*Wout+ow), channel.  bf16 NHWC: (H*W*C, C, 1); fp32 NCHW: (C*H*W, 1, H*W)
     // output
     int Hout, Wout, up, pool, act, out_fp32;
     float post_scale;
@@ -62,13 +63,23 @@ struct ConvGemm {
     int* err_flag;
 };
 
-enum { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2, ACT_TANH = 3 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2, ACT_TANH = 3, ACT_SIGMOID = 4 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == ACT_RELU) return v > 0.0f ? v : 0.0f;
     if (act == ACT_ELU) return v > 0.0f ? v : expm1f(v);
     if (act == ACT_TANH) return tanhf(v);
+    if (act == ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
     return v;
+}
+
+// nn.ELU(alpha=1) for bf16 outputs: ex2.approx-based exp for v <= -0.03, a cubic Taylor expm1
+// above it (exp(v)-1 would cancel); abs error < 1e-7, far below the bf16 output rounding.
+__device__ __forceinline__ float elu_fast(float v) {
+    const float e = __expf(v) - 1.0f;
+    const float t = v * fmaf(v, fmaf(v, 0.16666667f, 0.5f), 1.0f);
+    const float n = v > -0.03f ? t : e;
+    return v > 0.0f ? v : n;
 }
 
 }  // namespace ganrev

@@ -41,7 +41,7 @@ __global__ void conv_simt_kernel(const ConvGemm p, const long long total) {
         v = simt_conv_at(p, n, oh, ow, 0, co);
     }
     v = apply_act(v, p.act) * p.post_scale;
-    const size_t off = ((static_cast<size_t>(n) * p.Hout + oh) * p.Wout + ow) * static_cast<size_t>(p.out_cstride) + co;
+    const size_t off = static_cast<size_t>(n) * p.out_sN + (static_cast<size_t>(oh) * p.Wout + ow) * p.out_sP + static_cast<size_t>(co) * p.out_sC;
     if (p.out_fp32) reinterpret_cast<float*>(p.out)[off] = v;
     else reinterpret_cast<bf16*>(p.out)[off] = __float2bfloat16_rn(v);
 }

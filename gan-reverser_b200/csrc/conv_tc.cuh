@@ -14,15 +14,17 @@
 //  * epilogue: tcgen05.ld -> folded BatchNorm affine -> ReLU/ELU/tanh -> optional 2x2
 //    max-pool (warp shuffles) and x0.75 (SpatialDropout in eval) -> bf16 NHWC / fp32 store.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer,
-// warps 2..5 = epilogue (warp 2 also owns the TMEM allocation).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue
+// (two warps per TMEM lane quarter; warp 2 also owns the TMEM allocation).  Activation, pooling
+// and output type are template parameters so the epilogue is a short straight-line stream.
 #pragma once
 #include "common.cuh"
 
 namespace ganrev {
 namespace tc {
 
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quarter, interleaved 32-column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;               // bf16 elements = 128 bytes = one swizzle span
 constexpr int kABytes = kBlockM * kBlockK * 2;
@@ -32,9 +34,11 @@ template <int NT> struct Cfg {
     static constexpr int kBBytes = NT * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (NT >= 256) ? 4 : (NT >= 128 ? 6 : 8);
+    static constexpr int kChunk = NT < 32 ? NT : 32;   // accumulator columns per tcgen05.ld
     static constexpr int kTmemCols = (2 * NT <= 32) ? 32 : (2 * NT <= 64 ? 64 : (2 * NT <= 128 ? 128 : (2 * NT <= 256 ? 256 : 512)));
-    // stages + (2*stages + 4) mbarriers + tmem ptr, plus 1024 B alignment slack
-    static constexpr int kSmemBytes = kStages * kStageBytes + (2 * kStages + 4) * 8 + 16 + 1024;
+    // stages + (2*stages + 4) mbarriers + tmem ptr + double-buffered scale/shift, plus 1024 B alignment slack
+    static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 2 * 2 * NT * 4 + 1024;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -130,6 +134,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B (SBO), sm_100
@@ -154,6 +167,29 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+constexpr int ACT_RUNTIME = -1;
+template <int ACT> __device__ __forceinline__ float act_fn(float v, int runtime_act) {
+    if (ACT == ACT_RELU) return fmaxf(v, 0.0f);
+    if (ACT == ACT_ELU) return elu_fast(v);
+    if (ACT == ACT_NONE) return v;
+    if (ACT == ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-v));
+    return apply_act(v, runtime_act);
+}
+// Warp-uniform leader election: keeps the issuing code convergent so TMA / tcgen05 instructions
+// (which take uniform registers) compile to straight-line code instead of per-thread loops.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
 struct ItemCoord {
     int n0, h0, w0, phase, ntile;
 };
@@ -171,7 +207,7 @@ __device__ __forceinline__ ItemCoord decode_item(const ConvGemm& p, int item) {
     return c;
 }
 
-template <int NT>
+template <int NT, int ACT, bool POOL, bool OUT_FP32>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ ConvGemm p, const int n_items) {
@@ -203,7 +239,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 128);
+            mbar_init(tempty_bar(a), 32 * kEpiWarps);
         }
         fence_barrier_init();
     }
@@ -217,120 +253,135 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int cin_chunks = p.Cin / kBlockK;
 
     if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const ItemCoord c = decode_item(p, item);
-                const int brow = c.phase * p.cout_pad + c.ntile * NT;
-                for (int tap = 0; tap < p.ntaps; ++tap) {
-                    const int dy = p.dy[c.phase][tap], dx = p.dx[c.phase][tap];
-                    for (int cc = 0; cc < cin_chunks; ++cc) {
-                        mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 101);
+        // ------------------------------------------------------------ TMA producer (whole warp loops, one lane issues)
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const ItemCoord c = decode_item(p, item);
+            const int brow = c.phase * p.cout_pad + c.ntile * NT;
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+                const int wx = c.w0 + p.dx[c.phase][tap], hy = c.h0 + p.dy[c.phase][tap];
+                const int kcol0 = tap * p.Cin;
+                for (int cc = 0; cc < cin_chunks; ++cc) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 101);
+                    if (elect_one_sync()) {
                         const uint32_t a_dst = smem_base + stage * C::kStageBytes;
-                        const uint32_t b_dst = a_dst + kABytes;
                         mbar_expect_tx(full_bar(stage), C::kStageBytes);
-                        tma_load_4d(a_dst, &tmA, full_bar(stage), cc * kBlockK, c.w0 + dx, c.h0 + dy, c.n0);
-                        tma_load_2d(b_dst, &tmB, full_bar(stage), (tap * cin_chunks + cc) * kBlockK, brow);
-                        if (++stage == S) { stage = 0; phase ^= 1u; }
+                        tma_load_4d(a_dst, &tmA, full_bar(stage), cc * kBlockK, wx, hy, c.n0);
+                        tma_load_2d(a_dst + kABytes, &tmB, full_bar(stage), kcol0 + cc * kBlockK, brow);
                     }
+                    __syncwarp();
+                    if (++stage == S) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc<NT>();
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1u;
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 102);
+        // ------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
+        constexpr uint32_t idesc = make_idesc<NT>();
+        const uint64_t desc_base = make_smem_desc(0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1u;
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 102);
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * NT);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(full_bar(stage), phase, p.err_flag, 103);
                 tcgen05_fence_after();
-                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * NT);
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(full_bar(stage), phase, p.err_flag, 103);
-                    tcgen05_fence_after();
+                if (elect_one_sync()) {
                     const uint32_t a_addr = smem_base + stage * C::kStageBytes;
-                    const uint64_t adesc = make_smem_desc(a_addr);
-                    const uint64_t bdesc = make_smem_desc(a_addr + kABytes);
+                    const uint64_t adesc = desc_base | static_cast<uint64_t>((a_addr & 0x3FFFFu) >> 4);
+                    const uint64_t bdesc = desc_base | static_cast<uint64_t>(((a_addr + kABytes) & 0x3FFFFu) >> 4);
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         // +32 B per K=16 step inside the 128 B swizzle span (>>4 -> +2)
                         umma_bf16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(empty_bar(stage));           // frees the smem slot when the MMAs retire
-                    if (kb == kblocks - 1) umma_commit(tfull_bar(acc));  // accumulator complete
-                    if (++stage == S) { stage = 0; phase ^= 1u; }
+                    umma_commit(empty_bar(stage));                        // frees the smem slot when the MMAs retire
+                    if (kb == kblocks - 1) umma_commit(tfull_bar(acc));   // accumulator complete
                 }
+                __syncwarp();
+                if (++stage == S) { stage = 0; phase ^= 1u; }
             }
         }
     } else {
-        // ------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------ epilogue (warps 2..9)
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;       // which set of interleaved 32-column chunks
+        const int etid = threadIdx.x - 64;      // 0..255
         const int m = q * 32 + lane;            // tile row = pixel
         const int BW = 1 << p.lgBW;
         const int w_l = m & (BW - 1);
         const int h_l = (m >> p.lgBW) & ((1 << p.lgBH) - 1);
         const int n_l = m >> (p.lgBW + p.lgBH);
+        float* ss_base = reinterpret_cast<float*>(smem + S * C::kStageBytes + C::kBarBytes);
         int it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const ItemCoord c = decode_item(p, item);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1u;
+            const int cbase = c.ntile * NT;
+            // stage this item's folded-BN scale / shift (double-buffered; the named barrier of
+            // item i+1 proves every warp is done reading the buffer of item i)
+            float* ss = ss_base + acc * (2 * NT);
+            for (int i = etid; i < NT; i += 32 * kEpiWarps) {
+                ss[i] = __ldg(p.scale + cbase + i);
+                ss[NT + i] = __ldg(p.shift + cbase + i);
+            }
             const int n = c.n0 + n_l, h = c.h0 + h_l, w = c.w0 + w_l;
             int oh = h, ow = w;
             bool writer = n < p.n_img;
-            if (p.pool) {
+            if (POOL) {
                 oh = h >> 1; ow = w >> 1;
                 writer = writer && !(h & 1) && !(w & 1);
             } else if (p.up == 2) {
                 oh = 2 * h + (c.phase >> 1); ow = 2 * w + (c.phase & 1);
             }
-            const size_t pix_off = ((static_cast<size_t>(n) * p.Hout + oh) * p.Wout + ow) * static_cast<size_t>(p.out_cstride);
-            const int cbase = c.ntile * NT;
+            const size_t pix_off = static_cast<size_t>(n) * p.out_sN + (static_cast<size_t>(oh) * p.Wout + ow) * p.out_sP;
+            named_bar_sync(1, 32 * kEpiWarps);
 
             mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 104);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * NT);
+            constexpr int CW = C::kChunk;
 #pragma unroll 1
-            for (int c0 = 0; c0 < NT; c0 += 32) {
+            for (int c0 = half * CW; c0 < NT; c0 += 2 * CW) {
                 uint32_t r[32];
-                tmem_ld32(taddr + c0, r);
+                if (CW == 32) tmem_ld32(taddr + c0, r); else tmem_ld16(taddr + c0, r);
                 tmem_ld_wait();
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + cbase + c0 + j));
-                    const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + cbase + c0 + j));
+                for (int j = 0; j < CW; j += 4) {
+                    const float4 sc = *reinterpret_cast<const float4*>(ss + c0 + j);
+                    const float4 sh = *reinterpret_cast<const float4*>(ss + NT + c0 + j);
                     v[j + 0] = fmaf(__uint_as_float(r[j + 0]), sc.x, sh.x);
                     v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y);
                     v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z);
                     v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
                 }
-                if (p.pool) {
+                if (POOL) {
                     // 2x2 max: w-neighbour is lane^1, h-neighbour is lane^BW (BW <= 16)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
+                    for (int j = 0; j < CW; ++j) {
                         v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
                         v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], BW));
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act) * p.post_scale;
+                for (int j = 0; j < CW; ++j) v[j] = act_fn<ACT>(v[j], p.act) * p.post_scale;
                 if (writer) {
-                    if (p.out_fp32) {
-                        float* o = reinterpret_cast<float*>(p.out) + pix_off + cbase + c0;
+                    if (OUT_FP32) {
+                        float* o = reinterpret_cast<float*>(p.out) + pix_off + static_cast<size_t>(cbase + c0) * p.out_sC;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (cbase + c0 + j < p.cout_real) o[j] = v[j];
+                        for (int j = 0; j < CW; ++j)
+                            if (cbase + c0 + j < p.cout_real) o[static_cast<size_t>(j) * p.out_sC] = v[j];
                     } else {
                         uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + pix_off + cbase + c0);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int j = 0; j < CW / 8; ++j) {
                             uint4 pk;
                             pk.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
                             pk.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);

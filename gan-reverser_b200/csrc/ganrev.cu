@@ -31,8 +31,7 @@ struct TcLayer {
 struct GModel {
     bool loaded = false;
     int C = 0, H = 0, W = 0, nd = 0, kpad = 0, F = 0;
-    TcLayer lin, c1, c2;
-    DevBuf w3, b3;
+    TcLayer lin, c1, c2, c3;
 };
 struct RModel {
     bool loaded = false;
@@ -239,7 +238,7 @@ static int make_tmB(ganrev_ctx* ctx, TcLayer& L) {
 static int build_tc_layer(ganrev_ctx* ctx, TcLayer& L, const char* name, int NT, int Hin, int Win, int Cin, int nphase, int ntaps,
                           const int8_t (*dy)[9], const int8_t (*dx)[9], int cout_real, int n_tiles,
                           const std::vector<float>& wmat, const BnFold& bn, int Hout, int Wout, int out_cstride, int up, int pool,
-                          int act, float post_scale, int out_fp32) {
+                          int act, float post_scale, int out_fp32, bool nchw = false) {
     L.name = name;
     L.NT = NT;
     ConvGemm& g = L.g;
@@ -248,7 +247,9 @@ static int build_tc_layer(ganrev_ctx* ctx, TcLayer& L, const char* name, int NT,
     g.nphase = nphase; g.ntaps = ntaps;
     for (int p = 0; p < nphase; ++p)
         for (int t = 0; t < ntaps; ++t) { g.dy[p][t] = dy[p][t]; g.dx[p][t] = dx[p][t]; }
-    g.n_tiles = n_tiles; g.cout_pad = n_tiles * NT; g.cout_real = cout_real; g.out_cstride = out_cstride;
+    g.n_tiles = n_tiles; g.cout_pad = n_tiles * NT; g.cout_real = cout_real;
+    if (nchw) { g.out_sN = static_cast<long long>(out_cstride) * Hout * Wout; g.out_sP = 1; g.out_sC = Hout * Wout; }
+    else      { g.out_sN = static_cast<long long>(out_cstride) * Hout * Wout; g.out_sP = out_cstride; g.out_sC = 1; }
     g.Hout = Hout; g.Wout = Wout; g.up = up; g.pool = pool; g.act = act; g.post_scale = post_scale; g.out_fp32 = out_fp32;
     g.err_flag = ctx->d_err_flag;
     pick_box(g, pool != 0);
@@ -265,7 +266,7 @@ static int build_tc_layer(ganrev_ctx* ctx, TcLayer& L, const char* name, int NT,
     g.shift = reinterpret_cast<const float*>(L.shift.p);
     RC_TRY(make_tmB(ctx, L));
     const double px_in = static_cast<double>(Hin) * Win;
-    L.flops_per_img = 2.0 * px_in * nphase * g.cout_pad * L.Ktot;
+    L.flops_per_img = 2.0 * px_in * nphase * (out_fp32 ? cout_real : g.cout_pad) * L.Ktot;   // zero-padded output lanes are not work
     L.bytes_per_img = 2.0 * px_in * Cin + (out_fp32 ? 4.0 : 2.0) * Hout * Wout * cout_real;
     return GANREV_OK;
 }
@@ -316,18 +317,41 @@ static int check_geom(ganrev_ctx* ctx, int C, int H, int W, int nd) {
 // =================================================================================
 // layer launches
 // =================================================================================
-template <int NT>
+template <int NT, int ACT, bool POOL, bool OUT_FP32>
 static int launch_tc(ganrev_ctx* ctx, const TcLayer& L, const CUtensorMap& tmA, const ConvGemm& g, int n_items) {
     using C = tc::Cfg<NT>;
     static bool attr_set = false;
     if (!attr_set) {
-        CU_TRY(cudaFuncSetAttribute(tc::conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+        CU_TRY(cudaFuncSetAttribute(tc::conv_tc_kernel<NT, ACT, POOL, OUT_FP32>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
         attr_set = true;
     }
     const int grid = std::min(n_items, ctx->num_sms);
-    tc::conv_tc_kernel<NT><<<grid, tc::kThreads, C::kSmemBytes, ctx->stream>>>(tmA, L.tmB, g, n_items);
+    tc::conv_tc_kernel<NT, ACT, POOL, OUT_FP32><<<grid, tc::kThreads, C::kSmemBytes, ctx->stream>>>(tmA, L.tmB, g, n_items);
     CU_TRY(cudaGetLastError());
     return GANREV_OK;
+}
+// The layer shapes of G3 / R_default map onto this fixed set of kernel variants.
+static int dispatch_tc(ganrev_ctx* ctx, const TcLayer& L, const CUtensorMap& tmA, const ConvGemm& g, int n_items) {
+    const int NT = L.NT;
+    if (g.out_fp32 && g.act == ACT_SIGMOID && NT == 16) {   // G's last conv: 128 -> C, fp32 NCHW images
+        return launch_tc<16, ACT_SIGMOID, false, true>(ctx, L, tmA, g, n_items);
+    } else if (g.out_fp32) {   // final Linear(512 -> nd) [+ Tanh]
+        switch (NT) {
+            case 32: return launch_tc<32, tc::ACT_RUNTIME, false, true>(ctx, L, tmA, g, n_items);
+            case 64: return launch_tc<64, tc::ACT_RUNTIME, false, true>(ctx, L, tmA, g, n_items);
+            case 128: return launch_tc<128, tc::ACT_RUNTIME, false, true>(ctx, L, tmA, g, n_items);
+            case 256: return launch_tc<256, tc::ACT_RUNTIME, false, true>(ctx, L, tmA, g, n_items);
+        }
+    } else if (g.act == ACT_RELU && !g.pool) {
+        if (NT == 256) return launch_tc<256, ACT_RELU, false, false>(ctx, L, tmA, g, n_items);
+        if (NT == 128) return launch_tc<128, ACT_RELU, false, false>(ctx, L, tmA, g, n_items);
+    } else if (g.act == ACT_ELU) {
+        if (NT == 64 && !g.pool) return launch_tc<64, ACT_ELU, false, false>(ctx, L, tmA, g, n_items);
+        if (NT == 64 && g.pool) return launch_tc<64, ACT_ELU, true, false>(ctx, L, tmA, g, n_items);
+        if (NT == 128 && !g.pool) return launch_tc<128, ACT_ELU, false, false>(ctx, L, tmA, g, n_items);
+        if (NT == 128 && g.pool) return launch_tc<128, ACT_ELU, true, false>(ctx, L, tmA, g, n_items);
+    }
+    return fail(ctx, GANREV_EINVAL, "no tcgen05 kernel variant for layer %s (NT=%d act=%d pool=%d fp32=%d)", L.name.c_str(), NT, g.act, g.pool, g.out_fp32);
 }
 
 static int run_layer(ganrev_ctx* ctx, TcLayer& L, const void* in, void* out, int n_img, int64_t n_cap) {
@@ -356,13 +380,7 @@ static int run_layer(ganrev_ctx* ctx, TcLayer& L, const void* in, void* out, int
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, GANREV_ECUDA, "cuTensorMapEncodeTiled(A, %s) failed: %d", L.name.c_str(), (int)r);
-    switch (L.NT) {
-        case 32: return launch_tc<32>(ctx, L, tmA, g, n_items);
-        case 64: return launch_tc<64>(ctx, L, tmA, g, n_items);
-        case 128: return launch_tc<128>(ctx, L, tmA, g, n_items);
-        case 256: return launch_tc<256>(ctx, L, tmA, g, n_items);
-    }
-    return fail(ctx, GANREV_EINVAL, "unsupported NT=%d", L.NT);
+    return dispatch_tc(ctx, L, tmA, g, n_items);
 }
 
 // =================================================================================
@@ -415,13 +433,12 @@ static int load_G_impl(ganrev_ctx* ctx, int C, int H, int W, int nd, const float
         RC_TRY(build_tc_layer(ctx, G.c2, "g_conv2_up", 128, 2 * sH, 2 * sW, 256, 4, 4, kPhaseY, kPhaseX, 128, 1, conv_w_phase(w2, 128, 256), bn,
                               H, W, 128, 2, 0, ACT_RELU, 1.0f, 0));
     }
-    {   // conv3 weights fp32 [C][9][128]
-        std::vector<float> w3p(static_cast<size_t>(C) * 9 * 128);
-        for (int co = 0; co < C; ++co)
-            for (int ci = 0; ci < 128; ++ci)
-                for (int t = 0; t < 9; ++t) w3p[(static_cast<size_t>(co) * 9 + t) * 128 + ci] = w3[(static_cast<size_t>(co) * 128 + ci) * 9 + t];
-        RC_TRY(upload(ctx, G.w3, w3p.data(), w3p.size() * 4));
-        RC_TRY(upload(ctx, G.b3, b3, sizeof(float) * C));
+    {   // conv3 (128 -> C) + Sigmoid: N padded to 16, fp32 NCHW output = the image tensor itself
+        BnFold bn;
+        bn.scale.assign(16, 0.0f); bn.shift.assign(16, 0.0f);
+        for (int i = 0; i < C; ++i) { bn.scale[i] = 1.0f; bn.shift[i] = b3[i]; }
+        RC_TRY(build_tc_layer(ctx, G.c3, "g_conv3_sigmoid", 16, H, W, 128, 1, 9, kTaps9Y, kTaps9X, C, 1, conv_w_direct(w3, C, 128, 16), bn,
+                              H, W, C, 1, 0, ACT_SIGMOID, 1.0f, 1, /*nchw=*/true));
     }
     G.loaded = true;
     return GANREV_OK;
@@ -525,18 +542,7 @@ static int forward_G_dev(ganrev_ctx* ctx, const float* d_noise, int64_t N, float
         RC_TRY(run_layer(ctx, G.lin, ctx->noise_bf16.p, ctx->arena[0].p, n, CH));   // [n][sH][sW][512]
         RC_TRY(run_layer(ctx, G.c1, ctx->arena[0].p, ctx->arena[1].p, n, CH));      // [n][2sH][2sW][256]
         RC_TRY(run_layer(ctx, G.c2, ctx->arena[1].p, ctx->arena[0].p, n, CH));      // [n][H][W][128]
-        {
-            const double px = static_cast<double>(n) * G.H * G.W;
-            ProfScope ps(ctx, "g_conv3_sigmoid", 2.0 * px * 1152 * G.C, px * (128 * 2.0 + 4.0 * G.C));
-            const long long warps = static_cast<long long>(n) * (G.H * G.W / 32);
-            const unsigned blocks = static_cast<unsigned>((warps * 32 + 255) / 256);
-            float* o = d_images + n0 * G.C * G.H * G.W;
-            if (G.C == 1)
-                g_conv3_kernel<1><<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const bf16*>(ctx->arena[0].p), (const float*)G.w3.p, (const float*)G.b3.p, o, G.H, G.W, n);
-            else
-                g_conv3_kernel<3><<<blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const bf16*>(ctx->arena[0].p), (const float*)G.w3.p, (const float*)G.b3.p, o, G.H, G.W, n);
-            CU_TRY(cudaGetLastError());
-        }
+        RC_TRY(run_layer(ctx, G.c3, ctx->arena[0].p, d_images + n0 * G.C * G.H * G.W, n, CH));   // fp32 [n][C][H][W]
     }
     return GANREV_OK;
 }
@@ -621,8 +627,7 @@ void ganrev_destroy(ganrev_ctx* ctx) {
     prof_resolve(ctx);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
-    for (TcLayer* L : {&ctx->G.lin, &ctx->G.c1, &ctx->G.c2}) release_layer(*L);
-    release(ctx->G.w3); release(ctx->G.b3);
+    for (TcLayer* L : {&ctx->G.lin, &ctx->G.c1, &ctx->G.c2, &ctx->G.c3}) release_layer(*L);
     for (int s = 0; s < 2; ++s) {
         RModel& R = ctx->R[s];
         release(R.c1pack);

@@ -2,7 +2,6 @@
 //   * noise fp32 -> bf16 K-padded rows (A operand of G's Linear, models.lua:115)
 //   * R conv1  C->64, K = 9*C      (models.lua:399-411) fp32 NCHW in (+ explicit dropout
 //     mask fused into the loader), folded BN + ELU, bf16 NHWC out
-//   * G conv3  128->C, N = 1 or 3  (models.lua:132-133) bf16 NHWC in, fp32 NCHW out, sigmoid
 //   * torch.dist over image pairs  (apply_r.lua:366) in the canonical lane-tree order
 //   * the 15%-quantile threshold + flags (apply_r.lua:370-378) as a device radix select
 #pragma once
@@ -30,7 +29,7 @@ r_conv1_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mask, 
     for (int i = threadIdx.x; i < K * 64 + 128; i += blockDim.x) wsm[i] = wpack[i];
     __syncthreads();
     const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (pix >= npix_total) return;
+    const bool live = pix < npix_total;          // dead tail threads still take part in the warp store
     const int w = static_cast<int>(pix % W);
     const int h = static_cast<int>((pix / W) % H);
     const long long n = pix / (static_cast<long long>(W) * H);
@@ -47,7 +46,7 @@ r_conv1_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mask, 
             for (int kx = 0; kx < 3; ++kx) {
                 const int ww = w + kx - 1;
                 float x = 0.0f;
-                if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                if (live && hh >= 0 && hh < H && ww >= 0 && ww < W) {
                     const long long off = plane + static_cast<long long>(hh) * W + ww;
                     x = img[off];
                     if (mask != nullptr && mask[off] == 0) x = 0.0f;   // v1 dropout: x*mask, no rescale
@@ -66,89 +65,31 @@ r_conv1_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mask, 
     }
     const float* sc = wsm + K * 64;
     const float* sh = sc + 64;
-    uint4* o = reinterpret_cast<uint4*>(out + pix * 64);
+    // A warp's 32 pixels are 4 KB contiguous in the NHWC output: stage through shared memory
+    // (16-byte chunks XOR-swizzled by pixel) so the global stores are fully coalesced.
+    __shared__ uint4 stage[128 * 8];
+    const int lane = threadIdx.x & 31;
+    uint4* wstage = stage + (threadIdx.x >> 5) * 256;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         float v[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) v[t] = apply_act(fmaf(acc[8 * j + t], sc[8 * j + t], sh[8 * j + t]), ACT_ELU);
+        for (int t = 0; t < 8; ++t) v[t] = elu_fast(fmaf(acc[8 * j + t], sc[8 * j + t], sh[8 * j + t]));
         uint4 pk;
         __nv_bfloat162 b0 = __floats2bfloat162_rn(v[0], v[1]), b1 = __floats2bfloat162_rn(v[2], v[3]);
         __nv_bfloat162 b2 = __floats2bfloat162_rn(v[4], v[5]), b3 = __floats2bfloat162_rn(v[6], v[7]);
         pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
         pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
-        o[j] = pk;
+        wstage[lane * 8 + (j ^ (lane & 7))] = pk;
     }
-}
-
-// ------------------------------------------------------------------ G conv3 + sigmoid
-// act: NHWC bf16 [n][H][W][128]; w3: fp32 [C][9][128]; out: fp32 NCHW [n][C][H][W].
-// One warp produces 32 consecutive pixels (row-major) of an image; lane l owns channels 4l..4l+3 of every
-// tap, partial sums are reduced by shuffles and lane j keeps pixel j for a coalesced store.
-template <int COUT>
-__global__ void __launch_bounds__(256)
-g_conv3_kernel(const bf16* __restrict__ act, const float* __restrict__ w3, const float* __restrict__ b3,
-               float* __restrict__ out, int H, int W, long long n_img) {
-    const int lane = threadIdx.x & 31;
-    const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const int segs_per_img = (H * W) / 32;           // H*W is a multiple of 32 (H, W >= 16, powers of two)
-    const long long total_segs = n_img * segs_per_img;
-    if (warp_global >= total_segs) return;
-    const int seg = static_cast<int>(warp_global % segs_per_img);
-    const long long n = warp_global / segs_per_img;
-
-    float wreg[COUT][9][4];
+    __syncwarp();
+    const long long warp_pix0 = pix - lane;                       // first pixel of this warp
+    uint4* o = reinterpret_cast<uint4*>(out + warp_pix0 * 64);
 #pragma unroll
-    for (int co = 0; co < COUT; ++co)
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const float4 wv = __ldg(reinterpret_cast<const float4*>(w3 + (co * 9 + t) * 128 + lane * 4));
-            wreg[co][t][0] = wv.x; wreg[co][t][1] = wv.y; wreg[co][t][2] = wv.z; wreg[co][t][3] = wv.w;
-        }
-    float keep[COUT];
-#pragma unroll
-    for (int co = 0; co < COUT; ++co) keep[co] = 0.0f;
-
-    for (int j = 0; j < 32; ++j) {
-        const int pj = seg * 32 + j;
-        const int h = pj / W, w = pj - h * W;
-        float part[COUT];
-#pragma unroll
-        for (int co = 0; co < COUT; ++co) part[co] = 0.0f;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int hh = h + ky - 1;
-            if (hh < 0 || hh >= H) continue;
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int ww = w + kx - 1;
-                if (ww < 0 || ww >= W) continue;
-                const uint2 raw = __ldg(reinterpret_cast<const uint2*>(act + ((n * H + hh) * W + ww) * 128 + lane * 4));
-                const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
-                const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
-                const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
-#pragma unroll
-                for (int co = 0; co < COUT; ++co) {
-                    const float* wt = wreg[co][ky * 3 + kx];
-                    part[co] = fmaf(f0.x, wt[0], part[co]);
-                    part[co] = fmaf(f0.y, wt[1], part[co]);
-                    part[co] = fmaf(f1.x, wt[2], part[co]);
-                    part[co] = fmaf(f1.y, wt[3], part[co]);
-                }
-            }
-        }
-#pragma unroll
-        for (int co = 0; co < COUT; ++co) {
-            float s = part[co];
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (lane == j) keep[co] = s;
-        }
-    }
-#pragma unroll
-    for (int co = 0; co < COUT; ++co) {
-        const float v = keep[co] + __ldg(b3 + co);
-        out[(n * COUT + co) * static_cast<long long>(H) * W + seg * 32 + lane] = 1.0f / (1.0f + expf(-v));   // nn.Sigmoid
+    for (int i = 0; i < 8; ++i) {
+        const int e = i * 32 + lane;                              // 16-byte element of the 4 KB block
+        const int t = e >> 3, c = e & 7;
+        if (warp_pix0 + t < npix_total) o[e] = wstage[t * 8 + (c ^ (t & 7))];
     }
 }
 

@@ -1,0 +1,50 @@
+"""The C-ABI library loads on a CPU-only box, exports every symbol include/ganrev.h declares,
+and refuses to run without an sm_100 GPU (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "ganrev.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ganrev_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(pkg):
+    names = header_functions()
+    assert len(names) >= 25
+    lib = ctypes.CDLL(pkg._lib.SO_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"libganrev_cuda.so does not export {n}"
+    assert sorted(pkg._lib.EXPORTS) == names, "ctypes binding and header disagree"
+
+
+def test_no_torch_in_the_abi(pkg):
+    import subprocess
+    out = subprocess.run(["ldd", pkg._lib.SO_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in out and "cudnn" not in out and "cublas" not in out, out
+
+
+def test_create_fails_loudly_without_gpu(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.GanrevError):
+        pkg.Context(0)
+    with pytest.raises(NotImplementedError):
+        pkg.models._Module().float()          # MODEL:float() has no CPU path to fall back to
+
+
+def test_oracle_is_not_reachable_from_the_product():
+    """Nothing under gan-reverser_b200/ or include/ may mention the oracle."""
+    for base in ("gan-reverser_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".lua")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    assert "oracle" not in txt.replace("mirrored by oracle", "").replace("oracle/ganrev_oracle.c", "").replace("oracle orc_l2", ""), (dp, f)

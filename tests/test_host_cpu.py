@@ -1,0 +1,126 @@
+"""Host-side logic that needs no GPU: weight blob layout / init, shard arithmetic, the
+torch.distributed (gloo, world size 2) plumbing used to bootstrap the library's communicator,
+and the shard -> merge rule of the multi-GPU search checked with the oracle as the checker."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def test_blob_layout_roundtrip(pkg):
+    Wt = pkg.weights
+    for (C, H, W, nd) in [(1, 32, 32, 32), (3, 64, 64, 256)]:
+        for lay, init in ((Wt.g_layout(C, H, W, nd), Wt.init_G), (Wt.r_layout(C, H, W, nd), Wt.init_R)):
+            blob = init(C, H, W, nd, seed=9, stress=True)
+            assert blob.dtype == np.float32 and blob.size == Wt.blob_floats(lay)
+            p = Wt.unpack(blob, lay)
+            np.testing.assert_array_equal(Wt.pack(p, lay), blob)
+    # parameter counts (weights + biases, without BN) S: G 2.56M, R 4.65M
+    p = Wt.unpack(Wt.init_G(1, 32, 32, 32), Wt.g_layout(1, 32, 32, 32))
+    n = sum(v.size for k, v in p.items() if not k.startswith("bn"))
+    assert abs(n - 2.56e6) < 0.02e6
+
+
+def test_heuristic_init_distribution(pkg):
+    """weight-init.lua:14-16, 70-72: U(+-1/sqrt(fan_in)) weights, every bias (and BN beta) zero."""
+    Wt = pkg.weights
+    p = Wt.unpack(Wt.init_R(1, 32, 32, 32, seed=2), Wt.r_layout(1, 32, 32, 32))
+    for name, fan_in in (("c2.w", 576), ("c5.w", 1152), ("l1.w", 8192), ("l2.w", 512)):
+        w = p[name]
+        b = 1.0 / np.sqrt(fan_in)
+        assert np.abs(w).max() <= b and np.abs(w).max() > 0.95 * b
+        assert abs(w.std() - b / np.sqrt(3)) < 0.05 * b
+    for k, v in p.items():
+        if k.endswith(".b") and not k.startswith("bn") or k.startswith("bn") and k.endswith((".b", ".m")):
+            assert not v.any(), k
+        if k.startswith("bn") and k.endswith(".v"):
+            assert (v == 1).all()
+        if k.startswith("bn") and k.endswith(".g"):
+            assert v.min() >= 0 and v.max() <= 1
+
+
+def test_shard_range(pkg):
+    sr = pkg.dist.shard_range
+    for n in (0, 1, 7, 10_000, 1_000_000):
+        for world in (1, 2, 3, 8):
+            parts = [sr(n, world, r) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_noise_and_batch_helpers(pkg):
+    nu = pkg.NN_UTILS
+    z = nu.createNoiseInputs(1000, 32, "normal", np.random.default_rng(1))
+    assert z.shape == (1000, 32) and z.dtype == np.float32 and abs(z.std() - 1) < 0.05
+    u = nu.createNoiseInputs(1000, 32, "uniform", np.random.default_rng(1))
+    assert u.min() >= -1 and u.max() <= 1
+    with pytest.raises(ValueError):
+        nu.createNoiseInputs(1, 1, "bogus")
+    assert nu.toBatch(np.zeros((3, 4))).shape == (1, 3, 4)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, ret):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import torch.distributed as td
+    from __graft_entry__ import load_package
+    from oracle import oracle as orc
+    pkg = load_package()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # 1. the unique-id hand-off used by dist.init_comm (payload made on rank 0 only)
+        payload = pkg.dist.broadcast_bytes(b"\x01\x02uid-128-bytes" * 8 if rank == 0 else None, src=0)
+        assert payload == b"\x01\x02uid-128-bytes" * 8
+        # 2. row-sharded search: local top-k on each shard + allgather + merge by (score desc, id asc)
+        #    must equal the single-shard answer (the rule ganrev_search_cosine implements over NCCL)
+        rng = np.random.default_rng(5)
+        db = rng.normal(size=(999, 16)).astype(np.float32)
+        db[500:520] = db[10]                          # ties across the shard boundary
+        q = db[[10, 700]]
+        k = 25
+        lo, hi = pkg.dist.shard_range(999, world, rank)
+        ids, sc = orc.search_cosine(db[lo:hi], q, k)
+        ids = np.where(ids >= 0, ids + lo, -1)
+        box = [None] * world
+        td.all_gather_object(box, (ids, sc))
+        all_ids = np.concatenate([b[0] for b in box], axis=1)
+        all_sc = np.concatenate([b[1] for b in box], axis=1)
+        merged = np.empty((2, k), np.int64)
+        for r in range(2):
+            order = sorted(range(all_ids.shape[1]), key=lambda j: (all_ids[r, j] < 0, np.isnan(all_sc[r, j]), -all_sc[r, j], all_ids[r, j]))
+            merged[r] = all_ids[r, order[:k]]
+        want, _ = orc.search_cosine(db, q, k)
+        assert (merged == want).all()
+        # 3. kmeans: per-shard int64 sums + allreduce(sum) == single-shard sums (order-free accumulators)
+        shift = orc.kmeans_shift(db, 999)
+        part = np.rint(db[lo:hi].astype(np.float64) * 2.0 ** shift).astype(np.int64).sum(0)
+        import torch
+        t = torch.from_numpy(part.copy())
+        td.all_reduce(t)
+        full = np.rint(db.astype(np.float64) * 2.0 ** shift).astype(np.int64).sum(0)
+        assert (t.numpy() == full).all()
+        ret[rank] = "ok"
+    finally:
+        td.destroy_process_group()
+
+
+def test_gloo_world2_plumbing():
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}
