@@ -52,6 +52,8 @@ _SIGS = {
     "ganrev_profile_get": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.POINTER(C.c_double),
                                 C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ganrev_set_option": (_i, [_vp, C.c_char_p, _i64]),
+    "ganrev_debug_trace_arm": (_i, [_vp, C.c_char_p]),
+    "ganrev_debug_trace_read": (_i, [_vp, _vp]),
 }
 EXPORTS = sorted(_SIGS)
 
@@ -278,6 +280,14 @@ class Context:
             ms, fl, by = C.c_double(), C.c_double(), C.c_double()
             self._chk(lib().ganrev_profile_get(self._h, i, C.byref(name), C.byref(cnt), C.byref(ms), C.byref(fl), C.byref(by)))
             out[name.value.decode()] = {"launches": cnt.value, "ms": ms.value, "flops": fl.value, "bytes": by.value}
+        return out
+
+    def trace_arm(self, layer):
+        self._chk(lib().ganrev_debug_trace_arm(self._h, layer.encode()))
+
+    def trace_read(self):
+        out = np.zeros((8, 256), np.int64)
+        self._chk(lib().ganrev_debug_trace_read(self._h, _ptr(out)))
         return out
 
     def set_option(self, name, value):

@@ -61,6 +61,8 @@ struct ConvGemm {
     const bf16* A;             // raw pointers (CUDA-core kernel)
     const bf16* B;
     int* err_flag;
+    long long* trace;          // optional clock64 timeline of CTA 0 (ganrev_debug_trace), [8 roles][256 events]
+    int dbg;                   // timing experiments only: bit0 skip A loads, bit1 skip B loads (results are garbage)
 };
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2, ACT_TANH = 3, ACT_SIGMOID = 4 };

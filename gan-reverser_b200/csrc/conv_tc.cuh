@@ -32,8 +32,12 @@ constexpr unsigned long long kSpinLimitCycles = 4000000000ull;  // ~2 s: turn a 
 
 template <int NT> struct Cfg {
     static constexpr int kBBytes = NT * kBlockK * 2;
-    static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (NT >= 256) ? 4 : (NT >= 128 ? 6 : 8);
+    static constexpr int kKbBytes = kABytes + kBBytes;                  // one 64-wide k-block: A tile then B tile
+    // k-blocks per pipeline stage: one mbarrier round trip (~300+ cycles) is amortised over
+    // KPS * 4 MMAs, which matters most when NT is small and an MMA is only NT/2 cycles long.
+    static constexpr int kKPS = (NT >= 256) ? 1 : (NT >= 128 ? 2 : (NT >= 64 ? 3 : 3));
+    static constexpr int kStageBytes = kKPS * kKbBytes;
+    static constexpr int kStages = (NT >= 256) ? 4 : 3;
     static constexpr int kChunk = NT < 32 ? NT : 32;   // accumulator columns per tcgen05.ld
     static constexpr int kTmemCols = (2 * NT <= 32) ? 32 : (2 * NT <= 64 ? 64 : (2 * NT <= 128 ? 128 : (2 * NT <= 256 ? 256 : 512)));
     // stages + (2*stages + 4) mbarriers + tmem ptr + double-buffered scale/shift, plus 1024 B alignment slack
@@ -190,6 +194,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// debug timeline: role r, event e -> clock64 of CTA 0
+#define GANREV_TR(role, e)                                                                     \
+    do {                                                                                       \
+        if (p.trace != nullptr && blockIdx.x == 0 && (e) < 256) p.trace[(role) * 256 + (e)] = clock64(); \
+    } while (0)
+
 struct ItemCoord {
     int n0, h0, w0, phase, ntile;
 };
@@ -239,7 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 32 * kEpiWarps);
+            mbar_init(tempty_bar(a), kEpiWarps);   // one arrival per epilogue warp
         }
         fence_barrier_init();
     }
@@ -249,62 +259,78 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int kblocks = p.ntaps * (p.Cin / kBlockK);
     const int cin_chunks = p.Cin / kBlockK;
+    const int kblocks = p.ntaps * cin_chunks;
 
+    constexpr int KPS = C::kKPS;
     if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer (whole warp loops, one lane issues)
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const ItemCoord c = decode_item(p, item);
-            const int brow = c.phase * p.cout_pad + c.ntile * NT;
-            for (int tap = 0; tap < p.ntaps; ++tap) {
-                const int wx = c.w0 + p.dx[c.phase][tap], hy = c.h0 + p.dy[c.phase][tap];
-                const int kcol0 = tap * p.Cin;
-                for (int cc = 0; cc < cin_chunks; ++cc) {
+        // ------------------------------------------------------------ TMA producer (one elected thread)
+        if (elect_one_sync()) {
+            int stage = 0, tr_p = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const ItemCoord c = decode_item(p, item);
+                const int brow = c.phase * p.cout_pad + c.ntile * NT;
+                int tap = 0, cc = 0;
+                for (int kb0 = 0; kb0 < kblocks; kb0 += KPS) {
+                    const int nk = min(KPS, kblocks - kb0);
                     mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 101);
-                    if (elect_one_sync()) {
-                        const uint32_t a_dst = smem_base + stage * C::kStageBytes;
-                        mbar_expect_tx(full_bar(stage), C::kStageBytes);
-                        tma_load_4d(a_dst, &tmA, full_bar(stage), cc * kBlockK, wx, hy, c.n0);
-                        tma_load_2d(a_dst + kABytes, &tmB, full_bar(stage), kcol0 + cc * kBlockK, brow);
+                    GANREV_TR(0, tr_p);
+                    const uint32_t s_base = smem_base + stage * C::kStageBytes;
+                    mbar_expect_tx(full_bar(stage), nk * (((p.dbg & 1) ? 0 : kABytes) + ((p.dbg & 2) ? 0 : C::kBBytes)));
+                    for (int j = 0; j < nk; ++j) {
+                        const uint32_t a_dst = s_base + j * C::kKbBytes;
+                        if (!(p.dbg & 1))
+                            tma_load_4d(a_dst, &tmA, full_bar(stage), cc * kBlockK, c.w0 + p.dx[c.phase][tap], c.h0 + p.dy[c.phase][tap], c.n0);
+                        if (!(p.dbg & 2))
+                            tma_load_2d(a_dst + kABytes, &tmB, full_bar(stage), tap * p.Cin + cc * kBlockK, brow);
+                        if (++cc == cin_chunks) { cc = 0; ++tap; }
                     }
-                    __syncwarp();
+                    GANREV_TR(1, tr_p);
+                    ++tr_p;
                     if (++stage == S) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
-        constexpr uint32_t idesc = make_idesc<NT>();
-        const uint64_t desc_base = make_smem_desc(0);
-        int stage = 0;
-        uint32_t phase = 0;
-        int it = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1u;
-            mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 102);
-            tcgen05_fence_after();
-            const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * NT);
-            for (int kb = 0; kb < kblocks; ++kb) {
-                mbar_wait(full_bar(stage), phase, p.err_flag, 103);
+        // ------------------------------------------------------------ MMA issuer (one elected thread)
+        if (elect_one_sync()) {
+            constexpr uint32_t idesc = make_idesc<NT>();
+            const uint64_t desc_base = make_smem_desc(0);
+            int stage = 0, tr_m = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1u;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 102);
+                GANREV_TR(6, it);
                 tcgen05_fence_after();
-                if (elect_one_sync()) {
-                    const uint32_t a_addr = smem_base + stage * C::kStageBytes;
-                    const uint64_t adesc = desc_base | static_cast<uint64_t>((a_addr & 0x3FFFFu) >> 4);
-                    const uint64_t bdesc = desc_base | static_cast<uint64_t>(((a_addr + kABytes) & 0x3FFFFu) >> 4);
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * NT);
+                for (int kb0 = 0; kb0 < kblocks; kb0 += KPS) {
+                    const int nk = min(KPS, kblocks - kb0);
+                    mbar_wait(full_bar(stage), phase, p.err_flag, 103);
+                    GANREV_TR(2, tr_m);
+                    tcgen05_fence_after();
+                    const uint32_t s_base = smem_base + stage * C::kStageBytes;
+                    if (!(p.dbg & 8)) {
+                        for (int j = 0; j < nk; ++j) {
+                            const uint32_t a_addr = s_base + j * C::kKbBytes;
+                            const uint64_t adesc = desc_base | static_cast<uint64_t>((a_addr & 0x3FFFFu) >> 4);
+                            const uint64_t bdesc = desc_base | static_cast<uint64_t>(((a_addr + kABytes) & 0x3FFFFu) >> 4);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        // +32 B per K=16 step inside the 128 B swizzle span (>>4 -> +2)
-                        umma_bf16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < kBlockK / 16; ++k) {
+                                // +32 B per K=16 step inside the 128 B swizzle span (>>4 -> +2)
+                                umma_bf16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb0 + j > 0 || k > 0) ? 1u : 0u);
+                            }
+                        }
                     }
-                    umma_commit(empty_bar(stage));                        // frees the smem slot when the MMAs retire
-                    if (kb == kblocks - 1) umma_commit(tfull_bar(acc));   // accumulator complete
+                    umma_commit(empty_bar(stage));                              // frees the smem slot when the MMAs retire
+                    if (kb0 + KPS >= kblocks) umma_commit(tfull_bar(acc));      // accumulator complete
+                    GANREV_TR(3, tr_m);
+                    ++tr_m;
+                    if (++stage == S) { stage = 0; phase ^= 1u; }
                 }
-                __syncwarp();
-                if (++stage == S) { stage = 0; phase ^= 1u; }
             }
         }
     } else {
@@ -326,10 +352,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int cbase = c.ntile * NT;
             // stage this item's folded-BN scale / shift (double-buffered; the named barrier of
             // item i+1 proves every warp is done reading the buffer of item i)
-            float* ss = ss_base + acc * (2 * NT);
-            for (int i = etid; i < NT; i += 32 * kEpiWarps) {
-                ss[i] = __ldg(p.scale + cbase + i);
-                ss[NT + i] = __ldg(p.shift + cbase + i);
+            // (layers with a single N tile keep one copy for the whole kernel)
+            float* ss = ss_base + (p.n_tiles > 1 ? acc * (2 * NT) : 0);
+            if (p.n_tiles > 1 || it == 0) {
+                for (int i = etid; i < NT; i += 32 * kEpiWarps) {
+                    ss[i] = __ldg(p.scale + cbase + i);
+                    ss[NT + i] = __ldg(p.shift + cbase + i);
+                }
             }
             const int n = c.n0 + n_l, h = c.h0 + h_l, w = c.w0 + w_l;
             int oh = h, ow = w;
@@ -341,14 +370,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 oh = 2 * h + (c.phase >> 1); ow = 2 * w + (c.phase & 1);
             }
             const size_t pix_off = static_cast<size_t>(n) * p.out_sN + (static_cast<size_t>(oh) * p.Wout + ow) * p.out_sP;
-            named_bar_sync(1, 32 * kEpiWarps);
+            if (p.n_tiles > 1 || it == 0) named_bar_sync(1, 32 * kEpiWarps);
 
+            if (etid == 0) GANREV_TR(7, it);
             mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 104);
+            if (etid == 0) GANREV_TR(4, it);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * NT);
             constexpr int CW = C::kChunk;
 #pragma unroll 1
-            for (int c0 = half * CW; c0 < NT; c0 += 2 * CW) {
+            for (int c0 = half * CW + ((p.dbg & 4) ? NT : 0); c0 < NT; c0 += 2 * CW) {
                 uint32_t r[32];
                 if (CW == 32) tmem_ld32(taddr + c0, r); else tmem_ld16(taddr + c0, r);
                 tmem_ld_wait();
@@ -393,7 +424,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
             tcgen05_fence_before();
-            mbar_arrive(tempty_bar(acc));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (etid == 0) GANREV_TR(5, it);
         }
     }
 

@@ -60,6 +60,9 @@ struct ganrev_ctx {
     std::string err;
     int64_t chunk = 2048;
     int conv_impl = 0;
+    int dbg = 0;
+    DevBuf trace;
+    std::string trace_layer;
     uint64_t launches = 0;
     int* d_err_flag = nullptr;
     EncodeTiledFn encode = nullptr;
@@ -359,6 +362,8 @@ static int run_layer(ganrev_ctx* ctx, TcLayer& L, const void* in, void* out, int
     g.A = reinterpret_cast<const bf16*>(in);
     g.out = out;
     g.n_img = n_img;
+    g.dbg = ctx->dbg;
+    g.trace = (ctx->trace.p && L.name == ctx->trace_layer) ? static_cast<long long*>(ctx->trace.p) : nullptr;
     const int BN = 1 << g.lgBN;
     const int tiles_n = (n_img + BN - 1) / BN;
     const int n_items = tiles_n * g.tiles_h * g.tiles_w * g.nphase * g.n_tiles;
@@ -637,7 +642,7 @@ void ganrev_destroy(ganrev_ctx* ctx) {
     for (DevBuf* b : {&ctx->arena[0], &ctx->arena[1], &ctx->noise_bf16, &ctx->stage_a, &ctx->stage_b, &ctx->l2buf, &ctx->thr, &ctx->flags,
                       &ctx->db, &ctx->rdb, &ctx->maxabs, &ctx->q, &ctx->rq, &ctx->c2, &ctx->partial, &ctx->keys, &ctx->keys_all, &ctx->ids,
                       &ctx->scores, &ctx->cen, &ctx->acc, &ctx->cnt, &ctx->total, &ctx->labels, &ctx->cosv, &ctx->tcounts, &ctx->mids,
-                      &ctx->mcnt, &ctx->mmean})
+                      &ctx->mcnt, &ctx->mmean, &ctx->trace})
         release(*b);
     if (ctx->d_err_flag) cudaFree(ctx->d_err_flag);
     cudaStreamDestroy(ctx->stream);
@@ -1188,6 +1193,21 @@ int ganrev_profile_get(ganrev_ctx* ctx, int idx, const char** name, uint64_t* la
     if (bytes) *bytes = e.bytes;
     return GANREV_OK;
 }
+// Debug: arm a clock64 timeline of CTA 0 for the named tensor-core layer / read it back ([8][256] int64).
+int ganrev_debug_trace_arm(ganrev_ctx* ctx, const char* layer) {
+    if (!ctx || !layer) return GANREV_EINVAL;
+    CU_TRY(cudaSetDevice(ctx->device));
+    RC_TRY(ensure(ctx, ctx->trace, 8 * 256 * sizeof(long long)));
+    CU_TRY(cudaMemsetAsync(ctx->trace.p, 0, 8 * 256 * sizeof(long long), ctx->stream));
+    ctx->trace_layer = layer;
+    return finish(ctx);
+}
+int ganrev_debug_trace_read(ganrev_ctx* ctx, int64_t* out) {
+    if (!ctx || !out || !ctx->trace.p) return GANREV_EINVAL;
+    CU_TRY(cudaSetDevice(ctx->device));
+    CU_TRY(cudaMemcpyAsync(out, ctx->trace.p, 8 * 256 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    return finish(ctx);
+}
 int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return GANREV_EINVAL;
     if (!strcmp(name, "chunk")) {
@@ -1200,6 +1220,7 @@ int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value) {
         ctx->conv_impl = static_cast<int>(value);
         return GANREV_OK;
     }
+    if (!strcmp(name, "dbg")) { ctx->dbg = static_cast<int>(value); return GANREV_OK; }
     return fail(ctx, GANREV_EINVAL, "unknown option %s", name);
 }
 
