@@ -1,0 +1,205 @@
+--[[ ganrev.lua -- LuaJIT-FFI binding of libganrev_cuda.so (include/ganrev.h).
+
+Drop-in arithmetic for aleju/gan-reverser's apply_r.lua: the models.lua G/R constructors and
+apply_r.lua's search, cluster, fix and anomaly modes keep their names and call this module
+instead of nn / cudnn / unsup / torch.dist.  No cutorch, no cudnn, no CPU fallback.
+
+NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no lua/luajit/th.  Every call below
+is mirrored one-to-one by gan-reverser_b200/_lib.py (ctypes), which is what the tests drive.
+
+Usage (see INTEGRATION.md):
+    local ganrev = require 'ganrev'
+    local ctx = ganrev.new(OPT.gpu)                       -- replaces cutorch.setDevice(OPT.gpu + 1)
+    MODEL_G = ganrev.wrap_G(ctx, tmp.G, {1, 32, 32}, 100)  -- flattens the trained nn.Sequential
+    images  = MODEL_G:forward(noise)
+]]
+local ffi = require 'ffi'
+require 'torch'
+
+ffi.cdef[[
+typedef struct ganrev_ctx ganrev_ctx;
+int         ganrev_version(void);
+int         ganrev_create(ganrev_ctx** out, int device);
+void        ganrev_destroy(ganrev_ctx* ctx);
+const char* ganrev_last_error(const ganrev_ctx* ctx);
+int ganrev_comm_unique_id(ganrev_ctx* ctx, void* out, size_t cap, size_t* len);
+int ganrev_comm_init(ganrev_ctx* ctx, int world, int rank, const void* uid, size_t len);
+int ganrev_load_G(ganrev_ctx* ctx, int C, int H, int W, int noise_dim, const float* blob, size_t n_floats);
+int ganrev_load_R(ganrev_ctx* ctx, int slot, int C, int H, int W, int noise_dim, int tanh_out, const float* blob, size_t n_floats);
+int ganrev_forward_G(ganrev_ctx* ctx, const float* noise, int64_t N, float* images);
+int ganrev_forward_R(ganrev_ctx* ctx, int slot, const float* images, const uint8_t* mask, int64_t N, float* attrs);
+int ganrev_fix_l2(ganrev_ctx* ctx, int slot, const float* images, const uint8_t* mask, int64_t N, float* attrs, float* fixed, double* l2);
+int ganrev_l2(ganrev_ctx* ctx, const float* a, const float* b, int64_t N, int px, double* l2);
+int ganrev_anomaly_flags(ganrev_ctx* ctx, const double* l2, int64_t n_calc, int64_t n_show, double quantile, uint8_t* flags, double* thr);
+int ganrev_buffer_put(ganrev_ctx* ctx, int which, const void* host, int64_t rows);
+int ganrev_buffer_get(ganrev_ctx* ctx, int which, void* host, int64_t row0, int64_t rows);
+int ganrev_db_set(ganrev_ctx* ctx, const float* vecs, int64_t N, int d);
+int ganrev_cosine(ganrev_ctx* ctx, const float* a, const float* b, int d, float* out);
+int ganrev_search_cosine(ganrev_ctx* ctx, const float* queries, int Q, int k, int64_t* ids, float* scores);
+int ganrev_kmeans(ganrev_ctx* ctx, int k, int niter, const float* init_centroids, float* centroids, float* total_counts, int32_t* last_labels);
+int ganrev_assign_cosine_min(ganrev_ctx* ctx, const float* centroids, int k, int32_t* cluster, float* cosv);
+int ganrev_cluster_members(ganrev_ctx* ctx, int k, int m, const float* images, int px, int64_t* member_ids, int32_t* member_counts, float* mean_images);
+int ganrev_sync(ganrev_ctx* ctx);
+int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value);
+]]
+
+local lib = ffi.load(os.getenv('GANREV_LIB') or 'ganrev_cuda')   -- libganrev_cuda.so on LD_LIBRARY_PATH
+local M = {}
+
+local function check(ctx, rc)
+    if rc ~= 0 then error(string.format('ganrev error %d: %s', rc, ffi.string(lib.ganrev_last_error(ctx)))) end
+end
+local function fptr(t) return t and t:contiguous():data() or nil end   -- FloatTensor:data() -> float*
+
+function M.new(device)
+    local out = ffi.new('ganrev_ctx*[1]')
+    local rc = lib.ganrev_create(out, device or 0)
+    if rc ~= 0 then error('ganrev_create failed (needs an sm_100 GPU; there is no CPU fallback), rc=' .. rc) end
+    return ffi.gc(out[0], lib.ganrev_destroy)
+end
+
+-- multi-GPU: one Lua state per GPU.  Rank 0 creates the id, the launcher ships the bytes.
+function M.unique_id(ctx)
+    local buf, len = ffi.new('uint8_t[256]'), ffi.new('size_t[1]')
+    check(ctx, lib.ganrev_comm_unique_id(ctx, buf, 256, len))
+    return ffi.string(buf, len[0])
+end
+function M.comm_init(ctx, world, rank, id)
+    check(ctx, lib.ganrev_comm_init(ctx, world, rank, id, #id))
+end
+
+-- Flatten a trained nn.Sequential into the weight blob of include/ganrev.h: every Linear /
+-- (cudnn.)SpatialConvolution as weight then bias, every (Spatial)BatchNormalization as
+-- gamma, beta, running_mean, running_var -- in module order (models.lua:115-132, 409-451).
+function M.flatten(model)
+    local parts, n = {}, 0
+    local function push(t) t = t:float():contiguous():view(-1); table.insert(parts, t); n = n + t:nElement() end
+    for _, m in ipairs(model.modules) do
+        local tn = torch.typename(m)
+        if tn == 'nn.Linear' or tn:find('SpatialConvolution') then
+            push(m.weight); push(m.bias)
+        elseif tn:find('BatchNormalization') then
+            push(m.weight); push(m.bias); push(m.running_mean)
+            -- newer nn keeps running_var, cudnn R3-era nn kept running_std = 1/sqrt(var+eps)
+            if m.running_var then push(m.running_var)
+            else push(torch.pow(m.running_std:float(), -2):add(-(m.eps or 1e-5))) end
+        end
+    end
+    local blob, o = torch.FloatTensor(n), 1
+    for _, t in ipairs(parts) do blob:narrow(1, o, t:nElement()):copy(t); o = o + t:nElement() end
+    return blob
+end
+
+-- MODELS.create_G(dimensions, noiseDim, cuda) replacement: object with the nn.Module protocol
+-- apply_r.lua uses (:forward, :evaluate, :training, :float).
+function M.wrap_G(ctx, model, dimensions, noiseDim)
+    local blob = M.flatten(model)
+    check(ctx, lib.ganrev_load_G(ctx, dimensions[1], dimensions[2], dimensions[3], noiseDim, blob:data(), blob:nElement()))
+    local G = {ctx = ctx, dimensions = dimensions, noiseDim = noiseDim}
+    function G:forward(noise)                                  -- utils/nn_utils.lua:5-33 batches; the library chunks internally
+        noise = noise:float():contiguous()
+        if noise:dim() == 1 then noise = noise:view(1, -1) end
+        local N = noise:size(1)
+        local images = torch.FloatTensor(N, dimensions[1], dimensions[2], dimensions[3])
+        check(ctx, lib.ganrev_forward_G(ctx, noise:data(), N, images:data()))
+        self.output = images
+        return images
+    end
+    function G:evaluate() return self end
+    function G:training() error('libganrev_cuda implements inference only') end
+    function G:float() error('no CPU fallback: the apply_r path runs on the B200 only') end
+    function G:cuda() return self end
+    return G
+end
+
+-- MODELS.create_R(dimensions, noiseDim, noiseMethod, fixer, cuda) replacement.  slot 0 = R,
+-- slot 1 = R_fixer.  The fixer's always-on input Dropout(0.5) (models.lua:399-406) is drawn
+-- here with torch.bernoulli and passed down as an explicit mask (x*mask, no rescale).
+function M.wrap_R(ctx, model, slot, dimensions, noiseDim, noiseMethod, fixer)
+    assert(noiseMethod == 'normal' or noiseMethod == 'uniform')          -- models.lua:390
+    local blob = M.flatten(model)
+    check(ctx, lib.ganrev_load_R(ctx, slot, dimensions[1], dimensions[2], dimensions[3], noiseDim,
+                                 noiseMethod ~= 'normal' and 1 or 0, blob:data(), blob:nElement()))
+    local R = {ctx = ctx, slot = slot, fixer = fixer, noiseDim = noiseDim}
+    function R:forward(images, mask)
+        images = images:float():contiguous()
+        if images:dim() == 3 then images = images:view(1, images:size(1), images:size(2), images:size(3)) end
+        local N = images:size(1)
+        if self.fixer and mask == nil then
+            mask = torch.ByteTensor(images:size()):bernoulli(0.5)
+        end
+        local attrs = torch.FloatTensor(N, noiseDim)
+        check(ctx, lib.ganrev_forward_R(ctx, slot, images:data(), mask and mask:contiguous():data() or nil, N, attrs:data()))
+        self.output = attrs
+        return attrs
+    end
+    function R:evaluate() return self end
+    function R:training() error('libganrev_cuda implements inference only') end
+    function R:float() error('no CPU fallback: the apply_r path runs on the B200 only') end
+    function R:cuda() return self end
+    return R
+end
+
+-- cosineSimilarity(v1, v2)  apply_r.lua:396-400
+function M.cosineSimilarity(ctx, v1, v2)
+    local out = ffi.new('float[1]')
+    v1, v2 = v1:float():contiguous(), v2:float():contiguous()
+    check(ctx, lib.ganrev_cosine(ctx, v1:data(), v2:data(), v1:nElement(), out))
+    return tonumber(out[0])
+end
+
+-- unsup.kmeans(x, k, niter)  apply_r.lua:198 -> centroids, counts.  The N(0,1) row-normalised
+-- initial centroids unsup draws internally are drawn here (same torch RNG stream position).
+function M.kmeans(ctx, x, k, niter, init)
+    x = x:float():contiguous()
+    local N, d = x:size(1), x:size(2)
+    if not init then
+        init = torch.FloatTensor(k, d):normal()
+        for i = 1, k do init[i]:div(init[i]:norm()) end
+    end
+    check(ctx, lib.ganrev_db_set(ctx, x:data(), N, d))
+    local cen, counts = torch.FloatTensor(k, d), torch.FloatTensor(k)
+    check(ctx, lib.ganrev_kmeans(ctx, k, niter, init:contiguous():data(), cen:data(), counts:data(), nil))
+    return cen, counts
+end
+
+-- createClusterImages inner loops  apply_r.lua:206-243.  Returns 1-based img2cluster, the
+-- per-cluster member lists (1-based, sorted by cosine descending) and the mean faces.
+function M.cluster(ctx, attributes, centroids, images, nbMaxPerCluster)
+    attributes, images = attributes:float():contiguous(), images:float():contiguous()
+    local N, k = attributes:size(1), centroids:size(1)
+    check(ctx, lib.ganrev_db_set(ctx, attributes:data(), N, attributes:size(2)))
+    local cl, cv = torch.IntTensor(N), torch.FloatTensor(N)
+    check(ctx, lib.ganrev_assign_cosine_min(ctx, centroids:float():contiguous():data(), k, cl:data(), cv:data()))
+    local px = images:nElement() / N
+    local ids, cnt = torch.LongTensor(k, nbMaxPerCluster), torch.IntTensor(k)
+    local mean = torch.FloatTensor(k, px)
+    check(ctx, lib.ganrev_cluster_members(ctx, k, nbMaxPerCluster, images:data(), px, ids:data(), cnt:data(), mean:data()))
+    return cl:add(1), cv, ids:add(1), cnt, mean
+end
+
+-- createSimilaritySearchImages inner loops  apply_r.lua:267-282: ids (1-based) and scores of the
+-- k most similar database rows for each query row.
+function M.search(ctx, db, queries, k)
+    db, queries = db:float():contiguous(), queries:float():contiguous()
+    check(ctx, lib.ganrev_db_set(ctx, db:data(), db:size(1), db:size(2)))
+    local Q = queries:size(1)
+    local ids, scores = torch.LongTensor(Q, k), torch.FloatTensor(Q, k)
+    check(ctx, lib.ganrev_search_cosine(ctx, queries:data(), Q, k, ids:data(), scores:data()))
+    return ids:add(1), scores
+end
+
+-- detectAnomalies  apply_r.lua:355-378: fixed = G(attributesFixer); dist = torch.dist per image;
+-- flags = (1 - dist) <= sorted[floor(n*threshold)]
+function M.anomalies(ctx, images, fixed, nbImagesCalculations, nbImagesShow, threshold)
+    images, fixed = images:float():contiguous(), fixed:float():contiguous()
+    local n = nbImagesCalculations
+    local px = images:nElement() / images:size(1)
+    local l2 = torch.DoubleTensor(n)
+    check(ctx, lib.ganrev_l2(ctx, images:data(), fixed:data(), n, px, l2:data()))
+    local flags, thr = torch.ByteTensor(nbImagesShow), ffi.new('double[1]')
+    check(ctx, lib.ganrev_anomaly_flags(ctx, l2:data(), n, nbImagesShow, threshold, flags:data(), thr))
+    return flags, l2:mul(-1):add(1), tonumber(thr[0])
+end
+
+return M
