@@ -39,20 +39,28 @@ struct DevBuf {
 };
 
 // conv-as-GEMM layer description, shared by the tcgen05 kernel and the CUDA-core kernel.
+//
+// K loop: per item, `units` = ngroups * cin_chunks units; unit (g, cc) covers tap group g (one
+// horizontal offset gdx with ndy consecutive vertical offsets gdy0 .. gdy0+ndy-1) and input
+// channels [64*cc, 64*cc+64).  Weight K index = ((g*ndy + j)*Cin + ci).  With ndy > 1 the A
+// operand of a unit is ONE box of BH+ndy-1 rows; the ndy vertical taps are 1024B-aligned
+// offsets into it (halo reuse).  ndy == 1 expresses arbitrary tap lists (one tap per group).
 struct ConvGemm {
-    // A operand: NHWC bf16 activation [n_cap][Hin][Win][Cin]; M tile = box (64ch, BW, BH, BN)
+    // A operand: NHWC bf16 activation [n_cap][Hin][Win][Cin]; M tile = box (64ch, BW, BH(+ndy-1), BN)
     int Hin, Win, Cin;
-    int lgBW, lgBH, lgBN;      // log2 of the box extents, BW*BH*BN == 128
+    int lgBW, lgBH, lgBN;      // log2 of the M-tile extents, BW*BH*BN == 128
     int tiles_w, tiles_h;      // tiles per image
+    int total_tiles;           // M tiles in this launch
     int n_img;                 // valid images in this launch
-    int nphase, ntaps;         // phase-decomposed upsample: 4 phases x 4 taps; else 1 x {9,1}
-    int8_t dy[4][9], dx[4][9];
-    // B operand: bf16 weights [nphase*cout_pad][ntaps*Cin], K index = tap*Cin + ci
+    int nphase, ngroups, ndy;  // phase-decomposed upsample: 4 phases; else 1
+    int8_t gdx[4][9], gdy0[4][9];
+    int cin_chunks, units, ups, stages;
+    int a_unit_bytes, b_kb_bytes, unit_bytes, stage_bytes, dy_stride_bytes;
+    // B operand: bf16 weights [nphase*cout_pad][ngroups*ndy*Cin]
     int cout_pad, n_tiles;     // cout_pad = n_tiles*NT
     int cout_real;             // channels actually stored
     long long out_sN;          // output strides (elements): image,
     int out_sP, out_sC;        //   pixel (row-major oh*Wout+ow), channel.  bf16 NHWC: (H*W*C, C, 1); fp32 NCHW: (C*H*W, 1, H*W)
-    // output
     int Hout, Wout, up, pool, act, out_fp32;
     float post_scale;
     void* out;
@@ -62,7 +70,7 @@ struct ConvGemm {
     const bf16* B;
     int* err_flag;
     long long* trace;          // optional clock64 timeline of CTA 0 (ganrev_debug_trace), [8 roles][256 events]
-    int dbg;                   // timing experiments only: bit0 skip A loads, bit1 skip B loads (results are garbage)
+    int dbg;                   // timing experiments only: bit0 skip A loads, bit1 skip B loads, bit2 skip epilogue, bit3 skip MMAs
 };
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2, ACT_TANH = 3, ACT_SIGMOID = 4 };

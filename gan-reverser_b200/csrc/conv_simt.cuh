@@ -8,16 +8,17 @@
 namespace ganrev {
 
 __device__ __forceinline__ float simt_conv_at(const ConvGemm& p, int n, int h, int w, int phase, int co) {
-    const int Ktot = p.ntaps * p.Cin;
+    const int Ktot = p.ngroups * p.ndy * p.Cin;
     const bf16* wrow = p.B + (static_cast<size_t>(phase) * p.cout_pad + co) * Ktot;
     float acc = 0.0f;
-    for (int tap = 0; tap < p.ntaps; ++tap) {
-        const int hh = h + p.dy[phase][tap], ww = w + p.dx[phase][tap];
-        if (hh < 0 || hh >= p.Hin || ww < 0 || ww >= p.Win) continue;   // zero padding
-        const bf16* a = p.A + ((static_cast<size_t>(n) * p.Hin + hh) * p.Win + ww) * p.Cin;
-        const bf16* wt = wrow + static_cast<size_t>(tap) * p.Cin;
-        for (int ci = 0; ci < p.Cin; ++ci) acc = fmaf(__bfloat162float(a[ci]), __bfloat162float(wt[ci]), acc);
-    }
+    for (int g = 0; g < p.ngroups; ++g)
+        for (int j = 0; j < p.ndy; ++j) {
+            const int hh = h + p.gdy0[phase][g] + j, ww = w + p.gdx[phase][g];
+            if (hh < 0 || hh >= p.Hin || ww < 0 || ww >= p.Win) continue;   // zero padding
+            const bf16* a = p.A + ((static_cast<size_t>(n) * p.Hin + hh) * p.Win + ww) * p.Cin;
+            const bf16* wt = wrow + static_cast<size_t>(g * p.ndy + j) * p.Cin;
+            for (int ci = 0; ci < p.Cin; ++ci) acc = fmaf(__bfloat162float(a[ci]), __bfloat162float(wt[ci]), acc);
+        }
     return fmaf(acc, p.scale[co], p.shift[co]);
 }
 

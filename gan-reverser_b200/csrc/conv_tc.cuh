@@ -1,48 +1,56 @@
 // conv_tc.cuh -- implicit-GEMM convolution / linear layer on the 5th-gen tensor cores.
 //
-// One persistent kernel serves every "real contraction" layer of G3 and R_default
-// (models.lua:115-130, 414-451; SURVEY.md section 8a table "Implicit-GEMM view"):
-//   D[128 pixels x NT channels] = sum over (tap, 64-channel chunk) A_tap[128 x 64] * W[NT x 64]^T
-//  * A tiles are boxes (64 ch, BW, BH, BN) of the NHWC bf16 activation, fetched by TMA with
-//    the tap offset added to the (w, h) coordinates; out-of-bounds rows are zero-filled by
-//    the TMA unit, which *is* the conv's zero padding.  128B swizzle, K-major.
+// One persistent kernel template serves every "real contraction" layer of G3 and R_default
+// (models.lua:115-133, 414-451; SURVEY.md section 8a table "Implicit-GEMM view"):
+//   D[128*MT pixels x NT channels] = sum over units (tap group g, 64-channel chunk cc), vertical
+//   taps j < NDY:   A_{g,j,cc}[128 x 64] * W_{g,j,cc}[NT x 64]^T
+//  * A tiles are boxes (64 ch, BW, BH+NDY-1, BN) of the NHWC bf16 activation fetched by TMA with
+//    the tap offset added to the (w, h) coordinates; out-of-bounds rows are zero-filled by the
+//    TMA unit, which *is* the conv's zero padding.  128B swizzle, K-major.
+//  * HALO REUSE (NDY > 1): the NDY vertical taps of one horizontal offset read the same box
+//    through UMMA descriptors offset by j*BW*128 bytes (a multiple of the 1024 B swizzle atom),
+//    so a 3x3 conv ingests 3 boxes of BH+2 rows instead of 9 boxes of BH rows.
+//  * RESIDENT WEIGHTS (BRES): when the layer's whole weight matrix fits in shared memory it is
+//    loaded once per CTA and only activations stream.
+//  * MT accumulators per CTA: every weight tile feeds MT MMAs (M = 128*MT per item).
 //  * nearest-upsample + 3x3 conv (models.lua:121-122, 127-128) runs as four 2x2 phase
 //    convolutions on the low-res input (weights pre-summed per phase at load time).
-//  * tcgen05.mma (cta_group::1, kind::f16, bf16 x bf16 -> fp32) is issued by one thread;
-//    the accumulator lives in TMEM, double-buffered so the epilogue of tile i overlaps
-//    the MMAs of tile i+1.
-//  * epilogue: tcgen05.ld -> folded BatchNorm affine -> ReLU/ELU/tanh -> optional 2x2
+//  * tcgen05.mma (cta_group::1, kind::f16, bf16 x bf16 -> fp32) is issued by one elected thread;
+//    accumulators live in TMEM, double-buffered when 2*MT*NT <= 512 columns so the epilogue of
+//    item i overlaps the MMAs of item i+1.
+//  * epilogue: tcgen05.ld -> folded BatchNorm affine -> ReLU/ELU/tanh/sigmoid -> optional 2x2
 //    max-pool (warp shuffles) and x0.75 (SpatialDropout in eval) -> bf16 NHWC / fp32 store.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue
-// (two warps per TMEM lane quarter; warp 2 also owns the TMEM allocation).  Activation, pooling
-// and output type are template parameters so the epilogue is a short straight-line stream.
+// Why this shape (measured): a B200 SM ingests ~128 B/clk through TMA with
+// ~1300 cycles of latency, and the mbarrier round trip per pipeline stage costs 300+ cycles; a
+// 128x128x64 MMA block needs 32 KB per 256 cycles, so without operand reuse inside the SM the
+// tensor pipe idles.  Every knob above cuts ingested bytes per MMA-cycle.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread
+// each), warps 2..9 = epilogue (two warps per TMEM lane quarter; warp 2 owns the TMEM
+// allocation).  Shape, activation, pooling and output type are template parameters.
 #pragma once
 #include "common.cuh"
 
 namespace ganrev {
 namespace tc {
 
-constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quarter, interleaved 32-column chunks
+constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quarter, interleaved column chunks
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;               // bf16 elements = 128 bytes = one swizzle span
-constexpr int kABytes = kBlockM * kBlockK * 2;
+constexpr int kBlockK = 64;                  // bf16 elements = 128 bytes = one swizzle span
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 227 * 1024;
 constexpr unsigned long long kSpinLimitCycles = 4000000000ull;  // ~2 s: turn a hang into a trap
 
-template <int NT> struct Cfg {
-    static constexpr int kBBytes = NT * kBlockK * 2;
-    static constexpr int kKbBytes = kABytes + kBBytes;                  // one 64-wide k-block: A tile then B tile
-    // k-blocks per pipeline stage: one mbarrier round trip (~300+ cycles) is amortised over
-    // KPS * 4 MMAs, which matters most when NT is small and an MMA is only NT/2 cycles long.
-    static constexpr int kKPS = (NT >= 256) ? 1 : (NT >= 128 ? 2 : (NT >= 64 ? 3 : 3));
-    static constexpr int kStageBytes = kKPS * kKbBytes;
-    static constexpr int kStages = (NT >= 256) ? 4 : 3;
-    static constexpr int kChunk = NT < 32 ? NT : 32;   // accumulator columns per tcgen05.ld
-    static constexpr int kTmemCols = (2 * NT <= 32) ? 32 : (2 * NT <= 64 ? 64 : (2 * NT <= 128 ? 128 : (2 * NT <= 256 ? 256 : 512)));
-    // stages + (2*stages + 4) mbarriers + tmem ptr + double-buffered scale/shift, plus 1024 B alignment slack
-    static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 2 * 2 * NT * 4 + 1024;
+template <int NT, int MT> struct Cfg {
+    static constexpr int kBBytes = NT * kBlockK * 2;                    // one 64-wide weight tile
+    static constexpr int kNAcc = (2 * MT * NT <= 512) ? 2 : 1;          // accumulator buffers
+    static constexpr int kCols = kNAcc * MT * NT;
+    static constexpr int kTmemCols = kCols <= 32 ? 32 : (kCols <= 64 ? 64 : (kCols <= 128 ? 128 : (kCols <= 256 ? 256 : 512)));
+    static constexpr int kChunk = NT < 32 ? NT : 32;                    // accumulator columns per tcgen05.ld
+    static constexpr int kBarBytes = (2 * kMaxStages + 5) * 8 + 24;     // full/empty per stage, tfull/tempty x2, bres, tmem slot (16 B aligned)
+    static constexpr int kTailBytes = kBarBytes + 2 * 2 * NT * 4;       // + double-buffered scale/shift
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -200,40 +208,55 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
         if (p.trace != nullptr && blockIdx.x == 0 && (e) < 256) p.trace[(role) * 256 + (e)] = clock64(); \
     } while (0)
 
-struct ItemCoord {
-    int n0, h0, w0, phase, ntile;
+// M-tile index -> first image / row / column of the tile
+struct TileCoord {
+    int n0, h0, w0;
 };
-__device__ __forceinline__ ItemCoord decode_item(const ConvGemm& p, int item) {
-    ItemCoord c;
-    c.ntile = item % p.n_tiles;
-    int t = item / p.n_tiles;
-    c.phase = t % p.nphase;
-    t /= p.nphase;
-    c.w0 = (t % p.tiles_w) << p.lgBW;
-    t /= p.tiles_w;
+__device__ __forceinline__ TileCoord decode_tile(const ConvGemm& p, int tile) {
+    TileCoord c;
+    c.w0 = (tile % p.tiles_w) << p.lgBW;
+    int t = tile / p.tiles_w;
     c.h0 = (t % p.tiles_h) << p.lgBH;
     t /= p.tiles_h;
     c.n0 = t << p.lgBN;
     return c;
 }
+// item -> (M group, phase, N tile); N tile fastest so consecutive items share activations in L2
+struct ItemCoord {
+    int mgroup, phase, ntile;
+};
+__device__ __forceinline__ ItemCoord decode_item(const ConvGemm& p, int item) {
+    ItemCoord c;
+    c.ntile = item % p.n_tiles;
+    const int t = item / p.n_tiles;
+    c.phase = t % p.nphase;
+    c.mgroup = t / p.nphase;
+    return c;
+}
 
-template <int NT, int ACT, bool POOL, bool OUT_FP32>
+template <int NT, int MT, int NDY, bool BRES, int ACT, bool POOL, bool OUT_FP32>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ ConvGemm p, const int n_items) {
-    using C = Cfg<NT>;
-    constexpr int S = C::kStages;
+    using C = Cfg<NT, MT>;
+    constexpr int NACC = C::kNAcc;
     extern __shared__ uint8_t smem_raw[];
     // 128B swizzle needs 1024 B alignment of every operand tile
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t bar_base = smem_base + S * C::kStageBytes;
+    const int S = p.stages;
+    const int kb_total = p.units * NDY;                                   // k-blocks per item
+    const uint32_t bres_bytes = BRES ? static_cast<uint32_t>(kb_total) * C::kBBytes : 0u;
+    const uint32_t stage0 = smem_base + bres_bytes;                       // resident weights first, then the ring
+    const uint32_t tail_off = bres_bytes + static_cast<uint32_t>(S) * p.stage_bytes;
+    const uint32_t bar_base = smem_base + tail_off;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
-    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
-    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * S + 4);
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + S * C::kStageBytes + 8 * (2 * S + 4));
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
+    const uint32_t bres_bar = bar_base + 8u * (2 * kMaxStages + 4);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 5);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + tail_off + 8 * (2 * kMaxStages + 5));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -251,6 +274,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), kEpiWarps);   // one arrival per epilogue warp
         }
+        mbar_init(bres_bar, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_slot);
@@ -259,32 +283,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int cin_chunks = p.Cin / kBlockK;
-    const int kblocks = p.ntaps * cin_chunks;
-
-    constexpr int KPS = C::kKPS;
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (one elected thread)
         if (elect_one_sync()) {
+            if (BRES) {   // the whole weight matrix of this layer, once (nphase == n_tiles == 1)
+                mbar_expect_tx(bres_bar, bres_bytes);
+                for (int kb = 0; kb < kb_total; ++kb)
+                    tma_load_2d(smem_base + kb * C::kBBytes, &tmB, bres_bar, kb * kBlockK, 0);
+            }
             int stage = 0, tr_p = 0;
             uint32_t phase = 0;
+            const uint32_t unit_tx = ((p.dbg & 1) ? 0u : static_cast<uint32_t>(MT * p.a_unit_bytes)) +
+                                     ((BRES || (p.dbg & 2)) ? 0u : static_cast<uint32_t>(NDY * C::kBBytes));
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const ItemCoord c = decode_item(p, item);
                 const int brow = c.phase * p.cout_pad + c.ntile * NT;
-                int tap = 0, cc = 0;
-                for (int kb0 = 0; kb0 < kblocks; kb0 += KPS) {
-                    const int nk = min(KPS, kblocks - kb0);
+                TileCoord tc[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) tc[mt] = decode_tile(p, c.mgroup * MT + mt);   // tiles past the end read OOB zeros
+                int g = 0, cc = 0;
+                for (int u0 = 0; u0 < p.units; u0 += p.ups) {
+                    const int nu = min(p.ups, p.units - u0);
                     mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 101);
                     GANREV_TR(0, tr_p);
-                    const uint32_t s_base = smem_base + stage * C::kStageBytes;
-                    mbar_expect_tx(full_bar(stage), nk * (((p.dbg & 1) ? 0 : kABytes) + ((p.dbg & 2) ? 0 : C::kBBytes)));
-                    for (int j = 0; j < nk; ++j) {
-                        const uint32_t a_dst = s_base + j * C::kKbBytes;
-                        if (!(p.dbg & 1))
-                            tma_load_4d(a_dst, &tmA, full_bar(stage), cc * kBlockK, c.w0 + p.dx[c.phase][tap], c.h0 + p.dy[c.phase][tap], c.n0);
-                        if (!(p.dbg & 2))
-                            tma_load_2d(a_dst + kABytes, &tmB, full_bar(stage), tap * p.Cin + cc * kBlockK, brow);
-                        if (++cc == cin_chunks) { cc = 0; ++tap; }
+                    const uint32_t s_base = stage0 + stage * p.stage_bytes;
+                    mbar_expect_tx(full_bar(stage), nu * unit_tx);
+                    for (int x = 0; x < nu; ++x) {
+                        const uint32_t u_base = s_base + x * p.unit_bytes;
+                        const int dx = p.gdx[c.phase][g], dy = p.gdy0[c.phase][g];
+                        if (!(p.dbg & 1)) {
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt)
+                                tma_load_4d(u_base + mt * p.a_unit_bytes, &tmA, full_bar(stage), cc * kBlockK, tc[mt].w0 + dx, tc[mt].h0 + dy, tc[mt].n0);
+                        }
+                        if (!BRES && !(p.dbg & 2)) {
+#pragma unroll
+                            for (int j = 0; j < NDY; ++j)
+                                tma_load_2d(u_base + MT * p.a_unit_bytes + j * C::kBBytes, &tmB, full_bar(stage),
+                                            (g * NDY + j) * p.Cin + cc * kBlockK, brow);
+                        }
+                        if (++cc == p.cin_chunks) { cc = 0; ++g; }
                     }
                     GANREV_TR(1, tr_p);
                     ++tr_p;
@@ -297,36 +335,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (elect_one_sync()) {
             constexpr uint32_t idesc = make_idesc<NT>();
             const uint64_t desc_base = make_smem_desc(0);
+            auto desc_at = [&](uint32_t addr) { return desc_base | static_cast<uint64_t>((addr & 0x3FFFFu) >> 4); };
+            if (BRES) {
+                mbar_wait(bres_bar, 0u, p.err_flag, 105);
+                tcgen05_fence_after();
+            }
             int stage = 0, tr_m = 0;
             uint32_t phase = 0;
             int it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1u;
+                const int acc = it % NACC;
+                const uint32_t acc_phase = (it / NACC) & 1u;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 102);
                 GANREV_TR(6, it);
                 tcgen05_fence_after();
-                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * NT);
-                for (int kb0 = 0; kb0 < kblocks; kb0 += KPS) {
-                    const int nk = min(KPS, kblocks - kb0);
+                int g = 0, cc = 0;
+                for (int u0 = 0; u0 < p.units; u0 += p.ups) {
+                    const int nu = min(p.ups, p.units - u0);
                     mbar_wait(full_bar(stage), phase, p.err_flag, 103);
                     GANREV_TR(2, tr_m);
                     tcgen05_fence_after();
-                    const uint32_t s_base = smem_base + stage * C::kStageBytes;
-                    if (!(p.dbg & 8)) {
-                        for (int j = 0; j < nk; ++j) {
-                            const uint32_t a_addr = s_base + j * C::kKbBytes;
-                            const uint64_t adesc = desc_base | static_cast<uint64_t>((a_addr & 0x3FFFFu) >> 4);
-                            const uint64_t bdesc = desc_base | static_cast<uint64_t>(((a_addr + kABytes) & 0x3FFFFu) >> 4);
+                    const uint32_t s_base = stage0 + stage * p.stage_bytes;
+                    for (int x = 0; x < nu; ++x) {
+                        const uint32_t u_base = s_base + x * p.unit_bytes;
+                        const uint32_t b_base = BRES ? smem_base + ((g * NDY) * p.cin_chunks + cc) * C::kBBytes
+                                                     : u_base + MT * p.a_unit_bytes;
+                        const uint32_t b_step = BRES ? static_cast<uint32_t>(p.cin_chunks) * C::kBBytes : static_cast<uint32_t>(C::kBBytes);
+                        if (!(p.dbg & 8)) {
 #pragma unroll
-                            for (int k = 0; k < kBlockK / 16; ++k) {
-                                // +32 B per K=16 step inside the 128 B swizzle span (>>4 -> +2)
-                                umma_bf16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb0 + j > 0 || k > 0) ? 1u : 0u);
+                            for (int j = 0; j < NDY; ++j) {
+                                const uint64_t bdesc = desc_at(b_base + j * b_step);
+#pragma unroll
+                                for (int mt = 0; mt < MT; ++mt) {
+                                    // vertical tap j = the same box, j*BW rows (a multiple of the 1024 B atom) further down
+                                    const uint64_t adesc = desc_at(u_base + mt * p.a_unit_bytes + j * p.dy_stride_bytes);
+                                    const uint32_t tmem_d = tmem_base + static_cast<uint32_t>((acc * MT + mt) * NT);
+                                    const bool first = (u0 + x == 0) && (j == 0);
+#pragma unroll
+                                    for (int k = 0; k < kBlockK / 16; ++k)   // +32 B per K=16 step inside the swizzle span (>>4 -> +2)
+                                        umma_bf16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (first && k == 0) ? 0u : 1u);
+                                }
                             }
                         }
+                        if (++cc == p.cin_chunks) { cc = 0; ++g; }
                     }
                     umma_commit(empty_bar(stage));                              // frees the smem slot when the MMAs retire
-                    if (kb0 + KPS >= kblocks) umma_commit(tfull_bar(acc));      // accumulator complete
+                    if (u0 + p.ups >= p.units) umma_commit(tfull_bar(acc));     // accumulators complete
                     GANREV_TR(3, tr_m);
                     ++tr_m;
                     if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -336,89 +390,92 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..9)
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;       // which set of interleaved 32-column chunks
+        const int half = (warp - 2) >> 2;       // which set of interleaved column chunks
         const int etid = threadIdx.x - 64;      // 0..255
         const int m = q * 32 + lane;            // tile row = pixel
         const int BW = 1 << p.lgBW;
         const int w_l = m & (BW - 1);
         const int h_l = (m >> p.lgBW) & ((1 << p.lgBH) - 1);
         const int n_l = m >> (p.lgBW + p.lgBH);
-        float* ss_base = reinterpret_cast<float*>(smem + S * C::kStageBytes + C::kBarBytes);
+        float* ss_base = reinterpret_cast<float*>(smem + tail_off + C::kBarBytes);
         int it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const ItemCoord c = decode_item(p, item);
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1u;
+            const int acc = it % NACC;
+            const uint32_t acc_phase = (it / NACC) & 1u;
             const int cbase = c.ntile * NT;
-            // stage this item's folded-BN scale / shift (double-buffered; the named barrier of
-            // item i+1 proves every warp is done reading the buffer of item i)
-            // (layers with a single N tile keep one copy for the whole kernel)
-            float* ss = ss_base + (p.n_tiles > 1 ? acc * (2 * NT) : 0);
+            // stage this item's folded-BN scale / shift (double-buffered; the named barrier of item
+            // i+1 proves every warp is done reading the buffer of item i).  Layers with a single
+            // N tile keep one copy for the whole kernel.
+            float* ss = ss_base + (p.n_tiles > 1 ? (it & 1) * (2 * NT) : 0);
             if (p.n_tiles > 1 || it == 0) {
                 for (int i = etid; i < NT; i += 32 * kEpiWarps) {
                     ss[i] = __ldg(p.scale + cbase + i);
                     ss[NT + i] = __ldg(p.shift + cbase + i);
                 }
+                named_bar_sync(1, 32 * kEpiWarps);
             }
-            const int n = c.n0 + n_l, h = c.h0 + h_l, w = c.w0 + w_l;
-            int oh = h, ow = w;
-            bool writer = n < p.n_img;
-            if (POOL) {
-                oh = h >> 1; ow = w >> 1;
-                writer = writer && !(h & 1) && !(w & 1);
-            } else if (p.up == 2) {
-                oh = 2 * h + (c.phase >> 1); ow = 2 * w + (c.phase & 1);
-            }
-            const size_t pix_off = static_cast<size_t>(n) * p.out_sN + (static_cast<size_t>(oh) * p.Wout + ow) * p.out_sP;
-            if (p.n_tiles > 1 || it == 0) named_bar_sync(1, 32 * kEpiWarps);
-
             if (etid == 0) GANREV_TR(7, it);
             mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 104);
             if (etid == 0) GANREV_TR(4, it);
             tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * NT);
-            constexpr int CW = C::kChunk;
 #pragma unroll 1
-            for (int c0 = half * CW + ((p.dbg & 4) ? NT : 0); c0 < NT; c0 += 2 * CW) {
-                uint32_t r[32];
-                if (CW == 32) tmem_ld32(taddr + c0, r); else tmem_ld16(taddr + c0, r);
-                tmem_ld_wait();
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < CW; j += 4) {
-                    const float4 sc = *reinterpret_cast<const float4*>(ss + c0 + j);
-                    const float4 sh = *reinterpret_cast<const float4*>(ss + NT + c0 + j);
-                    v[j + 0] = fmaf(__uint_as_float(r[j + 0]), sc.x, sh.x);
-                    v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y);
-                    v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z);
-                    v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
-                }
+            for (int mt = 0; mt < MT; ++mt) {
+                const TileCoord t = decode_tile(p, c.mgroup * MT + mt);
+                const int n = t.n0 + n_l, h = t.h0 + h_l, w = t.w0 + w_l;
+                int oh = h, ow = w;
+                bool writer = n < p.n_img;
                 if (POOL) {
-                    // 2x2 max: w-neighbour is lane^1, h-neighbour is lane^BW (BW <= 16)
-#pragma unroll
-                    for (int j = 0; j < CW; ++j) {
-                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], BW));
-                    }
+                    oh = h >> 1; ow = w >> 1;
+                    writer = writer && !(h & 1) && !(w & 1);
+                } else if (p.up == 2) {
+                    oh = 2 * h + (c.phase >> 1); ow = 2 * w + (c.phase & 1);
                 }
+                const size_t pix_off = static_cast<size_t>(n) * p.out_sN + (static_cast<size_t>(oh) * p.Wout + ow) * p.out_sP;
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * MT + mt) * NT);
+                constexpr int CW = C::kChunk;
+#pragma unroll 1
+                for (int c0 = half * CW + ((p.dbg & 4) ? NT : 0); c0 < NT; c0 += 2 * CW) {
+                    uint32_t r[32];
+                    if (CW == 32) tmem_ld32(taddr + c0, r); else tmem_ld16(taddr + c0, r);
+                    tmem_ld_wait();
+                    float v[32];
 #pragma unroll
-                for (int j = 0; j < CW; ++j) v[j] = act_fn<ACT>(v[j], p.act) * p.post_scale;
-                if (writer) {
-                    if (OUT_FP32) {
-                        float* o = reinterpret_cast<float*>(p.out) + pix_off + static_cast<size_t>(cbase + c0) * p.out_sC;
+                    for (int j = 0; j < CW; j += 4) {
+                        const float4 sc = *reinterpret_cast<const float4*>(ss + c0 + j);
+                        const float4 sh = *reinterpret_cast<const float4*>(ss + NT + c0 + j);
+                        v[j + 0] = fmaf(__uint_as_float(r[j + 0]), sc.x, sh.x);
+                        v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y);
+                        v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z);
+                        v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
+                    }
+                    if (POOL) {
+                        // 2x2 max: w-neighbour is lane^1, h-neighbour is lane^BW (BW <= 16)
 #pragma unroll
-                        for (int j = 0; j < CW; ++j)
-                            if (cbase + c0 + j < p.cout_real) o[static_cast<size_t>(j) * p.out_sC] = v[j];
-                    } else {
-                        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + pix_off + cbase + c0);
+                        for (int j = 0; j < CW; ++j) {
+                            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+                            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], BW));
+                        }
+                    }
 #pragma unroll
-                        for (int j = 0; j < CW / 8; ++j) {
-                            uint4 pk;
-                            pk.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                            pk.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                            pk.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                            pk.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                            o[j] = pk;
+                    for (int j = 0; j < CW; ++j) v[j] = act_fn<ACT>(v[j], p.act) * p.post_scale;
+                    if (writer) {
+                        if (OUT_FP32) {
+                            float* o = reinterpret_cast<float*>(p.out) + pix_off + static_cast<size_t>(cbase + c0) * p.out_sC;
+#pragma unroll
+                            for (int j = 0; j < CW; ++j)
+                                if (cbase + c0 + j < p.cout_real) o[static_cast<size_t>(j) * p.out_sC] = v[j];
+                        } else {
+                            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + pix_off + cbase + c0);
+#pragma unroll
+                            for (int j = 0; j < CW / 8; ++j) {
+                                uint4 pk;
+                                pk.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                                pk.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                                pk.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                                pk.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                                o[j] = pk;
+                            }
                         }
                     }
                 }

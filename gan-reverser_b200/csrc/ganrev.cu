@@ -21,11 +21,13 @@ using namespace ganrev;
 struct TcLayer {
     std::string name;
     ConvGemm g{};
-    int NT = 0, Ktot = 0;
+    int NT = 0, MT = 1, NDY = 1, Ktot = 0;
+    bool bres = false;
+    size_t smem_bytes = 0;
     DevBuf w, scale, shift;
     CUtensorMap tmB{};
     double flops_per_img = 0.0;   // executed MAC*2 per image (phase form counts the folded work)
-    double bytes_per_img = 0.0;   // activation in + out (bf16) per image
+    double bytes_per_img = 0.0;   // activation in + out per image
 };
 
 struct GModel {
@@ -217,13 +219,7 @@ static int upload(ganrev_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-static void pick_box(ConvGemm& g, bool pool) {
-    const int BW = std::min(g.Win, pool ? 16 : 128);
-    const int BH = std::min(g.Hin, 128 / BW);
-    const int BN = 128 / (BW * BH);
-    g.lgBW = ilog2(BW); g.lgBH = ilog2(BH); g.lgBN = ilog2(BN);
-    g.tiles_w = g.Win / BW; g.tiles_h = g.Hin / BH;
-}
+enum LayerKind { KIND_LINEAR = 0, KIND_CONV3 = 1, KIND_UPCONV3 = 2 };
 
 static int make_tmB(ganrev_ctx* ctx, TcLayer& L) {
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(L.Ktot), static_cast<cuuint64_t>(L.g.nphase) * L.g.cout_pad};
@@ -237,30 +233,90 @@ static int make_tmB(ganrev_ctx* ctx, TcLayer& L) {
     return GANREV_OK;
 }
 
-// Generic layer builder.  wmat: [nphase*cout_pad][Ktot] fp32 (K index = tap*Cin + ci).
-static int build_tc_layer(ganrev_ctx* ctx, TcLayer& L, const char* name, int NT, int Hin, int Win, int Cin, int nphase, int ntaps,
-                          const int8_t (*dy)[9], const int8_t (*dx)[9], int cout_real, int n_tiles,
-                          const std::vector<float>& wmat, const BnFold& bn, int Hout, int Wout, int out_cstride, int up, int pool,
-                          int act, float post_scale, int out_fp32, bool nchw = false) {
-    L.name = name;
-    L.NT = NT;
+struct LayerDef {
+    const char* name;
+    LayerKind kind;
+    int NT, MT;              // N tile, accumulators per CTA
+    bool want_bres;          // keep the whole weight matrix resident in smem when it fits
+    int Hin, Win, Cin;
+    int cout_real, n_tiles;
+    int Hout, Wout, out_cstride;
+    int pool, act;
+    float post_scale;
+    int out_fp32;
+    bool nchw;
+};
+
+// w: conv weights [cout_real][Cin][3][3] (KIND_CONV3 / KIND_UPCONV3) or a ready matrix
+// [n_tiles*NT][Cin] (KIND_LINEAR).  BatchNorm arrives folded in `bn` (cout_pad entries).
+static int build_tc_layer(ganrev_ctx* ctx, TcLayer& L, const LayerDef& d, const float* w, const BnFold& bn) {
+    L.name = d.name;
+    L.NT = d.NT;
     ConvGemm& g = L.g;
     g = ConvGemm{};
-    g.Hin = Hin; g.Win = Win; g.Cin = Cin;
-    g.nphase = nphase; g.ntaps = ntaps;
-    for (int p = 0; p < nphase; ++p)
-        for (int t = 0; t < ntaps; ++t) { g.dy[p][t] = dy[p][t]; g.dx[p][t] = dx[p][t]; }
-    g.n_tiles = n_tiles; g.cout_pad = n_tiles * NT; g.cout_real = cout_real;
-    if (nchw) { g.out_sN = static_cast<long long>(out_cstride) * Hout * Wout; g.out_sP = 1; g.out_sC = Hout * Wout; }
-    else      { g.out_sN = static_cast<long long>(out_cstride) * Hout * Wout; g.out_sP = out_cstride; g.out_sC = 1; }
-    g.Hout = Hout; g.Wout = Wout; g.up = up; g.pool = pool; g.act = act; g.post_scale = post_scale; g.out_fp32 = out_fp32;
+    g.Hin = d.Hin; g.Win = d.Win; g.Cin = d.Cin;
+    if (d.Cin % 64 != 0) return fail(ctx, GANREV_EINVAL, "layer %s: Cin=%d not a multiple of 64", d.name, d.Cin);
+    g.cin_chunks = d.Cin / 64;
+    g.n_tiles = d.n_tiles; g.cout_pad = d.n_tiles * d.NT; g.cout_real = d.cout_real;
+    if (d.nchw) { g.out_sN = static_cast<long long>(d.out_cstride) * d.Hout * d.Wout; g.out_sP = 1; g.out_sC = d.Hout * d.Wout; }
+    else        { g.out_sN = static_cast<long long>(d.out_cstride) * d.Hout * d.Wout; g.out_sP = d.out_cstride; g.out_sC = 1; }
+    g.Hout = d.Hout; g.Wout = d.Wout; g.up = d.kind == KIND_UPCONV3 ? 2 : 1; g.pool = d.pool; g.act = d.act;
+    g.post_scale = d.post_scale; g.out_fp32 = d.out_fp32;
     g.err_flag = ctx->d_err_flag;
-    pick_box(g, pool != 0);
-    L.Ktot = ntaps * Cin;
-    if (Cin % 64 != 0) return fail(ctx, GANREV_EINVAL, "layer %s: Cin=%d not a multiple of 64", name, Cin);
-    if (wmat.size() != static_cast<size_t>(nphase) * g.cout_pad * L.Ktot) return fail(ctx, GANREV_EINVAL, "layer %s: bad weight matrix", name);
-    std::vector<uint16_t> wb(wmat.size());
-    for (size_t i = 0; i < wmat.size(); ++i) wb[i] = f2bf(wmat[i]);
+
+    // ---- M tile and tap groups.  Halo reuse needs a whole 128-pixel tile inside one image.
+    const bool halo = d.kind != KIND_LINEAR && d.Hin * d.Win >= 128 && d.Win >= 8;
+    int BW, BH, BN;
+    if (halo) { BW = std::min(d.Win, 16); BH = 128 / BW; BN = 1; }
+    else      { BW = std::min(d.Win, d.pool ? 16 : 128); BH = std::min(d.Hin, 128 / BW); BN = 128 / (BW * BH); }
+    g.lgBW = ilog2(BW); g.lgBH = ilog2(BH); g.lgBN = ilog2(BN);
+    g.tiles_w = d.Win / BW; g.tiles_h = d.Hin / BH;
+    g.nphase = d.kind == KIND_UPCONV3 ? 4 : 1;
+    if (d.kind == KIND_LINEAR) { g.ngroups = 1; g.ndy = 1; }
+    else if (d.kind == KIND_CONV3) {
+        if (halo) { g.ngroups = 3; g.ndy = 3; for (int x = 0; x < 3; ++x) { g.gdx[0][x] = static_cast<int8_t>(x - 1); g.gdy0[0][x] = -1; } }
+        else      { g.ngroups = 9; g.ndy = 1; for (int t = 0; t < 9; ++t) { g.gdy0[0][t] = static_cast<int8_t>(t / 3 - 1); g.gdx[0][t] = static_cast<int8_t>(t % 3 - 1); } }
+    } else {   // phase p = a*2 + b reads low-res rows a-1..a and columns b-1..b
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 2; ++b) {
+                const int ph = a * 2 + b;
+                if (halo) { g.ngroups = 2; g.ndy = 2; for (int x = 0; x < 2; ++x) { g.gdx[ph][x] = static_cast<int8_t>(b - 1 + x); g.gdy0[ph][x] = static_cast<int8_t>(a - 1); } }
+                else      { g.ngroups = 4; g.ndy = 1; for (int t = 0; t < 4; ++t) { g.gdy0[ph][t] = static_cast<int8_t>(a - 1 + t / 2); g.gdx[ph][t] = static_cast<int8_t>(b - 1 + t % 2); } }
+            }
+    }
+    L.NDY = g.ndy;
+    L.MT = d.MT;
+    g.units = g.ngroups * g.cin_chunks;
+    const int ntap = g.ngroups * g.ndy;
+    L.Ktot = ntap * d.Cin;
+
+    // ---- weight matrix [nphase*cout_pad][Ktot], K = (g*ndy + j)*Cin + ci
+    std::vector<uint16_t> wb(static_cast<size_t>(g.nphase) * g.cout_pad * L.Ktot, 0);
+    if (d.kind == KIND_LINEAR) {
+        for (size_t i = 0; i < static_cast<size_t>(g.cout_pad) * d.Cin; ++i) wb[i] = f2bf(w[i]);
+    } else {
+        // nearest-upsample x2 then 3x3/pad1 == four 2x2 convolutions on the low-res input: output row
+        // 2y+a reads low-res rows {y-1: ky=0 | y: ky=1,2} (a=0) or {y: ky=0,1 | y+1: ky=2} (a=1).
+        static const int S[2][2][2] = {{{0, 0}, {1, 2}}, {{0, 1}, {2, 2}}};   // S[a][t] = {first, last} ky
+        for (int ph = 0; ph < g.nphase; ++ph)
+            for (int gi = 0; gi < g.ngroups; ++gi)
+                for (int j = 0; j < g.ndy; ++j) {
+                    const int dy = g.gdy0[ph][gi] + j, dx = g.gdx[ph][gi];
+                    int ky0, ky1, kx0, kx1;
+                    if (d.kind == KIND_CONV3) { ky0 = ky1 = dy + 1; kx0 = kx1 = dx + 1; }
+                    else {
+                        const int a = ph >> 1, b = ph & 1, ty = dy - (a - 1), tx = dx - (b - 1);
+                        ky0 = S[a][ty][0]; ky1 = S[a][ty][1]; kx0 = S[b][tx][0]; kx1 = S[b][tx][1];
+                    }
+                    for (int co = 0; co < d.cout_real; ++co)
+                        for (int ci = 0; ci < d.Cin; ++ci) {
+                            double sum = 0.0;
+                            for (int ky = ky0; ky <= ky1; ++ky)
+                                for (int kx = kx0; kx <= kx1; ++kx) sum += w[((static_cast<size_t>(co) * d.Cin + ci) * 3 + ky) * 3 + kx];
+                            wb[(static_cast<size_t>(ph) * g.cout_pad + co) * L.Ktot + static_cast<size_t>(gi * g.ndy + j) * d.Cin + ci] = f2bf(static_cast<float>(sum));
+                        }
+                }
+    }
     RC_TRY(upload(ctx, L.w, wb.data(), wb.size() * 2));
     RC_TRY(upload(ctx, L.scale, bn.scale.data(), bn.scale.size() * 4));
     RC_TRY(upload(ctx, L.shift, bn.shift.data(), bn.shift.size() * 4));
@@ -268,45 +324,31 @@ static int build_tc_layer(ganrev_ctx* ctx, TcLayer& L, const char* name, int NT,
     g.scale = reinterpret_cast<const float*>(L.scale.p);
     g.shift = reinterpret_cast<const float*>(L.shift.p);
     RC_TRY(make_tmB(ctx, L));
-    const double px_in = static_cast<double>(Hin) * Win;
-    L.flops_per_img = 2.0 * px_in * nphase * (out_fp32 ? cout_real : g.cout_pad) * L.Ktot;   // zero-padded output lanes are not work
-    L.bytes_per_img = 2.0 * px_in * Cin + (out_fp32 ? 4.0 : 2.0) * Hout * Wout * cout_real;
+
+    // ---- shared-memory plan: [resident weights][stages x (ups units)][barriers, scale/shift]
+    g.a_unit_bytes = (BH + g.ndy - 1) * BW * BN * 128;
+    g.b_kb_bytes = d.NT * 128;
+    g.dy_stride_bytes = BW * BN * 128;
+    const int tail = (2 * tc::kMaxStages + 5) * 8 + 24 + 2 * 2 * d.NT * 4;
+    const int budget = tc::kSmemBudget - 1024 - tail;
+    const size_t wbytes = static_cast<size_t>(g.units) * g.ndy * g.b_kb_bytes;
+    L.bres = d.want_bres && g.nphase == 1 && g.n_tiles == 1 && wbytes + 2 * static_cast<size_t>(L.MT) * g.a_unit_bytes <= static_cast<size_t>(budget);
+    for (;;) {
+        const int res = L.bres ? static_cast<int>(wbytes) : 0;
+        g.unit_bytes = L.MT * g.a_unit_bytes + (L.bres ? 0 : g.ndy * g.b_kb_bytes);
+        const int cyc_unit = L.MT * g.ndy * 4 * std::max(d.NT / 2, 32);          // MMA cycles per unit
+        g.ups = std::max(1, std::min({4, g.units, (512 + cyc_unit - 1) / cyc_unit}));
+        while (g.ups > 1 && (budget - res) / (g.ups * g.unit_bytes) < 3) --g.ups;
+        g.stage_bytes = g.ups * g.unit_bytes;
+        g.stages = std::min(tc::kMaxStages, (budget - res) / g.stage_bytes);
+        if (g.stages >= 2) { L.smem_bytes = static_cast<size_t>(res) + static_cast<size_t>(g.stages) * g.stage_bytes + tail + 1024; break; }
+        if (L.bres) { L.bres = false; continue; }
+        return fail(ctx, GANREV_EINVAL, "layer %s does not fit in shared memory", d.name);
+    }
+    const double px_in = static_cast<double>(d.Hin) * d.Win;
+    L.flops_per_img = 2.0 * px_in * g.nphase * (d.out_fp32 ? d.cout_real : g.cout_pad) * L.Ktot;   // zero-padded output lanes are not work
+    L.bytes_per_img = 2.0 * px_in * d.Cin + (d.out_fp32 ? 4.0 : 2.0) * d.Hout * d.Wout * d.cout_real;
     return GANREV_OK;
-}
-
-static const int8_t kTaps9Y[1][9] = {{-1, -1, -1, 0, 0, 0, 1, 1, 1}};
-static const int8_t kTaps9X[1][9] = {{-1, 0, 1, -1, 0, 1, -1, 0, 1}};
-static const int8_t kTap1[1][9] = {{0, 0, 0, 0, 0, 0, 0, 0, 0}};
-// phase p = a*2 + b, tap t = ty*2 + tx: low-res offset (a-1+ty, b-1+tx)
-static const int8_t kPhaseY[4][9] = {{-1, -1, 0, 0}, {-1, -1, 0, 0}, {0, 0, 1, 1}, {0, 0, 1, 1}};
-static const int8_t kPhaseX[4][9] = {{-1, 0, -1, 0}, {0, 1, 0, 1}, {-1, 0, -1, 0}, {0, 1, 0, 1}};
-
-// [Cout][Cin][3][3] -> [Cout_pad][9*Cin], K = tap*Cin + ci
-static std::vector<float> conv_w_direct(const float* w, int Cout, int Cin, int cout_pad) {
-    std::vector<float> m(static_cast<size_t>(cout_pad) * 9 * Cin, 0.0f);
-    for (int co = 0; co < Cout; ++co)
-        for (int ci = 0; ci < Cin; ++ci)
-            for (int t = 0; t < 9; ++t) m[(static_cast<size_t>(co) * 9 + t) * Cin + ci] = w[(static_cast<size_t>(co) * Cin + ci) * 9 + t];
-    return m;
-}
-// nearest-upsample x2 followed by 3x3/pad1 == four 2x2 convolutions on the low-res input:
-// output row 2y+a reads low-res rows {y-1: ky=0 | y: ky=1,2} (a=0) or {y: ky=0,1 | y+1: ky=2} (a=1).
-static std::vector<float> conv_w_phase(const float* w, int Cout, int Cin) {
-    static const int S[2][2][2] = {{{0, 0}, {1, 2}}, {{0, 1}, {2, 2}}};   // S[a][t] = {first, last} ky
-    std::vector<float> m(static_cast<size_t>(4) * Cout * 4 * Cin, 0.0f);
-    for (int a = 0; a < 2; ++a)
-        for (int b = 0; b < 2; ++b)
-            for (int co = 0; co < Cout; ++co)
-                for (int ty = 0; ty < 2; ++ty)
-                    for (int tx = 0; tx < 2; ++tx)
-                        for (int ci = 0; ci < Cin; ++ci) {
-                            double s = 0.0;
-                            for (int ky = S[a][ty][0]; ky <= S[a][ty][1]; ++ky)
-                                for (int kx = S[b][tx][0]; kx <= S[b][tx][1]; ++kx)
-                                    s += w[((static_cast<size_t>(co) * Cin + ci) * 3 + ky) * 3 + kx];
-                            m[((static_cast<size_t>(a * 2 + b) * Cout + co) * 4 + (ty * 2 + tx)) * Cin + ci] = static_cast<float>(s);
-                        }
-    return m;
 }
 
 static int check_geom(ganrev_ctx* ctx, int C, int H, int W, int nd) {
@@ -320,41 +362,50 @@ static int check_geom(ganrev_ctx* ctx, int C, int H, int W, int nd) {
 // =================================================================================
 // layer launches
 // =================================================================================
-template <int NT, int ACT, bool POOL, bool OUT_FP32>
+template <int NT, int MT, int NDY, bool BRES, int ACT, bool POOL, bool OUT_FP32>
 static int launch_tc(ganrev_ctx* ctx, const TcLayer& L, const CUtensorMap& tmA, const ConvGemm& g, int n_items) {
-    using C = tc::Cfg<NT>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU_TRY(cudaFuncSetAttribute(tc::conv_tc_kernel<NT, ACT, POOL, OUT_FP32>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-        attr_set = true;
+    static size_t attr_max = 0;
+    if (L.smem_bytes > attr_max) {
+        CU_TRY(cudaFuncSetAttribute(tc::conv_tc_kernel<NT, MT, NDY, BRES, ACT, POOL, OUT_FP32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(L.smem_bytes)));
+        attr_max = L.smem_bytes;
     }
     const int grid = std::min(n_items, ctx->num_sms);
-    tc::conv_tc_kernel<NT, ACT, POOL, OUT_FP32><<<grid, tc::kThreads, C::kSmemBytes, ctx->stream>>>(tmA, L.tmB, g, n_items);
+    tc::conv_tc_kernel<NT, MT, NDY, BRES, ACT, POOL, OUT_FP32><<<grid, tc::kThreads, L.smem_bytes, ctx->stream>>>(tmA, L.tmB, g, n_items);
     CU_TRY(cudaGetLastError());
     return GANREV_OK;
 }
-// The layer shapes of G3 / R_default map onto this fixed set of kernel variants.
+// The layer shapes of G3 / R_default map onto this fixed set of kernel variants
+// (NT, MT, NDY, BRES, ACT, POOL, FP32OUT).  NDY=1 rows serve geometries too small for halo reuse.
 static int dispatch_tc(ganrev_ctx* ctx, const TcLayer& L, const CUtensorMap& tmA, const ConvGemm& g, int n_items) {
-    const int NT = L.NT;
-    if (g.out_fp32 && g.act == ACT_SIGMOID && NT == 16) {   // G's last conv: 128 -> C, fp32 NCHW images
-        return launch_tc<16, ACT_SIGMOID, false, true>(ctx, L, tmA, g, n_items);
-    } else if (g.out_fp32) {   // final Linear(512 -> nd) [+ Tanh]
-        switch (NT) {
-            case 32: return launch_tc<32, tc::ACT_RUNTIME, false, true>(ctx, L, tmA, g, n_items);
-            case 64: return launch_tc<64, tc::ACT_RUNTIME, false, true>(ctx, L, tmA, g, n_items);
-            case 128: return launch_tc<128, tc::ACT_RUNTIME, false, true>(ctx, L, tmA, g, n_items);
-            case 256: return launch_tc<256, tc::ACT_RUNTIME, false, true>(ctx, L, tmA, g, n_items);
-        }
-    } else if (g.act == ACT_RELU && !g.pool) {
-        if (NT == 256) return launch_tc<256, ACT_RELU, false, false>(ctx, L, tmA, g, n_items);
-        if (NT == 128) return launch_tc<128, ACT_RELU, false, false>(ctx, L, tmA, g, n_items);
-    } else if (g.act == ACT_ELU) {
-        if (NT == 64 && !g.pool) return launch_tc<64, ACT_ELU, false, false>(ctx, L, tmA, g, n_items);
-        if (NT == 64 && g.pool) return launch_tc<64, ACT_ELU, true, false>(ctx, L, tmA, g, n_items);
-        if (NT == 128 && !g.pool) return launch_tc<128, ACT_ELU, false, false>(ctx, L, tmA, g, n_items);
-        if (NT == 128 && g.pool) return launch_tc<128, ACT_ELU, true, false>(ctx, L, tmA, g, n_items);
-    }
-    return fail(ctx, GANREV_EINVAL, "no tcgen05 kernel variant for layer %s (NT=%d act=%d pool=%d fp32=%d)", L.name.c_str(), NT, g.act, g.pool, g.out_fp32);
+#define TC_CASE(NT_, MT_, NDY_, BRES_, ACT_, POOL_, FP32_)                                                              \
+    if (L.NT == NT_ && L.MT == MT_ && L.NDY == NDY_ && L.bres == BRES_ && (ACT_ == tc::ACT_RUNTIME || g.act == ACT_) && \
+        (g.pool != 0) == POOL_ && (g.out_fp32 != 0) == FP32_)                                                           \
+        return launch_tc<NT_, MT_, NDY_, BRES_, ACT_, POOL_, FP32_>(ctx, L, tmA, g, n_items);
+    // G
+    TC_CASE(256, 1, 1, false, ACT_RELU, false, false)      // Linear
+    TC_CASE(256, 2, 1, false, ACT_RELU, false, false)      // Up+Conv 512->256 on < 128-pixel inputs
+    TC_CASE(256, 2, 2, false, ACT_RELU, false, false)      // ... with halo reuse
+    TC_CASE(128, 2, 1, false, ACT_RELU, false, false)      // Up+Conv 256->128
+    TC_CASE(128, 2, 2, false, ACT_RELU, false, false)
+    TC_CASE(16, 2, 3, true, ACT_SIGMOID, false, true)      // Conv 128->C + Sigmoid, fp32 NCHW images
+    // R
+    TC_CASE(64, 2, 3, true, ACT_ELU, false, false)         // Conv 64->64
+    TC_CASE(64, 2, 3, true, ACT_ELU, true, false)          // Conv 64->64 + MaxPool
+    TC_CASE(128, 1, 3, true, ACT_ELU, false, false)        // Conv 64->128
+    TC_CASE(128, 1, 1, true, ACT_ELU, false, false)
+    TC_CASE(128, 2, 3, false, ACT_ELU, false, false)       // Conv 128->128
+    TC_CASE(128, 2, 3, false, ACT_ELU, true, false)        // Conv 128->128 + x0.75 + MaxPool
+    TC_CASE(128, 2, 1, false, ACT_ELU, false, false)
+    TC_CASE(128, 2, 1, false, ACT_ELU, true, false)
+    TC_CASE(64, 1, 1, false, ACT_ELU, false, false)        // Linear 8192->512
+    TC_CASE(32, 1, 1, false, tc::ACT_RUNTIME, false, true) // Linear 512->nd (+Tanh)
+    TC_CASE(64, 1, 1, false, tc::ACT_RUNTIME, false, true)
+    TC_CASE(128, 1, 1, false, tc::ACT_RUNTIME, false, true)
+    TC_CASE(256, 1, 1, false, tc::ACT_RUNTIME, false, true)
+#undef TC_CASE
+    return fail(ctx, GANREV_EINVAL, "no tcgen05 kernel variant for layer %s (NT=%d MT=%d NDY=%d bres=%d act=%d pool=%d fp32=%d)", L.name.c_str(),
+                L.NT, L.MT, L.NDY, (int)L.bres, g.act, g.pool, g.out_fp32);
 }
 
 static int run_layer(ganrev_ctx* ctx, TcLayer& L, const void* in, void* out, int n_img, int64_t n_cap) {
@@ -366,7 +417,9 @@ static int run_layer(ganrev_ctx* ctx, TcLayer& L, const void* in, void* out, int
     g.trace = (ctx->trace.p && L.name == ctx->trace_layer) ? static_cast<long long*>(ctx->trace.p) : nullptr;
     const int BN = 1 << g.lgBN;
     const int tiles_n = (n_img + BN - 1) / BN;
-    const int n_items = tiles_n * g.tiles_h * g.tiles_w * g.nphase * g.n_tiles;
+    g.total_tiles = tiles_n * g.tiles_h * g.tiles_w;
+    const int mgroups = (g.total_tiles + L.MT - 1) / L.MT;
+    const int n_items = mgroups * g.nphase * g.n_tiles;
     ProfScope ps(ctx, L.name, L.flops_per_img * n_img, L.bytes_per_img * n_img);
     if (ctx->conv_impl == 1) {
         const long long total = static_cast<long long>(n_img) * g.Hout * g.Wout * g.cout_real;
@@ -379,7 +432,7 @@ static int run_layer(ganrev_ctx* ctx, TcLayer& L, const void* in, void* out, int
                                 static_cast<cuuint64_t>(n_cap)};
     const cuuint64_t strides[3] = {static_cast<cuuint64_t>(g.Cin) * 2, static_cast<cuuint64_t>(g.Win) * g.Cin * 2,
                                    static_cast<cuuint64_t>(g.Hin) * g.Win * g.Cin * 2};
-    const cuuint32_t box[4] = {64u, 1u << g.lgBW, 1u << g.lgBH, 1u << g.lgBN};
+    const cuuint32_t box[4] = {64u, 1u << g.lgBW, (1u << g.lgBH) + static_cast<cuuint32_t>(g.ndy - 1), 1u << g.lgBN};
     const cuuint32_t es[4] = {1u, 1u, 1u, 1u};
     CUresult r = ctx->encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), dims, strides, box, es,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -426,24 +479,25 @@ static int load_G_impl(ganrev_ctx* ctx, int C, int H, int W, int nd, const float
                 bb[fn] = lb[fo]; gg[fn] = g0[fo]; be[fn] = be0[fo]; mm[fn] = m0[fo]; vv[fn] = v0[fo];
             }
         BnFold bn = fold_bn(bb.data(), gg.data(), be.data(), mm.data(), vv.data(), F, F);
-        RC_TRY(build_tc_layer(ctx, G.lin, "g_linear", 256, 1, 1, G.kpad, 1, 1, kTap1, kTap1, F, F / 256, wm, bn, 1, 1, F, 1, 0, ACT_RELU, 1.0f, 0));
+        const LayerDef d{"g_linear", KIND_LINEAR, 256, 1, false, 1, 1, G.kpad, F, F / 256, 1, 1, F, 0, ACT_RELU, 1.0f, 0, false};
+        RC_TRY(build_tc_layer(ctx, G.lin, d, wm.data(), bn));
     }
     {
         BnFold bn = fold_bn(b1, g1, be1, m1, v1, 256, 256);
-        RC_TRY(build_tc_layer(ctx, G.c1, "g_conv1_up", 256, sH, sW, 512, 4, 4, kPhaseY, kPhaseX, 256, 1, conv_w_phase(w1, 256, 512), bn,
-                              2 * sH, 2 * sW, 256, 2, 0, ACT_RELU, 1.0f, 0));
+        const LayerDef d{"g_conv1_up", KIND_UPCONV3, 256, 2, false, sH, sW, 512, 256, 1, 2 * sH, 2 * sW, 256, 0, ACT_RELU, 1.0f, 0, false};
+        RC_TRY(build_tc_layer(ctx, G.c1, d, w1, bn));
     }
     {
         BnFold bn = fold_bn(b2, g2, be2, m2, v2, 128, 128);
-        RC_TRY(build_tc_layer(ctx, G.c2, "g_conv2_up", 128, 2 * sH, 2 * sW, 256, 4, 4, kPhaseY, kPhaseX, 128, 1, conv_w_phase(w2, 128, 256), bn,
-                              H, W, 128, 2, 0, ACT_RELU, 1.0f, 0));
+        const LayerDef d{"g_conv2_up", KIND_UPCONV3, 128, 2, false, 2 * sH, 2 * sW, 256, 128, 1, H, W, 128, 0, ACT_RELU, 1.0f, 0, false};
+        RC_TRY(build_tc_layer(ctx, G.c2, d, w2, bn));
     }
     {   // conv3 (128 -> C) + Sigmoid: N padded to 16, fp32 NCHW output = the image tensor itself
         BnFold bn;
         bn.scale.assign(16, 0.0f); bn.shift.assign(16, 0.0f);
         for (int i = 0; i < C; ++i) { bn.scale[i] = 1.0f; bn.shift[i] = b3[i]; }
-        RC_TRY(build_tc_layer(ctx, G.c3, "g_conv3_sigmoid", 16, H, W, 128, 1, 9, kTaps9Y, kTaps9X, C, 1, conv_w_direct(w3, C, 128, 16), bn,
-                              H, W, C, 1, 0, ACT_SIGMOID, 1.0f, 1, /*nchw=*/true));
+        const LayerDef d{"g_conv3_sigmoid", KIND_CONV3, 16, 2, true, H, W, 128, C, 1, H, W, C, 0, ACT_SIGMOID, 1.0f, 1, true};
+        RC_TRY(build_tc_layer(ctx, G.c3, d, w3, bn));
     }
     G.loaded = true;
     return GANREV_OK;
@@ -485,24 +539,25 @@ static int load_R_impl(ganrev_ctx* ctx, int slot, int C, int H, int W, int nd, i
         memcpy(&pack[static_cast<size_t>(K) * 64 + 64], bn.shift.data(), 64 * 4);
         RC_TRY(upload(ctx, R.c1pack, pack.data(), pack.size() * 4));
     }
-    auto conv_layer = [&](TcLayer& L, const char* name, const CB& c, int co, int ci, int Hin, int Win, int pool, float post) {
+    auto conv_layer = [&](TcLayer& L, const char* name, const CB& c, int co, int ci, int Hin, int Win, int pool, float post, int MT, bool bres) {
         BnFold bn = fold_bn(c.b, c.g, c.be, c.m, c.v, co, co);
         const int Ho = pool ? Hin / 2 : Hin, Wo = pool ? Win / 2 : Win;
-        return build_tc_layer(ctx, L, name, co, Hin, Win, ci, 1, 9, kTaps9Y, kTaps9X, co, 1, conv_w_direct(c.w, co, ci, co), bn, Ho, Wo, co, 1,
-                              pool, ACT_ELU, post, 0);
+        const LayerDef d{name, KIND_CONV3, co, MT, bres, Hin, Win, ci, co, 1, Ho, Wo, co, pool, ACT_ELU, post, 0, false};
+        return build_tc_layer(ctx, L, d, c.w, bn);
     };
-    RC_TRY(conv_layer(R.c2, "r_conv2", c2, 64, 64, H, W, 0, 1.0f));
-    RC_TRY(conv_layer(R.c3, "r_conv3_pool", c3, 64, 64, H, W, 1, 1.0f));
-    RC_TRY(conv_layer(R.c4, "r_conv4", c4, 128, 64, Hh, Wh, 0, 1.0f));
-    RC_TRY(conv_layer(R.c5, "r_conv5", c5, 128, 128, Hh, Wh, 0, 1.0f));
-    RC_TRY(conv_layer(R.c6, "r_conv6_pool", c6, 128, 128, Hh, Wh, 1, 0.75f));   // SpatialDropout(0.25) in eval: x0.75
+    RC_TRY(conv_layer(R.c2, "r_conv2", c2, 64, 64, H, W, 0, 1.0f, 2, true));
+    RC_TRY(conv_layer(R.c3, "r_conv3_pool", c3, 64, 64, H, W, 1, 1.0f, 2, true));
+    RC_TRY(conv_layer(R.c4, "r_conv4", c4, 128, 64, Hh, Wh, 0, 1.0f, 1, true));
+    RC_TRY(conv_layer(R.c5, "r_conv5", c5, 128, 128, Hh, Wh, 0, 1.0f, 2, false));
+    RC_TRY(conv_layer(R.c6, "r_conv6_pool", c6, 128, 128, Hh, Wh, 1, 0.75f, 2, false));   // SpatialDropout(0.25) in eval: x0.75
     {   // Linear(F -> 512) + BN1d + ELU; input columns re-ordered from View (NCHW flatten, models.lua:446) to NHWC
         std::vector<float> wm(static_cast<size_t>(512) * F);
         for (int o = 0; o < 512; ++o)
             for (int c = 0; c < 128; ++c)
                 for (int s = 0; s < HWq; ++s) wm[static_cast<size_t>(o) * F + s * 128 + c] = l1w[static_cast<size_t>(o) * F + c * HWq + s];
         BnFold bn = fold_bn(l1b, g7, be7, m7, v7, 512, 512);
-        RC_TRY(build_tc_layer(ctx, R.l1, "r_linear1", 64, 1, 1, F, 1, 1, kTap1, kTap1, 512, 8, wm, bn, 1, 1, 512, 1, 0, ACT_ELU, 1.0f, 0));
+        const LayerDef d{"r_linear1", KIND_LINEAR, 64, 1, false, 1, 1, F, 512, 8, 1, 1, 512, 0, ACT_ELU, 1.0f, 0, false};
+        RC_TRY(build_tc_layer(ctx, R.l1, d, wm.data(), bn));
     }
     {   // Linear(512 -> nd) [+ Tanh], fp32 output
         const int NT = nd <= 32 ? 32 : (nd <= 64 ? 64 : (nd <= 128 ? 128 : 256));
@@ -512,8 +567,8 @@ static int load_R_impl(ganrev_ctx* ctx, int slot, int C, int H, int W, int nd, i
         BnFold bn;
         bn.scale.assign(cp, 0.0f); bn.shift.assign(cp, 0.0f);
         for (int i = 0; i < nd; ++i) { bn.scale[i] = 1.0f; bn.shift[i] = l2b[i]; }
-        RC_TRY(build_tc_layer(ctx, R.l2, "r_linear2", NT, 1, 1, 512, 1, 1, kTap1, kTap1, nd, n_tiles, wm, bn, 1, 1, nd, 1, 0,
-                              tanh_out ? ACT_TANH : ACT_NONE, 1.0f, 1));
+        const LayerDef d{"r_linear2", KIND_LINEAR, NT, 1, false, 1, 1, 512, nd, n_tiles, 1, 1, nd, 0, tanh_out ? ACT_TANH : ACT_NONE, 1.0f, 1, false};
+        RC_TRY(build_tc_layer(ctx, R.l2, d, wm.data(), bn));
     }
     R.loaded = true;
     return GANREV_OK;
