@@ -28,14 +28,15 @@
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread
 // each), warps 2..9 = epilogue (two warps per TMEM lane quarter; warp 2 owns the TMEM
-// allocation).  Shape, activation, pooling and output type are template parameters.
+// allocation).  Only ONE lane ever polls an mbarrier: the other epilogue threads park on a
+// hardware named barrier, because spinning try_waits measurably slow the TMA / MMA handshakes.  Shape, activation, pooling and output type are template parameters.
 #pragma once
 #include "common.cuh"
 
 namespace ganrev {
 namespace tc {
 
-constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quarter, interleaved column chunks
+constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quarter; (sub-tile, column chunk) pairs round-robin
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                  // bf16 elements = 128 bytes = one swizzle span
@@ -50,7 +51,8 @@ template <int NT, int MT> struct Cfg {
     static constexpr int kTmemCols = kCols <= 32 ? 32 : (kCols <= 64 ? 64 : (kCols <= 128 ? 128 : (kCols <= 256 ? 256 : 512)));
     static constexpr int kChunk = NT < 32 ? NT : 32;                    // accumulator columns per tcgen05.ld
     static constexpr int kBarBytes = (2 * kMaxStages + 5) * 8 + 24;     // full/empty per stage, tfull/tempty x2, bres, tmem slot (16 B aligned)
-    static constexpr int kTailBytes = kBarBytes + 2 * 2 * NT * 4;       // + double-buffered scale/shift
+    static constexpr int kSsBytes = 2 * 2 * NT * 4;                     // double-buffered scale/shift
+    static constexpr int kXposeBytes = kEpiWarps * 32 * 64;             // per-warp 32 px x 64 B store-transpose buffers
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -390,7 +392,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..9)
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;       // which set of interleaved column chunks
+        const int sub = (warp - 2) >> 2;        // which (sub-tile, chunk) pairs this warp takes
         const int etid = threadIdx.x - 64;      // 0..255
         const int m = q * 32 + lane;            // tile row = pixel
         const int BW = 1 << p.lgBW;
@@ -398,6 +400,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int h_l = (m >> p.lgBW) & ((1 << p.lgBH) - 1);
         const int n_l = m >> (p.lgBW + p.lgBH);
         float* ss_base = reinterpret_cast<float*>(smem + tail_off + C::kBarBytes);
+        uint4* xpose = reinterpret_cast<uint4*>(smem + tail_off + C::kBarBytes + C::kSsBytes) + (warp - 2) * 128;   // 2 KB per warp
+        constexpr int CW = C::kChunk;
+        constexpr int kChunksPerTile = NT / CW;
+        const bool rescale = p.post_scale != 1.0f;
         int it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const ItemCoord c = decode_item(p, item);
@@ -415,68 +421,104 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 named_bar_sync(1, 32 * kEpiWarps);
             }
-            if (etid == 0) GANREV_TR(7, it);
-            mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 104);
-            if (etid == 0) GANREV_TR(4, it);
+            if (etid == 0) {
+                GANREV_TR(7, it);
+                mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 104);   // the only poller
+                GANREV_TR(4, it);
+            }
+            named_bar_sync(2, 32 * kEpiWarps);
             tcgen05_fence_after();
+            int cur_mt = -1;
+            size_t pix_off = 0;
+            bool writer = false;
+            long long offs[4] = {-1, -1, -1, -1};       // store-transpose: offsets of pixels (lane>>2) + 8*i
 #pragma unroll 1
-            for (int mt = 0; mt < MT; ++mt) {
-                const TileCoord t = decode_tile(p, c.mgroup * MT + mt);
-                const int n = t.n0 + n_l, h = t.h0 + h_l, w = t.w0 + w_l;
-                int oh = h, ow = w;
-                bool writer = n < p.n_img;
-                if (POOL) {
-                    oh = h >> 1; ow = w >> 1;
-                    writer = writer && !(h & 1) && !(w & 1);
-                } else if (p.up == 2) {
-                    oh = 2 * h + (c.phase >> 1); ow = 2 * w + (c.phase & 1);
+            for (int pair = sub + ((p.dbg & 4) ? MT * kChunksPerTile : 0); pair < MT * kChunksPerTile; pair += kEpiWarps / 4) {
+                const int mt = pair / kChunksPerTile;
+                const int c0 = (pair - mt * kChunksPerTile) * CW;
+                if (mt != cur_mt) {
+                    cur_mt = mt;
+                    const TileCoord t = decode_tile(p, c.mgroup * MT + mt);
+                    const int n = t.n0 + n_l, h = t.h0 + h_l, w = t.w0 + w_l;
+                    int oh = h, ow = w;
+                    writer = n < p.n_img;
+                    if (POOL) {
+                        oh = h >> 1; ow = w >> 1;
+                        writer = writer && !(h & 1) && !(w & 1);
+                    } else if (p.up == 2) {
+                        oh = 2 * h + (c.phase >> 1); ow = 2 * w + (c.phase & 1);
+                    }
+                    pix_off = static_cast<size_t>(n) * p.out_sN + (static_cast<size_t>(oh) * p.Wout + ow) * p.out_sP;
+                    if (!OUT_FP32) {
+                        const long long my_off = writer ? static_cast<long long>(pix_off) : -1ll;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) offs[i] = __shfl_sync(0xffffffffu, my_off, (lane >> 2) + 8 * i);
+                    }
                 }
-                const size_t pix_off = static_cast<size_t>(n) * p.out_sN + (static_cast<size_t>(oh) * p.Wout + ow) * p.out_sP;
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * MT + mt) * NT);
-                constexpr int CW = C::kChunk;
-#pragma unroll 1
-                for (int c0 = half * CW + ((p.dbg & 4) ? NT : 0); c0 < NT; c0 += 2 * CW) {
-                    uint32_t r[32];
+                uint32_t r[32];
+                if (!(p.dbg & 32)) {
                     if (CW == 32) tmem_ld32(taddr + c0, r); else tmem_ld16(taddr + c0, r);
                     tmem_ld_wait();
-                    float v[32];
+                } else {
 #pragma unroll
-                    for (int j = 0; j < CW; j += 4) {
-                        const float4 sc = *reinterpret_cast<const float4*>(ss + c0 + j);
-                        const float4 sh = *reinterpret_cast<const float4*>(ss + NT + c0 + j);
-                        v[j + 0] = fmaf(__uint_as_float(r[j + 0]), sc.x, sh.x);
-                        v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y);
-                        v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z);
-                        v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
+                    for (int j = 0; j < 32; ++j) r[j] = 0x3f800000u + j + c0;
+                }
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < CW; j += 4) {
+                    const float4 sc = *reinterpret_cast<const float4*>(ss + c0 + j);
+                    const float4 sh = *reinterpret_cast<const float4*>(ss + NT + c0 + j);
+                    v[j + 0] = fmaf(__uint_as_float(r[j + 0]), sc.x, sh.x);
+                    v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y);
+                    v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z);
+                    v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
+                }
+                if (POOL) {
+                    // 2x2 max: w-neighbour is lane^1, h-neighbour is lane^BW (BW <= 16)
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) {
+                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], BW));
                     }
-                    if (POOL) {
-                        // 2x2 max: w-neighbour is lane^1, h-neighbour is lane^BW (BW <= 16)
+                }
 #pragma unroll
-                        for (int j = 0; j < CW; ++j) {
-                            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-                            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], BW));
-                        }
-                    }
+                for (int j = 0; j < CW; ++j) v[j] = act_fn<ACT>(v[j], p.act);
+                if (rescale) {
 #pragma unroll
-                    for (int j = 0; j < CW; ++j) v[j] = act_fn<ACT>(v[j], p.act) * p.post_scale;
+                    for (int j = 0; j < CW; ++j) v[j] *= p.post_scale;
+                }
+                if (OUT_FP32 && !(p.dbg & 16)) {
                     if (writer) {
-                        if (OUT_FP32) {
-                            float* o = reinterpret_cast<float*>(p.out) + pix_off + static_cast<size_t>(cbase + c0) * p.out_sC;
+                        float* o = reinterpret_cast<float*>(p.out) + pix_off + static_cast<size_t>(cbase + c0) * p.out_sC;
 #pragma unroll
-                            for (int j = 0; j < CW; ++j)
-                                if (cbase + c0 + j < p.cout_real) o[static_cast<size_t>(j) * p.out_sC] = v[j];
-                        } else {
-                            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + pix_off + cbase + c0);
+                        for (int j = 0; j < CW; ++j)
+                            if (cbase + c0 + j < p.cout_real) o[static_cast<size_t>(j) * p.out_sC] = v[j];
+                    }
+                }
+                if (!OUT_FP32 && !(p.dbg & 16)) {
+                    // bf16 NHWC: each lane owns one pixel's 64 B of this chunk.  Transpose through an
+                    // XOR-swizzled smem buffer so 4 lanes store one pixel's contiguous 64 B (8 pixels
+                    // per instruction) instead of 32 lanes hitting 32 different lines.
+                    static_assert(OUT_FP32 || CW == 32, "bf16 outputs use 32-column chunks");
+                    __syncwarp();
 #pragma unroll
-                            for (int j = 0; j < CW / 8; ++j) {
-                                uint4 pk;
-                                pk.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                                pk.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                                pk.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                                pk.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                                o[j] = pk;
-                            }
-                        }
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 pk;
+                        pk.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                        pk.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                        pk.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                        pk.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                        xpose[lane * 4 + (j ^ ((lane >> 1) & 3))] = pk;
+                    }
+                    __syncwarp();
+                    const int jj = lane & 3;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int px = (lane >> 2) + 8 * i;
+                        const uint4 val = xpose[px * 4 + (jj ^ ((px >> 1) & 3))];
+                        if (offs[i] >= 0)
+                            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + offs[i] + cbase + c0 + jj * 8) = val;
                     }
                 }
             }

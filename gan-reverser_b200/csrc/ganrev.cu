@@ -329,7 +329,7 @@ static int build_tc_layer(ganrev_ctx* ctx, TcLayer& L, const LayerDef& d, const 
     g.a_unit_bytes = (BH + g.ndy - 1) * BW * BN * 128;
     g.b_kb_bytes = d.NT * 128;
     g.dy_stride_bytes = BW * BN * 128;
-    const int tail = (2 * tc::kMaxStages + 5) * 8 + 24 + 2 * 2 * d.NT * 4;
+    const int tail = (2 * tc::kMaxStages + 5) * 8 + 24 + 2 * 2 * d.NT * 4 + tc::kEpiWarps * 32 * 64;   // barriers, scale/shift, store-transpose buffers
     const int budget = tc::kSmemBudget - 1024 - tail;
     const size_t wbytes = static_cast<size_t>(g.units) * g.ndy * g.b_kb_bytes;
     L.bres = d.want_bres && g.nphase == 1 && g.n_tiles == 1 && wbytes + 2 * static_cast<size_t>(L.MT) * g.a_unit_bytes <= static_cast<size_t>(budget);
