@@ -83,13 +83,13 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
-// nn.ELU(alpha=1) for bf16 outputs: ex2.approx-based exp for v <= -0.03, a cubic Taylor expm1
-// above it (exp(v)-1 would cancel); abs error < 1e-7, far below the bf16 output rounding.
+// nn.ELU(alpha=1) for bf16 outputs: exp via one ex2.approx (abs error ~2e-7, below the bf16
+// rounding of anything that matters next to O(1e-3)+ activations); 4 instructions per element.
 __device__ __forceinline__ float elu_fast(float v) {
-    const float e = __expf(v) - 1.0f;
-    const float t = v * fmaf(v, fmaf(v, 0.16666667f, 0.5f), 1.0f);
-    const float n = v > -0.03f ? t : e;
-    return v > 0.0f ? v : n;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));
+    e -= 1.0f;
+    return v > 0.0f ? v : e;
 }
 
 }  // namespace ganrev

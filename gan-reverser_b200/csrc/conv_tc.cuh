@@ -488,7 +488,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < CW; ++j) v[j] *= p.post_scale;
                 }
-                if (OUT_FP32 && !(p.dbg & 16)) {
+                if (OUT_FP32 && NT == 16 && p.out_sC == 1 && !(p.dbg & 16)) {
+                    // fp32 records of 16 floats (64 B per pixel, G conv3 pass 1): same transposed store
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        xpose[lane * 4 + (j ^ ((lane >> 1) & 3))] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                                                             __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+                    __syncwarp();
+                    long long o4[4];
+                    const long long my_off = writer ? static_cast<long long>(pix_off) : -1ll;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) o4[i] = __shfl_sync(0xffffffffu, my_off, (lane >> 2) + 8 * i);
+                    const int jj = lane & 3;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int px = (lane >> 2) + 8 * i;
+                        const uint4 val = xpose[px * 4 + (jj ^ ((px >> 1) & 3))];
+                        if (o4[i] >= 0) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + o4[i] + jj * 4) = val;
+                    }
+                } else if (OUT_FP32 && !(p.dbg & 16)) {
                     if (writer) {
                         float* o = reinterpret_cast<float*>(p.out) + pix_off + static_cast<size_t>(cbase + c0) * p.out_sC;
 #pragma unroll

@@ -33,7 +33,8 @@ struct TcLayer {
 struct GModel {
     bool loaded = false;
     int C = 0, H = 0, W = 0, nd = 0, kpad = 0, F = 0;
-    TcLayer lin, c1, c2, c3;
+    TcLayer lin, c1, c2, c3;   // c3 = pass 1 of the last conv (per-pixel tap products)
+    DevBuf b3;
 };
 struct RModel {
     bool loaded = false;
@@ -60,7 +61,7 @@ struct ganrev_ctx {
     int device = 0, num_sms = 0;
     cudaStream_t stream = nullptr;
     std::string err;
-    int64_t chunk = 2048;
+    int64_t chunk = 4096;
     int conv_impl = 0;
     int dbg = 0;
     DevBuf trace;
@@ -388,7 +389,8 @@ static int dispatch_tc(ganrev_ctx* ctx, const TcLayer& L, const CUtensorMap& tmA
     TC_CASE(256, 2, 2, false, ACT_RELU, false, false)      // ... with halo reuse
     TC_CASE(128, 2, 1, false, ACT_RELU, false, false)      // Up+Conv 256->128
     TC_CASE(128, 2, 2, false, ACT_RELU, false, false)
-    TC_CASE(16, 2, 3, true, ACT_SIGMOID, false, true)      // Conv 128->C + Sigmoid, fp32 NCHW images
+    TC_CASE(16, 1, 1, false, ACT_NONE, false, true)        // last conv pass 1: per-pixel tap products, C = 1
+    TC_CASE(32, 1, 1, false, ACT_NONE, false, true)        // ... C = 3
     // R
     TC_CASE(64, 2, 3, true, ACT_ELU, false, false)         // Conv 64->64
     TC_CASE(64, 2, 3, true, ACT_ELU, true, false)          // Conv 64->64 + MaxPool
@@ -492,12 +494,18 @@ static int load_G_impl(ganrev_ctx* ctx, int C, int H, int W, int nd, const float
         const LayerDef d{"g_conv2_up", KIND_UPCONV3, 128, 2, false, 2 * sH, 2 * sW, 256, 128, 1, H, W, 128, 0, ACT_RELU, 1.0f, 0, false};
         RC_TRY(build_tc_layer(ctx, G.c2, d, w2, bn));
     }
-    {   // conv3 (128 -> C) + Sigmoid: N padded to 16, fp32 NCHW output = the image tensor itself
+    {   // conv3 (128 -> C) + Sigmoid in two passes: a 1x1 GEMM giving every input pixel's 9*C tap
+        // products (N = 16 or 32 fp32 per pixel), then g_conv3_gather_kernel sums the 9 neighbours.
+        const int NT3 = C == 1 ? 16 : 32;
+        std::vector<float> wm(static_cast<size_t>(NT3) * 128, 0.0f);
+        for (int t = 0; t < 9; ++t)
+            for (int co = 0; co < C; ++co)
+                for (int ci = 0; ci < 128; ++ci) wm[static_cast<size_t>(t * C + co) * 128 + ci] = w3[(static_cast<size_t>(co) * 128 + ci) * 9 + t];
         BnFold bn;
-        bn.scale.assign(16, 0.0f); bn.shift.assign(16, 0.0f);
-        for (int i = 0; i < C; ++i) { bn.scale[i] = 1.0f; bn.shift[i] = b3[i]; }
-        const LayerDef d{"g_conv3_sigmoid", KIND_CONV3, 16, 2, true, H, W, 128, C, 1, H, W, C, 0, ACT_SIGMOID, 1.0f, 1, true};
-        RC_TRY(build_tc_layer(ctx, G.c3, d, w3, bn));
+        bn.scale.assign(NT3, 1.0f); bn.shift.assign(NT3, 0.0f);
+        const LayerDef d{"g_conv3_taps", KIND_LINEAR, NT3, 1, false, 1, 1, 128, 9 * C, 1, 1, 1, NT3, 0, ACT_NONE, 1.0f, 1, false};
+        RC_TRY(build_tc_layer(ctx, G.c3, d, wm.data(), bn));
+        RC_TRY(upload(ctx, G.b3, b3, sizeof(float) * C));
     }
     G.loaded = true;
     return GANREV_OK;
@@ -602,7 +610,17 @@ static int forward_G_dev(ganrev_ctx* ctx, const float* d_noise, int64_t N, float
         RC_TRY(run_layer(ctx, G.lin, ctx->noise_bf16.p, ctx->arena[0].p, n, CH));   // [n][sH][sW][512]
         RC_TRY(run_layer(ctx, G.c1, ctx->arena[0].p, ctx->arena[1].p, n, CH));      // [n][2sH][2sW][256]
         RC_TRY(run_layer(ctx, G.c2, ctx->arena[1].p, ctx->arena[0].p, n, CH));      // [n][H][W][128]
-        RC_TRY(run_layer(ctx, G.c3, ctx->arena[0].p, d_images + n0 * G.C * G.H * G.W, n, CH));   // fp32 [n][C][H][W]
+        {   // last conv: per-pixel tap products (tensor cores), then the 3x3 gather + bias + sigmoid
+            const long long npix = static_cast<long long>(n) * G.H * G.W;
+            const int NT3 = G.c3.NT;
+            RC_TRY(run_layer(ctx, G.c3, ctx->arena[0].p, ctx->arena[1].p, static_cast<int>(npix), CH * G.H * G.W));   // fp32 [pixels][NT3]
+            ProfScope ps(ctx, "g_conv3_gather", 9.0 * npix * G.C, npix * (4.0 * NT3 + 4.0 * G.C));
+            const unsigned blocks = static_cast<unsigned>((npix + 255) / 256);
+            float* o = d_images + n0 * G.C * G.H * G.W;
+            if (G.C == 1) g_conv3_gather_kernel<1><<<blocks, 256, 0, ctx->stream>>>(static_cast<const float*>(ctx->arena[1].p), NT3, static_cast<const float*>(G.b3.p), o, G.H, G.W, n);
+            else          g_conv3_gather_kernel<3><<<blocks, 256, 0, ctx->stream>>>(static_cast<const float*>(ctx->arena[1].p), NT3, static_cast<const float*>(G.b3.p), o, G.H, G.W, n);
+            CU_TRY(cudaGetLastError());
+        }
     }
     return GANREV_OK;
 }
@@ -688,6 +706,7 @@ void ganrev_destroy(ganrev_ctx* ctx) {
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
     for (TcLayer* L : {&ctx->G.lin, &ctx->G.c1, &ctx->G.c2, &ctx->G.c3}) release_layer(*L);
+    release(ctx->G.b3);
     for (int s = 0; s < 2; ++s) {
         RModel& R = ctx->R[s];
         release(R.c1pack);

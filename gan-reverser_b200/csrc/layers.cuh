@@ -93,6 +93,42 @@ r_conv1_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mask, 
     }
 }
 
+// ------------------------------------------------------------------ G conv3, pass 2
+// Pass 1 (tensor cores) left P[n][y][x][tap*C + co] = w[co][:, tap] . act[n][y][x][:] for every
+// INPUT pixel; the 3x3 conv output is the sum of the 9 neighbours' matching tap products
+// (out-of-image neighbours contribute nothing = zero padding), + bias, then Sigmoid
+// (models.lua:132-133).  fp32 NCHW out.  One thread per output pixel and channel.
+template <int COUT>
+__global__ void __launch_bounds__(256)
+g_conv3_gather_kernel(const float* __restrict__ P, int pstride, const float* __restrict__ bias, float* __restrict__ out,
+                      int H, int W, long long n_img) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = n_img * H * W;
+    if (idx >= total) return;
+    const int x = static_cast<int>(idx % W);
+    const int y = static_cast<int>((idx / W) % H);
+    const long long n = idx / (static_cast<long long>(W) * H);
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = __ldg(bias + co);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int xx = x + kx - 1;
+            if (xx < 0 || xx >= W) continue;
+            const float* rec = P + ((n * H + yy) * W + xx) * pstride + (ky * 3 + kx) * COUT;
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) acc[co] += __ldg(rec + co);
+        }
+    }
+#pragma unroll
+    for (int co = 0; co < COUT; ++co)
+        out[((n * COUT + co) * H + y) * static_cast<long long>(W) + x] = 1.0f / (1.0f + __expf(-acc[co]));
+}
+
 // ------------------------------------------------------------------ torch.dist, batched
 // Canonical order (mirrored by oracle orc_l2): element i belongs to lane (i/4)%32, each lane
 // adds its fp32 squares in ascending i into a double, then an xor-butterfly over the lanes.
