@@ -194,26 +194,13 @@ def main():
 
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
 
-    def queries_from_attrs_resident():
-        """queries = recovered rows of rank 0, fetched from the resident ATTRS0 buffer (Q small rows)."""
-        if rank == 0:
-            lo, hi = int(qrows.min()), int(qrows.max()) + 1
-            span = ctx.buffer_get(pkg._lib.BUF_ATTRS0, lo, hi - lo)
-            q = np.ascontiguousarray(span[qrows - lo])
-        else:
-            q = None
-        if world > 1:
-            box = [q]
-            td.broadcast_object_list(box, src=0)
-            q = box[0]
-        return q
+    qrows64 = qrows.astype(np.int64)     # needles = recovered rows of rank 0's shard (global ids: rank 0 owns [0, N))
 
     def step_resident():
         ctx.forward_G(None, N=N, want_images=False)
         ctx.forward_R(0, None, N=N, want_attrs=False)
         ctx.db_set(None, N=N, d=ND)
-        q = queries_from_attrs_resident()
-        return ctx.search_cosine(q, TOPK)
+        return ctx.search_rows(qrows64, TOPK)                 # queries gathered on the device from the database rows
 
     def step_e2e():
         ctx.forward_G(noise, want_images=False)              # H2D noise

@@ -40,6 +40,7 @@ _SIGS = {
     "ganrev_db_set": (_i, [_vp, _vp, _i64, _i]),
     "ganrev_cosine": (_i, [_vp, _vp, _vp, _i, C.POINTER(C.c_float)]),
     "ganrev_search_cosine": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "ganrev_search_rows": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "ganrev_kmeans": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "ganrev_assign_cosine_min": (_i, [_vp, _vp, _i, _vp, _vp]),
     "ganrev_cluster_members": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
@@ -225,6 +226,14 @@ class Context:
         ids = np.empty((Q, k), np.int64)
         scores = np.empty((Q, k), np.float32)
         self._chk(lib().ganrev_search_cosine(self._h, _ptr(queries), Q, k, _ptr(ids), _ptr(scores)))
+        return ids, scores
+
+    def search_rows(self, rows, k):
+        rows = _arr(rows, np.int64)
+        Q = rows.shape[0]
+        ids = np.empty((Q, k), np.int64)
+        scores = np.empty((Q, k), np.float32)
+        self._chk(lib().ganrev_search_rows(self._h, _ptr(rows), Q, k, _ptr(ids), _ptr(scores)))
         return ids, scores
 
     def kmeans(self, k, niter, init, want_labels=True):

@@ -58,10 +58,10 @@ def createSimilaritySearchImages(nbSimilarNeedles, nbShowMax, images, attributes
     needles = np.array([i * 100 - 1 for i in range(1, nbSimilarNeedles + 1)])
     out = {}
     ctx.db_set(attributes)                                       # similarityMeasureAttributes :303-305
-    out["attributes"] = ctx.search_cosine(attributes[needles], n)
+    out["attributes"] = ctx.search_rows(needles, n)            # the needles are rows of the searched tensor
     flat = images.reshape(N, -1)                                 # similarityMeasurePixelwise :308-314
     ctx.db_set(flat)
-    out["pixelwise"] = ctx.search_cosine(flat[needles], n)
+    out["pixelwise"] = ctx.search_rows(needles, n)
     return out
 
 

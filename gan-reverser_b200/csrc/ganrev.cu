@@ -1021,16 +1021,28 @@ static int launch_search(ganrev_ctx* ctx, const scan::ScanParams& p, int splits)
 }
 
 extern "C" {
-int ganrev_search_cosine(ganrev_ctx* ctx, const float* queries, int Q, int k, int64_t* ids, float* scores) {
-    if (!ctx || !queries || Q < 0 || k < 1 || k > 128 || !ids || !scores) return ctx ? fail(ctx, GANREV_EINVAL, "bad search arguments (k must be 1..128)") : GANREV_EINVAL;
-    if (!ctx->db.p) return fail(ctx, GANREV_ESTATE, "database not set");
-    if (Q == 0) return GANREV_OK;
-    CU_TRY(cudaSetDevice(ctx->device));
+}  // extern "C"
+template <int E>
+static int launch_search_wide(ganrev_ctx* ctx, const scan::ScanParams& p, int splits) {
+    constexpr int QT = 64, K2 = 32 * E;
+    const size_t smem = sizeof(float) * (static_cast<size_t>(p.d) * scan::XS + static_cast<size_t>(p.d) * QT) +
+                        sizeof(unsigned long long) * (QT * K2 + QT * scan::CAP + QT) + sizeof(int) * QT;
+    static size_t attr_max = 0;
+    if (smem > attr_max) {
+        CU_TRY(cudaFuncSetAttribute(scan::search_kernel_wide<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr_max = smem;
+    }
+    dim3 grid(splits, (p.nq + QT - 1) / QT);
+    scan::search_kernel_wide<E><<<grid, scan::kThreads, smem, ctx->stream>>>(p);
+    CU_TRY(cudaGetLastError());
+    return GANREV_OK;
+}
+
+// queries already on the device in ctx->q (Q x d)
+static int search_dev(ganrev_ctx* ctx, int Q, int k, int64_t* ids, float* scores) {
     const int d = ctx->db_d;
     const int64_t N = ctx->db_n;
-    RC_TRY(ensure(ctx, ctx->q, sizeof(float) * static_cast<size_t>(Q) * d));
     RC_TRY(ensure(ctx, ctx->rq, sizeof(float) * Q));
-    CU_TRY(cudaMemcpyAsync(ctx->q.p, queries, sizeof(float) * static_cast<size_t>(Q) * d, cudaMemcpyHostToDevice, ctx->stream));
     RC_TRY(vec_prep(ctx, static_cast<const float*>(ctx->q.p), Q, d, static_cast<float*>(ctx->rq.p), nullptr, nullptr));
     const int TQ = Q <= 16 ? 1 : 4;
     const int QT = 16 * TQ;
@@ -1049,8 +1061,10 @@ int ganrev_search_cosine(ganrev_ctx* ctx, const float* queries, int Q, int k, in
     p.partial = static_cast<unsigned long long*>(ctx->partial.p); p.rows_per_split = rows_per_split;
     {
         ProfScope ps(ctx, "search_scan", 2.0 * N * Q * d, 4.0 * N * d + 4.0 * Q * d + 8.0 * splits * Q * k);
-        if (TQ == 1) { if (k <= 32) RC_TRY((launch_search<1, 1>(ctx, p, splits))); else RC_TRY((launch_search<1, 4>(ctx, p, splits))); }
-        else         { if (k <= 32) RC_TRY((launch_search<4, 1>(ctx, p, splits))); else RC_TRY((launch_search<4, 4>(ctx, p, splits))); }
+        const bool wide = TQ == 4 && d <= 128;
+        if (TQ == 1)   { if (k <= 32) RC_TRY((launch_search<1, 1>(ctx, p, splits))); else RC_TRY((launch_search<1, 4>(ctx, p, splits))); }
+        else if (wide) { if (k <= 32) RC_TRY((launch_search_wide<1>(ctx, p, splits))); else RC_TRY((launch_search_wide<4>(ctx, p, splits))); }
+        else           { if (k <= 32) RC_TRY((launch_search<4, 1>(ctx, p, splits))); else RC_TRY((launch_search<4, 4>(ctx, p, splits))); }
     }
     const unsigned mblocks = static_cast<unsigned>((static_cast<long long>(Q) * 32 + scan::kThreads - 1) / scan::kThreads);
     const bool multi = ctx->world > 1;
@@ -1085,6 +1099,39 @@ int ganrev_search_cosine(ganrev_ctx* ctx, const float* queries, int Q, int k, in
     return finish(ctx);
 }
 
+extern "C" {
+int ganrev_search_cosine(ganrev_ctx* ctx, const float* queries, int Q, int k, int64_t* ids, float* scores) {
+    if (!ctx || !queries || Q < 0 || k < 1 || k > 128 || !ids || !scores) return ctx ? fail(ctx, GANREV_EINVAL, "bad search arguments (k must be 1..128)") : GANREV_EINVAL;
+    if (!ctx->db.p) return fail(ctx, GANREV_ESTATE, "database not set");
+    if (Q == 0) return GANREV_OK;
+    CU_TRY(cudaSetDevice(ctx->device));
+    RC_TRY(ensure(ctx, ctx->q, sizeof(float) * static_cast<size_t>(Q) * ctx->db_d));
+    CU_TRY(cudaMemcpyAsync(ctx->q.p, queries, sizeof(float) * static_cast<size_t>(Q) * ctx->db_d, cudaMemcpyHostToDevice, ctx->stream));
+    return search_dev(ctx, Q, k, ids, scores);
+}
+
+int ganrev_search_rows(ganrev_ctx* ctx, const int64_t* rows, int Q, int k, int64_t* ids, float* scores) {
+    if (!ctx || !rows || Q < 0 || k < 1 || k > 128 || !ids || !scores) return ctx ? fail(ctx, GANREV_EINVAL, "bad search_rows arguments (k must be 1..128)") : GANREV_EINVAL;
+    if (!ctx->db.p) return fail(ctx, GANREV_ESTATE, "database not set");
+    if (Q == 0) return GANREV_OK;
+    for (int i = 0; i < Q; ++i)
+        if (rows[i] < 0 || rows[i] >= ctx->db_total) return fail(ctx, GANREV_EINVAL, "row id %lld outside the database", (long long)rows[i]);
+    CU_TRY(cudaSetDevice(ctx->device));
+    const int d = ctx->db_d;
+    RC_TRY(ensure(ctx, ctx->q, sizeof(float) * static_cast<size_t>(Q) * d));
+    RC_TRY(ensure(ctx, ctx->stage_b, sizeof(long long) * static_cast<size_t>(Q)));
+    CU_TRY(cudaMemcpyAsync(ctx->stage_b.p, rows, sizeof(long long) * Q, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        ProfScope ps(ctx, "gather_rows", 0.0, 8.0 * Q * d);
+        const long long tot = static_cast<long long>(Q) * d;
+        scan::gather_rows_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ctx->stream>>>(
+            static_cast<const float*>(ctx->db.p), ctx->db_n, d, ctx->db_offset, static_cast<const long long*>(ctx->stage_b.p), Q, static_cast<float*>(ctx->q.p));
+        CU_TRY(cudaGetLastError());
+    }
+    if (ctx->world > 1)   // exactly one rank holds each row; the others contribute +0.0f (all-zero bits)
+        NCCL_TRY(ctx->nccl.AllReduce(ctx->q.p, ctx->q.p, static_cast<size_t>(Q) * d, ncclUint32, ncclMax, ctx->comm, ctx->stream));
+    return search_dev(ctx, Q, k, ids, scores);
+}
 }  // extern "C"
 template <int TQ, int MODE>
 static int launch_assign(ganrev_ctx* ctx, const scan::ScanParams& p) {

@@ -36,6 +36,7 @@ int ganrev_buffer_get(ganrev_ctx* ctx, int which, void* host, int64_t row0, int6
 int ganrev_db_set(ganrev_ctx* ctx, const float* vecs, int64_t N, int d);
 int ganrev_cosine(ganrev_ctx* ctx, const float* a, const float* b, int d, float* out);
 int ganrev_search_cosine(ganrev_ctx* ctx, const float* queries, int Q, int k, int64_t* ids, float* scores);
+int ganrev_search_rows(ganrev_ctx* ctx, const int64_t* rows, int Q, int k, int64_t* ids, float* scores);
 int ganrev_kmeans(ganrev_ctx* ctx, int k, int niter, const float* init_centroids, float* centroids, float* total_counts, int32_t* last_labels);
 int ganrev_assign_cosine_min(ganrev_ctx* ctx, const float* centroids, int k, int32_t* cluster, float* cosv);
 int ganrev_cluster_members(ganrev_ctx* ctx, int k, int m, const float* images, int px, int64_t* member_ids, int32_t* member_counts, float* mean_images);
@@ -186,6 +187,17 @@ function M.search(ctx, db, queries, k)
     local Q = queries:size(1)
     local ids, scores = torch.LongTensor(Q, k), torch.FloatTensor(Q, k)
     check(ctx, lib.ganrev_search_cosine(ctx, queries:data(), Q, k, ids:data(), scores:data()))
+    return ids:add(1), scores
+end
+
+-- the same with the needles given as (1-based) rows of db itself, apply_r.lua:268
+function M.search_rows(ctx, db, needle_rows, k)
+    db = db:float():contiguous()
+    check(ctx, lib.ganrev_db_set(ctx, db:data(), db:size(1), db:size(2)))
+    local Q = needle_rows:size(1)
+    local rows0 = needle_rows:long():add(-1):contiguous()
+    local ids, scores = torch.LongTensor(Q, k), torch.FloatTensor(Q, k)
+    check(ctx, lib.ganrev_search_rows(ctx, rows0:data(), Q, k, ids:data(), scores:data()))
     return ids:add(1), scores
 end
 

@@ -120,6 +120,11 @@ int ganrev_cosine(ganrev_ctx* ctx, const float* a, const float* b, int d, float*
  * (-1 past the end of the database), scores [Q x k].  k <= 128. */
 int ganrev_search_cosine(ganrev_ctx* ctx, const float* queries, int Q, int k,
                          int64_t* ids, float* scores);
+/* The same search with the queries given as database rows ("search by example"): apply_r.lua's
+ * needles are rows i*100 of the searched tensor itself (apply_r.lua:268-272).  rows [Q] are global
+ * 0-based row ids; the query vectors never leave the device (across ranks they are assembled with
+ * one integer max-allreduce). */
+int ganrev_search_rows(ganrev_ctx* ctx, const int64_t* rows, int Q, int k, int64_t* ids, float* scores);
 /* unsup.kmeans(x, k, niter)   apply_r.lua:198.  init_centroids [k x d] is explicit
  * (unsup draws N(0,1) rows and normalises them; the shim does that and passes them in).
  * total_counts [k] = counts summed over iterations; last_labels [N local rows] or NULL. */

@@ -45,6 +45,51 @@ def test_search_exact(orc, ctx, case):
     assert_bitexact(sc, want_sc, "scores")
 
 
+def test_search_rows_equals_search_by_vector(orc, ctx):
+    """apply_r.lua:268: needles are rows i*100 of the searched tensor."""
+    db = _db(10000, 32, 5)
+    rows = np.array([99, 199, 299, 399, 499], np.int64)
+    ctx.db_set(db)
+    ids_r, sc_r = ctx.search_rows(rows, 100)
+    ids_v, sc_v = ctx.search_cosine(db[rows], 100)
+    np.testing.assert_array_equal(ids_r, ids_v)
+    assert_bitexact(sc_r, sc_v)
+    want_ids, want_sc = orc.search_cosine(db, db[rows], 100)
+    np.testing.assert_array_equal(ids_r, want_ids)
+    assert_bitexact(sc_r, want_sc)
+    assert (ids_r[:, 0] == rows).all()
+    big = np.arange(0, 7000, 100, dtype=np.int64)            # 70 needles: the wide kernel
+    ids_b, sc_b = ctx.search_rows(big, 20)
+    want_ids, want_sc = orc.search_cosine(db, db[big], 20)
+    np.testing.assert_array_equal(ids_b, want_ids)
+    assert_bitexact(sc_b, want_sc)
+
+
+def test_search_full_size_properties(ctx):
+    """BASELINE config 4 size (1M x 100, 4096 queries, top-20): too big for the CPU oracle, so check
+    size-independent properties: every needle finds itself first with score ~1, scores are sorted,
+    ids are unique and in range, and splitting the queries differently gives the identical answer."""
+    rng = np.random.default_rng(31)
+    N, d, Q, k = 1_000_000, 100, 4096, 20
+    db = rng.standard_normal(size=(N, d), dtype=np.float32)
+    rows = (np.arange(1, Q + 1, dtype=np.int64) * 244)
+    ctx.db_set(db)
+    ids, sc = ctx.search_rows(rows, k)
+    assert (ids[:, 0] == rows).all() and np.abs(sc[:, 0] - 1.0).max() < 1e-5
+    assert (np.diff(sc, axis=1) <= 0).all()
+    assert ids.min() >= 0 and ids.max() < N
+    assert all(len(set(r.tolist())) == k for r in ids[::97])
+    ids2, sc2 = ctx.search_cosine(db[rows[:70]], k)           # different query tiling / split count
+    np.testing.assert_array_equal(ids2, ids[:70])
+    assert_bitexact(sc2, sc[:70])
+    # spot-check 3 needles against a float64 brute force
+    for qi in (0, 2047, 4095):
+        ref = (db @ db[rows[qi]].astype(np.float64)) / (np.linalg.norm(db, axis=1).astype(np.float64) * np.linalg.norm(db[rows[qi]].astype(np.float64)))
+        top = np.argsort(-ref)[:k]
+        assert len(set(top[:15].tolist()) - set(ids[qi].tolist())) == 0
+        assert np.abs(sc[qi] - ref[ids[qi]]).max() < 1e-5
+
+
 def test_search_ties_nan_zero(orc, ctx):
     """Duplicate rows (exact score ties -> lowest id first), zero rows, NaN rows (sorted last)."""
     rng = np.random.default_rng(7)
