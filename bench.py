@@ -118,6 +118,44 @@ def cpu_port(n_img, n_db, n_q, threads=None):
     return n_img / t_gr, n_q / t_s, cores, sample, t_gr, t_s
 
 
+def hbm_kernels(ctx, pkg, peak_gbs):
+    """Bandwidth rooflines of the HBM-bound kernels of the path (north_star: L2, kmeans, small-Q search), each on
+    inputs larger than L2, timed with CUDA events on the library stream (ganrev_profile_*)."""
+    out = {}
+    rng = np.random.default_rng(11)
+
+    def timed(name, fn, alg_bytes, reps):
+        fn()                                                       # warm-up
+        ctx.profile_reset(); ctx.profile_enable(True)
+        for _ in range(reps):
+            fn()
+        ctx.profile_enable(False)
+        e = ctx.profile()[name]
+        ms = e["ms"] / max(e["launches"], 1)
+        gbs = alg_bytes / (ms * 1e-3) * 1e-9
+        return {"bound": "hbm", "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs, "ms_per_launch": ms}
+
+    # torch.dist over 200k pairs of 32x32 faces (apply_r.lua:366): 8*C*H*W algorithmic bytes per pair
+    n = 200_000
+    a = rng.random((n, 1024), dtype=np.float32)
+    b = a[::-1].copy()
+    out["l2_pairs"] = timed("l2_pairs", lambda: ctx.l2(a, b), 8.0 * n * 1024, 2)
+    out["l2_pairs"]["workload"] = f"{n} pairs of 32x32 fp32 faces, 8*C*H*W algorithmic bytes per pair"
+    # kmeans k=20 over 4M x 100 rows (recovered-vector shape): 4*N*d algorithmic bytes per iteration
+    N, d, k = 4_000_000, ND, 20
+    x = rng.standard_normal(size=(N, d), dtype=np.float32)
+    init = rng.standard_normal(size=(k, d), dtype=np.float32)
+    init /= np.linalg.norm(init, axis=1, keepdims=True)
+    ctx.db_set(x)
+    out["kmeans_assign_k20"] = timed("kmeans_assign", lambda: ctx.kmeans(k, 2, init, want_labels=False), 4.0 * N * d, 2)
+    out["kmeans_assign_k20"]["workload"] = f"k=20 over {N} x {d} fp32 rows, 4*N*d algorithmic bytes per iteration"
+    # cosine top-20 for 4 needles (BASELINE config 1 shape) over the same rows: 4*N*d algorithmic bytes
+    rows = np.array([99, 199, 299, 399], np.int64)
+    out["search_q4"] = timed("search_scan", lambda: ctx.search_rows(rows, TOPK), 4.0 * N * d, 3)
+    out["search_q4"]["workload"] = f"4 needles, top-{TOPK}, over {N} x {d} fp32 rows, 4*N*d algorithmic bytes"
+    return out
+
+
 def run_reference(args, world, rank):
     """--impl reference: the reference's CPU implementation of the path on host cores.  Torch7
     cannot run here (no lua/luajit/th, un-vendored rocks), so this is the oracle port."""
@@ -155,6 +193,7 @@ def main():
     ap.add_argument("--ref-images", type=int, default=384, help="CPU-arm sample size per step")
     ap.add_argument("--cpu-images", type=int, default=512, help="cpu_baseline sample size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hbm-kernels", action="store_true", help="skip the L2 / kmeans / small-Q search bandwidth rooflines")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -271,8 +310,15 @@ def main():
         exec_tf = e["flops"] / max(e["ms"], 1e-9) * 1e-9
         alg = FLOP_DIRECT.get(dom)
         alg_tf = (alg * imgs_launch) / (ms_launch * 1e-3) * 1e-12 if alg else exec_tf
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01", "ncu_traffic.json")))
+            if dom in tj:
+                traffic = tj[dom]["dram_bytes_per_image"] * imgs_launch     # bytes per launch, from the committed ncu capture
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "kernel": dom, "achieved": alg_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": alg_tf / peak_tf, "traffic": None,
+                    "frac": alg_tf / peak_tf, "traffic": traffic,
                     "achieved_executed": exec_tf, "frac_executed": exec_tf / peak_tf,
                     "note": "achieved = direct-form (algorithmic) FLOPs of the layer / CUDA-event time per launch; "
                             "executed = FLOPs actually issued (upsample folded into 4 phase convs = 2.25x fewer); peak = " + peak_src,
@@ -298,6 +344,8 @@ def main():
         "roofline": roofline,
         "kernels": kernels,
     }
+    if world == 1 and not args.no_hbm_kernels:
+        line["hbm_kernels"] = hbm_kernels(ctx, pkg, peak_gbs)
     if world == 1 and not args.no_cpu_baseline:
         ips, qps, cores, sample, _, _ = cpu_port(args.cpu_images, 20000, 64)
         line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample,

@@ -432,10 +432,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             size_t pix_off = 0;
             bool writer = false;
             long long offs[4] = {-1, -1, -1, -1};       // store-transpose: offsets of pixels (lane>>2) + 8*i
+            constexpr int kPairs = MT * kChunksPerTile;
+            constexpr int kStep = kEpiWarps / 4;
+            const uint32_t tq_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * MT * NT);
+            // software pipeline: the TMEM load of pair i+1 is in flight while pair i is processed
+            uint32_t r[32], rn[32];
+            int pair = sub + ((p.dbg & 4) ? kPairs : 0);
+            if (pair < kPairs) {
+                if (CW == 32) tmem_ld32(tq_base + pair * CW, r); else tmem_ld16(tq_base + pair * CW, r);
+            }
 #pragma unroll 1
-            for (int pair = sub + ((p.dbg & 4) ? MT * kChunksPerTile : 0); pair < MT * kChunksPerTile; pair += kEpiWarps / 4) {
+            for (; pair < kPairs; pair += kStep) {
                 const int mt = pair / kChunksPerTile;
                 const int c0 = (pair - mt * kChunksPerTile) * CW;
+                // folded-BN scale / shift of this chunk: issued before the TMEM wait
+                float4 sc[CW / 4], sh[CW / 4];
+#pragma unroll
+                for (int j = 0; j < CW / 4; ++j) {
+                    sc[j] = *reinterpret_cast<const float4*>(ss + c0 + 4 * j);
+                    sh[j] = *reinterpret_cast<const float4*>(ss + NT + c0 + 4 * j);
+                }
                 if (mt != cur_mt) {
                     cur_mt = mt;
                     const TileCoord t = decode_tile(p, c.mgroup * MT + mt);
@@ -449,30 +465,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         oh = 2 * h + (c.phase >> 1); ow = 2 * w + (c.phase & 1);
                     }
                     pix_off = static_cast<size_t>(n) * p.out_sN + (static_cast<size_t>(oh) * p.Wout + ow) * p.out_sP;
-                    if (!OUT_FP32) {
+                    if (!OUT_FP32 || NT == 16) {
                         const long long my_off = writer ? static_cast<long long>(pix_off) : -1ll;
 #pragma unroll
                         for (int i = 0; i < 4; ++i) offs[i] = __shfl_sync(0xffffffffu, my_off, (lane >> 2) + 8 * i);
                     }
                 }
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * MT + mt) * NT);
-                uint32_t r[32];
-                if (!(p.dbg & 32)) {
-                    if (CW == 32) tmem_ld32(taddr + c0, r); else tmem_ld16(taddr + c0, r);
-                    tmem_ld_wait();
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = 0x3f800000u + j + c0;
+                tmem_ld_wait();                                  // r[] (this pair) has landed
+                const int nxt = pair + kStep;
+                if (nxt < kPairs) {                              // next pair's accumulator columns: in flight during the math below
+                    if (CW == 32) tmem_ld32(tq_base + nxt * CW, rn); else tmem_ld16(tq_base + nxt * CW, rn);
                 }
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < CW; j += 4) {
-                    const float4 sc = *reinterpret_cast<const float4*>(ss + c0 + j);
-                    const float4 sh = *reinterpret_cast<const float4*>(ss + NT + c0 + j);
-                    v[j + 0] = fmaf(__uint_as_float(r[j + 0]), sc.x, sh.x);
-                    v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y);
-                    v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z);
-                    v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
+                for (int j = 0; j < CW / 4; ++j) {
+                    v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), sc[j].x, sh[j].x);
+                    v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), sc[j].y, sh[j].y);
+                    v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), sc[j].z, sh[j].z);
+                    v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), sc[j].w, sh[j].w);
                 }
                 if (POOL) {
                     // 2x2 max: w-neighbour is lane^1, h-neighbour is lane^BW (BW <= 16)
@@ -488,24 +498,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < CW; ++j) v[j] *= p.post_scale;
                 }
-                if (OUT_FP32 && NT == 16 && p.out_sC == 1 && !(p.dbg & 16)) {
-                    // fp32 records of 16 floats (64 B per pixel, G conv3 pass 1): same transposed store
+                if ((!OUT_FP32 || (NT == 16 && p.out_sC == 1)) && !(p.dbg & 16)) {
+                    // Each lane owns one pixel's 64 B of this chunk (32 bf16 channels, or the 16-float
+                    // record of G conv3 pass 1).  Transpose through an XOR-swizzled smem buffer so 4
+                    // lanes store one pixel's contiguous 64 B (8 pixels per instruction) instead of
+                    // 32 lanes hitting 32 different lines.
                     __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        xpose[lane * 4 + (j ^ ((lane >> 1) & 3))] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
-                                                                             __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 pk;
+                        if (OUT_FP32) {
+                            pk = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+                        } else {
+                            pk.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                            pk.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                            pk.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                            pk.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                        }
+                        xpose[lane * 4 + (j ^ ((lane >> 1) & 3))] = pk;
+                    }
                     __syncwarp();
-                    long long o4[4];
-                    const long long my_off = writer ? static_cast<long long>(pix_off) : -1ll;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) o4[i] = __shfl_sync(0xffffffffu, my_off, (lane >> 2) + 8 * i);
                     const int jj = lane & 3;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int px = (lane >> 2) + 8 * i;
                         const uint4 val = xpose[px * 4 + (jj ^ ((px >> 1) & 3))];
-                        if (o4[i] >= 0) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + o4[i] + jj * 4) = val;
+                        if (offs[i] >= 0) {
+                            if (OUT_FP32) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + offs[i] + jj * 4) = val;
+                            else *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + offs[i] + cbase + c0 + jj * 8) = val;
+                        }
                     }
                 } else if (OUT_FP32 && !(p.dbg & 16)) {
                     if (writer) {
@@ -515,31 +536,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (cbase + c0 + j < p.cout_real) o[static_cast<size_t>(j) * p.out_sC] = v[j];
                     }
                 }
-                if (!OUT_FP32 && !(p.dbg & 16)) {
-                    // bf16 NHWC: each lane owns one pixel's 64 B of this chunk.  Transpose through an
-                    // XOR-swizzled smem buffer so 4 lanes store one pixel's contiguous 64 B (8 pixels
-                    // per instruction) instead of 32 lanes hitting 32 different lines.
-                    static_assert(OUT_FP32 || CW == 32, "bf16 outputs use 32-column chunks");
-                    __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 pk;
-                        pk.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                        pk.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                        pk.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                        pk.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                        xpose[lane * 4 + (j ^ ((lane >> 1) & 3))] = pk;
-                    }
-                    __syncwarp();
-                    const int jj = lane & 3;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int px = (lane >> 2) + 8 * i;
-                        const uint4 val = xpose[px * 4 + (jj ^ ((px >> 1) & 3))];
-                        if (offs[i] >= 0)
-                            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + offs[i] + cbase + c0 + jj * 8) = val;
-                    }
-                }
+                for (int j = 0; j < 32; ++j) r[j] = rn[j];
             }
             tcgen05_fence_before();
             __syncwarp();

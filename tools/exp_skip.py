@@ -10,7 +10,7 @@ ctx.load_G(C, H, W, ND, pkg.weights.init_G(C, H, W, ND))
 ctx.load_R(0, C, H, W, ND, pkg.weights.init_R(C, H, W, ND))
 noise = np.random.default_rng(0).normal(size=(N, ND)).astype(np.float32)
 ctx.buffer_put(pkg._lib.BUF_NOISE, noise)
-for dbg in (0, 4):
+for dbg in (0, 3, 4, 8, 15):
     ctx.set_option("dbg", dbg)
     for rep in range(2):
         ctx.profile_reset(); ctx.profile_enable(True)
