@@ -1038,12 +1038,111 @@ static int launch_search_wide(ganrev_ctx* ctx, const scan::ScanParams& p, int sp
     return GANREV_OK;
 }
 
+// ---- streaming kernels (nq <= 32, d % 4 == 0): plan + launch
+static bool stream_plan(ganrev_ctx* ctx, const scan::ScanParams& p, int NQ, int mode, int K2, scan::StreamParams& sp, size_t& smem, int& grid) {
+    if (p.d % 4 != 0 || p.nq > 32) return false;
+    if (mode == 1 && p.d > 128) return false;                 // the update pass needs the whole row tile in smem
+    sp.s = p;
+    sp.dc = std::min(p.d, 128);
+    sp.dc_pad = sp.dc + (((sp.dc / 4) % 2 == 0) ? 4 : 0);     // odd number of 16-byte pieces per row: conflict-free
+    sp.n_chunks = (p.d + sp.dc - 1) / sp.dc;
+    sp.c4_magic = static_cast<unsigned>(((1ull << 32) + (sp.dc / 4) - 1) / (sp.dc / 4));
+    sp.groups = mode == 1 ? std::max(1, scan::kThreads / (p.d / 4)) : 0;      // thread groups of d/4 threads (4 columns each)
+    smem = sizeof(float) * (static_cast<size_t>(scan::SSTAGES) * scan::SR * sp.dc_pad + static_cast<size_t>(p.d) * NQ);
+    if (mode == 0) smem += sizeof(unsigned long long) * (static_cast<size_t>(NQ) * K2 + NQ * scan::CAP + NQ) + sizeof(int) * NQ;
+    else smem += (mode == 1 ? sizeof(unsigned long long) * (static_cast<size_t>(p.nq) * p.d + p.nq) : 0) + 4 * sizeof(int) * scan::SR;
+    if (smem > 220 * 1024) return false;
+    const long long n_tiles = (p.n_rows + scan::SR - 1) / scan::SR;
+    grid = static_cast<int>(std::max<long long>(1, std::min<long long>(n_tiles, ctx->num_sms)));
+    sp.tiles_per_block = (n_tiles + grid - 1) / grid;
+    grid = static_cast<int>(std::max<long long>(1, (n_tiles + sp.tiles_per_block - 1) / sp.tiles_per_block));
+    return true;
+}
+template <int NQ, int MODE, int E>
+static int launch_stream(ganrev_ctx* ctx, const scan::StreamParams& sp, size_t smem, int grid) {
+    static size_t attr_max = 0;
+    if (smem > attr_max) {
+        CU_TRY(cudaFuncSetAttribute(scan::stream_kernel<NQ, MODE, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr_max = smem;
+    }
+    scan::stream_kernel<NQ, MODE, E><<<grid, scan::kThreads, smem, ctx->stream>>>(sp);
+    CU_TRY(cudaGetLastError());
+    return GANREV_OK;
+}
+template <int MODE, int E>
+static int dispatch_stream(ganrev_ctx* ctx, int NQ, const scan::StreamParams& sp, size_t smem, int grid) {
+    switch (NQ) {
+        case 8: return launch_stream<8, MODE, E>(ctx, sp, smem, grid);
+        case 16: return launch_stream<16, MODE, E>(ctx, sp, smem, grid);
+        case 24: return launch_stream<24, MODE, E>(ctx, sp, smem, grid);
+        case 32: return launch_stream<32, MODE, E>(ctx, sp, smem, grid);
+    }
+    return fail(ctx, GANREV_EINVAL, "bad NQ %d", NQ);
+}
+static int stream_nq(int nq) { return nq <= 8 ? 8 : (nq <= 16 ? 16 : (nq <= 24 ? 24 : 32)); }
+
+// merge the per-split lists, (multi-GPU) allgather + merge across ranks, copy results out
+static int search_finish(ganrev_ctx* ctx, const unsigned long long* partial, int splits, int Q, int k, int64_t* ids, float* scores) {
+    const unsigned mblocks = static_cast<unsigned>((static_cast<long long>(Q) * 32 + scan::kThreads - 1) / scan::kThreads);
+    const bool multi = ctx->world > 1;
+    if (multi) {
+        RC_TRY(ensure(ctx, ctx->keys, sizeof(unsigned long long) * static_cast<size_t>(Q) * k));
+        RC_TRY(ensure(ctx, ctx->keys_all, sizeof(unsigned long long) * static_cast<size_t>(Q) * k * ctx->world));
+    }
+    {
+        ProfScope ps(ctx, "search_merge", 0.0, 8.0 * splits * Q * k + 12.0 * Q * k);
+        if (k <= 32)
+            scan::merge_kernel<1><<<mblocks, scan::kThreads, 0, ctx->stream>>>(partial, splits, Q, k, ctx->db_offset, multi ? 1 : 0,
+                static_cast<long long*>(ctx->ids.p), static_cast<float*>(ctx->scores.p), static_cast<unsigned long long*>(ctx->keys.p));
+        else
+            scan::merge_kernel<4><<<mblocks, scan::kThreads, 0, ctx->stream>>>(partial, splits, Q, k, ctx->db_offset, multi ? 1 : 0,
+                static_cast<long long*>(ctx->ids.p), static_cast<float*>(ctx->scores.p), static_cast<unsigned long long*>(ctx->keys.p));
+        CU_TRY(cudaGetLastError());
+    }
+    if (multi) {
+        // per-query top-k allgather (Q*k*8 B per rank), then the same merge over `world` partial lists
+        NCCL_TRY(ctx->nccl.AllGather(ctx->keys.p, ctx->keys_all.p, static_cast<size_t>(Q) * k, ncclUint64, ctx->comm, ctx->stream));
+        ProfScope ps(ctx, "search_merge_global", 0.0, 8.0 * ctx->world * Q * k + 12.0 * Q * k);
+        if (k <= 32)
+            scan::merge_kernel<1><<<mblocks, scan::kThreads, 0, ctx->stream>>>(static_cast<const unsigned long long*>(ctx->keys_all.p), ctx->world, Q, k, 0, 0,
+                static_cast<long long*>(ctx->ids.p), static_cast<float*>(ctx->scores.p), nullptr);
+        else
+            scan::merge_kernel<4><<<mblocks, scan::kThreads, 0, ctx->stream>>>(static_cast<const unsigned long long*>(ctx->keys_all.p), ctx->world, Q, k, 0, 0,
+                static_cast<long long*>(ctx->ids.p), static_cast<float*>(ctx->scores.p), nullptr);
+        CU_TRY(cudaGetLastError());
+    }
+    CU_TRY(cudaMemcpyAsync(ids, ctx->ids.p, sizeof(long long) * static_cast<size_t>(Q) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(scores, ctx->scores.p, sizeof(float) * static_cast<size_t>(Q) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    return finish(ctx);
+}
+
+
 // queries already on the device in ctx->q (Q x d)
 static int search_dev(ganrev_ctx* ctx, int Q, int k, int64_t* ids, float* scores) {
     const int d = ctx->db_d;
     const int64_t N = ctx->db_n;
     RC_TRY(ensure(ctx, ctx->rq, sizeof(float) * Q));
     RC_TRY(vec_prep(ctx, static_cast<const float*>(ctx->q.p), Q, d, static_cast<float*>(ctx->rq.p), nullptr, nullptr));
+    if (Q <= 16 && d % 4 == 0) {   // HBM-bound regime: stream the database once
+        scan::ScanParams p{};
+        p.db = static_cast<const float*>(ctx->db.p); p.rdb = static_cast<const float*>(ctx->rdb.p); p.n_rows = N; p.d = d;
+        p.q = static_cast<const float*>(ctx->q.p); p.rq = static_cast<const float*>(ctx->rq.p); p.nq = Q; p.k = k;
+        scan::StreamParams sp{};
+        size_t smem = 0;
+        int grid = 0;
+        const int NQ = stream_nq(Q), K2 = k <= 32 ? 32 : 128;
+        if (stream_plan(ctx, p, NQ, 0, K2, sp, smem, grid)) {
+            RC_TRY(ensure(ctx, ctx->partial, sizeof(unsigned long long) * static_cast<size_t>(grid) * Q * k));
+            RC_TRY(ensure(ctx, ctx->ids, sizeof(long long) * static_cast<size_t>(Q) * k));
+            RC_TRY(ensure(ctx, ctx->scores, sizeof(float) * static_cast<size_t>(Q) * k));
+            sp.s.partial = static_cast<unsigned long long*>(ctx->partial.p);
+            {
+                ProfScope ps(ctx, "search_scan", 2.0 * N * Q * d, 4.0 * N * d + 4.0 * Q * d + 8.0 * grid * Q * k);
+                if (k <= 32) RC_TRY((dispatch_stream<0, 1>(ctx, NQ, sp, smem, grid))); else RC_TRY((dispatch_stream<0, 4>(ctx, NQ, sp, smem, grid)));
+            }
+            return search_finish(ctx, sp.s.partial, grid, Q, k, ids, scores);
+        }
+    }
     const int TQ = Q <= 16 ? 1 : 4;
     const int QT = 16 * TQ;
     const int qtiles = (Q + QT - 1) / QT;
@@ -1066,37 +1165,7 @@ static int search_dev(ganrev_ctx* ctx, int Q, int k, int64_t* ids, float* scores
         else if (wide) { if (k <= 32) RC_TRY((launch_search_wide<1>(ctx, p, splits))); else RC_TRY((launch_search_wide<4>(ctx, p, splits))); }
         else           { if (k <= 32) RC_TRY((launch_search<4, 1>(ctx, p, splits))); else RC_TRY((launch_search<4, 4>(ctx, p, splits))); }
     }
-    const unsigned mblocks = static_cast<unsigned>((static_cast<long long>(Q) * 32 + scan::kThreads - 1) / scan::kThreads);
-    const bool multi = ctx->world > 1;
-    if (multi) {
-        RC_TRY(ensure(ctx, ctx->keys, sizeof(unsigned long long) * static_cast<size_t>(Q) * k));
-        RC_TRY(ensure(ctx, ctx->keys_all, sizeof(unsigned long long) * static_cast<size_t>(Q) * k * ctx->world));
-    }
-    {
-        ProfScope ps(ctx, "search_merge", 0.0, 8.0 * splits * Q * k + 12.0 * Q * k);
-        if (k <= 32)
-            scan::merge_kernel<1><<<mblocks, scan::kThreads, 0, ctx->stream>>>(p.partial, splits, Q, k, ctx->db_offset, multi ? 1 : 0,
-                static_cast<long long*>(ctx->ids.p), static_cast<float*>(ctx->scores.p), static_cast<unsigned long long*>(ctx->keys.p));
-        else
-            scan::merge_kernel<4><<<mblocks, scan::kThreads, 0, ctx->stream>>>(p.partial, splits, Q, k, ctx->db_offset, multi ? 1 : 0,
-                static_cast<long long*>(ctx->ids.p), static_cast<float*>(ctx->scores.p), static_cast<unsigned long long*>(ctx->keys.p));
-        CU_TRY(cudaGetLastError());
-    }
-    if (multi) {
-        // per-query top-k allgather (Q*k*8 B per rank), then the same merge over `world` partial lists
-        NCCL_TRY(ctx->nccl.AllGather(ctx->keys.p, ctx->keys_all.p, static_cast<size_t>(Q) * k, ncclUint64, ctx->comm, ctx->stream));
-        ProfScope ps(ctx, "search_merge_global", 0.0, 8.0 * ctx->world * Q * k + 12.0 * Q * k);
-        if (k <= 32)
-            scan::merge_kernel<1><<<mblocks, scan::kThreads, 0, ctx->stream>>>(static_cast<const unsigned long long*>(ctx->keys_all.p), ctx->world, Q, k, 0, 0,
-                static_cast<long long*>(ctx->ids.p), static_cast<float*>(ctx->scores.p), nullptr);
-        else
-            scan::merge_kernel<4><<<mblocks, scan::kThreads, 0, ctx->stream>>>(static_cast<const unsigned long long*>(ctx->keys_all.p), ctx->world, Q, k, 0, 0,
-                static_cast<long long*>(ctx->ids.p), static_cast<float*>(ctx->scores.p), nullptr);
-        CU_TRY(cudaGetLastError());
-    }
-    CU_TRY(cudaMemcpyAsync(ids, ctx->ids.p, sizeof(long long) * static_cast<size_t>(Q) * k, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaMemcpyAsync(scores, ctx->scores.p, sizeof(float) * static_cast<size_t>(Q) * k, cudaMemcpyDeviceToHost, ctx->stream));
-    return finish(ctx);
+    return search_finish(ctx, p.partial, splits, Q, k, ids, scores);
 }
 
 extern "C" {
@@ -1192,7 +1261,12 @@ int ganrev_kmeans(ganrev_ctx* ctx, int k, int niter, const float* init_centroids
         RC_TRY(vec_prep(ctx, static_cast<const float*>(ctx->cen.p), k, d, nullptr, static_cast<float*>(ctx->c2.p), nullptr));
         {
             ProfScope ps(ctx, "kmeans_assign", 2.0 * N * k * d + 1.0 * N * d, 8.0 * N * d + 4.0 * N + 4.0 * kd);
-            if (k <= 16) RC_TRY((launch_assign<1, 1>(ctx, p))); else RC_TRY((launch_assign<4, 1>(ctx, p)));
+            scan::StreamParams sp{};
+            size_t smem = 0;
+            int grid = 0;
+            if (stream_plan(ctx, p, stream_nq(k), 1, 0, sp, smem, grid)) RC_TRY((dispatch_stream<1, 1>(ctx, stream_nq(k), sp, smem, grid)));
+            else if (k <= 16) RC_TRY((launch_assign<1, 1>(ctx, p)));
+            else RC_TRY((launch_assign<4, 1>(ctx, p)));
         }
         if (ctx->world > 1)   // centroid sums + counts: one order-free int64 allreduce per iteration
             NCCL_TRY(ctx->nccl.AllReduce(ctx->acc.p, ctx->acc.p, kd + k, ncclUint64, ncclSum, ctx->comm, ctx->stream));
@@ -1231,7 +1305,12 @@ int ganrev_assign_cosine_min(ganrev_ctx* ctx, const float* centroids, int k, int
     p.labels = static_cast<int*>(ctx->labels.p); p.cosv = static_cast<float*>(ctx->cosv.p);
     {
         ProfScope ps(ctx, "assign_cosine_min", 2.0 * N * k * d, 4.0 * N * d + 8.0 * N + 4.0 * kd);
-        if (k <= 16) RC_TRY((launch_assign<1, 2>(ctx, p))); else RC_TRY((launch_assign<4, 2>(ctx, p)));
+        scan::StreamParams sp{};
+        size_t smem = 0;
+        int grid = 0;
+        if (stream_plan(ctx, p, stream_nq(k), 2, 0, sp, smem, grid)) RC_TRY((dispatch_stream<2, 1>(ctx, stream_nq(k), sp, smem, grid)));
+        else if (k <= 16) RC_TRY((launch_assign<1, 2>(ctx, p)));
+        else RC_TRY((launch_assign<4, 2>(ctx, p)));
     }
     ctx->assigned = true; ctx->assigned_k = k;
     if (cluster && N > 0) CU_TRY(cudaMemcpyAsync(cluster, ctx->labels.p, sizeof(int) * N, cudaMemcpyDeviceToHost, ctx->stream));

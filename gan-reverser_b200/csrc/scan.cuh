@@ -408,6 +408,307 @@ __global__ void gather_rows_kernel(const float* __restrict__ db, long long n_row
     out[idx] = (r >= 0 && r < n_rows) ? db[r * d + c] : 0.0f;
 }
 
+// ------------------------------------------------------------------ label selection rules (kmeans / cosine-min)
+struct Best {
+    float v;
+    int j;
+};
+// MODE 1 (unsup.kmeans, TH max scan "!(v <= best)", break on NaN): first NaN wins, else the
+// largest value, lowest index on ties.
+// MODE 2 (apply_r.lua:206-218 "dist < minDist"): a NaN at j == 0 sticks, otherwise NaNs never
+// win; smallest value, lowest index on ties.
+template <int MODE>
+__device__ __forceinline__ bool better(const Best a, const Best b) {   // is a strictly preferable to b?
+    if (b.j < 0) return a.j >= 0;
+    if (a.j < 0) return false;
+    const bool an = a.v != a.v, bn = b.v != b.v;
+    if (MODE == 1) {
+        if (an || bn) return an && (!bn || a.j < b.j);
+        return a.v > b.v || (a.v == b.v && a.j < b.j);
+    } else {
+        const bool a0 = an && a.j == 0, b0 = bn && b.j == 0;
+        if (a0 || b0) return a0;
+        if (an || bn) return !an && bn ? true : (an && bn ? a.j < b.j : false);
+        return a.v < b.v || (a.v == b.v && a.j < b.j);
+    }
+}
+
+// ------------------------------------------------------------------ streaming kernels, nq <= 32
+// The HBM-bound regime (a handful of needles, k = 20 centroids): ONE THREAD PER ROW keeps all nq
+// accumulators in registers -- still one sequential fmaf chain per (query,row) pair -- while the
+// rows stream through a cp.async double-buffered shared-memory tile (rows of dc_pad floats,
+// dc_pad/4 odd so the per-thread 128-bit reads are bank-conflict free) and the queries are
+// broadcast from shared memory.  Algorithmic traffic = 4*N*d bytes, read exactly once.
+//   MODE 0  cosine top-k      (apply_r.lua:267-282)
+//   MODE 1  kmeans label + int64 fixed-point centroid sums (unsup.kmeans, apply_r.lua:198), d <= 128
+//   MODE 2  cosine-min assignment (apply_r.lua:206-218)
+struct StreamParams {
+    ScanParams s;
+    int dc, dc_pad, n_chunks;   // columns per staged chunk (multiple of 4), padded row stride, chunks per row
+    unsigned c4_magic;          // ceil(2^32 / (dc/4))
+    long long tiles_per_block;  // contiguous row tiles per block
+    int groups;                 // MODE 1: accumulator copies (thread groups) in shared memory
+};
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int SR = 128;        // rows per streamed tile
+constexpr int SSTAGES = 3;     // cp.async ring depth
+
+// 256 threads: thread t owns row (t & 127) and the query half (t >> 7), i.e. NQ/2 accumulators.
+template <int NQ, int MODE, int E>
+__global__ void __launch_bounds__(kThreads)
+stream_kernel(const StreamParams sp) {
+    const ScanParams& p = sp.s;
+    constexpr int K2 = 32 * E;
+    constexpr int NH = NQ / 2;                                // accumulators per thread
+    static_assert(NQ % 8 == 0, "NQ/2 must be a multiple of 4");
+    extern __shared__ __align__(16) uint8_t sm[];
+    const int d = p.d, dc = sp.dc, dcp = sp.dc_pad;
+    float* stage0 = reinterpret_cast<float*>(sm);             // [SSTAGES][SR][dc_pad]
+    float* qs = stage0 + SSTAGES * SR * dcp;                  // [d][NQ]
+    uint8_t* tail = reinterpret_cast<uint8_t*>(qs + static_cast<size_t>(d) * NQ);
+    // MODE 0
+    unsigned long long* lists = reinterpret_cast<unsigned long long*>(tail);
+    unsigned long long* cand = lists + NQ * K2;
+    unsigned long long* tau = cand + NQ * CAP;
+    int* ccount = reinterpret_cast<int*>(tau + NQ);
+    // MODE 1 / 2
+    unsigned long long* sacc = reinterpret_cast<unsigned long long*>(tail);      // [nq*d + nq]  (MODE 1)
+    float* hv = reinterpret_cast<float*>(sacc + (MODE == 1 ? static_cast<size_t>(p.nq) * d + p.nq : 0));   // [SR] half-1 best value
+    int* hj = reinterpret_cast<int*>(hv + SR);                // [SR] half-1 best index
+    int* slab = hj + SR;                                      // [SR] final labels of the tile
+    int* perm = slab + SR;                                    // [SR] rows of the tile grouped by label (MODE 1)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rloc = tid & (SR - 1), qh = tid >> 7;           // row in tile, query half
+    const int jbase = qh * NH;
+    for (int i = tid; i < d * NQ; i += kThreads) {
+        const int c = i / NQ, j = i - c * NQ;
+        qs[i] = j < p.nq ? __ldg(p.q + static_cast<long long>(j) * d + c) : 0.0f;
+    }
+    if (MODE == 0) {
+        for (int i = tid; i < NQ * K2; i += kThreads) lists[i] = 0ull;
+        for (int i = tid; i < NQ; i += kThreads) { tau[i] = 0ull; ccount[i] = 0; }
+    }
+    if (MODE == 1)
+        for (int i = tid; i < p.nq * d + p.nq; i += kThreads) sacc[i] = 0ull;
+    float aux[NH];                                            // rq (MODE 0/2) or c2 (MODE 1) of this thread's queries
+#pragma unroll
+    for (int j = 0; j < NH; ++j) aux[j] = jbase + j < p.nq ? __ldg((MODE == 1 ? p.c2 : p.rq) + jbase + j) : 0.0f;
+
+    const long long tile_begin = static_cast<long long>(blockIdx.x) * sp.tiles_per_block;
+    const long long n_tiles_all = (p.n_rows + SR - 1) / SR;
+    const long long tile_end = min(n_tiles_all, tile_begin + sp.tiles_per_block);
+    const long long n_steps = max(0ll, tile_end - tile_begin) * sp.n_chunks;
+
+    const unsigned c4magic = sp.c4_magic;                     // ceil(2^32 / (dc/4)): exact floor division for piece indices
+    auto issue = [&](long long step) {                        // cp.async one (tile, chunk) into ring slot step % SSTAGES
+        if (step < n_steps) {
+            const long long tile = tile_begin + step / sp.n_chunks;
+            const int c0 = static_cast<int>(step % sp.n_chunks) * dc;
+            const int kk4 = min(dc, d - c0) >> 2;             // 16-byte pieces per row in this chunk
+            float* buf = stage0 + static_cast<int>(step % SSTAGES) * SR * dcp;
+            const long long row0 = tile * SR;
+            const int rows_live = static_cast<int>(min(static_cast<long long>(SR), p.n_rows - row0));
+            const float* src0 = p.db + row0 * d + c0;
+            if (kk4 * 4 == d && dcp == d) {                   // whole rows, unpadded: the tile is one contiguous block
+                const int total = rows_live * kk4;
+                for (int g = tid; g < total; g += kThreads) cp_async16(buf + 4 * g, src0 + 4 * g);
+            } else {
+                const int c4 = dc >> 2;
+                const int total = rows_live * c4;
+                for (int g = tid; g < total; g += kThreads) {
+                    const int r = c4 == 1 ? g : static_cast<int>(__umulhi(static_cast<unsigned>(g), c4magic));
+                    const int col = g - r * c4;
+                    if (col < kk4) cp_async16(buf + r * dcp + 4 * col, src0 + static_cast<long long>(r) * d + 4 * col);
+                }
+            }
+        }
+        cp_async_commit();                                    // (possibly empty) group: keeps the wait counts uniform
+    };
+
+    issue(0);
+    issue(1);
+    float acc[NH];
+    for (long long step = 0; step < n_steps; ++step) {
+        const int chunk = static_cast<int>(step % sp.n_chunks);
+        const long long tile = tile_begin + step / sp.n_chunks;
+        __syncthreads();                                      // ring slot (step+2) % 3 == (step-1) % 3 is free again
+        issue(step + 2);
+        cp_async_wait<2>();                                   // this thread's pieces of `step` have landed
+        __syncthreads();                                      // ... and everyone else's
+        if (chunk == 0) {
+#pragma unroll
+            for (int j = 0; j < NH; ++j) acc[j] = 0.0f;
+        }
+        const int c0 = chunk * dc;
+        const int kk = min(dc, d - c0);
+        const float* tilep = stage0 + static_cast<int>(step % SSTAGES) * SR * dcp;
+        const float* xr = tilep + rloc * dcp;
+        // this row's 1/(|x|^2+eps) (MODE 0/2) is fetched now so its latency hides behind the dot products
+        const long long row = tile * SR + rloc;
+        const bool live = row < p.n_rows;
+        float rx = 0.0f;
+        if (MODE != 1 && chunk == sp.n_chunks - 1 && live) rx = __ldg(p.rdb + row);
+        for (int i = 0; i < kk; i += 4) {
+            const float4 x4 = *reinterpret_cast<const float4*>(xr + i);
+            const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+            float4 qv[4][NH / 4];                             // all operand loads first, then 4*NH independent-ish FMAs
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int v = 0; v < NH / 4; ++v) qv[e][v] = *reinterpret_cast<const float4*>(qs + (c0 + i + e) * NQ + jbase + 4 * v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int v = 0; v < NH / 4; ++v) {
+                    acc[4 * v + 0] = __fmaf_rn(qv[e][v].x, xv[e], acc[4 * v + 0]);
+                    acc[4 * v + 1] = __fmaf_rn(qv[e][v].y, xv[e], acc[4 * v + 1]);
+                    acc[4 * v + 2] = __fmaf_rn(qv[e][v].z, xv[e], acc[4 * v + 2]);
+                    acc[4 * v + 3] = __fmaf_rn(qv[e][v].w, xv[e], acc[4 * v + 3]);
+                }
+        }
+        if (chunk != sp.n_chunks - 1) continue;
+        // ---------------------------------------------------------------- row finished
+        if (MODE == 0) {
+            unsigned pend = 0u;
+#pragma unroll
+            for (int j = 0; j < NH; ++j) {
+                acc[j] = cos_from(acc[j], aux[j], rx);        // exact score, in place
+                if (live && jbase + j < p.nq && make_key(acc[j], static_cast<uint32_t>(row)) > tau[jbase + j]) pend |= 1u << j;
+            }
+            while (__syncthreads_or(pend != 0u)) {
+#pragma unroll
+                for (int j = 0; j < NH; ++j) {
+                    if (pend & (1u << j)) {
+                        const unsigned long long key = make_key(acc[j], static_cast<uint32_t>(row));
+                        if (key > tau[jbase + j]) {
+                            const int slot = atomicAdd(&ccount[jbase + j], 1);
+                            if (slot < CAP) { cand[(jbase + j) * CAP + slot] = key; pend &= ~(1u << j); }
+                        } else {
+                            pend &= ~(1u << j);
+                        }
+                    }
+                }
+                __syncthreads();
+                for (int j = warp; j < NQ; j += kThreads / 32) {
+                    const int n = min(ccount[j], CAP);
+                    if (n > 0) {
+                        unsigned long long L[E];
+#pragma unroll
+                        for (int t = 0; t < E; ++t) L[t] = lists[j * K2 + lane * E + t];
+                        for (int t = 0; t < n; ++t) list_insert<E>(L, cand[j * CAP + t], lane);
+#pragma unroll
+                        for (int t = 0; t < E; ++t) lists[j * K2 + lane * E + t] = L[t];
+                        const unsigned long long kth = list_kth<E>(L, p.k);
+                        __syncwarp();
+                        if (lane == 0) { tau[j] = kth; ccount[j] = 0; }
+                    }
+                }
+            }
+        } else {
+            // this thread's half of the centroids, scanned in index order; the two halves are then
+            // combined with the same total order, which equals the reference's sequential scan
+            Best b;
+            b.v = 0.0f; b.j = -1;
+#pragma unroll
+            for (int j = 0; j < NH; ++j) {
+                if (jbase + j < p.nq) {
+                    Best c;
+                    c.j = jbase + j;
+                    c.v = MODE == 1 ? __fsub_rn(acc[j], aux[j]) : cos_from(acc[j], rx, aux[j]);
+                    if (better<MODE>(c, b)) b = c;
+                }
+            }
+            if (qh == 1) { hv[rloc] = b.v; hj[rloc] = b.j; }
+            __syncthreads();
+            if (qh == 0) {
+                Best o;
+                o.v = hv[rloc]; o.j = hj[rloc];
+                if (better<MODE>(o, b)) b = o;
+                slab[rloc] = live ? b.j : -1;
+                if (live) {
+                    p.labels[row] = b.j;
+                    if (MODE == 2) p.cosv[row] = b.v;
+                }
+            }
+            if (MODE == 1) {
+                // centroid sums.  (1) counting-sort the tile's rows by label: perm[] lists the rows
+                // grouped by label.  (2) thread (g, c) owns column c of accumulator copy g and walks
+                // perm[g], perm[g+groups], ...: consecutive rows mostly share a label, so the int64
+                // fixed-point sum of a run lives in a register and shared memory is touched once per
+                // run -- no atomics, no per-row read-modify-write chain.  Integer adds are associative,
+                // so neither the order nor the split can change the result.
+                __syncthreads();
+                if (tid < SR) {
+                    const int mine = slab[tid];
+                    int rank = 0;
+                    for (int r = 0; r < SR; ++r) {
+                        const int o = slab[r];
+                        rank += (o < mine || (o == mine && r < tid)) ? 1 : 0;
+                    }
+                    perm[rank] = tid;                          // dead rows (label -1) sort first
+                }
+                __syncthreads();
+                // thread (g, c4): 4 consecutive columns of a contiguous segment of the sorted rows
+                const int tpg = d >> 2;                       // threads per group
+                const int g = tid / tpg, c = (tid - g * tpg) * 4;
+                if (g < sp.groups) {
+                    const int seg = (SR + sp.groups - 1) / sp.groups;
+                    const int pos_end = min(SR, (g + 1) * seg);
+                    int cur = -1;
+                    long long run0 = 0, run1 = 0, run2 = 0, run3 = 0, cnt = 0;
+                    auto flush = [&]() {
+                        if (cur >= 0) {
+                            unsigned long long* a = sacc + cur * d + c;
+                            atomicAdd(a + 0, static_cast<unsigned long long>(run0));
+                            atomicAdd(a + 1, static_cast<unsigned long long>(run1));
+                            atomicAdd(a + 2, static_cast<unsigned long long>(run2));
+                            atomicAdd(a + 3, static_cast<unsigned long long>(run3));
+                            if (c == 0) atomicAdd(sacc + p.nq * d + cur, static_cast<unsigned long long>(cnt));
+                        }
+                    };
+                    for (int pos = g * seg; pos < pos_end; ++pos) {
+                        const int r = perm[pos];
+                        const int lab = slab[r];
+                        if (lab < 0) continue;
+                        if (lab != cur) { flush(); cur = lab; run0 = run1 = run2 = run3 = 0; cnt = 0; }
+                        const float4 x4 = *reinterpret_cast<const float4*>(tilep + r * dcp + c);
+                        run0 += __double2ll_rn(static_cast<double>(x4.x) * p.sc);
+                        run1 += __double2ll_rn(static_cast<double>(x4.y) * p.sc);
+                        run2 += __double2ll_rn(static_cast<double>(x4.z) * p.sc);
+                        run3 += __double2ll_rn(static_cast<double>(x4.w) * p.sc);
+                        ++cnt;
+                    }
+                    flush();
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    if (MODE == 0) {
+        for (int i = tid; i < NQ * p.k; i += kThreads) {
+            const int j = i / p.k, t = i - j * p.k;
+            if (j < p.nq) p.partial[(static_cast<long long>(blockIdx.x) * p.nq + j) * p.k + t] = lists[j * K2 + t];
+        }
+    }
+    if (MODE == 1) {
+        const int per = p.nq * d + p.nq;
+        for (int i = tid; i < per; i += kThreads) {
+            const unsigned long long v = sacc[i];
+            if (v != 0ull) {
+                if (i < p.nq * d) atomicAdd(&p.acc[i], v);
+                else atomicAdd(&p.cnt[i - p.nq * d], v);
+            }
+        }
+    }
+}
+
 // Merge [parts][nq][k] partial lists per query (one warp per query).
 //   mode 0: write ids (int64, + id_offset) and scores
 //   mode 1: write keys re-based to global ids (for the NCCL allgather)
@@ -462,31 +763,7 @@ merge_kernel(const unsigned long long* __restrict__ partial, int parts, int nq, 
     }
 }
 
-// ------------------------------------------------------------------ kmeans label / cosine-min assign
-struct Best {
-    float v;
-    int j;
-};
-// MODE 1 (unsup.kmeans, TH max scan "!(v <= best)", break on NaN): first NaN wins, else the
-// largest value, lowest index on ties.
-// MODE 2 (apply_r.lua:206-218 "dist < minDist"): a NaN at j == 0 sticks, otherwise NaNs never
-// win; smallest value, lowest index on ties.
-template <int MODE>
-__device__ __forceinline__ bool better(const Best a, const Best b) {   // is a strictly preferable to b?
-    if (b.j < 0) return a.j >= 0;
-    if (a.j < 0) return false;
-    const bool an = a.v != a.v, bn = b.v != b.v;
-    if (MODE == 1) {
-        if (an || bn) return an && (!bn || a.j < b.j);
-        return a.v > b.v || (a.v == b.v && a.j < b.j);
-    } else {
-        const bool a0 = an && a.j == 0, b0 = bn && b.j == 0;
-        if (a0 || b0) return a0;
-        if (an || bn) return !an && bn ? true : (an && bn ? a.j < b.j : false);
-        return a.v < b.v || (a.v == b.v && a.j < b.j);
-    }
-}
-
+// ------------------------------------------------------------------ kmeans label / cosine-min assign (SGEMM-tile path)
 template <int TQ, int MODE>
 __global__ void __launch_bounds__(kThreads)
 assign_kernel(const ScanParams p, const long long n_tiles) {
