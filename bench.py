@@ -192,10 +192,21 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="pipeline chunk (0 = library default)")
     ap.add_argument("--ref-images", type=int, default=384, help="CPU-arm sample size per step")
     ap.add_argument("--cpu-images", type=int, default=512, help="cpu_baseline sample size")
+    ap.add_argument("--geom", default="", help="C,H,W,nd of another geometry (e.g. 3,64,64,256 = BASELINE configs[4]'s G/R); default configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm-kernels", action="store_true", help="skip the L2 / kmeans / small-Q search bandwidth rooflines")
     args = ap.parse_args()
 
+    global C, H, W, ND, FLOP_G, FLOP_R, FLOP_DIRECT
+    workload_name = "configs[3]: G->R reversal of 32x32 grayscale faces (nd=100) + 4096-query cosine top-20 over the recovered set"
+    if args.geom:
+        C, H, W, ND = (int(v) for v in args.geom.split(","))
+        px = H * W
+        # direct-form MACs per image: Linear, Up+Conv 512->256 @ (H/2)^2, Up+Conv 256->128 @ H*W, Conv 128->C
+        FLOP_G = 2.0 * (ND * 512 * px / 16 + (px / 4) * 256 * 4608 + px * 128 * 2304 + px * C * 1152)
+        FLOP_R = 2.0 * (px * 64 * 9 * C + 2 * px * 64 * 576 + (px / 4) * (128 * 576 + 2 * 128 * 1152) + (128 * px / 16) * 512 + 512 * ND)
+        FLOP_DIRECT = {"g_conv1_up": 2.0 * (px / 4) * 256 * 4608, "g_conv2_up": 2.0 * px * 128 * 2304}
+        workload_name = f"G->R reversal of {C}x{H}x{W} faces (nd={ND}) + 4096-query cosine top-20 over the recovered set"
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -332,7 +343,7 @@ def main():
         "metric": "g2r_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "configs[3]: G->R reversal of 32x32 grayscale faces (nd=100) + 4096-query cosine top-20 over the recovered set",
+        "config": {"workload": workload_name,
                    "images_per_gpu": N, "queries": Q, "top_k": TOPK, "noise_dim": ND, "weights": "random-init (weight-init.lua heuristic)",
                    "l2_flush": "inputs larger than L2 (activation stream per chunk >> 126 MB)", "arith": "bf16 operands, fp32 accumulate (conv GEMMs); fp32 fmaf (search)"},
         "search_queries_per_sec": Q * world / (srch_ms * 1e-3) if srch_ms > 0 else None,

@@ -465,7 +465,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         oh = 2 * h + (c.phase >> 1); ow = 2 * w + (c.phase & 1);
                     }
                     pix_off = static_cast<size_t>(n) * p.out_sN + (static_cast<size_t>(oh) * p.Wout + ow) * p.out_sP;
-                    if (!OUT_FP32 || NT == 16) {
+                    if (!OUT_FP32 || NT == 16 || NT == 32) {
                         const long long my_off = writer ? static_cast<long long>(pix_off) : -1ll;
 #pragma unroll
                         for (int i = 0; i < 4; ++i) offs[i] = __shfl_sync(0xffffffffu, my_off, (lane >> 2) + 8 * i);
@@ -498,34 +498,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < CW; ++j) v[j] *= p.post_scale;
                 }
-                if ((!OUT_FP32 || (NT == 16 && p.out_sC == 1)) && !(p.dbg & 16)) {
-                    // Each lane owns one pixel's 64 B of this chunk (32 bf16 channels, or the 16-float
-                    // record of G conv3 pass 1).  Transpose through an XOR-swizzled smem buffer so 4
-                    // lanes store one pixel's contiguous 64 B (8 pixels per instruction) instead of
-                    // 32 lanes hitting 32 different lines.
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 pk;
-                        if (OUT_FP32) {
-                            pk = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
-                        } else {
-                            pk.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                            pk.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                            pk.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                            pk.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                        }
-                        xpose[lane * 4 + (j ^ ((lane >> 1) & 3))] = pk;
-                    }
-                    __syncwarp();
+                constexpr bool kRec = OUT_FP32 && (NT == 16 || NT == 32);   // fp32 records of 16 / 32 floats per pixel (G conv3 pass 1)
+                if ((!OUT_FP32 || (kRec && p.out_sC == 1 && p.out_sP == NT)) && !(p.dbg & 16)) {
+                    // Each lane owns one pixel's 64 B of this chunk (32 bf16 channels, or 16 floats of
+                    // the G conv3 tap record; 32-float records take two passes).  Transpose through an
+                    // XOR-swizzled smem buffer so 4 lanes store one pixel's contiguous 64 B (8 pixels
+                    // per instruction) instead of 32 lanes hitting 32 different lines.
+                    constexpr int kPasses = (OUT_FP32 && NT == 32) ? 2 : 1;
                     const int jj = lane & 3;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int px = (lane >> 2) + 8 * i;
-                        const uint4 val = xpose[px * 4 + (jj ^ ((px >> 1) & 3))];
-                        if (offs[i] >= 0) {
-                            if (OUT_FP32) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + offs[i] + jj * 4) = val;
-                            else *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + offs[i] + cbase + c0 + jj * 8) = val;
+                    for (int hpass = 0; hpass < kPasses; ++hpass) {
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 pk;
+                            if (OUT_FP32) {
+                                const int b0 = 16 * hpass + 4 * j;
+                                pk = make_uint4(__float_as_uint(v[b0]), __float_as_uint(v[b0 + 1]), __float_as_uint(v[b0 + 2]), __float_as_uint(v[b0 + 3]));
+                            } else {
+                                pk.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                                pk.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                                pk.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                                pk.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                            }
+                            xpose[lane * 4 + (j ^ ((lane >> 1) & 3))] = pk;
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int px = (lane >> 2) + 8 * i;
+                            const uint4 val = xpose[px * 4 + (jj ^ ((px >> 1) & 3))];
+                            if (offs[i] >= 0) {
+                                if (OUT_FP32) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + offs[i] + 16 * hpass + jj * 4) = val;
+                                else *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + offs[i] + cbase + c0 + jj * 8) = val;
+                            }
                         }
                     }
                 } else if (OUT_FP32 && !(p.dbg & 16)) {

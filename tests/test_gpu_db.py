@@ -149,6 +149,37 @@ def test_kmeans_exact(orc, ctx, case):
     assert_bitexact(cen, want_c, "centroids")
 
 
+def test_kmeans_full_size_properties(ctx):
+    """1M x 100 rows, k=20 (the shape of BASELINE configs 3/4): too slow for the oracle's sort-free
+    checks at this size, so test what must hold at any size: counts add up, the final centroids are the
+    float64 means of the rows labelled in the last iteration, and -- because the centroid sums are
+    int64 fixed point -- a row permutation changes neither centroids nor labels by a single bit."""
+    rng = np.random.default_rng(41)
+    N, d, k, niter = 1_000_000, 100, 20, 3
+    x = rng.standard_normal(size=(N, d), dtype=np.float32)
+    x += (3.0 * rng.integers(0, 2, size=(N, 1))).astype(np.float32)
+    init = _init(k, d, 42)
+    ctx.db_set(x)
+    cen, tot, lab = ctx.kmeans(k, niter, init)
+    assert tot.sum() == niter * N and lab.min() >= 0 and lab.max() < k
+    for j in range(k):
+        m = lab == j
+        if m.any():
+            assert np.abs(cen[j] - x[m].astype(np.float64).mean(0)).max() < 2e-5
+    perm = rng.permutation(N)
+    ctx.db_set(x[perm])
+    cen_p, tot_p, lab_p = ctx.kmeans(k, niter, init)
+    assert_bitexact(cen_p, cen, "centroids under a row permutation")
+    assert_bitexact(tot_p, tot)
+    np.testing.assert_array_equal(lab_p, lab[perm])
+    # cosine-min assignment at the same size against float64 (ties / rounding aside)
+    cl, cv = ctx.assign_cosine_min(cen)
+    xs = x[perm][:20000].astype(np.float64)
+    ref = (xs / np.linalg.norm(xs, axis=1, keepdims=True)) @ (cen / np.linalg.norm(cen, axis=1, keepdims=True)).astype(np.float64).T
+    assert (ref.argmin(1) == cl[:20000]).mean() > 0.9995
+    assert np.abs(ref.min(1) - cv[:20000]).max() < 1e-5
+
+
 def test_kmeans_empty_cluster_and_zero_iters(orc, ctx):
     x = _db(500, 16, 12)
     init = _init(5, 16)
