@@ -44,8 +44,8 @@ constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr unsigned long long kSpinLimitCycles = 4000000000ull;  // ~2 s: turn a hang into a trap
 
-template <int NT, int MT> struct Cfg {
-    static constexpr int kBBytes = NT * kBlockK * 2;                    // one 64-wide weight tile
+template <int NT, int MT, int CG = 1> struct Cfg {
+    static constexpr int kBBytes = (NT / CG) * kBlockK * 2;             // this CTA's share of one 64-wide weight tile
     static constexpr int kNAcc = (2 * MT * NT <= 512) ? 2 : 1;          // accumulator buffers
     static constexpr int kCols = kNAcc * MT * NT;
     static constexpr int kTmemCols = kCols <= 32 ? 32 : (kCols <= 64 ? 64 : (kCols <= 128 ? 128 : (kCols <= 256 ? 256 : 512)));
@@ -114,6 +114,59 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+// ---- cta_group::2 (CTA pair on one TPC): one MMA spans both SMs (M = 256); each SM supplies its own
+// 128 rows of A and HALF of the B tile, so the per-SM shared-memory operand reads per MMA drop.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit: "the leader CTA's copy of this barrier"
+__device__ __forceinline__ void tma_load_4d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar, uint32_t cta) {   // arrive on the same barrier in CTA `cta` of the cluster
+    asm volatile(
+        "{\n\t.reg .b32 remAddr32;\n\t"
+        "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t}"
+        ::"r"(bar), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+template <int COLS> __device__ __forceinline__ void tmem_alloc_cg2(uint32_t dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS> __device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
 template <int COLS> __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -171,9 +224,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return d;
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=NT.
-template <int NT> __device__ __forceinline__ constexpr uint32_t make_idesc() {
+template <int NT, int M = kBlockM> __device__ __forceinline__ constexpr uint32_t make_idesc() {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(NT >> 3) << 17) |
-           (static_cast<uint32_t>(kBlockM >> 4) << 24);
+           (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -236,12 +289,15 @@ __device__ __forceinline__ ItemCoord decode_item(const ConvGemm& p, int item) {
     return c;
 }
 
-template <int NT, int MT, int NDY, bool BRES, int ACT, bool POOL, bool OUT_FP32>
+template <int NT, int MT, int NDY, bool BRES, int ACT, bool POOL, bool OUT_FP32, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ ConvGemm p, const int n_items) {
-    using C = Cfg<NT, MT>;
+    using C = Cfg<NT, MT, CG>;
     constexpr int NACC = C::kNAcc;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;          // CG == 2: rank 0 is the leader (issues the MMAs)
+    const int unit0 = static_cast<int>(blockIdx.x) / CG;             // persistent loop over items, one CTA pair (or CTA) each
+    const int ustep = static_cast<int>(gridDim.x) / CG;
     extern __shared__ uint8_t smem_raw[];
     // 128B swizzle needs 1024 B alignment of every operand tile
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -269,60 +325,76 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full_bar(s), 1);
+            mbar_init(full_bar(s), CG);                // CG == 2: the leader's copy collects both producers
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), kEpiWarps);   // one arrival per epilogue warp
+            mbar_init(tempty_bar(a), CG * kEpiWarps);  // one arrival per epilogue warp (of both CTAs, on the leader)
         }
         mbar_init(bres_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_slot);
+    if (warp == 2) { if (CG == 2) tmem_alloc_cg2<C::kTmemCols>(tmem_slot); else tmem_alloc<C::kTmemCols>(tmem_slot); }
     tcgen05_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (BRES && CG == 2) {
+        // Resident weights of BOTH CTAs must be in place before the leader issues an MMA that reads
+        // the peer's half: each CTA loads its rows, one thread waits, then the pair synchronises.
+        if (warp == 0 && elect_one_sync()) {
+            mbar_expect_tx(bres_bar, bres_bytes);
+            for (int kb = 0; kb < kb_total; ++kb)
+                tma_load_2d(smem_base + kb * C::kBBytes, &tmB, bres_bar, kb * kBlockK, static_cast<int>(rank) * (NT / CG));
+        }
+        if (threadIdx.x == 32) mbar_wait(bres_bar, 0u, p.err_flag, 105);
+        cluster_sync_all();
+    }
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (one elected thread)
         if (elect_one_sync()) {
-            if (BRES) {   // the whole weight matrix of this layer, once (nphase == n_tiles == 1)
+            if (BRES && CG == 1) {   // the whole weight matrix of this layer, once (nphase == n_tiles == 1)
                 mbar_expect_tx(bres_bar, bres_bytes);
                 for (int kb = 0; kb < kb_total; ++kb)
-                    tma_load_2d(smem_base + kb * C::kBBytes, &tmB, bres_bar, kb * kBlockK, 0);
+                    tma_load_2d(smem_base + kb * C::kBBytes, &tmB, bres_bar, kb * kBlockK, static_cast<int>(rank) * (NT / CG));
             }
             int stage = 0, tr_p = 0;
             uint32_t phase = 0;
             const uint32_t unit_tx = ((p.dbg & 1) ? 0u : static_cast<uint32_t>(MT * p.a_unit_bytes)) +
                                      ((BRES || (p.dbg & 2)) ? 0u : static_cast<uint32_t>(NDY * C::kBBytes));
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (int item = unit0; item < n_items; item += ustep) {
                 const ItemCoord c = decode_item(p, item);
-                const int brow = c.phase * p.cout_pad + c.ntile * NT;
+                const int brow = c.phase * p.cout_pad + c.ntile * NT + static_cast<int>(rank) * (NT / CG);
                 TileCoord tc[MT];
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) tc[mt] = decode_tile(p, c.mgroup * MT + mt);   // tiles past the end read OOB zeros
+                for (int mt = 0; mt < MT; ++mt) tc[mt] = decode_tile(p, (c.mgroup * CG + static_cast<int>(rank)) * MT + mt);   // tiles past the end read OOB zeros
                 int g = 0, cc = 0;
                 for (int u0 = 0; u0 < p.units; u0 += p.ups) {
                     const int nu = min(p.ups, p.units - u0);
                     mbar_wait(empty_bar(stage), phase ^ 1u, p.err_flag, 101);
                     GANREV_TR(0, tr_p);
                     const uint32_t s_base = stage0 + stage * p.stage_bytes;
-                    mbar_expect_tx(full_bar(stage), nu * unit_tx);
+                    if (CG == 1 || rank == 0) mbar_expect_tx(full_bar(stage), nu * unit_tx * CG);   // bytes of both CTAs land on the leader's barrier
+                    else mbar_arrive_cta(full_bar(stage), 0);
                     for (int x = 0; x < nu; ++x) {
                         const uint32_t u_base = s_base + x * p.unit_bytes;
                         const int dx = p.gdx[c.phase][g], dy = p.gdy0[c.phase][g];
                         if (!(p.dbg & 1)) {
 #pragma unroll
-                            for (int mt = 0; mt < MT; ++mt)
-                                tma_load_4d(u_base + mt * p.a_unit_bytes, &tmA, full_bar(stage), cc * kBlockK, tc[mt].w0 + dx, tc[mt].h0 + dy, tc[mt].n0);
+                            for (int mt = 0; mt < MT; ++mt) {
+                                if (CG == 2) tma_load_4d_cg2(u_base + mt * p.a_unit_bytes, &tmA, full_bar(stage), cc * kBlockK, tc[mt].w0 + dx, tc[mt].h0 + dy, tc[mt].n0);
+                                else tma_load_4d(u_base + mt * p.a_unit_bytes, &tmA, full_bar(stage), cc * kBlockK, tc[mt].w0 + dx, tc[mt].h0 + dy, tc[mt].n0);
+                            }
                         }
                         if (!BRES && !(p.dbg & 2)) {
 #pragma unroll
-                            for (int j = 0; j < NDY; ++j)
-                                tma_load_2d(u_base + MT * p.a_unit_bytes + j * C::kBBytes, &tmB, full_bar(stage),
-                                            (g * NDY + j) * p.Cin + cc * kBlockK, brow);
+                            for (int j = 0; j < NDY; ++j) {
+                                if (CG == 2) tma_load_2d_cg2(u_base + MT * p.a_unit_bytes + j * C::kBBytes, &tmB, full_bar(stage), (g * NDY + j) * p.Cin + cc * kBlockK, brow);
+                                else tma_load_2d(u_base + MT * p.a_unit_bytes + j * C::kBBytes, &tmB, full_bar(stage), (g * NDY + j) * p.Cin + cc * kBlockK, brow);
+                            }
                         }
                         if (++cc == p.cin_chunks) { cc = 0; ++g; }
                     }
@@ -333,19 +405,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (one elected thread)
-        if (elect_one_sync()) {
-            constexpr uint32_t idesc = make_idesc<NT>();
+        // ------------------------------------------------------------ MMA issuer (one elected thread; CG == 2: leader CTA only)
+        if (rank == 0 && elect_one_sync()) {
+            constexpr uint32_t idesc = make_idesc<NT, kBlockM * CG>();
             const uint64_t desc_base = make_smem_desc(0);
             auto desc_at = [&](uint32_t addr) { return desc_base | static_cast<uint64_t>((addr & 0x3FFFFu) >> 4); };
-            if (BRES) {
+            if (BRES && CG == 1) {                   // (CG == 2: both CTAs' resident weights were awaited before the cluster sync below)
                 mbar_wait(bres_bar, 0u, p.err_flag, 105);
                 tcgen05_fence_after();
             }
             int stage = 0, tr_m = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            for (int item = unit0; item < n_items; item += ustep, ++it) {
                 const int acc = it % NACC;
                 const uint32_t acc_phase = (it / NACC) & 1u;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err_flag, 102);
@@ -374,15 +446,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     const uint32_t tmem_d = tmem_base + static_cast<uint32_t>((acc * MT + mt) * NT);
                                     const bool first = (u0 + x == 0) && (j == 0);
 #pragma unroll
-                                    for (int k = 0; k < kBlockK / 16; ++k)   // +32 B per K=16 step inside the swizzle span (>>4 -> +2)
-                                        umma_bf16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (first && k == 0) ? 0u : 1u);
+                                    for (int k = 0; k < kBlockK / 16; ++k) {   // +32 B per K=16 step inside the swizzle span (>>4 -> +2)
+                                        if (CG == 2) umma_bf16_cg2(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (first && k == 0) ? 0u : 1u);
+                                        else umma_bf16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (first && k == 0) ? 0u : 1u);
+                                    }
                                 }
                             }
                         }
                         if (++cc == p.cin_chunks) { cc = 0; ++g; }
                     }
-                    umma_commit(empty_bar(stage));                              // frees the smem slot when the MMAs retire
-                    if (u0 + p.ups >= p.units) umma_commit(tfull_bar(acc));     // accumulators complete
+                    if (CG == 2) {
+                        umma_commit_cg2(empty_bar(stage));                          // frees the slot in BOTH CTAs when the MMAs retire
+                        if (u0 + p.ups >= p.units) umma_commit_cg2(tfull_bar(acc)); // accumulators complete (both CTAs' epilogues)
+                    } else {
+                        umma_commit(empty_bar(stage));                              // frees the smem slot when the MMAs retire
+                        if (u0 + p.ups >= p.units) umma_commit(tfull_bar(acc));     // accumulators complete
+                    }
                     GANREV_TR(3, tr_m);
                     ++tr_m;
                     if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -405,7 +484,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int kChunksPerTile = NT / CW;
         const bool rescale = p.post_scale != 1.0f;
         int it = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        for (int item = unit0; item < n_items; item += ustep, ++it) {
             const ItemCoord c = decode_item(p, item);
             const int acc = it % NACC;
             const uint32_t acc_phase = (it / NACC) & 1u;
@@ -454,7 +533,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 if (mt != cur_mt) {
                     cur_mt = mt;
-                    const TileCoord t = decode_tile(p, c.mgroup * MT + mt);
+                    const TileCoord t = decode_tile(p, (c.mgroup * CG + static_cast<int>(rank)) * MT + mt);
                     const int n = t.n0 + n_l, h = t.h0 + h_l, w = t.w0 + w_l;
                     int oh = h, ow = w;
                     writer = n < p.n_img;
@@ -547,16 +626,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) { if (CG == 2) mbar_arrive_cta(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc)); }
             if (etid == 0) GANREV_TR(5, it);
         }
     }
 
     tcgen05_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();   // the leader's MMAs read the peer's smem: nobody leaves early
     if (warp == 2) {
         tcgen05_fence_after();
-        tmem_dealloc<C::kTmemCols>(tmem_base);
+        if (CG == 2) tmem_dealloc_cg2<C::kTmemCols>(tmem_base); else tmem_dealloc<C::kTmemCols>(tmem_base);
     }
 }
 

@@ -21,7 +21,7 @@ using namespace ganrev;
 struct TcLayer {
     std::string name;
     ConvGemm g{};
-    int NT = 0, MT = 1, NDY = 1, Ktot = 0;
+    int NT = 0, MT = 1, NDY = 1, CG = 1, Ktot = 0;
     bool bres = false;
     size_t smem_bytes = 0;
     DevBuf w, scale, shift;
@@ -63,6 +63,8 @@ struct ganrev_ctx {
     std::string err;
     int64_t chunk = 4096;
     int conv_impl = 0;
+    int cta_pairs = 0x1f;     // which layers use tcgen05 cta_group::2 CTA pairs (bit0 G conv1, bit1 G conv2, bit2 R conv2/3,
+                              // bit3 R conv4, bit4 R conv5/6); takes effect at the next ganrev_load_*.  Default = measured best.
     int dbg = 0;
     DevBuf trace;
     std::string trace_layer;
@@ -225,7 +227,7 @@ enum LayerKind { KIND_LINEAR = 0, KIND_CONV3 = 1, KIND_UPCONV3 = 2 };
 static int make_tmB(ganrev_ctx* ctx, TcLayer& L) {
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(L.Ktot), static_cast<cuuint64_t>(L.g.nphase) * L.g.cout_pad};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(L.Ktot) * 2};
-    const cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(L.NT)};
+    const cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(L.NT / L.CG)};
     const cuuint32_t es[2] = {1u, 1u};
     CUresult r = ctx->encode(&L.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, L.w.p, dims, strides, box, es,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -238,6 +240,7 @@ struct LayerDef {
     const char* name;
     LayerKind kind;
     int NT, MT;              // N tile, accumulators per CTA
+    int cg;                  // 1, or 2 = CTA pairs (tcgen05 cta_group::2: M = 256 per MMA, each CTA holds half of B)
     bool want_bres;          // keep the whole weight matrix resident in smem when it fits
     int Hin, Win, Cin;
     int cout_real, n_tiles;
@@ -253,6 +256,7 @@ struct LayerDef {
 static int build_tc_layer(ganrev_ctx* ctx, TcLayer& L, const LayerDef& d, const float* w, const BnFold& bn) {
     L.name = d.name;
     L.NT = d.NT;
+    L.CG = d.cg;
     ConvGemm& g = L.g;
     g = ConvGemm{};
     g.Hin = d.Hin; g.Win = d.Win; g.Cin = d.Cin;
@@ -287,6 +291,7 @@ static int build_tc_layer(ganrev_ctx* ctx, TcLayer& L, const LayerDef& d, const 
     }
     L.NDY = g.ndy;
     L.MT = d.MT;
+    if (!halo && !(d.kind == KIND_UPCONV3 && d.NT == 256)) L.CG = 1;   // CTA-pair variants exist for the halo layers and G conv1
     g.units = g.ngroups * g.cin_chunks;
     const int ntap = g.ngroups * g.ndy;
     L.Ktot = ntap * d.Cin;
@@ -328,7 +333,7 @@ static int build_tc_layer(ganrev_ctx* ctx, TcLayer& L, const LayerDef& d, const 
 
     // ---- shared-memory plan: [resident weights][stages x (ups units)][barriers, scale/shift]
     g.a_unit_bytes = (BH + g.ndy - 1) * BW * BN * 128;
-    g.b_kb_bytes = d.NT * 128;
+    g.b_kb_bytes = (d.NT / L.CG) * 128;          // this CTA's share of a 64-wide weight tile
     g.dy_stride_bytes = BW * BN * 128;
     const int tail = (2 * tc::kMaxStages + 5) * 8 + 24 + 2 * 2 * d.NT * 4 + tc::kEpiWarps * 32 * 64;   // barriers, scale/shift, store-transpose buffers
     const int budget = tc::kSmemBudget - 1024 - tail;
@@ -363,26 +368,46 @@ static int check_geom(ganrev_ctx* ctx, int C, int H, int W, int nd) {
 // =================================================================================
 // layer launches
 // =================================================================================
-template <int NT, int MT, int NDY, bool BRES, int ACT, bool POOL, bool OUT_FP32>
+template <int NT, int MT, int NDY, bool BRES, int ACT, bool POOL, bool OUT_FP32, int CG>
 static int launch_tc(ganrev_ctx* ctx, const TcLayer& L, const CUtensorMap& tmA, const ConvGemm& g, int n_items) {
+    auto kern = tc::conv_tc_kernel<NT, MT, NDY, BRES, ACT, POOL, OUT_FP32, CG>;
     static size_t attr_max = 0;
     if (L.smem_bytes > attr_max) {
-        CU_TRY(cudaFuncSetAttribute(tc::conv_tc_kernel<NT, MT, NDY, BRES, ACT, POOL, OUT_FP32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(L.smem_bytes)));
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.smem_bytes)));
         attr_max = L.smem_bytes;
     }
-    const int grid = std::min(n_items, ctx->num_sms);
-    tc::conv_tc_kernel<NT, MT, NDY, BRES, ACT, POOL, OUT_FP32><<<grid, tc::kThreads, L.smem_bytes, ctx->stream>>>(tmA, L.tmB, g, n_items);
-    CU_TRY(cudaGetLastError());
+    int grid = std::min(n_items * CG, ctx->num_sms);
+    grid -= grid % CG;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(tc::kThreads);
+    cfg.dynamicSmemBytes = L.smem_bytes;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CG == 2 ? 1 : 0;
+    CU_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, L.tmB, g, n_items));
     return GANREV_OK;
 }
 // The layer shapes of G3 / R_default map onto this fixed set of kernel variants
 // (NT, MT, NDY, BRES, ACT, POOL, FP32OUT).  NDY=1 rows serve geometries too small for halo reuse.
 static int dispatch_tc(ganrev_ctx* ctx, const TcLayer& L, const CUtensorMap& tmA, const ConvGemm& g, int n_items) {
-#define TC_CASE(NT_, MT_, NDY_, BRES_, ACT_, POOL_, FP32_)                                                              \
+#define TC_CASE_CG(NT_, MT_, NDY_, BRES_, ACT_, POOL_, FP32_, CG_)                                                      \
     if (L.NT == NT_ && L.MT == MT_ && L.NDY == NDY_ && L.bres == BRES_ && (ACT_ == tc::ACT_RUNTIME || g.act == ACT_) && \
-        (g.pool != 0) == POOL_ && (g.out_fp32 != 0) == FP32_)                                                           \
-        return launch_tc<NT_, MT_, NDY_, BRES_, ACT_, POOL_, FP32_>(ctx, L, tmA, g, n_items);
+        (g.pool != 0) == POOL_ && (g.out_fp32 != 0) == FP32_ && L.CG == CG_)                                            \
+        return launch_tc<NT_, MT_, NDY_, BRES_, ACT_, POOL_, FP32_, CG_>(ctx, L, tmA, g, n_items);
+#define TC_CASE(NT_, MT_, NDY_, BRES_, ACT_, POOL_, FP32_) TC_CASE_CG(NT_, MT_, NDY_, BRES_, ACT_, POOL_, FP32_, 1)
+    // CTA-pair (cta_group::2) variants of the halo layers
+    TC_CASE_CG(256, 2, 1, false, ACT_RELU, false, false, 2)   // G Up+Conv 512->256
+    TC_CASE_CG(256, 2, 2, false, ACT_RELU, false, false, 2)
+    TC_CASE_CG(128, 2, 2, false, ACT_RELU, false, false, 2)   // G Up+Conv 256->128
+    TC_CASE_CG(64, 2, 3, true, ACT_ELU, false, false, 2)      // R Conv 64->64
+    TC_CASE_CG(64, 2, 3, true, ACT_ELU, true, false, 2)
+    TC_CASE_CG(128, 1, 3, true, ACT_ELU, false, false, 2)     // R Conv 64->128
+    TC_CASE_CG(128, 2, 3, false, ACT_ELU, false, false, 2)    // R Conv 128->128
+    TC_CASE_CG(128, 2, 3, false, ACT_ELU, true, false, 2)
     // G
     TC_CASE(256, 1, 1, false, ACT_RELU, false, false)      // Linear
     TC_CASE(256, 2, 1, false, ACT_RELU, false, false)      // Up+Conv 512->256 on < 128-pixel inputs
@@ -406,8 +431,9 @@ static int dispatch_tc(ganrev_ctx* ctx, const TcLayer& L, const CUtensorMap& tmA
     TC_CASE(128, 1, 1, false, tc::ACT_RUNTIME, false, true)
     TC_CASE(256, 1, 1, false, tc::ACT_RUNTIME, false, true)
 #undef TC_CASE
-    return fail(ctx, GANREV_EINVAL, "no tcgen05 kernel variant for layer %s (NT=%d MT=%d NDY=%d bres=%d act=%d pool=%d fp32=%d)", L.name.c_str(),
-                L.NT, L.MT, L.NDY, (int)L.bres, g.act, g.pool, g.out_fp32);
+#undef TC_CASE_CG
+    return fail(ctx, GANREV_EINVAL, "no tcgen05 kernel variant for layer %s (NT=%d MT=%d NDY=%d bres=%d act=%d pool=%d fp32=%d cg=%d)", L.name.c_str(),
+                L.NT, L.MT, L.NDY, (int)L.bres, g.act, g.pool, g.out_fp32, L.CG);
 }
 
 static int run_layer(ganrev_ctx* ctx, TcLayer& L, const void* in, void* out, int n_img, int64_t n_cap) {
@@ -420,7 +446,7 @@ static int run_layer(ganrev_ctx* ctx, TcLayer& L, const void* in, void* out, int
     const int BN = 1 << g.lgBN;
     const int tiles_n = (n_img + BN - 1) / BN;
     g.total_tiles = tiles_n * g.tiles_h * g.tiles_w;
-    const int mgroups = (g.total_tiles + L.MT - 1) / L.MT;
+    const int mgroups = (g.total_tiles + L.MT * L.CG - 1) / (L.MT * L.CG);
     const int n_items = mgroups * g.nphase * g.n_tiles;
     ProfScope ps(ctx, L.name, L.flops_per_img * n_img, L.bytes_per_img * n_img);
     if (ctx->conv_impl == 1) {
@@ -470,6 +496,7 @@ static int load_G_impl(ganrev_ctx* ctx, int C, int H, int W, int nd, const float
     const float* b3 = p;
 
     G.C = C; G.H = H; G.W = W; G.nd = nd; G.F = F;
+    const int pairs1 = (ctx->cta_pairs & 1) ? 2 : 1, pairs2 = (ctx->cta_pairs & 2) ? 2 : 1;
     G.kpad = (nd + 63) / 64 * 64;
     {   // Linear + BN1d + ReLU; output features re-ordered from View(512,sH,sW) (NCHW, models.lua:118) to NHWC
         std::vector<float> wm(static_cast<size_t>(F) * G.kpad, 0.0f);
@@ -481,17 +508,17 @@ static int load_G_impl(ganrev_ctx* ctx, int C, int H, int W, int nd, const float
                 bb[fn] = lb[fo]; gg[fn] = g0[fo]; be[fn] = be0[fo]; mm[fn] = m0[fo]; vv[fn] = v0[fo];
             }
         BnFold bn = fold_bn(bb.data(), gg.data(), be.data(), mm.data(), vv.data(), F, F);
-        const LayerDef d{"g_linear", KIND_LINEAR, 256, 1, false, 1, 1, G.kpad, F, F / 256, 1, 1, F, 0, ACT_RELU, 1.0f, 0, false};
+        const LayerDef d{"g_linear", KIND_LINEAR, 256, 1, 1, false, 1, 1, G.kpad, F, F / 256, 1, 1, F, 0, ACT_RELU, 1.0f, 0, false};
         RC_TRY(build_tc_layer(ctx, G.lin, d, wm.data(), bn));
     }
     {
         BnFold bn = fold_bn(b1, g1, be1, m1, v1, 256, 256);
-        const LayerDef d{"g_conv1_up", KIND_UPCONV3, 256, 2, false, sH, sW, 512, 256, 1, 2 * sH, 2 * sW, 256, 0, ACT_RELU, 1.0f, 0, false};
+        const LayerDef d{"g_conv1_up", KIND_UPCONV3, 256, 2, pairs1, false, sH, sW, 512, 256, 1, 2 * sH, 2 * sW, 256, 0, ACT_RELU, 1.0f, 0, false};
         RC_TRY(build_tc_layer(ctx, G.c1, d, w1, bn));
     }
     {
         BnFold bn = fold_bn(b2, g2, be2, m2, v2, 128, 128);
-        const LayerDef d{"g_conv2_up", KIND_UPCONV3, 128, 2, false, 2 * sH, 2 * sW, 256, 128, 1, H, W, 128, 0, ACT_RELU, 1.0f, 0, false};
+        const LayerDef d{"g_conv2_up", KIND_UPCONV3, 128, 2, pairs2, false, 2 * sH, 2 * sW, 256, 128, 1, H, W, 128, 0, ACT_RELU, 1.0f, 0, false};
         RC_TRY(build_tc_layer(ctx, G.c2, d, w2, bn));
     }
     {   // conv3 (128 -> C) + Sigmoid in two passes: a 1x1 GEMM giving every input pixel's 9*C tap
@@ -503,7 +530,7 @@ static int load_G_impl(ganrev_ctx* ctx, int C, int H, int W, int nd, const float
                 for (int ci = 0; ci < 128; ++ci) wm[static_cast<size_t>(t * C + co) * 128 + ci] = w3[(static_cast<size_t>(co) * 128 + ci) * 9 + t];
         BnFold bn;
         bn.scale.assign(NT3, 1.0f); bn.shift.assign(NT3, 0.0f);
-        const LayerDef d{"g_conv3_taps", KIND_LINEAR, NT3, 1, false, 1, 1, 128, 9 * C, 1, 1, 1, NT3, 0, ACT_NONE, 1.0f, 1, false};
+        const LayerDef d{"g_conv3_taps", KIND_LINEAR, NT3, 1, 1, false, 1, 1, 128, 9 * C, 1, 1, 1, NT3, 0, ACT_NONE, 1.0f, 1, false};
         RC_TRY(build_tc_layer(ctx, G.c3, d, wm.data(), bn));
         RC_TRY(upload(ctx, G.b3, b3, sizeof(float) * C));
     }
@@ -547,24 +574,24 @@ static int load_R_impl(ganrev_ctx* ctx, int slot, int C, int H, int W, int nd, i
         memcpy(&pack[static_cast<size_t>(K) * 64 + 64], bn.shift.data(), 64 * 4);
         RC_TRY(upload(ctx, R.c1pack, pack.data(), pack.size() * 4));
     }
-    auto conv_layer = [&](TcLayer& L, const char* name, const CB& c, int co, int ci, int Hin, int Win, int pool, float post, int MT, bool bres) {
+    auto conv_layer = [&](TcLayer& L, const char* name, const CB& c, int co, int ci, int Hin, int Win, int pool, float post, int MT, bool bres, int pairs) {
         BnFold bn = fold_bn(c.b, c.g, c.be, c.m, c.v, co, co);
         const int Ho = pool ? Hin / 2 : Hin, Wo = pool ? Win / 2 : Win;
-        const LayerDef d{name, KIND_CONV3, co, MT, bres, Hin, Win, ci, co, 1, Ho, Wo, co, pool, ACT_ELU, post, 0, false};
+        const LayerDef d{name, KIND_CONV3, co, MT, pairs, bres, Hin, Win, ci, co, 1, Ho, Wo, co, pool, ACT_ELU, post, 0, false};
         return build_tc_layer(ctx, L, d, c.w, bn);
     };
-    RC_TRY(conv_layer(R.c2, "r_conv2", c2, 64, 64, H, W, 0, 1.0f, 2, true));
-    RC_TRY(conv_layer(R.c3, "r_conv3_pool", c3, 64, 64, H, W, 1, 1.0f, 2, true));
-    RC_TRY(conv_layer(R.c4, "r_conv4", c4, 128, 64, Hh, Wh, 0, 1.0f, 1, true));
-    RC_TRY(conv_layer(R.c5, "r_conv5", c5, 128, 128, Hh, Wh, 0, 1.0f, 2, false));
-    RC_TRY(conv_layer(R.c6, "r_conv6_pool", c6, 128, 128, Hh, Wh, 1, 0.75f, 2, false));   // SpatialDropout(0.25) in eval: x0.75
+    RC_TRY(conv_layer(R.c2, "r_conv2", c2, 64, 64, H, W, 0, 1.0f, 2, true, (ctx->cta_pairs & 4) ? 2 : 1));
+    RC_TRY(conv_layer(R.c3, "r_conv3_pool", c3, 64, 64, H, W, 1, 1.0f, 2, true, (ctx->cta_pairs & 4) ? 2 : 1));
+    RC_TRY(conv_layer(R.c4, "r_conv4", c4, 128, 64, Hh, Wh, 0, 1.0f, 1, true, (ctx->cta_pairs & 8) ? 2 : 1));
+    RC_TRY(conv_layer(R.c5, "r_conv5", c5, 128, 128, Hh, Wh, 0, 1.0f, 2, false, (ctx->cta_pairs & 16) ? 2 : 1));
+    RC_TRY(conv_layer(R.c6, "r_conv6_pool", c6, 128, 128, Hh, Wh, 1, 0.75f, 2, false, (ctx->cta_pairs & 16) ? 2 : 1));   // SpatialDropout(0.25) in eval: x0.75
     {   // Linear(F -> 512) + BN1d + ELU; input columns re-ordered from View (NCHW flatten, models.lua:446) to NHWC
         std::vector<float> wm(static_cast<size_t>(512) * F);
         for (int o = 0; o < 512; ++o)
             for (int c = 0; c < 128; ++c)
                 for (int s = 0; s < HWq; ++s) wm[static_cast<size_t>(o) * F + s * 128 + c] = l1w[static_cast<size_t>(o) * F + c * HWq + s];
         BnFold bn = fold_bn(l1b, g7, be7, m7, v7, 512, 512);
-        const LayerDef d{"r_linear1", KIND_LINEAR, 64, 1, false, 1, 1, F, 512, 8, 1, 1, 512, 0, ACT_ELU, 1.0f, 0, false};
+        const LayerDef d{"r_linear1", KIND_LINEAR, 64, 1, 1, false, 1, 1, F, 512, 8, 1, 1, 512, 0, ACT_ELU, 1.0f, 0, false};
         RC_TRY(build_tc_layer(ctx, R.l1, d, wm.data(), bn));
     }
     {   // Linear(512 -> nd) [+ Tanh], fp32 output
@@ -575,7 +602,7 @@ static int load_R_impl(ganrev_ctx* ctx, int slot, int C, int H, int W, int nd, i
         BnFold bn;
         bn.scale.assign(cp, 0.0f); bn.shift.assign(cp, 0.0f);
         for (int i = 0; i < nd; ++i) { bn.scale[i] = 1.0f; bn.shift[i] = l2b[i]; }
-        const LayerDef d{"r_linear2", KIND_LINEAR, NT, 1, false, 1, 1, 512, nd, n_tiles, 1, 1, nd, 0, tanh_out ? ACT_TANH : ACT_NONE, 1.0f, 1, false};
+        const LayerDef d{"r_linear2", KIND_LINEAR, NT, 1, 1, false, 1, 1, 512, nd, n_tiles, 1, 1, nd, 0, tanh_out ? ACT_TANH : ACT_NONE, 1.0f, 1, false};
         RC_TRY(build_tc_layer(ctx, R.l2, d, wm.data(), bn));
     }
     R.loaded = true;
@@ -1420,6 +1447,7 @@ int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value) {
         ctx->conv_impl = static_cast<int>(value);
         return GANREV_OK;
     }
+    if (!strcmp(name, "cta_pairs")) { ctx->cta_pairs = static_cast<int>(value); return GANREV_OK; }
     if (!strcmp(name, "dbg")) { ctx->dbg = static_cast<int>(value); return GANREV_OK; }
     return fail(ctx, GANREV_EINVAL, "unknown option %s", name);
 }

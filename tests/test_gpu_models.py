@@ -1,6 +1,8 @@
 """GPU parity of G3 / R_default (models.lua:104-143, 389-464) through the C ABI against the
 CPU oracle.  Tolerances are north_star's: generated pixels within 2e-2 max-abs, recovered
 vectors cosine >= 0.999 -- plus a relative-L2 bound so a constant offset cannot hide errors."""
+import os
+
 import numpy as np
 import pytest
 
@@ -32,6 +34,7 @@ def ctx(pkg):
 def _setup(pkg, ctx, geom, stress, impl):
     C, H, W, nd, N = geom
     ctx.set_option("conv_impl", impl)
+    ctx.set_option("cta_pairs", int(os.environ.get("GANREV_CTA_PAIRS", "0")))   # A/B: tcgen05 cta_group::2 variants
     ctx.set_option("chunk", 16)        # several chunks, the last one ragged
     gb = pkg.weights.init_G(C, H, W, nd, seed=1, stress=stress)
     rb = pkg.weights.init_R(C, H, W, nd, seed=2, stress=stress)
