@@ -400,8 +400,8 @@ static int dispatch_tc(ganrev_ctx* ctx, const TcLayer& L, const CUtensorMap& tmA
         return launch_tc<NT_, MT_, NDY_, BRES_, ACT_, POOL_, FP32_, CG_>(ctx, L, tmA, g, n_items);
 #define TC_CASE(NT_, MT_, NDY_, BRES_, ACT_, POOL_, FP32_) TC_CASE_CG(NT_, MT_, NDY_, BRES_, ACT_, POOL_, FP32_, 1)
     // CTA-pair (cta_group::2) variants of the halo layers
-    TC_CASE_CG(256, 2, 1, false, ACT_RELU, false, false, 2)   // G Up+Conv 512->256
-    TC_CASE_CG(256, 2, 2, false, ACT_RELU, false, false, 2)
+    TC_CASE_CG(256, 1, 1, false, ACT_RELU, false, false, 2)   // G Up+Conv 512->256
+    TC_CASE_CG(256, 1, 2, false, ACT_RELU, false, false, 2)
     TC_CASE_CG(128, 2, 2, false, ACT_RELU, false, false, 2)   // G Up+Conv 256->128
     TC_CASE_CG(64, 2, 3, true, ACT_ELU, false, false, 2)      // R Conv 64->64
     TC_CASE_CG(64, 2, 3, true, ACT_ELU, true, false, 2)
@@ -513,7 +513,8 @@ static int load_G_impl(ganrev_ctx* ctx, int C, int H, int W, int nd, const float
     }
     {
         BnFold bn = fold_bn(b1, g1, be1, m1, v1, 256, 256);
-        const LayerDef d{"g_conv1_up", KIND_UPCONV3, 256, 2, pairs1, false, sH, sW, 512, 256, 1, 2 * sH, 2 * sW, 256, 0, ACT_RELU, 1.0f, 0, false};
+        const LayerDef d{"g_conv1_up", KIND_UPCONV3, 256, pairs1 == 2 ? 1 : 2, pairs1, false,   // pairs: one double-buffered accumulator per CTA, B shared by the pair
+                          sH, sW, 512, 256, 1, 2 * sH, 2 * sW, 256, 0, ACT_RELU, 1.0f, 0, false};
         RC_TRY(build_tc_layer(ctx, G.c1, d, w1, bn));
     }
     {

@@ -33,8 +33,9 @@ def ctx(pkg):
 
 def _setup(pkg, ctx, geom, stress, impl):
     C, H, W, nd, N = geom
-    ctx.set_option("conv_impl", impl)
-    ctx.set_option("cta_pairs", int(os.environ.get("GANREV_CTA_PAIRS", "0")))   # A/B: tcgen05 cta_group::2 variants
+    # impl: 1 = CUDA-core A/B kernel, 0 = tcgen05 with the default CTA-pair (cta_group::2) layers, 2 = tcgen05 single-CTA
+    ctx.set_option("conv_impl", 1 if impl == 1 else 0)
+    ctx.set_option("cta_pairs", 0 if impl == 2 else int(os.environ.get("GANREV_CTA_PAIRS", "31")))
     ctx.set_option("chunk", 16)        # several chunks, the last one ragged
     gb = pkg.weights.init_G(C, H, W, nd, seed=1, stress=stress)
     rb = pkg.weights.init_R(C, H, W, nd, seed=2, stress=stress)
@@ -46,7 +47,7 @@ def _setup(pkg, ctx, geom, stress, impl):
     return gb, rb, rfb, noise
 
 
-@pytest.mark.parametrize("impl", [1, 0], ids=["cudacore", "tcgen05"])
+@pytest.mark.parametrize("impl", [1, 0, 2], ids=["cudacore", "tcgen05", "tcgen05_1cta"])
 @pytest.mark.parametrize("geom", GEOMS, ids=lambda g: "C%dx%dx%d_nd%d_N%d" % g)
 def test_G_matches_oracle(pkg, orc, ctx, geom, impl):
     C, H, W, nd, N = geom
@@ -59,7 +60,7 @@ def test_G_matches_oracle(pkg, orc, ctx, geom, impl):
     assert err <= PIX_TOL, f"max |pixel diff| {err}"
 
 
-@pytest.mark.parametrize("impl", [1, 0], ids=["cudacore", "tcgen05"])
+@pytest.mark.parametrize("impl", [1, 0, 2], ids=["cudacore", "tcgen05", "tcgen05_1cta"])
 @pytest.mark.parametrize("geom", GEOMS, ids=lambda g: "C%dx%dx%d_nd%d_N%d" % g)
 def test_R_matches_oracle(pkg, orc, ctx, geom, impl):
     C, H, W, nd, N = geom

@@ -6,7 +6,8 @@ from __graft_entry__ import load_package
 pkg = load_package()
 C, H, W, ND, N = 1, 32, 32, 100, 32768
 ctx = pkg.Context(0)
-ctx.set_option("cta_pairs", int(os.environ.get("GANREV_CTA_PAIRS", "0")))
+if "GANREV_CTA_PAIRS" in os.environ:
+    ctx.set_option("cta_pairs", int(os.environ["GANREV_CTA_PAIRS"]))
 ctx.load_G(C, H, W, ND, pkg.weights.init_G(C, H, W, ND))
 ctx.load_R(0, C, H, W, ND, pkg.weights.init_R(C, H, W, ND))
 noise = np.random.default_rng(0).normal(size=(N, ND)).astype(np.float32)
