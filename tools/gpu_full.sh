@@ -15,4 +15,4 @@ for k, v in d['kernels'].items():
     print("  %-22s n=%-5d ms=%-9.3f share=%.3f  TF=%-8.2f GB/s=%.1f" % (k, v['launches'], v['ms'], v['share'], v['tflops_executed'], v['gbs']))
 PY
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --images 16384 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 0 -c 11 -f -o gpurun_out/prof_r01b python bench.py --images 8192 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 0 -c 11 -f -o gpurun_out/prof_r01c python bench.py --images 8192 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?"
