@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libganrev_cuda.so")
+# GANREV_CUDA_LIB: another build of the SAME library (e.g. `make trace`), never a different backend
+SO_PATH = os.environ.get("GANREV_CUDA_LIB") or os.path.join(_HERE, "libganrev_cuda.so")
 
 OK, EINVAL, ECUDA, ENODEV, ESTATE, ENCCL, ENOMEM = range(7)
 BUF_NOISE, BUF_IMAGES, BUF_ATTRS0, BUF_ATTRS1, BUF_FIXED, BUF_MASK = range(6)

@@ -49,7 +49,9 @@ struct ConvGemm {
     // A operand: NHWC bf16 activation [n_cap][Hin][Win][Cin]; M tile = box (64ch, BW, BH(+ndy-1), BN)
     int Hin, Win, Cin;
     int lgBW, lgBH, lgBN;      // log2 of the M-tile extents, BW*BH*BN == 128
-    int tiles_w, tiles_h;      // tiles per image
+    int tiles_w, tiles_h;      // tiles per image (powers of two: H, W are)
+    int lgTW, lgTH;            // log2 of the above
+    int lgNT;                  // log2(n_tiles), or -1 when n_tiles is not a power of two
     int total_tiles;           // M tiles in this launch
     int n_img;                 // valid images in this launch
     int nphase, ngroups, ndy;  // phase-decomposed upsample: 4 phases; else 1
@@ -64,8 +66,7 @@ struct ConvGemm {
     int Hout, Wout, up, pool, act, out_fp32;
     float post_scale;
     void* out;
-    const float* scale;        // [cout_pad] folded BN scale
-    const float* shift;        // [cout_pad] folded BN shift (+ conv bias)
+    const float* shift;        // [cout_pad] folded BN shift (+ conv bias); the BN scale is folded into B
     const bf16* A;             // raw pointers (CUDA-core kernel)
     const bf16* B;
     int* err_flag;

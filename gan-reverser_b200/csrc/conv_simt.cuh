@@ -19,7 +19,7 @@ __device__ __forceinline__ float simt_conv_at(const ConvGemm& p, int n, int h, i
             const bf16* wt = wrow + static_cast<size_t>(g * p.ndy + j) * p.Cin;
             for (int ci = 0; ci < p.Cin; ++ci) acc = fmaf(__bfloat162float(a[ci]), __bfloat162float(wt[ci]), acc);
         }
-    return fmaf(acc, p.scale[co], p.shift[co]);
+    return acc + p.shift[co];   // BN scale is folded into the weights
 }
 
 __global__ void conv_simt_kernel(const ConvGemm p, const long long total) {
@@ -41,7 +41,7 @@ __global__ void conv_simt_kernel(const ConvGemm p, const long long total) {
     } else {
         v = simt_conv_at(p, n, oh, ow, 0, co);
     }
-    v = apply_act(v, p.act) * p.post_scale;
+    v = apply_act(v, p.act);
     const size_t off = static_cast<size_t>(n) * p.out_sN + (static_cast<size_t>(oh) * p.Wout + ow) * p.out_sP + static_cast<size_t>(co) * p.out_sC;
     if (p.out_fp32) reinterpret_cast<float*>(p.out)[off] = v;
     else reinterpret_cast<bf16*>(p.out)[off] = __float2bfloat16_rn(v);

@@ -51,7 +51,7 @@ template <int NT, int MT, int CG = 1> struct Cfg {
     static constexpr int kTmemCols = kCols <= 32 ? 32 : (kCols <= 64 ? 64 : (kCols <= 128 ? 128 : (kCols <= 256 ? 256 : 512)));
     static constexpr int kChunk = NT < 32 ? NT : 32;                    // accumulator columns per tcgen05.ld
     static constexpr int kBarBytes = (2 * kMaxStages + 5) * 8 + 24;     // full/empty per stage, tfull/tempty x2, bres, tmem slot (16 B aligned)
-    static constexpr int kSsBytes = 2 * 2 * NT * 4;                     // double-buffered scale/shift
+    static constexpr int kSsBytes = 2 * NT * 4;                         // double-buffered shift
     static constexpr int kXposeBytes = kEpiWarps * 32 * 64;             // per-warp 32 px x 64 B store-transpose buffers
 };
 
@@ -258,10 +258,22 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 }
 
 // debug timeline: role r, event e -> clock64 of CTA 0
+#ifndef GANREV_EPI_TRACE
 #define GANREV_TR(role, e)                                                                     \
     do {                                                                                       \
         if (p.trace != nullptr && blockIdx.x == 0 && (e) < 256) p.trace[(role) * 256 + (e)] = clock64(); \
     } while (0)
+#define GANREV_TRE(role, e) do {} while (0)
+#else   // -DGANREV_EPI_TRACE: rows 0..3 hold the phases of epilogue thread 0's chunks instead of the producer / MMA events
+#define GANREV_TR(role, e)                                                                     \
+    do {                                                                                       \
+        if ((role) >= 4 && p.trace != nullptr && blockIdx.x == 0 && (e) < 256) p.trace[(role) * 256 + (e)] = clock64(); \
+    } while (0)
+#define GANREV_TRE(role, e)                                                                    \
+    do {                                                                                       \
+        if (etid == 0 && p.trace != nullptr && blockIdx.x == 0 && (e) < 256) p.trace[(role) * 256 + (e)] = clock64(); \
+    } while (0)
+#endif
 
 // M-tile index -> first image / row / column of the tile
 struct TileCoord {
@@ -269,11 +281,10 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord decode_tile(const ConvGemm& p, int tile) {
     TileCoord c;
-    c.w0 = (tile % p.tiles_w) << p.lgBW;
-    int t = tile / p.tiles_w;
-    c.h0 = (t % p.tiles_h) << p.lgBH;
-    t /= p.tiles_h;
-    c.n0 = t << p.lgBN;
+    c.w0 = (tile & (p.tiles_w - 1)) << p.lgBW;      // tiles_w, tiles_h are powers of two
+    const int t = tile >> p.lgTW;
+    c.h0 = (t & (p.tiles_h - 1)) << p.lgBH;
+    c.n0 = (t >> p.lgTH) << p.lgBN;
     return c;
 }
 // item -> (M group, phase, N tile); N tile fastest so consecutive items share activations in L2
@@ -282,10 +293,11 @@ struct ItemCoord {
 };
 __device__ __forceinline__ ItemCoord decode_item(const ConvGemm& p, int item) {
     ItemCoord c;
-    c.ntile = item % p.n_tiles;
-    const int t = item / p.n_tiles;
-    c.phase = t % p.nphase;
-    c.mgroup = t / p.nphase;
+    int t;
+    if (p.lgNT >= 0) { c.ntile = item & (p.n_tiles - 1); t = item >> p.lgNT; }
+    else             { t = item / p.n_tiles; c.ntile = item - t * p.n_tiles; }
+    c.phase = p.nphase == 4 ? (t & 3) : 0;          // nphase is 1 or 4
+    c.mgroup = p.nphase == 4 ? (t >> 2) : t;
     return c;
 }
 
@@ -482,23 +494,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint4* xpose = reinterpret_cast<uint4*>(smem + tail_off + C::kBarBytes + C::kSsBytes) + (warp - 2) * 128;   // 2 KB per warp
         constexpr int CW = C::kChunk;
         constexpr int kChunksPerTile = NT / CW;
-        const bool rescale = p.post_scale != 1.0f;
+        constexpr int kPairs = MT * kChunksPerTile;           // (sub-tile, column chunk) pairs per item
+        constexpr int kStep = kEpiWarps / 4;                  // warps per TMEM lane quarter
+        constexpr int kIters = (kPairs + kStep - 1) / kStep;  // pairs per warp
+        static_assert(kPairs % kStep == 0 || kIters == 1, "pairs must split evenly over the warps of a quarter");
+        static_assert(MT == 1 || kChunksPerTile % kStep == 0, "a warp's sub-tile index must be a compile-time constant");
+        constexpr bool kRec = OUT_FP32 && (NT == 16 || NT == 32);   // fp32 records of 16 / 32 floats per pixel (G conv3 pass 1)
+        // transposed (coalesced) store path: bf16 NHWC, or the fp32 tap records
+        const bool xposed = !OUT_FP32 || (kRec && p.out_sC == 1 && p.out_sP == NT);
+        const bool run = !(p.dbg & 4) && sub < kPairs;
+        const bool no_store = (p.dbg & 16) != 0;
+        const int jj = lane & 3;
         int it = 0;
         for (int item = unit0; item < n_items; item += ustep, ++it) {
             const ItemCoord c = decode_item(p, item);
             const int acc = it % NACC;
             const uint32_t acc_phase = (it / NACC) & 1u;
             const int cbase = c.ntile * NT;
-            // stage this item's folded-BN scale / shift (double-buffered; the named barrier of item
+            // stage this item's folded-BN shift (double-buffered; the named barrier of item
             // i+1 proves every warp is done reading the buffer of item i).  Layers with a single
             // N tile keep one copy for the whole kernel.
-            float* ss = ss_base + (p.n_tiles > 1 ? (it & 1) * (2 * NT) : 0);
+            float* ss = ss_base + (p.n_tiles > 1 ? (it & 1) * NT : 0);
             if (p.n_tiles > 1 || it == 0) {
-                for (int i = etid; i < NT; i += 32 * kEpiWarps) {
-                    ss[i] = __ldg(p.scale + cbase + i);
-                    ss[NT + i] = __ldg(p.shift + cbase + i);
-                }
+                for (int i = etid; i < NT; i += 32 * kEpiWarps) ss[i] = __ldg(p.shift + cbase + i);
                 named_bar_sync(1, 32 * kEpiWarps);
+            }
+            // Output offsets of this item's tiles, computed while the MMAs are still running.
+            // offs[mt][i]: element offset of pixel (lane>>2) + 8*i of this warp's quarter (the pixel a
+            // group of 4 lanes stores after the transpose), -1 = nothing to store.
+            long long offs[MT][4];
+            size_t pix_off[MT];
+            bool writer[MT];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const TileCoord t = decode_tile(p, (c.mgroup * CG + static_cast<int>(rank)) * MT + mt);
+                const int n = t.n0 + n_l, h = t.h0 + h_l, w = t.w0 + w_l;
+                int oh = h, ow = w;
+                writer[mt] = n < p.n_img;
+                if (POOL) {
+                    oh = h >> 1; ow = w >> 1;
+                    writer[mt] = writer[mt] && !(h & 1) && !(w & 1);
+                } else if (p.up == 2) {
+                    oh = 2 * h + (c.phase >> 1); ow = 2 * w + (c.phase & 1);
+                }
+                pix_off[mt] = static_cast<size_t>(n) * p.out_sN + (static_cast<size_t>(oh) * p.Wout + ow) * p.out_sP;
+                const long long my_off = (writer[mt] && !no_store) ? static_cast<long long>(pix_off[mt]) : -1ll;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) offs[mt][i] = xposed ? __shfl_sync(0xffffffffu, my_off, (lane >> 2) + 8 * i) : -1ll;
             }
             if (etid == 0) {
                 GANREV_TR(7, it);
@@ -507,61 +549,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             named_bar_sync(2, 32 * kEpiWarps);
             tcgen05_fence_after();
-            int cur_mt = -1;
-            size_t pix_off = 0;
-            bool writer = false;
-            long long offs[4] = {-1, -1, -1, -1};       // store-transpose: offsets of pixels (lane>>2) + 8*i
-            constexpr int kPairs = MT * kChunksPerTile;
-            constexpr int kStep = kEpiWarps / 4;
             const uint32_t tq_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * MT * NT);
-            // software pipeline: the TMEM load of pair i+1 is in flight while pair i is processed
-            uint32_t r[32], rn[32];
-            int pair = sub + ((p.dbg & 4) ? kPairs : 0);
-            if (pair < kPairs) {
-                if (CW == 32) tmem_ld32(tq_base + pair * CW, r); else tmem_ld16(tq_base + pair * CW, r);
-            }
-#pragma unroll 1
-            for (; pair < kPairs; pair += kStep) {
-                const int mt = pair / kChunksPerTile;
-                const int c0 = (pair - mt * kChunksPerTile) * CW;
-                // folded-BN scale / shift of this chunk: issued before the TMEM wait
-                float4 sc[CW / 4], sh[CW / 4];
+
+            // accumulator columns -> shift, pool, activation (registers only; two of these back to
+            // back form one basic block, so the compiler interleaves their dependency chains)
+            auto math = [&](const int pair, const uint32_t (&a)[32], float (&v)[32]) {
+                const int c0 = (pair % kChunksPerTile) * CW;
 #pragma unroll
-                for (int j = 0; j < CW / 4; ++j) {
-                    sc[j] = *reinterpret_cast<const float4*>(ss + c0 + 4 * j);
-                    sh[j] = *reinterpret_cast<const float4*>(ss + NT + c0 + 4 * j);
-                }
-                if (mt != cur_mt) {
-                    cur_mt = mt;
-                    const TileCoord t = decode_tile(p, (c.mgroup * CG + static_cast<int>(rank)) * MT + mt);
-                    const int n = t.n0 + n_l, h = t.h0 + h_l, w = t.w0 + w_l;
-                    int oh = h, ow = w;
-                    writer = n < p.n_img;
-                    if (POOL) {
-                        oh = h >> 1; ow = w >> 1;
-                        writer = writer && !(h & 1) && !(w & 1);
-                    } else if (p.up == 2) {
-                        oh = 2 * h + (c.phase >> 1); ow = 2 * w + (c.phase & 1);
-                    }
-                    pix_off = static_cast<size_t>(n) * p.out_sN + (static_cast<size_t>(oh) * p.Wout + ow) * p.out_sP;
-                    if (!OUT_FP32 || NT == 16 || NT == 32) {
-                        const long long my_off = writer ? static_cast<long long>(pix_off) : -1ll;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) offs[i] = __shfl_sync(0xffffffffu, my_off, (lane >> 2) + 8 * i);
-                    }
-                }
-                tmem_ld_wait();                                  // r[] (this pair) has landed
-                const int nxt = pair + kStep;
-                if (nxt < kPairs) {                              // next pair's accumulator columns: in flight during the math below
-                    if (CW == 32) tmem_ld32(tq_base + nxt * CW, rn); else tmem_ld16(tq_base + nxt * CW, rn);
-                }
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < CW / 4; ++j) {
-                    v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), sc[j].x, sh[j].x);
-                    v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), sc[j].y, sh[j].y);
-                    v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), sc[j].z, sh[j].z);
-                    v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), sc[j].w, sh[j].w);
+                for (int j = 0; j < CW / 4; ++j) {   // folded-BN shift (the scale lives in the weights)
+                    const float4 sh = *reinterpret_cast<const float4*>(ss + c0 + 4 * j);
+                    v[4 * j + 0] = __uint_as_float(a[4 * j + 0]) + sh.x;
+                    v[4 * j + 1] = __uint_as_float(a[4 * j + 1]) + sh.y;
+                    v[4 * j + 2] = __uint_as_float(a[4 * j + 2]) + sh.z;
+                    v[4 * j + 3] = __uint_as_float(a[4 * j + 3]) + sh.w;
                 }
                 if (POOL) {
                     // 2x2 max: w-neighbour is lane^1, h-neighbour is lane^BW (BW <= 16)
@@ -573,18 +573,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
 #pragma unroll
                 for (int j = 0; j < CW; ++j) v[j] = act_fn<ACT>(v[j], p.act);
-                if (rescale) {
+            };
+            auto store = [&](const int pair, const int mt, const float (&v)[32]) {
+                const int c0 = (pair % kChunksPerTile) * CW;
+                long long o4[4] = {-1, -1, -1, -1};
+                size_t po = 0;
+                bool wr = false;
 #pragma unroll
-                    for (int j = 0; j < CW; ++j) v[j] *= p.post_scale;
-                }
-                constexpr bool kRec = OUT_FP32 && (NT == 16 || NT == 32);   // fp32 records of 16 / 32 floats per pixel (G conv3 pass 1)
-                if ((!OUT_FP32 || (kRec && p.out_sC == 1 && p.out_sP == NT)) && !(p.dbg & 16)) {
+                for (int m2 = 0; m2 < MT; ++m2)
+                    if (m2 == mt) {
+                        po = pix_off[m2]; wr = writer[m2];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) o4[i] = offs[m2][i];
+                    }
+                if (xposed) {
                     // Each lane owns one pixel's 64 B of this chunk (32 bf16 channels, or 16 floats of
                     // the G conv3 tap record; 32-float records take two passes).  Transpose through an
                     // XOR-swizzled smem buffer so 4 lanes store one pixel's contiguous 64 B (8 pixels
                     // per instruction) instead of 32 lanes hitting 32 different lines.
                     constexpr int kPasses = (OUT_FP32 && NT == 32) ? 2 : 1;
-                    const int jj = lane & 3;
 #pragma unroll
                     for (int hpass = 0; hpass < kPasses; ++hpass) {
                         __syncwarp();
@@ -607,26 +614,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int i = 0; i < 4; ++i) {
                             const int px = (lane >> 2) + 8 * i;
                             const uint4 val = xpose[px * 4 + (jj ^ ((px >> 1) & 3))];
-                            if (offs[i] >= 0) {
-                                if (OUT_FP32) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + offs[i] + 16 * hpass + jj * 4) = val;
-                                else *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + offs[i] + cbase + c0 + jj * 8) = val;
+                            if (o4[i] >= 0) {
+                                // st.global.cg: activations are consumed by the NEXT kernel, never re-read here
+                                if (OUT_FP32) __stcg(reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + o4[i] + 16 * hpass + jj * 4), val);
+                                else __stcg(reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + o4[i] + cbase + c0 + jj * 8), val);
                             }
                         }
                     }
-                } else if (OUT_FP32 && !(p.dbg & 16)) {
-                    if (writer) {
-                        float* o = reinterpret_cast<float*>(p.out) + pix_off + static_cast<size_t>(cbase + c0) * p.out_sC;
+                } else if (OUT_FP32) {
+                    if (wr && !no_store) {
+                        float* o = reinterpret_cast<float*>(p.out) + po + static_cast<size_t>(cbase + c0) * p.out_sC;
 #pragma unroll
                         for (int j = 0; j < CW; ++j)
                             if (cbase + c0 + j < p.cout_real) o[static_cast<size_t>(j) * p.out_sC] = v[j];
                     }
                 }
+            };
+            // Two pairs per round: both tcgen05.ld are issued together and awaited once, then the
+            // math of both runs as one instruction stream.  After the LAST load has landed the
+            // accumulator stage is handed back to the MMA warp at once -- the registers are the
+            // third buffer, so the tensor pipe never waits for activation math or stores.
+            if (run) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = rn[j];
+                for (int i0 = 0; i0 < kIters; i0 += 2) {
+                    const bool two = i0 + 1 < kIters;
+                    const int pa = sub + i0 * kStep, pb = pa + kStep;
+                    // kChunksPerTile is a multiple of kStep (or MT == 1), so the sub-tile is known at compile time
+                    const int mta = (i0 * kStep) / kChunksPerTile, mtb = ((i0 + 1) * kStep) / kChunksPerTile;
+                    uint32_t ra[32], rb[32];
+                    if (CW == 32) tmem_ld32(tq_base + pa * CW, ra); else tmem_ld16(tq_base + pa * CW, ra);
+                    if (two) { if (CW == 32) tmem_ld32(tq_base + pb * CW, rb); else tmem_ld16(tq_base + pb * CW, rb); }
+                    tmem_ld_wait();
+                    GANREV_TRE(0, it * 4 + i0);
+                    if (i0 + 2 >= kIters) {
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { if (CG == 2) mbar_arrive_cta(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc)); }
+                    }
+                    float va[32], vb[32];
+                    math(pa, ra, va);
+                    if (two) math(pb, rb, vb);
+                    GANREV_TRE(1, it * 4 + i0);
+                    store(pa, mta < MT ? mta : 0, va);
+                    GANREV_TRE(2, it * 4 + i0);
+                    if (two) store(pb, mtb < MT ? mtb : 0, vb);
+                    GANREV_TRE(3, it * 4 + i0);
+                }
             }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) { if (CG == 2) mbar_arrive_cta(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc)); }
+            if (!run) {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) { if (CG == 2) mbar_arrive_cta(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc)); }
+            }
             if (etid == 0) GANREV_TR(5, it);
         }
     }

@@ -24,7 +24,7 @@ struct TcLayer {
     int NT = 0, MT = 1, NDY = 1, CG = 1, Ktot = 0;
     bool bres = false;
     size_t smem_bytes = 0;
-    DevBuf w, scale, shift;
+    DevBuf w, shift;
     CUtensorMap tmB{};
     double flops_per_img = 0.0;   // executed MAC*2 per image (phase form counts the folded work)
     double bytes_per_img = 0.0;   // activation in + out per image
@@ -266,6 +266,7 @@ static int build_tc_layer(ganrev_ctx* ctx, TcLayer& L, const LayerDef& d, const 
     if (d.nchw) { g.out_sN = static_cast<long long>(d.out_cstride) * d.Hout * d.Wout; g.out_sP = 1; g.out_sC = d.Hout * d.Wout; }
     else        { g.out_sN = static_cast<long long>(d.out_cstride) * d.Hout * d.Wout; g.out_sP = d.out_cstride; g.out_sC = 1; }
     g.Hout = d.Hout; g.Wout = d.Wout; g.up = d.kind == KIND_UPCONV3 ? 2 : 1; g.pool = d.pool; g.act = d.act;
+    if (d.post_scale != 1.0f) return fail(ctx, GANREV_EINVAL, "layer %s: fold the post-scale into the next layer's weights", d.name);
     g.post_scale = d.post_scale; g.out_fp32 = d.out_fp32;
     g.err_flag = ctx->d_err_flag;
 
@@ -276,6 +277,8 @@ static int build_tc_layer(ganrev_ctx* ctx, TcLayer& L, const LayerDef& d, const 
     else      { BW = std::min(d.Win, d.pool ? 16 : 128); BH = std::min(d.Hin, 128 / BW); BN = 128 / (BW * BH); }
     g.lgBW = ilog2(BW); g.lgBH = ilog2(BH); g.lgBN = ilog2(BN);
     g.tiles_w = d.Win / BW; g.tiles_h = d.Hin / BH;
+    g.lgTW = ilog2(g.tiles_w); g.lgTH = ilog2(g.tiles_h);
+    g.lgNT = is_pow2(g.n_tiles) ? ilog2(g.n_tiles) : -1;
     g.nphase = d.kind == KIND_UPCONV3 ? 4 : 1;
     if (d.kind == KIND_LINEAR) { g.ngroups = 1; g.ndy = 1; }
     else if (d.kind == KIND_CONV3) {
@@ -296,10 +299,12 @@ static int build_tc_layer(ganrev_ctx* ctx, TcLayer& L, const LayerDef& d, const 
     const int ntap = g.ngroups * g.ndy;
     L.Ktot = ntap * d.Cin;
 
-    // ---- weight matrix [nphase*cout_pad][Ktot], K = (g*ndy + j)*Cin + ci
+    // ---- weight matrix [nphase*cout_pad][Ktot], K = (g*ndy + j)*Cin + ci.  The folded BatchNorm scale is
+    // multiplied into each output row BEFORE the one rounding to bf16, so the epilogue only adds `shift`.
     std::vector<uint16_t> wb(static_cast<size_t>(g.nphase) * g.cout_pad * L.Ktot, 0);
     if (d.kind == KIND_LINEAR) {
-        for (size_t i = 0; i < static_cast<size_t>(g.cout_pad) * d.Cin; ++i) wb[i] = f2bf(w[i]);
+        for (int co = 0; co < g.cout_pad; ++co)
+            for (int ci = 0; ci < d.Cin; ++ci) wb[static_cast<size_t>(co) * d.Cin + ci] = f2bf(w[static_cast<size_t>(co) * d.Cin + ci] * bn.scale[co]);
     } else {
         // nearest-upsample x2 then 3x3/pad1 == four 2x2 convolutions on the low-res input: output row
         // 2y+a reads low-res rows {y-1: ky=0 | y: ky=1,2} (a=0) or {y: ky=0,1 | y+1: ky=2} (a=1).
@@ -319,23 +324,21 @@ static int build_tc_layer(ganrev_ctx* ctx, TcLayer& L, const LayerDef& d, const 
                             double sum = 0.0;
                             for (int ky = ky0; ky <= ky1; ++ky)
                                 for (int kx = kx0; kx <= kx1; ++kx) sum += w[((static_cast<size_t>(co) * d.Cin + ci) * 3 + ky) * 3 + kx];
-                            wb[(static_cast<size_t>(ph) * g.cout_pad + co) * L.Ktot + static_cast<size_t>(gi * g.ndy + j) * d.Cin + ci] = f2bf(static_cast<float>(sum));
+                            wb[(static_cast<size_t>(ph) * g.cout_pad + co) * L.Ktot + static_cast<size_t>(gi * g.ndy + j) * d.Cin + ci] = f2bf(static_cast<float>(sum * bn.scale[co]));
                         }
                 }
     }
     RC_TRY(upload(ctx, L.w, wb.data(), wb.size() * 2));
-    RC_TRY(upload(ctx, L.scale, bn.scale.data(), bn.scale.size() * 4));
     RC_TRY(upload(ctx, L.shift, bn.shift.data(), bn.shift.size() * 4));
     g.B = reinterpret_cast<const bf16*>(L.w.p);
-    g.scale = reinterpret_cast<const float*>(L.scale.p);
     g.shift = reinterpret_cast<const float*>(L.shift.p);
     RC_TRY(make_tmB(ctx, L));
 
-    // ---- shared-memory plan: [resident weights][stages x (ups units)][barriers, scale/shift]
+    // ---- shared-memory plan: [resident weights][stages x (ups units)][barriers, shift]
     g.a_unit_bytes = (BH + g.ndy - 1) * BW * BN * 128;
     g.b_kb_bytes = (d.NT / L.CG) * 128;          // this CTA's share of a 64-wide weight tile
     g.dy_stride_bytes = BW * BN * 128;
-    const int tail = (2 * tc::kMaxStages + 5) * 8 + 24 + 2 * 2 * d.NT * 4 + tc::kEpiWarps * 32 * 64;   // barriers, scale/shift, store-transpose buffers
+    const int tail = (2 * tc::kMaxStages + 5) * 8 + 24 + 2 * d.NT * 4 + tc::kEpiWarps * 32 * 64;   // barriers, shift (double-buffered), store-transpose buffers
     const int budget = tc::kSmemBudget - 1024 - tail;
     const size_t wbytes = static_cast<size_t>(g.units) * g.ndy * g.b_kb_bytes;
     L.bres = d.want_bres && g.nphase == 1 && g.n_tiles == 1 && wbytes + 2 * static_cast<size_t>(L.MT) * g.a_unit_bytes <= static_cast<size_t>(budget);
@@ -472,7 +475,7 @@ static int run_layer(ganrev_ctx* ctx, TcLayer& L, const void* in, void* out, int
 // =================================================================================
 // model loading
 // =================================================================================
-static void release_layer(TcLayer& L) { release(L.w); release(L.scale); release(L.shift); }
+static void release_layer(TcLayer& L) { release(L.w); release(L.shift); }
 
 static int load_G_impl(ganrev_ctx* ctx, int C, int H, int W, int nd, const float* blob, size_t n_floats) {
     RC_TRY(check_geom(ctx, C, H, W, nd));
@@ -585,12 +588,14 @@ static int load_R_impl(ganrev_ctx* ctx, int slot, int C, int H, int W, int nd, i
     RC_TRY(conv_layer(R.c3, "r_conv3_pool", c3, 64, 64, H, W, 1, 1.0f, 2, true, (ctx->cta_pairs & 4) ? 2 : 1));
     RC_TRY(conv_layer(R.c4, "r_conv4", c4, 128, 64, Hh, Wh, 0, 1.0f, 1, true, (ctx->cta_pairs & 8) ? 2 : 1));
     RC_TRY(conv_layer(R.c5, "r_conv5", c5, 128, 128, Hh, Wh, 0, 1.0f, 2, false, (ctx->cta_pairs & 16) ? 2 : 1));
-    RC_TRY(conv_layer(R.c6, "r_conv6_pool", c6, 128, 128, Hh, Wh, 1, 0.75f, 2, false, (ctx->cta_pairs & 16) ? 2 : 1));   // SpatialDropout(0.25) in eval: x0.75
-    {   // Linear(F -> 512) + BN1d + ELU; input columns re-ordered from View (NCHW flatten, models.lua:446) to NHWC
+    RC_TRY(conv_layer(R.c6, "r_conv6_pool", c6, 128, 128, Hh, Wh, 1, 1.0f, 2, false, (ctx->cta_pairs & 16) ? 2 : 1));   // its SpatialDropout(0.25) x0.75 is folded into r_linear1
+    {   // Linear(F -> 512) + BN1d + ELU; input columns re-ordered from View (NCHW flatten, models.lua:446) to NHWC.
+        // The eval-mode SpatialDropout(0.25) in front of it (y = 0.75 x, models.lua:439; it commutes with the max-pool after it) is linear, so it
+        // is folded into these weights instead of costing a multiply per activation in conv6's epilogue.
         std::vector<float> wm(static_cast<size_t>(512) * F);
         for (int o = 0; o < 512; ++o)
             for (int c = 0; c < 128; ++c)
-                for (int s = 0; s < HWq; ++s) wm[static_cast<size_t>(o) * F + s * 128 + c] = l1w[static_cast<size_t>(o) * F + c * HWq + s];
+                for (int s = 0; s < HWq; ++s) wm[static_cast<size_t>(o) * F + s * 128 + c] = 0.75f * l1w[static_cast<size_t>(o) * F + c * HWq + s];
         BnFold bn = fold_bn(l1b, g7, be7, m7, v7, 512, 512);
         const LayerDef d{"r_linear1", KIND_LINEAR, 64, 1, 1, false, 1, 1, F, 512, 8, 1, 1, 512, 0, ACT_ELU, 1.0f, 0, false};
         RC_TRY(build_tc_layer(ctx, R.l1, d, wm.data(), bn));
