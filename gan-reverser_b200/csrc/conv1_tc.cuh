@@ -1,0 +1,165 @@
+// conv1_tc.cuh -- R conv1 (C -> 64, 3x3/pad1, folded BN, ELU; models.lua:399-411) on tcgen05.
+//
+// The layer has K = 9*C taps per pixel: far too thin for the TMA/implicit-GEMM kernel (its A
+// operand would need 64-channel pixels), and on CUDA cores its 576*C FMAs per pixel are bound by
+// shared-memory weight broadcasts.  Here the threads build the im2col tile themselves:
+//   * thread t of a CTA owns pixel t of a 128-pixel tile: it gathers the 9*C taps from the fp32
+//     NCHW image (explicit dropout mask fused, models.lua:399-406), splits every tap into
+//     bf16 hi + bf16 lo (x = hi + lo to 2^-17, so the INPUT is not quantised to bf16) and writes
+//     its K-major row straight into the 128B-swizzled UMMA layout (row = 128 B, 16-byte chunk c
+//     of row r at position c ^ (r & 7));
+//   * one thread issues KP/16 tcgen05.mma (M=128, N=64) against the resident weight tile
+//     [64][KP] = [w*bnscale | w*bnscale | 0] and commits to an mbarrier;
+//   * every warp reads its TMEM lane quarter (one pixel per lane, 64 channels), adds the folded
+//     BN shift, applies ELU, packs bf16 and stores the warp's 32 pixels = 4 KB contiguous NHWC
+//     through an XOR-swizzled staging buffer (the tile's own A rows, free once the MMA retired).
+// Several CTAs per SM overlap gather / MMA latency / epilogue; nothing here is GEMM-heavy, the
+// point is to take the 576*C FMAs per pixel off the FP32 pipe.
+#pragma once
+#include "conv_tc.cuh"
+
+namespace ganrev {
+namespace tc {
+
+template <int CIN> struct Conv1Cfg {
+    static constexpr int K9 = CIN * 9;
+    static constexpr int KP = CIN == 1 ? 32 : 64;          // 2*K9 (hi | lo) padded to a multiple of 16
+    static constexpr int kSteps = KP / 16;
+    static constexpr int kChunks = KP / 8;                 // 16-byte chunks per row actually used
+    static constexpr int kABytes = 128 * 128;              // 128 rows x 128 B
+    static constexpr int kBBytes = 64 * 128;
+    static constexpr int kSmemBytes = kABytes + kBBytes + 64 * 4 + 16 + 1024;   // + shift, barrier/slot, alignment slack
+};
+
+// wB: bf16 [64][KP] K-major (BN scale folded, hi and lo halves identical); shift: [64].
+template <int CIN>
+__global__ void __launch_bounds__(128)
+r_conv1_tc_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mask, const bf16* __restrict__ wB,
+                  const float* __restrict__ shift, bf16* __restrict__ out, int H, int W, int lgW, int lgHW,
+                  long long npix_total, int n_tiles, int* err_flag) {
+    using C = Conv1Cfg<CIN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    uint4* sA = reinterpret_cast<uint4*>(smem);                         // [128 rows][8 chunks]
+    uint4* sB = reinterpret_cast<uint4*>(smem + C::kABytes);            // [64 rows][8 chunks]
+    float* s_shift = reinterpret_cast<float*>(smem + C::kABytes + C::kBBytes);
+    const uint32_t bar = smem_base + C::kABytes + C::kBBytes + 64 * 4;
+    const uint32_t tmem_slot = bar + 8;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + C::kABytes + C::kBBytes + 64 * 4 + 8);
+
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    if (t == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc<64>(tmem_slot);
+    if (t < 64) {                                                       // weight row t -> swizzled K-major row
+        s_shift[t] = shift[t];
+        const uint4* wrow = reinterpret_cast<const uint4*>(wB + static_cast<size_t>(t) * C::KP);
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c) sB[t * 8 + (c ^ (t & 7))] = wrow[c];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    constexpr uint32_t idesc = make_idesc<64, 128>();
+    const uint64_t adesc = make_smem_desc(smem_base), bdesc = make_smem_desc(smem_base + C::kABytes);
+    const int HW = 1 << lgHW;                                           // H, W are powers of two (check_geom)
+    uint32_t phase = 0;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // ---- gather: this thread's pixel, 9*CIN taps, hi/lo split, swizzled row
+        const long long pix = static_cast<long long>(tile) * 128 + t;
+        const bool live = pix < npix_total;
+        const long long n = pix >> lgHW;
+        const int rem = static_cast<int>(pix) & (HW - 1);
+        const int h = rem >> lgW, w = rem & (W - 1);
+        __nv_bfloat16 row[C::KP];
+#pragma unroll
+        for (int k = 2 * C::K9; k < C::KP; ++k) row[k] = __float2bfloat16_rn(0.0f);
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+            const long long plane = (n * CIN + ci) * static_cast<long long>(HW);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int hh = h + ky - 1;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ww = w + kx - 1;
+                    float x = 0.0f;
+                    if (live && hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                        const long long off = plane + static_cast<long long>(hh) * W + ww;
+                        x = __ldg(img + off);
+                        if (mask != nullptr && __ldg(mask + off) == 0) x = 0.0f;   // v1 dropout: x*mask, no rescale
+                    }
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+                    const int k = (ci * 3 + ky) * 3 + kx;
+                    row[k] = hi;
+                    row[C::K9 + k] = __float2bfloat16_rn(x - __bfloat162float(hi));
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < C::kChunks; ++c) {
+            uint4 pk;
+            pk.x = static_cast<uint32_t>(__bfloat16_as_ushort(row[8 * c + 0])) | (static_cast<uint32_t>(__bfloat16_as_ushort(row[8 * c + 1])) << 16);
+            pk.y = static_cast<uint32_t>(__bfloat16_as_ushort(row[8 * c + 2])) | (static_cast<uint32_t>(__bfloat16_as_ushort(row[8 * c + 3])) << 16);
+            pk.z = static_cast<uint32_t>(__bfloat16_as_ushort(row[8 * c + 4])) | (static_cast<uint32_t>(__bfloat16_as_ushort(row[8 * c + 5])) << 16);
+            pk.w = static_cast<uint32_t>(__bfloat16_as_ushort(row[8 * c + 6])) | (static_cast<uint32_t>(__bfloat16_as_ushort(row[8 * c + 7])) << 16);
+            sA[t * 8 + (c ^ (t & 7))] = pk;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        tcgen05_fence_before();                                        // (and this thread's TMEM reads of the previous tile are done)
+        __syncthreads();
+        // ---- MMA: one elected thread
+        if (warp == 0 && elect_one_sync()) {
+            tcgen05_fence_after();
+#pragma unroll
+            for (int k = 0; k < C::kSteps; ++k) umma_bf16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, k > 0 ? 1u : 0u);
+            umma_commit(bar);
+        }
+        __syncwarp();
+        mbar_wait(bar, phase, err_flag, 106);
+        phase ^= 1u;
+        tcgen05_fence_after();
+        // ---- epilogue: lane = pixel, 64 channels
+        uint32_t r0[32], r1[32];
+        const uint32_t tq = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+        tmem_ld32(tq, r0);
+        tmem_ld32(tq + 32, r1);
+        tmem_ld_wait();
+        // staging buffer: this warp's own 32 A rows (4 KB), free now that the MMA has retired
+        uint4* wstage = sA + warp * 256;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int ch = 8 * j + e;
+                const float a = __uint_as_float(ch < 32 ? r0[ch & 31] : r1[ch & 31]);
+                v[e] = elu_fast(a + s_shift[ch]);
+            }
+            uint4 pk;
+            pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+            pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+            wstage[lane * 8 + (j ^ (lane & 7))] = pk;
+        }
+        __syncwarp();
+        const long long warp_pix0 = static_cast<long long>(tile) * 128 + warp * 32;
+        uint4* o = reinterpret_cast<uint4*>(out + warp_pix0 * 64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int e = i * 32 + lane;                              // 16-byte element of the warp's 4 KB block
+            const int px = e >> 3, c = e & 7;
+            if (warp_pix0 + px < npix_total) __stcg(o + e, wstage[px * 8 + (c ^ (px & 7))]);
+        }
+        __syncwarp();                                                  // stores have read the staging rows before the next gather overwrites them
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) { tcgen05_fence_after(); tmem_dealloc<64>(tmem_base); }
+}
+
+}  // namespace tc
+}  // namespace ganrev

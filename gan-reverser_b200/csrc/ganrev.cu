@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "conv_simt.cuh"
 #include "conv_tc.cuh"
+#include "conv1_tc.cuh"
 #include "layers.cuh"
 #include "scan.cuh"
 
@@ -39,7 +40,8 @@ struct GModel {
 struct RModel {
     bool loaded = false;
     int C = 0, H = 0, W = 0, nd = 0, tanh_out = 0;
-    DevBuf c1pack;
+    DevBuf c1pack;              // CUDA-core conv1 (conv_impl 1): fp32 weights + scale + shift
+    DevBuf c1w, c1shift;        // tcgen05 conv1: bf16 [64][KP] weights (BN scale folded, hi|lo halves), shift[64]
     TcLayer c2, c3, c4, c5, c6, l1, l2;
 };
 
@@ -577,6 +579,13 @@ static int load_R_impl(ganrev_ctx* ctx, int slot, int C, int H, int W, int nd, i
         memcpy(&pack[static_cast<size_t>(K) * 64], bn.scale.data(), 64 * 4);
         memcpy(&pack[static_cast<size_t>(K) * 64 + 64], bn.shift.data(), 64 * 4);
         RC_TRY(upload(ctx, R.c1pack, pack.data(), pack.size() * 4));
+        // tcgen05 conv1 (conv1_tc.cuh): K index k = (ci*3+ky)*3+kx for the bf16 hi part of a tap, K + k for its lo part
+        const int KP = C == 1 ? 32 : 64;
+        std::vector<uint16_t> wb(static_cast<size_t>(64) * KP, 0);
+        for (int co = 0; co < 64; ++co)
+            for (int k = 0; k < K; ++k) wb[static_cast<size_t>(co) * KP + k] = wb[static_cast<size_t>(co) * KP + K + k] = f2bf(c1.w[static_cast<size_t>(co) * K + k] * bn.scale[co]);
+        RC_TRY(upload(ctx, R.c1w, wb.data(), wb.size() * 2));
+        RC_TRY(upload(ctx, R.c1shift, bn.shift.data(), 64 * 4));
     }
     auto conv_layer = [&](TcLayer& L, const char* name, const CB& c, int co, int ci, int Hin, int Win, int pool, float post, int MT, bool bres, int pairs) {
         BnFold bn = fold_bn(c.b, c.g, c.be, c.m, c.v, co, co);
@@ -674,7 +683,17 @@ static int forward_R_dev(ganrev_ctx* ctx, int slot, const float* d_images, const
             const unsigned blocks = static_cast<unsigned>((npix + 127) / 128);
             const float* in = d_images + n0 * img_elems;
             const uint8_t* mk = d_mask ? d_mask + n0 * img_elems : nullptr;
-            if (R.C == 1)
+            if (ctx->conv_impl == 0) {
+                const int n_tiles = static_cast<int>(blocks);
+                const int grid = std::min(n_tiles, ctx->num_sms * 5);   // 5 CTAs of 128 threads x ~96 registers per SM
+                const int lgW = ilog2(R.W), lgHW = ilog2(R.H * R.W);
+                if (R.C == 1)
+                    tc::r_conv1_tc_kernel<1><<<grid, 128, tc::Conv1Cfg<1>::kSmemBytes, ctx->stream>>>(in, mk, reinterpret_cast<const bf16*>(R.c1w.p), reinterpret_cast<const float*>(R.c1shift.p),
+                        reinterpret_cast<bf16*>(ctx->arena[0].p), R.H, R.W, lgW, lgHW, npix, n_tiles, ctx->d_err_flag);
+                else
+                    tc::r_conv1_tc_kernel<3><<<grid, 128, tc::Conv1Cfg<3>::kSmemBytes, ctx->stream>>>(in, mk, reinterpret_cast<const bf16*>(R.c1w.p), reinterpret_cast<const float*>(R.c1shift.p),
+                        reinterpret_cast<bf16*>(ctx->arena[0].p), R.H, R.W, lgW, lgHW, npix, n_tiles, ctx->d_err_flag);
+            } else if (R.C == 1)
                 r_conv1_kernel<1><<<blocks, 128, 0, ctx->stream>>>(in, mk, (const float*)R.c1pack.p, reinterpret_cast<bf16*>(ctx->arena[0].p), R.H, R.W, npix);
             else
                 r_conv1_kernel<3><<<blocks, 128, 0, ctx->stream>>>(in, mk, (const float*)R.c1pack.p, reinterpret_cast<bf16*>(ctx->arena[0].p), R.H, R.W, npix);
@@ -742,7 +761,7 @@ void ganrev_destroy(ganrev_ctx* ctx) {
     release(ctx->G.b3);
     for (int s = 0; s < 2; ++s) {
         RModel& R = ctx->R[s];
-        release(R.c1pack);
+        release(R.c1pack); release(R.c1w); release(R.c1shift);
         for (TcLayer* L : {&R.c2, &R.c3, &R.c4, &R.c5, &R.c6, &R.l1, &R.l2}) release_layer(*L);
     }
     for (auto& b : ctx->buf) release(b);
