@@ -67,16 +67,13 @@ r_conv1_tc_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mas
     const int HW = 1 << lgHW;                                           // H, W are powers of two (check_geom)
     uint32_t phase = 0;
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // ---- gather: this thread's pixel, 9*CIN taps, hi/lo split, swizzled row
+    // taps of pixel t of a tile (0 outside the image / masked), as fp32
+    auto gather = [&](const int tile, float (&x)[C::K9]) {
         const long long pix = static_cast<long long>(tile) * 128 + t;
         const bool live = pix < npix_total;
         const long long n = pix >> lgHW;
         const int rem = static_cast<int>(pix) & (HW - 1);
         const int h = rem >> lgW, w = rem & (W - 1);
-        __nv_bfloat16 row[C::KP];
-#pragma unroll
-        for (int k = 2 * C::K9; k < C::KP; ++k) row[k] = __float2bfloat16_rn(0.0f);
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci) {
             const long long plane = (n * CIN + ci) * static_cast<long long>(HW);
@@ -86,18 +83,30 @@ r_conv1_tc_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mas
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
                     const int ww = w + kx - 1;
-                    float x = 0.0f;
+                    float v = 0.0f;
                     if (live && hh >= 0 && hh < H && ww >= 0 && ww < W) {
                         const long long off = plane + static_cast<long long>(hh) * W + ww;
-                        x = __ldg(img + off);
-                        if (mask != nullptr && __ldg(mask + off) == 0) x = 0.0f;   // v1 dropout: x*mask, no rescale
+                        v = __ldg(img + off);
+                        if (mask != nullptr && __ldg(mask + off) == 0) v = 0.0f;   // v1 dropout: x*mask, no rescale
                     }
-                    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
-                    const int k = (ci * 3 + ky) * 3 + kx;
-                    row[k] = hi;
-                    row[C::K9 + k] = __float2bfloat16_rn(x - __bfloat162float(hi));
+                    x[(ci * 3 + ky) * 3 + kx] = v;
                 }
             }
+        }
+    };
+    float x[C::K9];
+    if (static_cast<int>(blockIdx.x) < n_tiles) gather(blockIdx.x, x);
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // ---- this thread's pixel: hi/lo split of its taps, swizzled K-major row
+        __nv_bfloat16 row[C::KP];
+#pragma unroll
+        for (int k = 2 * C::K9; k < C::KP; ++k) row[k] = __float2bfloat16_rn(0.0f);
+#pragma unroll
+        for (int k = 0; k < C::K9; ++k) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(x[k]);
+            row[k] = hi;
+            row[C::K9 + k] = __float2bfloat16_rn(x[k] - __bfloat162float(hi));
         }
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c) {
@@ -119,6 +128,8 @@ r_conv1_tc_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mas
             umma_commit(bar);
         }
         __syncwarp();
+        // next tile's taps: the global loads are in flight while this tile's MMA retires and its epilogue runs
+        if (tile + static_cast<int>(gridDim.x) < n_tiles) gather(tile + gridDim.x, x);
         mbar_wait(bar, phase, err_flag, 106);
         phase ^= 1u;
         tcgen05_fence_after();

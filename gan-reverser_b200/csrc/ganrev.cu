@@ -685,7 +685,18 @@ static int forward_R_dev(ganrev_ctx* ctx, int slot, const float* d_images, const
             const uint8_t* mk = d_mask ? d_mask + n0 * img_elems : nullptr;
             if (ctx->conv_impl == 0) {
                 const int n_tiles = static_cast<int>(blocks);
-                const int grid = std::min(n_tiles, ctx->num_sms * 5);   // 5 CTAs of 128 threads x ~96 registers per SM
+                // resident CTAs per SM: bounded by registers (128 threads each) and 512 TMEM columns / 64; shared memory
+                // (26 KB each) is not the limit once the carve-out favours it.  One even wave of persistent CTAs.
+                static int occ1 = 0, occ3 = 0;
+                int& occ = R.C == 1 ? occ1 : occ3;
+                if (occ == 0) {
+                    cudaFuncAttributes fa{};
+                    if (R.C == 1) { CU_TRY(cudaFuncGetAttributes(&fa, tc::r_conv1_tc_kernel<1>)); CU_TRY(cudaFuncSetAttribute(tc::r_conv1_tc_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); }
+                    else          { CU_TRY(cudaFuncGetAttributes(&fa, tc::r_conv1_tc_kernel<3>)); CU_TRY(cudaFuncSetAttribute(tc::r_conv1_tc_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); }
+                    const int regs = ((std::max(fa.numRegs, 32) + 7) / 8) * 8;
+                    occ = std::max(1, std::min(8, 65536 / (128 * regs)));
+                }
+                const int grid = std::min(n_tiles, ctx->num_sms * occ);
                 const int lgW = ilog2(R.W), lgHW = ilog2(R.H * R.W);
                 if (R.C == 1)
                     tc::r_conv1_tc_kernel<1><<<grid, 128, tc::Conv1Cfg<1>::kSmemBytes, ctx->stream>>>(in, mk, reinterpret_cast<const bf16*>(R.c1w.p), reinterpret_cast<const float*>(R.c1shift.p),
@@ -1090,6 +1101,23 @@ static int launch_search_wide(ganrev_ctx* ctx, const scan::ScanParams& p, int sp
     return GANREV_OK;
 }
 
+template <int E>
+static int launch_search_wide4(ganrev_ctx* ctx, const scan::ScanParams& p, int splits) {
+    constexpr int QT = 64, K2 = 32 * E;
+    const int S = scan::wide4_stride(p.d);
+    const size_t smem = sizeof(float) * (static_cast<size_t>(2 * scan::RT + QT) * S) +
+                        sizeof(unsigned long long) * (QT * K2 + QT * scan::CAP + QT) + sizeof(int) * QT;
+    static size_t attr_max = 0;
+    if (smem > attr_max) {
+        CU_TRY(cudaFuncSetAttribute(scan::search_kernel_wide4<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr_max = smem;
+    }
+    dim3 grid(splits, (p.nq + QT - 1) / QT);
+    scan::search_kernel_wide4<E><<<grid, scan::kThreads, smem, ctx->stream>>>(p);
+    CU_TRY(cudaGetLastError());
+    return GANREV_OK;
+}
+
 // ---- streaming kernels (nq <= 32, d % 4 == 0): plan + launch
 static bool stream_plan(ganrev_ctx* ctx, const scan::ScanParams& p, int NQ, int mode, int K2, scan::StreamParams& sp, size_t& smem, int& grid) {
     if (p.d % 4 != 0 || p.nq > 32) return false;
@@ -1214,6 +1242,7 @@ static int search_dev(ganrev_ctx* ctx, int Q, int k, int64_t* ids, float* scores
         ProfScope ps(ctx, "search_scan", 2.0 * N * Q * d, 4.0 * N * d + 4.0 * Q * d + 8.0 * splits * Q * k);
         const bool wide = TQ == 4 && d <= 128;
         if (TQ == 1)   { if (k <= 32) RC_TRY((launch_search<1, 1>(ctx, p, splits))); else RC_TRY((launch_search<1, 4>(ctx, p, splits))); }
+        else if (wide && p.d % 4 == 0) { if (k <= 32) RC_TRY((launch_search_wide4<1>(ctx, p, splits))); else RC_TRY((launch_search_wide4<4>(ctx, p, splits))); }
         else if (wide) { if (k <= 32) RC_TRY((launch_search_wide<1>(ctx, p, splits))); else RC_TRY((launch_search_wide<4>(ctx, p, splits))); }
         else           { if (k <= 32) RC_TRY((launch_search<4, 1>(ctx, p, splits))); else RC_TRY((launch_search<4, 4>(ctx, p, splits))); }
     }

@@ -397,6 +397,165 @@ search_kernel_wide(const ScanParams p) {
     }
 }
 
+// ------------------------------------------------------------------ wide search, d % 4 == 0
+// Same contract and candidate machinery as search_kernel_wide, different data movement: the
+// row tile and the queries stay ROW-major in shared memory (stride S floats, S % 32 == 4, so
+// the 16 lanes of a half-warp reading 16 consecutive rows with 16-byte loads hit 32 distinct
+// banks), tiles arrive by 16-byte cp.async into a double buffer (the register-staged
+// prefetch of the older kernel was serialised by the compiler into load->store pairs: 40% of
+// its stall samples), and the inner loop walks d four elements at a time.  Each (query, row)
+// accumulator still sees fmaf(q_i, x_i, acc) for i = 0 .. d-1 in order: bit-identical.
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+    const int n = valid ? 16 : 0;                             // src-size 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__host__ __device__ __forceinline__ int wide4_stride(int d) { return d + ((4 - (d % 32) + 32) % 32); }   // smallest S >= d, S % 32 == 4
+
+template <int E>
+__global__ void __launch_bounds__(kThreads)
+search_kernel_wide4(const ScanParams p) {
+    constexpr int TQ = 4, QT = 64, K2 = 32 * E;
+    extern __shared__ __align__(16) uint8_t sm[];
+    const int d = p.d, S = wide4_stride(d), d4 = d >> 2;
+    float* xs0 = reinterpret_cast<float*>(sm);                // [RT][S] x 2
+    float* qs = xs0 + 2 * RT * S;                             // [QT][S]
+    unsigned long long* lists = reinterpret_cast<unsigned long long*>(qs + QT * S);
+    unsigned long long* cand = lists + QT * K2;
+    unsigned long long* tau = cand + QT * CAP;
+    int* ccount = reinterpret_cast<int*>(tau + QT);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tq = tid >> 4, tr = tid & 15;
+    auto row_at = [&](int u) { return u * 16 + tr; };         // this thread's 8 rows of the tile
+    const int qbase = blockIdx.y * QT;
+    for (int i = tid; i < QT * K2; i += kThreads) lists[i] = 0ull;
+    for (int i = tid; i < QT; i += kThreads) { tau[i] = 0ull; ccount[i] = 0; }
+    for (int g = tid; g < QT * d4; g += kThreads) {           // queries, row-major
+        const int r = g / d4, c4 = g - r * d4;
+        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (qbase + r < p.nq) v = __ldg(reinterpret_cast<const float4*>(p.q + static_cast<long long>(qbase + r) * d) + c4);
+        *reinterpret_cast<float4*>(qs + r * S + 4 * c4) = v;
+    }
+    float rqv[TQ];
+    bool qok[TQ];
+#pragma unroll
+    for (int v = 0; v < TQ; ++v) {
+        qok[v] = qbase + tq * TQ + v < p.nq;
+        rqv[v] = qok[v] ? __ldg(p.rq + qbase + tq * TQ + v) : 0.0f;
+    }
+
+    const long long r_begin = static_cast<long long>(blockIdx.x) * p.rows_per_split;
+    const long long r_end = min(p.n_rows, r_begin + p.rows_per_split);
+    auto issue = [&](long long row0, float* dst) {            // one row tile -> smem (rows past the end: zeros)
+        for (int g = tid; g < RT * d4; g += kThreads) {
+            const int r = g / d4, c4 = g - r * d4;
+            const long long row = row0 + r;
+            const bool ok = row < r_end;
+            cp_async16_zfill(dst + r * S + 4 * c4, p.db + (ok ? row : r_begin) * d + 4 * c4, ok);
+        }
+        cp_async_commit_group();
+    };
+    if (r_begin < r_end) issue(r_begin, xs0);
+    int buf = 0;
+    for (long long row0 = r_begin; row0 < r_end; row0 += RT, buf ^= 1) {
+        cp_async_wait_all();
+        __syncthreads();                                      // tile `buf` landed; everyone is done with the other buffer
+        if (row0 + RT < r_end) issue(row0 + RT, xs0 + (buf ^ 1) * RT * S);
+        const float* xs = xs0 + buf * RT * S;
+        float acc[TQ][8];
+#pragma unroll
+        for (int v = 0; v < TQ; ++v)
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[v][u] = 0.0f;
+#pragma unroll 2
+        for (int i = 0; i < d; i += 4) {
+            float4 qv[TQ], xv[8];
+#pragma unroll
+            for (int v = 0; v < TQ; ++v) qv[v] = *reinterpret_cast<const float4*>(qs + (tq * TQ + v) * S + i);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xv[u] = *reinterpret_cast<const float4*>(xs + row_at(u) * S + i);
+#pragma unroll
+            for (int v = 0; v < TQ; ++v)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    float a = acc[v][u];
+                    a = __fmaf_rn(qv[v].x, xv[u].x, a);
+                    a = __fmaf_rn(qv[v].y, xv[u].y, a);
+                    a = __fmaf_rn(qv[v].z, xv[u].z, a);
+                    a = __fmaf_rn(qv[v].w, xv[u].w, a);
+                    acc[v][u] = a;
+                }
+        }
+        float rxv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const long long row = row0 + row_at(u);
+            rxv[u] = row < r_end ? __ldg(p.rdb + row) : 0.0f;
+        }
+        unsigned pend = 0u;
+#pragma unroll
+        for (int v = 0; v < TQ; ++v) {
+            const unsigned long long t = tau[tq * TQ + v];
+            const uint32_t thi = static_cast<uint32_t>(t >> 32);
+            const float thr = score_unkey32(thi);
+            const bool pass_all = thi == 0u || !(fabsf(thr) < 3.0e38f);   // list not full, k-th entry NaN, or infinite
+            const float thr_adj = thr - fabsf(thr) * 3.814697265625e-06f;   // 2^-18 relative margin
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float rw = rqv[v] * rxv[u];
+                float sq;
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(rw));
+                const float sa = acc[v][u] * sq;
+                const bool maybe = pass_all || sa >= thr_adj || rw < 1e-30f;
+                if (maybe && qok[v] && row0 + row_at(u) < r_end) pend |= 1u << (v * 8 + u);
+            }
+        }
+        while (__syncthreads_or(pend != 0u)) {
+#pragma unroll
+            for (int v = 0; v < TQ; ++v) {
+                const int ql = tq * TQ + v;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const unsigned bit = 1u << (v * 8 + u);
+                    if (pend & bit) {
+                        const float s = cos_from(acc[v][u], rqv[v], rxv[u]);          // exact score
+                        const unsigned long long key = make_key(s, static_cast<uint32_t>(row0 + row_at(u)));
+                        if (key > tau[ql]) {
+                            const int slot = atomicAdd(&ccount[ql], 1);
+                            if (slot < CAP) { cand[ql * CAP + slot] = key; pend &= ~bit; }
+                        } else {
+                            pend &= ~bit;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            for (int ql = warp; ql < QT; ql += kThreads / 32) {
+                const int n = min(ccount[ql], CAP);
+                if (n > 0) {
+                    unsigned long long L[E];
+#pragma unroll
+                    for (int j = 0; j < E; ++j) L[j] = lists[ql * K2 + lane * E + j];
+                    for (int t = 0; t < n; ++t) list_insert<E>(L, cand[ql * CAP + t], lane);
+#pragma unroll
+                    for (int j = 0; j < E; ++j) lists[ql * K2 + lane * E + j] = L[j];
+                    const unsigned long long kth = list_kth<E>(L, p.k);
+                    __syncwarp();
+                    if (lane == 0) { tau[ql] = kth; ccount[ql] = 0; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < QT * p.k; i += kThreads) {
+        const int ql = i / p.k, t = i - ql * p.k;
+        if (qbase + ql < p.nq)
+            p.partial[(static_cast<long long>(blockIdx.x) * p.nq + qbase + ql) * p.k + t] = lists[ql * K2 + t];
+    }
+}
+
 // database rows -> query matrix (search by example row, apply_r.lua:268-272); rows this shard
 // does not own stay zero so an integer max-allreduce assembles them exactly across ranks.
 __global__ void gather_rows_kernel(const float* __restrict__ db, long long n_rows, int d, long long row_offset,
