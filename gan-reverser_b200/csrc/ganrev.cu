@@ -1105,7 +1105,7 @@ template <int E>
 static int launch_search_wide4(ganrev_ctx* ctx, const scan::ScanParams& p, int splits) {
     constexpr int QT = 64, K2 = 32 * E;
     const int S = scan::wide4_stride(p.d);
-    const size_t smem = sizeof(float) * (static_cast<size_t>(2 * scan::RT + QT) * S) +
+    const size_t smem = sizeof(float) * (static_cast<size_t>(scan::RT + QT) * S) +
                         sizeof(unsigned long long) * (QT * K2 + QT * scan::CAP + QT) + sizeof(int) * QT;
     static size_t attr_max = 0;
     if (smem > attr_max) {
@@ -1229,6 +1229,19 @@ static int search_dev(ganrev_ctx* ctx, int Q, int k, int64_t* ids, float* scores
     // row splits: fill the machine about 4 blocks per SM deep, at least one 128-row tile each
     const int64_t row_tiles = std::max<int64_t>(1, (N + scan::RT - 1) / scan::RT);
     int splits = static_cast<int>(std::min<int64_t>(row_tiles, std::max<int64_t>(1, (4LL * ctx->num_sms + qtiles - 1) / qtiles)));
+    const bool wide4 = TQ == 4 && d <= 128 && d % 4 == 0;
+    if (wide4) {
+        // two blocks of the wide kernel are resident per SM: pick the split count whose block total wastes the
+        // least of its last wave (and keeps at least 8 row tiles per split so the top-k lists warm up once)
+        const int64_t R = 2LL * ctx->num_sms;
+        double best = 1e30;
+        for (int m = 2; m <= 16; ++m) {
+            const int64_t sp = std::min<int64_t>(std::max<int64_t>(1, row_tiles / 8), std::max<int64_t>(1, m * R / qtiles));
+            const int64_t total = sp * qtiles, waves = (total + R - 1) / R;
+            const double waste = static_cast<double>(waves * R) / static_cast<double>(total) + 0.002 * m;   // mild preference for fewer, longer splits
+            if (waste < best) { best = waste; splits = static_cast<int>(sp); }
+        }
+    }
     const int64_t rows_per_split = ((row_tiles + splits - 1) / splits) * scan::RT;
     splits = static_cast<int>(std::max<int64_t>(1, (N + rows_per_split - 1) / rows_per_split));
     RC_TRY(ensure(ctx, ctx->partial, sizeof(unsigned long long) * static_cast<size_t>(splits) * Q * k));

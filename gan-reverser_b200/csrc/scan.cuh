@@ -401,9 +401,10 @@ search_kernel_wide(const ScanParams p) {
 // Same contract and candidate machinery as search_kernel_wide, different data movement: the
 // row tile and the queries stay ROW-major in shared memory (stride S floats, S % 32 == 4, so
 // the 16 lanes of a half-warp reading 16 consecutive rows with 16-byte loads hit 32 distinct
-// banks), tiles arrive by 16-byte cp.async into a double buffer (the register-staged
-// prefetch of the older kernel was serialised by the compiler into load->store pairs: 40% of
-// its stall samples), and the inner loop walks d four elements at a time.  Each (query, row)
+// banks), tiles arrive by 16-byte cp.async (the register-staged prefetch of the older kernel was
+// serialised by the compiler into load->store pairs: 40% of its stall samples), and the inner
+// loop walks d four elements at a time.  ONE tile buffer per block keeps shared memory at
+// ~110 KB so two blocks share an SM (16 warps): the other block's math hides this block's load.  Each (query, row)
 // accumulator still sees fmaf(q_i, x_i, acc) for i = 0 .. d-1 in order: bit-identical.
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
     const int n = valid ? 16 : 0;                             // src-size 0: the 16 bytes are zero-filled
@@ -414,13 +415,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __host__ __device__ __forceinline__ int wide4_stride(int d) { return d + ((4 - (d % 32) + 32) % 32); }   // smallest S >= d, S % 32 == 4
 
 template <int E>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 search_kernel_wide4(const ScanParams p) {
     constexpr int TQ = 4, QT = 64, K2 = 32 * E;
     extern __shared__ __align__(16) uint8_t sm[];
     const int d = p.d, S = wide4_stride(d), d4 = d >> 2;
-    float* xs0 = reinterpret_cast<float*>(sm);                // [RT][S] x 2
-    float* qs = xs0 + 2 * RT * S;                             // [QT][S]
+    float* xs = reinterpret_cast<float*>(sm);                 // [RT][S]
+    float* qs = xs + RT * S;                                  // [QT][S]
     unsigned long long* lists = reinterpret_cast<unsigned long long*>(qs + QT * S);
     unsigned long long* cand = lists + QT * K2;
     unsigned long long* tau = cand + QT * CAP;
@@ -457,13 +458,11 @@ search_kernel_wide4(const ScanParams p) {
         }
         cp_async_commit_group();
     };
-    if (r_begin < r_end) issue(r_begin, xs0);
-    int buf = 0;
-    for (long long row0 = r_begin; row0 < r_end; row0 += RT, buf ^= 1) {
+    for (long long row0 = r_begin; row0 < r_end; row0 += RT) {
+        __syncthreads();                                      // everyone is done with the previous tile (and the set-up above)
+        issue(row0, xs);
         cp_async_wait_all();
-        __syncthreads();                                      // tile `buf` landed; everyone is done with the other buffer
-        if (row0 + RT < r_end) issue(row0 + RT, xs0 + (buf ^ 1) * RT * S);
-        const float* xs = xs0 + buf * RT * S;
+        __syncthreads();
         float acc[TQ][8];
 #pragma unroll
         for (int v = 0; v < TQ; ++v)
