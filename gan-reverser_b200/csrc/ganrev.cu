@@ -654,13 +654,17 @@ static int forward_G_dev(ganrev_ctx* ctx, const float* d_noise, int64_t N, float
         RC_TRY(run_layer(ctx, G.c2, ctx->arena[1].p, ctx->arena[0].p, n, CH));      // [n][H][W][128]
         {   // last conv: per-pixel tap products (tensor cores), then the 3x3 gather + bias + sigmoid
             const long long npix = static_cast<long long>(n) * G.H * G.W;
-            const int NT3 = G.c3.NT;
-            RC_TRY(run_layer(ctx, G.c3, ctx->arena[0].p, ctx->arena[1].p, static_cast<int>(npix), CH * G.H * G.W));   // fp32 [pixels][NT3]
-            ProfScope ps(ctx, "g_conv3_gather", 9.0 * npix * G.C, npix * (4.0 * NT3 + 4.0 * G.C));
+            // tap products as 9*C planes of `plane` floats, P[tap*C + co][pixel]: the kernel's stores and the gather's
+            // loads are then 128 contiguous bytes per warp, and the zero-padded columns 9*C..NT3-1 are never written
+            const long long plane = static_cast<long long>(CH) * G.H * G.W;
+            G.c3.g.out_sN = 1; G.c3.g.out_sP = 1; G.c3.g.out_sC = static_cast<int>(plane);
+            G.c3.bytes_per_img = 2.0 * 128 + 4.0 * 9 * G.C;
+            RC_TRY(run_layer(ctx, G.c3, ctx->arena[0].p, ctx->arena[1].p, static_cast<int>(npix), CH * G.H * G.W));
+            ProfScope ps(ctx, "g_conv3_gather", 9.0 * npix * G.C, npix * (4.0 * 9 * G.C + 4.0 * G.C));
             const unsigned blocks = static_cast<unsigned>((npix + 255) / 256);
             float* o = d_images + n0 * G.C * G.H * G.W;
-            if (G.C == 1) g_conv3_gather_kernel<1><<<blocks, 256, 0, ctx->stream>>>(static_cast<const float*>(ctx->arena[1].p), NT3, static_cast<const float*>(G.b3.p), o, G.H, G.W, n);
-            else          g_conv3_gather_kernel<3><<<blocks, 256, 0, ctx->stream>>>(static_cast<const float*>(ctx->arena[1].p), NT3, static_cast<const float*>(G.b3.p), o, G.H, G.W, n);
+            if (G.C == 1) g_conv3_gather_kernel<1><<<blocks, 256, 0, ctx->stream>>>(static_cast<const float*>(ctx->arena[1].p), plane, static_cast<const float*>(G.b3.p), o, G.H, G.W, n);
+            else          g_conv3_gather_kernel<3><<<blocks, 256, 0, ctx->stream>>>(static_cast<const float*>(ctx->arena[1].p), plane, static_cast<const float*>(G.b3.p), o, G.H, G.W, n);
             CU_TRY(cudaGetLastError());
         }
     }

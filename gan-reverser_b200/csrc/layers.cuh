@@ -94,13 +94,13 @@ r_conv1_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mask, 
 }
 
 // ------------------------------------------------------------------ G conv3, pass 2
-// Pass 1 (tensor cores) left P[n][y][x][tap*C + co] = w[co][:, tap] . act[n][y][x][:] for every
-// INPUT pixel; the 3x3 conv output is the sum of the 9 neighbours' matching tap products
+// Pass 1 (tensor cores) left P[tap*C + co][n][y][x] = w[co][:, tap] . act[n][y][x][:] (one plane of
+// `plane` floats per tap and output channel) for every INPUT pixel; the 3x3 conv output is the sum of the 9 neighbours' matching tap products
 // (out-of-image neighbours contribute nothing = zero padding), + bias, then Sigmoid
 // (models.lua:132-133).  fp32 NCHW out.  One thread per output pixel and channel.
 template <int COUT>
 __global__ void __launch_bounds__(256)
-g_conv3_gather_kernel(const float* __restrict__ P, int pstride, const float* __restrict__ bias, float* __restrict__ out,
+g_conv3_gather_kernel(const float* __restrict__ P, long long plane, const float* __restrict__ bias, float* __restrict__ out,
                       int H, int W, long long n_img) {
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const long long total = n_img * H * W;
@@ -119,9 +119,10 @@ g_conv3_gather_kernel(const float* __restrict__ P, int pstride, const float* __r
         for (int kx = 0; kx < 3; ++kx) {
             const int xx = x + kx - 1;
             if (xx < 0 || xx >= W) continue;
-            const float* rec = P + ((n * H + yy) * W + xx) * pstride + (ky * 3 + kx) * COUT;
+            // planar tap products P[tap*COUT + co][pixel]: the 32 lanes of a warp read 32 consecutive floats
+            const float* rec = P + static_cast<long long>((ky * 3 + kx) * COUT) * plane + (n * H + yy) * W + xx;
 #pragma unroll
-            for (int co = 0; co < COUT; ++co) acc[co] += __ldg(rec + co);
+            for (int co = 0; co < COUT; ++co) acc[co] += __ldg(rec + co * plane);
         }
     }
 #pragma unroll
