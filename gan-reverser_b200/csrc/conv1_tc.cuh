@@ -5,7 +5,7 @@
 // shared-memory weight broadcasts.  Here the threads build the im2col tile themselves:
 //   * thread t of a CTA owns pixel t of a 128-pixel tile: it gathers the 9*C taps from the fp32
 //     NCHW image (explicit dropout mask fused, models.lua:399-406), splits every tap into
-//     bf16 hi + bf16 lo (x = hi + lo to 2^-17, so the INPUT is not quantised to bf16) and writes
+//     bf16 hi + bf16 lo (x = hi + lo to 2^-16, so the INPUT is not quantised to bf16) and writes
 //     its K-major row straight into the 128B-swizzled UMMA layout (row = 128 B, 16-byte chunk c
 //     of row r at position c ^ (r & 7));
 //   * one thread issues KP/16 tcgen05.mma (M=128, N=64) against the resident weight tile
@@ -67,8 +67,10 @@ r_conv1_tc_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mas
     const int HW = 1 << lgHW;                                           // H, W are powers of two (check_geom)
     uint32_t phase = 0;
 
-    // taps of pixel t of a tile (0 outside the image / masked), as fp32
-    auto gather = [&](const int tile, float (&x)[C::K9]) {
+    // Raw taps of pixel t of a tile (0 outside the image) and their dropout-mask bytes.  Nothing here
+    // CONSUMES a loaded value: the loads stay in flight across the epilogue of the current tile and
+    // are first touched when the next tile's row is built.
+    auto gather = [&](const int tile, float (&x)[C::K9], uint32_t (&mk)[C::K9]) {
         const long long pix = static_cast<long long>(tile) * 128 + t;
         const bool live = pix < npix_total;
         const long long n = pix >> lgHW;
@@ -84,37 +86,44 @@ r_conv1_tc_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mas
                 for (int kx = 0; kx < 3; ++kx) {
                     const int ww = w + kx - 1;
                     float v = 0.0f;
+                    uint32_t m = 1u;
                     if (live && hh >= 0 && hh < H && ww >= 0 && ww < W) {
                         const long long off = plane + static_cast<long long>(hh) * W + ww;
                         v = __ldg(img + off);
-                        if (mask != nullptr && __ldg(mask + off) == 0) v = 0.0f;   // v1 dropout: x*mask, no rescale
+                        if (mask != nullptr) m = __ldg(mask + off);
                     }
                     x[(ci * 3 + ky) * 3 + kx] = v;
+                    mk[(ci * 3 + ky) * 3 + kx] = m;
                 }
             }
         }
     };
     float x[C::K9];
-    if (static_cast<int>(blockIdx.x) < n_tiles) gather(blockIdx.x, x);
+    uint32_t mk[C::K9];
+    if (static_cast<int>(blockIdx.x) < n_tiles) gather(blockIdx.x, x, mk);
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // ---- this thread's pixel: hi/lo split of its taps, swizzled K-major row
-        __nv_bfloat16 row[C::KP];
+        // hi = the tap truncated to its top 16 bits (a bf16 value, exactly), lo = tap - hi (exact in fp32,
+        // rounded to bf16 when packed): tap = hi + lo to 2^-16.  Integer ops + one pack per pair -- the
+        // conversion unit is this kernel's scarcest pipe (64 ex2 per pixel already go through it).
+        float f[C::KP];
 #pragma unroll
-        for (int k = 2 * C::K9; k < C::KP; ++k) row[k] = __float2bfloat16_rn(0.0f);
+        for (int k = 2 * C::K9; k < C::KP; ++k) f[k] = 0.0f;
 #pragma unroll
         for (int k = 0; k < C::K9; ++k) {
-            const __nv_bfloat16 hi = __float2bfloat16_rn(x[k]);
-            row[k] = hi;
-            row[C::K9 + k] = __float2bfloat16_rn(x[k] - __bfloat162float(hi));
+            const float xv = mk[k] != 0u ? x[k] : 0.0f;               // v1 dropout: x*mask, no rescale (models.lua:399-406)
+            const float hi = __uint_as_float(__float_as_uint(xv) & 0xFFFF0000u);
+            f[k] = hi;
+            f[C::K9 + k] = xv - hi;
         }
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c) {
             uint4 pk;
-            pk.x = static_cast<uint32_t>(__bfloat16_as_ushort(row[8 * c + 0])) | (static_cast<uint32_t>(__bfloat16_as_ushort(row[8 * c + 1])) << 16);
-            pk.y = static_cast<uint32_t>(__bfloat16_as_ushort(row[8 * c + 2])) | (static_cast<uint32_t>(__bfloat16_as_ushort(row[8 * c + 3])) << 16);
-            pk.z = static_cast<uint32_t>(__bfloat16_as_ushort(row[8 * c + 4])) | (static_cast<uint32_t>(__bfloat16_as_ushort(row[8 * c + 5])) << 16);
-            pk.w = static_cast<uint32_t>(__bfloat16_as_ushort(row[8 * c + 6])) | (static_cast<uint32_t>(__bfloat16_as_ushort(row[8 * c + 7])) << 16);
+            pk.x = pack_bf16x2(f[8 * c + 0], f[8 * c + 1]);
+            pk.y = pack_bf16x2(f[8 * c + 2], f[8 * c + 3]);
+            pk.z = pack_bf16x2(f[8 * c + 4], f[8 * c + 5]);
+            pk.w = pack_bf16x2(f[8 * c + 6], f[8 * c + 7]);
             sA[t * 8 + (c ^ (t & 7))] = pk;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
@@ -129,7 +138,7 @@ r_conv1_tc_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mas
         }
         __syncwarp();
         // next tile's taps: the global loads are in flight while this tile's MMA retires and its epilogue runs
-        if (tile + static_cast<int>(gridDim.x) < n_tiles) gather(tile + gridDim.x, x);
+        if (tile + static_cast<int>(gridDim.x) < n_tiles) gather(tile + gridDim.x, x, mk);
         mbar_wait(bar, phase, err_flag, 106);
         phase ^= 1u;
         tcgen05_fence_after();
