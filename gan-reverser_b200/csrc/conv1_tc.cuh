@@ -13,8 +13,11 @@
 //   * every warp reads its TMEM lane quarter (one pixel per lane, 64 channels), adds the folded
 //     BN shift, applies ELU, packs bf16 and stores the warp's 32 pixels = 4 KB contiguous NHWC
 //     through an XOR-swizzled staging buffer (the tile's own A rows, free once the MMA retired).
-// Several CTAs per SM overlap gather / MMA latency / epilogue; nothing here is GEMM-heavy, the
-// point is to take the 576*C FMAs per pixel off the FP32 pipe.
+// Each CTA is software-pipelined over its tiles (two A buffers, two 64-column accumulators: tile
+// i+1's MMA is in flight and tile i+2's taps are being fetched while tile i's epilogue runs) and
+// four CTAs share an SM.  Nothing here is GEMM-heavy: the point is to take the 576*C FMAs per
+// pixel off the FP32 pipe.  What is left is bound by the conversion/transcendental unit (16
+// lanes/clk/SM): 64 ex2 (ELU) + 48 bf16 packs per pixel, ~900 cycles per 128-pixel tile.
 #pragma once
 #include "conv_tc.cuh"
 
@@ -28,7 +31,7 @@ template <int CIN> struct Conv1Cfg {
     static constexpr int kChunks = KP / 8;                 // 16-byte chunks per row actually used
     static constexpr int kABytes = 128 * 128;              // 128 rows x 128 B
     static constexpr int kBBytes = 64 * 128;
-    static constexpr int kSmemBytes = kABytes + kBBytes + 64 * 4 + 16 + 1024;   // + shift, barrier/slot, alignment slack
+    static constexpr int kSmemBytes = 2 * kABytes + kBBytes + 64 * 4 + 32 + 1024;   // two A tiles, + shift, barriers/slot, alignment slack
 };
 
 // wB: bf16 [64][KP] K-major (BN scale folded, hi and lo halves identical); shift: [64].
@@ -41,16 +44,16 @@ r_conv1_tc_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mas
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-    uint4* sA = reinterpret_cast<uint4*>(smem);                         // [128 rows][8 chunks]
-    uint4* sB = reinterpret_cast<uint4*>(smem + C::kABytes);            // [64 rows][8 chunks]
-    float* s_shift = reinterpret_cast<float*>(smem + C::kABytes + C::kBBytes);
-    const uint32_t bar = smem_base + C::kABytes + C::kBBytes + 64 * 4;
-    const uint32_t tmem_slot = bar + 8;
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + C::kABytes + C::kBBytes + 64 * 4 + 8);
+    uint4* sA = reinterpret_cast<uint4*>(smem);                         // 2 x [128 rows][8 chunks]
+    uint4* sB = reinterpret_cast<uint4*>(smem + 2 * C::kABytes);        // [64 rows][8 chunks]
+    float* s_shift = reinterpret_cast<float*>(smem + 2 * C::kABytes + C::kBBytes);
+    const uint32_t bar = smem_base + 2 * C::kABytes + C::kBBytes + 64 * 4;   // bar, bar + 8: MMA of the even / odd tiles retired
+    const uint32_t tmem_slot = bar + 16;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + 2 * C::kABytes + C::kBBytes + 64 * 4 + 16);
 
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    if (t == 0) { mbar_init(bar, 1); fence_barrier_init(); }
-    if (warp == 0) tmem_alloc<64>(tmem_slot);
+    if (t == 0) { mbar_init(bar, 1); mbar_init(bar + 8, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc<128>(tmem_slot);               // two 64-column accumulators
     if (t < 64) {                                                       // weight row t -> swizzled K-major row
         s_shift[t] = shift[t];
         const uint4* wrow = reinterpret_cast<const uint4*>(wB + static_cast<size_t>(t) * C::KP);
@@ -63,9 +66,8 @@ r_conv1_tc_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mas
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     constexpr uint32_t idesc = make_idesc<64, 128>();
-    const uint64_t adesc = make_smem_desc(smem_base), bdesc = make_smem_desc(smem_base + C::kABytes);
+    const uint64_t bdesc = make_smem_desc(smem_base + 2 * C::kABytes);
     const int HW = 1 << lgHW;                                           // H, W are powers of two (check_geom)
-    uint32_t phase = 0;
 
     // Raw taps of pixel t of a tile (0 outside the image) and their dropout-mask bytes.  Nothing here
     // CONSUMES a loaded value: the loads stay in flight across the epilogue of the current tile and
@@ -102,8 +104,10 @@ r_conv1_tc_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mas
     uint32_t mk[C::K9];
     if (static_cast<int>(blockIdx.x) < n_tiles) gather(blockIdx.x, x, mk);
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // ---- this thread's pixel: hi/lo split of its taps, swizzled K-major row
+    // Build tile's A rows from the prefetched taps into buffer `b`, then one elected thread issues its MMAs
+    // into accumulator `b`; their completion arrives on bar + 8*b.
+    auto build_and_issue = [&](const int b) {
+        uint4* A = sA + b * (C::kABytes / 16);
         // hi = the tap truncated to its top 16 bits (a bf16 value, exactly), lo = tap - hi (exact in fp32,
         // rounded to bf16 when packed): tap = hi + lo to 2^-16.  Integer ops + one pack per pair -- the
         // conversion unit is this kernel's scarcest pipe (64 ex2 per pixel already go through it).
@@ -124,32 +128,44 @@ r_conv1_tc_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mas
             pk.y = pack_bf16x2(f[8 * c + 2], f[8 * c + 3]);
             pk.z = pack_bf16x2(f[8 * c + 4], f[8 * c + 5]);
             pk.w = pack_bf16x2(f[8 * c + 6], f[8 * c + 7]);
-            sA[t * 8 + (c ^ (t & 7))] = pk;
+            A[t * 8 + (c ^ (t & 7))] = pk;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-        tcgen05_fence_before();                                        // (and this thread's TMEM reads of the previous tile are done)
+        tcgen05_fence_before();                                        // (and this thread's TMEM reads of the tile before last are done)
         __syncthreads();
-        // ---- MMA: one elected thread
         if (warp == 0 && elect_one_sync()) {
             tcgen05_fence_after();
+            const uint64_t adesc = make_smem_desc(smem_base + b * C::kABytes);
 #pragma unroll
-            for (int k = 0; k < C::kSteps; ++k) umma_bf16(tmem_base, adesc + 2u * k, bdesc + 2u * k, idesc, k > 0 ? 1u : 0u);
-            umma_commit(bar);
+            for (int k = 0; k < C::kSteps; ++k) umma_bf16(tmem_base + b * 64, adesc + 2u * k, bdesc + 2u * k, idesc, k > 0 ? 1u : 0u);
+            umma_commit(bar + 8 * b);
         }
         __syncwarp();
-        // next tile's taps: the global loads are in flight while this tile's MMA retires and its epilogue runs
-        if (tile + static_cast<int>(gridDim.x) < n_tiles) gather(tile + gridDim.x, x, mk);
-        mbar_wait(bar, phase, err_flag, 106);
-        phase ^= 1u;
+    };
+    // Software pipeline: while tile i's epilogue runs, tile i+1's MMA is already in flight (second A buffer,
+    // second accumulator) and tile i+2's taps are being fetched.
+    const int first = blockIdx.x, step = gridDim.x;
+    if (first < n_tiles) {
+        build_and_issue(0);
+        if (first + step < n_tiles) gather(first + step, x, mk);
+    }
+    int it = 0;
+    for (int tile = first; tile < n_tiles; tile += step, ++it) {
+        const int b = it & 1;
+        if (tile + step < n_tiles) {
+            build_and_issue(b ^ 1);
+            if (tile + 2 * step < n_tiles) gather(tile + 2 * step, x, mk);
+        }
+        mbar_wait(bar + 8 * b, static_cast<uint32_t>(it >> 1) & 1u, err_flag, 106);
         tcgen05_fence_after();
         // ---- epilogue: lane = pixel, 64 channels
         uint32_t r0[32], r1[32];
-        const uint32_t tq = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+        const uint32_t tq = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + b * 64;
         tmem_ld32(tq, r0);
         tmem_ld32(tq + 32, r1);
         tmem_ld_wait();
-        // staging buffer: this warp's own 32 A rows (4 KB), free now that the MMA has retired
-        uint4* wstage = sA + warp * 256;
+        // staging buffer: this warp's own 32 rows (4 KB) of THIS tile's A buffer, free now that its MMA has retired
+        uint4* wstage = sA + b * (C::kABytes / 16) + warp * 256;
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -178,7 +194,7 @@ r_conv1_tc_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mas
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 0) { tcgen05_fence_after(); tmem_dealloc<64>(tmem_base); }
+    if (warp == 0) { tcgen05_fence_after(); tmem_dealloc<128>(tmem_base); }
 }
 
 }  // namespace tc
