@@ -35,6 +35,7 @@ _SIGS = {
     "ganrev_forward_R": (_i, [_vp, _i, _vp, _vp, _i64, _vp]),
     "ganrev_fix_l2": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
     "ganrev_l2": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
+    "ganrev_nearest_l2": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _vp]),
     "ganrev_anomaly_flags": (_i, [_vp, _vp, _i64, _i64, C.c_double, _vp, C.POINTER(C.c_double)]),
     "ganrev_buffer_put": (_i, [_vp, _i, _vp, _i64]),
     "ganrev_buffer_get": (_i, [_vp, _i, _vp, _i64, _i64]),
@@ -182,6 +183,27 @@ class Context:
         out = np.empty((N,), np.float64)
         self._chk(lib().ganrev_l2(self._h, _ptr(a), _ptr(b), N, px, _ptr(out)))
         return out
+
+    def nearest_l2(self, queries, images=None, N=None):
+        """sample.lua:128-148: per query image the set image with the first strictly smallest torch.dist.
+        images=None scans the first N resident IMAGES.  Returns (ids int64 [Q], dist float64 [Q])."""
+        q = _arr(queries, np.float32)
+        Q = q.shape[0]
+        px = q.size // max(Q, 1)
+        if images is not None:
+            x = _arr(images, np.float32)
+            N = x.shape[0]
+            assert N == 0 or x.size // N == px
+            xp = _ptr(x) if N else None
+        else:
+            assert N is not None
+            xp = None
+        ids = np.empty((Q,), np.int64)
+        dist = np.empty((Q,), np.float64)
+        if images is not None and N == 0:
+            xp = _ptr(np.zeros((1,), np.float32))   # any non-NULL pointer: an EMPTY explicit set, not the resident images
+        self._chk(lib().ganrev_nearest_l2(self._h, _ptr(q), Q, xp, N, px, _ptr(ids), _ptr(dist)))
+        return ids, dist
 
     def anomaly_flags(self, l2, n_calc, n_show, quantile):
         l2 = _arr(l2, np.float64)

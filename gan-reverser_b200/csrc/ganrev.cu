@@ -86,6 +86,7 @@ struct ganrev_ctx {
     DevBuf buf[GANREV_BUF_COUNT];
     int64_t buf_rows[GANREV_BUF_COUNT] = {0, 0, 0, 0, 0, 0};
     DevBuf arena[2], noise_bf16, stage_a, stage_b, l2buf, thr, flags;
+    DevBuf nn_partial, nn_ids, nn_dist, nn_flag;   // ganrev_nearest_l2 scratch
     // database
     DevBuf db, rdb, maxabs;
     int64_t db_n = 0, db_offset = 0, db_total = 0;
@@ -780,6 +781,7 @@ void ganrev_destroy(ganrev_ctx* ctx) {
         for (TcLayer* L : {&R.c2, &R.c3, &R.c4, &R.c5, &R.c6, &R.l1, &R.l2}) release_layer(*L);
     }
     for (auto& b : ctx->buf) release(b);
+    for (DevBuf* b : {&ctx->nn_partial, &ctx->nn_ids, &ctx->nn_dist, &ctx->nn_flag}) release(*b);
     for (DevBuf* b : {&ctx->arena[0], &ctx->arena[1], &ctx->noise_bf16, &ctx->stage_a, &ctx->stage_b, &ctx->l2buf, &ctx->thr, &ctx->flags,
                       &ctx->db, &ctx->rdb, &ctx->maxabs, &ctx->q, &ctx->rq, &ctx->c2, &ctx->partial, &ctx->keys, &ctx->keys_all, &ctx->ids,
                       &ctx->scores, &ctx->cen, &ctx->acc, &ctx->cnt, &ctx->total, &ctx->labels, &ctx->cosv, &ctx->tcounts, &ctx->mids,
@@ -975,6 +977,52 @@ int ganrev_l2(ganrev_ctx* ctx, const float* a, const float* b, int64_t N, int px
     CU_TRY(cudaMemcpyAsync(ctx->stage_b.p, b, bytes, cudaMemcpyHostToDevice, ctx->stream));
     RC_TRY(l2_dev(ctx, static_cast<const float*>(ctx->stage_a.p), static_cast<const float*>(ctx->stage_b.p), N, px, static_cast<double*>(ctx->l2buf.p)));
     CU_TRY(cudaMemcpyAsync(l2, ctx->l2buf.p, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    return finish(ctx);
+}
+
+int ganrev_nearest_l2(ganrev_ctx* ctx, const float* queries, int Q, const float* set, int64_t N, int px, int64_t* ids, double* dist) {
+    if (!ctx || !queries || Q < 0 || N < 0 || px < 1 || !ids || !dist) return ctx ? fail(ctx, GANREV_EINVAL, "bad nearest_l2 arguments") : GANREV_EINVAL;
+    if (Q == 0) return GANREV_OK;
+    CU_TRY(cudaSetDevice(ctx->device));
+    const float* d_set = nullptr;
+    if (set) {
+        RC_TRY(ensure(ctx, ctx->stage_a, sizeof(float) * static_cast<size_t>(std::max<int64_t>(N, 1)) * px));
+        if (N > 0) CU_TRY(cudaMemcpyAsync(ctx->stage_a.p, set, sizeof(float) * static_cast<size_t>(N) * px, cudaMemcpyHostToDevice, ctx->stream));
+        d_set = static_cast<const float*>(ctx->stage_a.p);
+    } else {
+        if (ctx->buf_rows[GANREV_BUF_IMAGES] < N || (N > 0 && buf_row_bytes(ctx, GANREV_BUF_IMAGES) != sizeof(float) * static_cast<size_t>(px)))
+            return fail(ctx, GANREV_ESTATE, "resident IMAGES do not hold %lld rows of %d floats", (long long)N, px);
+        d_set = static_cast<const float*>(ctx->buf[GANREV_BUF_IMAGES].p);
+    }
+    RC_TRY(ensure(ctx, ctx->stage_b, sizeof(float) * static_cast<size_t>(Q) * px));
+    CU_TRY(cudaMemcpyAsync(ctx->stage_b.p, queries, sizeof(float) * static_cast<size_t>(Q) * px, cudaMemcpyHostToDevice, ctx->stream));
+    // one warp per set row, 8 warps per block, a few blocks per SM; never more warps than rows
+    const long long want_warps = std::max<long long>(1, std::min<long long>(N, 8LL * 4 * ctx->num_sms));
+    const int blocks = static_cast<int>((want_warps + 7) / 8);
+    const long long n_warps = 8LL * blocks;
+    RC_TRY(ensure(ctx, ctx->nn_partial, sizeof(NearestRec) * static_cast<size_t>(n_warps) * NL2_QB));
+    RC_TRY(ensure(ctx, ctx->nn_ids, sizeof(long long) * static_cast<size_t>(Q)));
+    RC_TRY(ensure(ctx, ctx->nn_dist, sizeof(double) * static_cast<size_t>(Q)));
+    RC_TRY(ensure(ctx, ctx->nn_flag, static_cast<size_t>(Q)));
+    CU_TRY(cudaMemsetAsync(ctx->nn_flag.p, 0, static_cast<size_t>(Q), ctx->stream));
+    for (int q0 = 0; q0 < Q; q0 += NL2_QB) {
+        const int nq = std::min(NL2_QB, Q - q0);
+        {
+            ProfScope ps(ctx, "nearest_l2", 3.0 * N * px * nq, 4.0 * N * px);
+            nearest_l2_kernel<<<blocks, 256, 0, ctx->stream>>>(static_cast<const float*>(ctx->stage_b.p), Q, q0, d_set, N, px,
+                                                               static_cast<NearestRec*>(ctx->nn_partial.p), static_cast<unsigned char*>(ctx->nn_flag.p));
+            CU_TRY(cudaGetLastError());
+        }
+        {
+            ProfScope ps(ctx, "nearest_l2_merge", 0.0, 16.0 * n_warps * nq);
+            nearest_l2_merge_kernel<<<nq, 32, 0, ctx->stream>>>(static_cast<const NearestRec*>(ctx->nn_partial.p), n_warps, Q, q0, N,
+                                                               static_cast<const unsigned char*>(ctx->nn_flag.p), static_cast<long long*>(ctx->nn_ids.p), static_cast<double*>(ctx->nn_dist.p));
+            CU_TRY(cudaGetLastError());
+        }
+    }
+    static_assert(sizeof(long long) == sizeof(int64_t), "ids are copied out as int64");
+    CU_TRY(cudaMemcpyAsync(ids, ctx->nn_ids.p, sizeof(int64_t) * Q, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(dist, ctx->nn_dist.p, sizeof(double) * Q, cudaMemcpyDeviceToHost, ctx->stream));
     return finish(ctx);
 }
 

@@ -183,6 +183,111 @@ l2_pairs_kernel(const float* __restrict__ a, const float* __restrict__ b, long l
     if (lane == 0) l2[pair] = __dsqrt_rn(s);
 }
 
+// ------------------------------------------------------------------ nearest set image by torch.dist
+// sample.lua:128-148 (findClosestNeighboursOf): for each query image scan the whole training set and
+// keep the first strictly smaller torch.dist.  One warp per set row, QB queries per pass: the row's
+// 128-float pieces are loaded once and compared against QB query rows (L1/L2 resident), each
+// (row, query) distance summed in the canonical lane order of l2_pairs_kernel.  Every warp keeps its
+// own best (distance, row) per query -- rows arrive in ascending order inside a warp, so strict <
+// keeps the lowest row -- and a second kernel merges the warps by (distance, row) and applies the
+// reference's quirk that row 0 is taken unconditionally (a NaN there sticks).
+constexpr int NL2_QB = 8;
+struct NearestRec { double d; long long id; };
+
+__global__ void __launch_bounds__(256)
+nearest_l2_kernel(const float* __restrict__ q, int Q, int q0, const float* __restrict__ set, long long N, int px,
+                  NearestRec* __restrict__ partial /* [gridDim.x * 8 warps][NL2_QB] */, unsigned char* __restrict__ row0_nan /* [Q] */) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const int nq = min(NL2_QB, Q - q0);
+    double bd[NL2_QB];
+    long long bi[NL2_QB];
+#pragma unroll
+    for (int v = 0; v < NL2_QB; ++v) { bd[v] = 0.0; bi[v] = -1; }
+    const bool vec = ((px & 3) == 0) && ((reinterpret_cast<uintptr_t>(set) & 15) == 0) && ((reinterpret_cast<uintptr_t>(q) & 15) == 0);
+    for (long long row = gw; row < N; row += nw) {
+        const float* x = set + row * px;
+        double s[NL2_QB];
+#pragma unroll
+        for (int v = 0; v < NL2_QB; ++v) s[v] = 0.0;
+        if (vec) {
+            const float4* x4 = reinterpret_cast<const float4*>(x);
+            const int n4 = px >> 2;
+            for (int i = lane; i < n4; i += 32) {
+                const float4 xv = __ldcs(x4 + i);
+#pragma unroll
+                for (int v = 0; v < NL2_QB; ++v) {
+                    if (v < nq) {
+                        const float4 yv = __ldg(reinterpret_cast<const float4*>(q + static_cast<long long>(q0 + v) * px) + i);
+                        // torch.dist(trainingSet[j], img): set row minus query, squared in fp32, summed in double
+                        const float d0 = __fsub_rn(xv.x, yv.x), d1 = __fsub_rn(xv.y, yv.y);
+                        const float d2 = __fsub_rn(xv.z, yv.z), d3 = __fsub_rn(xv.w, yv.w);
+                        s[v] += static_cast<double>(__fmul_rn(d0, d0));
+                        s[v] += static_cast<double>(__fmul_rn(d1, d1));
+                        s[v] += static_cast<double>(__fmul_rn(d2, d2));
+                        s[v] += static_cast<double>(__fmul_rn(d3, d3));
+                    }
+                }
+            }
+        } else {
+            for (int base = lane * 4; base < px; base += 128)
+                for (int j = 0; j < 4 && base + j < px; ++j) {
+                    const float xv = x[base + j];
+#pragma unroll
+                    for (int v = 0; v < NL2_QB; ++v)
+                        if (v < nq) {
+                            const float d = __fsub_rn(xv, q[static_cast<long long>(q0 + v) * px + base + j]);
+                            s[v] += static_cast<double>(__fmul_rn(d, d));
+                        }
+                }
+        }
+#pragma unroll
+        for (int v = 0; v < NL2_QB; ++v) {
+            double t = s[v];
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) t = t + __shfl_xor_sync(0xffffffffu, t, off);
+            const double dist = __dsqrt_rn(t);
+            if (v < nq) {
+                if (bi[v] < 0 ? !(dist != dist) : dist < bd[v]) { bd[v] = dist; bi[v] = row; }   // NaN never wins here
+                if (row == 0 && lane == 0) row0_nan[q0 + v] = (dist != dist) ? 1 : 0;
+            }
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int v = 0; v < NL2_QB; ++v) { partial[gw * NL2_QB + v].d = bd[v]; partial[gw * NL2_QB + v].id = bi[v]; }
+    }
+}
+
+// one warp per query of the pass: min over the per-warp records by (distance, row)
+__global__ void nearest_l2_merge_kernel(const NearestRec* __restrict__ partial, long long n_warps, int Q, int q0, long long N,
+                                        const unsigned char* __restrict__ row0_nan, long long* __restrict__ ids, double* __restrict__ dist) {
+    const int v = blockIdx.x, lane = threadIdx.x;
+    if (q0 + v >= Q) return;
+    double bd = 0.0;
+    long long bi = -1;
+    for (long long w = lane; w < n_warps; w += 32) {
+        const NearestRec r = partial[w * NL2_QB + v];
+        if (r.id >= 0 && (bi < 0 || r.d < bd || (r.d == bd && r.id < bi))) { bd = r.d; bi = r.id; }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, bd, off);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (oi >= 0 && (bi < 0 || od < bd || (od == bd && oi < bi))) { bd = od; bi = oi; }
+    }
+    if (lane == 0) {
+        if (N > 0 && (row0_nan[q0 + v] || bi < 0)) {      // row 0 was NaN (it sticks), or every distance was NaN (row 0 again)
+            ids[q0 + v] = 0;
+            dist[q0 + v] = __longlong_as_double(0x7ff8000000000000ll);
+        } else {
+            ids[q0 + v] = bi;
+            dist[q0 + v] = bi < 0 ? __longlong_as_double(0x7ff0000000000000ll) : bd;   // empty set: -1, +inf
+        }
+    }
+}
+
 // ------------------------------------------------------------------ quantile threshold + flags
 __device__ __forceinline__ unsigned long long f64_key(double v) {   // ascending order-preserving
     const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));

@@ -30,6 +30,7 @@ int ganrev_forward_G(ganrev_ctx* ctx, const float* noise, int64_t N, float* imag
 int ganrev_forward_R(ganrev_ctx* ctx, int slot, const float* images, const uint8_t* mask, int64_t N, float* attrs);
 int ganrev_fix_l2(ganrev_ctx* ctx, int slot, const float* images, const uint8_t* mask, int64_t N, float* attrs, float* fixed, double* l2);
 int ganrev_l2(ganrev_ctx* ctx, const float* a, const float* b, int64_t N, int px, double* l2);
+int ganrev_nearest_l2(ganrev_ctx* ctx, const float* queries, int Q, const float* set, int64_t N, int px, int64_t* ids, double* dist);
 int ganrev_anomaly_flags(ganrev_ctx* ctx, const double* l2, int64_t n_calc, int64_t n_show, double quantile, uint8_t* flags, double* thr);
 int ganrev_buffer_put(ganrev_ctx* ctx, int which, const void* host, int64_t rows);
 int ganrev_buffer_get(ganrev_ctx* ctx, int which, void* host, int64_t row0, int64_t rows);
@@ -212,6 +213,24 @@ function M.anomalies(ctx, images, fixed, nbImagesCalculations, nbImagesShow, thr
     local flags, thr = torch.ByteTensor(nbImagesShow), ffi.new('double[1]')
     check(ctx, lib.ganrev_anomaly_flags(ctx, l2:data(), n, nbImagesShow, threshold, flags:data(), thr))
     return flags, l2:mul(-1):add(1), tonumber(thr[0])
+end
+
+-- findClosestNeighboursOf  sample.lua:128-148: images = list of image tensors, trainingSet = N x C x H x W tensor.
+-- Returns the same list of {image, closest training image, distance}.
+function M.findClosestNeighboursOf(ctx, images, trainingSet)
+    local Q = #images
+    if Q == 0 then return {} end
+    local q = torch.FloatTensor(Q, images[1]:nElement())
+    for i = 1, Q do q[i]:copy(images[i]:float():view(-1)) end
+    local ts = trainingSet:float():contiguous()
+    local N, px = ts:size(1), ts:nElement() / ts:size(1)
+    local ids, dist = torch.LongTensor(Q), torch.DoubleTensor(Q)
+    check(ctx, lib.ganrev_nearest_l2(ctx, q:data(), Q, ts:data(), N, px, ids:data(), dist:data()))
+    local result = {}
+    for i = 1, Q do
+        table.insert(result, {images[i], ts[ids[i] + 1]:clone(), dist[i]})
+    end
+    return result
 end
 
 return M

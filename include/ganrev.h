@@ -101,6 +101,12 @@ int ganrev_fix_l2(ganrev_ctx* ctx, int slot, const float* images, const uint8_t*
                   float* attrs, float* fixed, double* l2);
 /* torch.dist(a[i], b[i]) for N pairs of px-element vectors (apply_r.lua:366). */
 int ganrev_l2(ganrev_ctx* ctx, const float* a, const float* b, int64_t N, int px, double* l2);
+/* SURVEY 8(f) rank 3 -- findClosestNeighboursOf   sample.lua:128-148: for each of Q query images [Q x px] the
+ * row of `set` [N x px] (NULL = the first N resident IMAGES) with the smallest torch.dist, first strict minimum
+ * in row order (row 0 is always taken first, so a NaN there sticks, as in the Lua loop).  ids [Q] 0-based
+ * (-1 when N == 0), dist [Q] (+inf when N == 0).  Single-rank. */
+int ganrev_nearest_l2(ganrev_ctx* ctx, const float* queries, int Q, const float* set, int64_t N, int px,
+                      int64_t* ids, double* dist);
 /* apply_r.lua:370-378: sims = 1 - l2; thr = ascending sims[floor(n_calc*quantile)] (1-based);
  * flags[i] = sims[i] <= thr, i < n_show.  thr may be NULL. */
 int ganrev_anomaly_flags(ganrev_ctx* ctx, const double* l2, int64_t n_calc, int64_t n_show,

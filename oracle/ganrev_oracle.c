@@ -468,24 +468,24 @@ int orc_cluster_members(const int32_t* cluster, const float* cosv, int64_t N, in
 }
 
 /* apply_r.lua:366, torch.dist(a,b) = sqrt(sum((a-b)^2)) [upstream TH: float pow, double sum] */
+static double l2_one(const float* x, const float* y, int px) {
+    double lane[32];
+    for (int l = 0; l < 32; ++l) lane[l] = 0.0;
+    for (int i = 0; i < px; ++i) {
+        const float dd = x[i] - y[i];
+        const float sq = dd * dd;
+        lane[(i >> 2) & 31] += (double)sq;
+    }
+    for (int off = 16; off >= 1; off >>= 1) {
+        double nxt[32];
+        for (int l = 0; l < 32; ++l) nxt[l] = lane[l] + lane[l ^ off];
+        memcpy(lane, nxt, sizeof(lane));
+    }
+    return sqrt(lane[0]);
+}
 int orc_l2(const float* a, const float* b, int64_t N, int px, double* l2) {
 #pragma omp parallel for schedule(static)
-    for (int64_t n = 0; n < N; ++n) {
-        const float* x = a + n * px; const float* y = b + n * px;
-        double lane[32];
-        for (int l = 0; l < 32; ++l) lane[l] = 0.0;
-        for (int i = 0; i < px; ++i) {
-            const float dd = x[i] - y[i];
-            const float sq = dd * dd;
-            lane[(i >> 2) & 31] += (double)sq;
-        }
-        for (int off = 16; off >= 1; off >>= 1) {
-            double nxt[32];
-            for (int l = 0; l < 32; ++l) nxt[l] = lane[l] + lane[l ^ off];
-            memcpy(lane, nxt, sizeof(lane));
-        }
-        l2[n] = sqrt(lane[0]);
-    }
+    for (int64_t n = 0; n < N; ++n) l2[n] = l2_one(a + n * px, b + n * px, px);
     return 0;
 }
 int orc_l2_sequential(const float* a, const float* b, int64_t N, int px, double* l2) {
@@ -494,6 +494,26 @@ int orc_l2_sequential(const float* a, const float* b, int64_t N, int px, double*
         double s = 0.0;
         for (int i = 0; i < px; ++i) { const float dd = x[i] - y[i]; const float sq = dd * dd; s += (double)sq; }
         l2[n] = sqrt(s);
+    }
+    return 0;
+}
+
+/* sample.lua:128-148 findClosestNeighboursOf: for every query image scan the whole set with
+ * torch.dist and keep the first strictly smaller distance ("closestDist == nil or dist < closestDist").
+ * Row 0 is always taken first, so a NaN distance at row 0 sticks (every later "dist < NaN" is false);
+ * NaN distances at later rows are never taken.  Distances use orc_l2's canonical summation order. */
+int orc_nearest_l2(const float* q, int Q, const float* set, int64_t N, int px, int64_t* ids, double* dist) {
+    if (Q < 0 || N < 0 || px < 1) return 1;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < Q; ++i) {
+        int64_t best = -1;
+        double bd = 0.0;
+        for (int64_t j = 0; j < N; ++j) {
+            const double dj = l2_one(set + j * px, q + (int64_t)i * px, px);
+            if (best < 0 || dj < bd) { best = j; bd = dj; }
+        }
+        ids[i] = best;
+        dist[i] = best < 0 ? INFINITY : bd;
     }
     return 0;
 }

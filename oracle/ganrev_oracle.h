@@ -72,6 +72,8 @@ int orc_cluster_members(const int32_t* cluster, const float* cosv, int64_t N, in
 /* apply_r.lua:366 torch.dist(a,b): canonical lane-tree order (lane=(i/4)%32,
  * fp32 diff, fp32 square, double partial sums, xor-butterfly), sqrt in double. */
 int orc_l2(const float* a, const float* b, int64_t N, int px, double* l2);
+/* sample.lua:128-148: nearest set image per query by torch.dist, first strict minimum; ids -1 / dist inf when N == 0 */
+int orc_nearest_l2(const float* q, int Q, const float* set, int64_t N, int px, int64_t* ids, double* dist);
 /* Same quantity in TH's plain sequential order (for bounding the order effect). */
 int orc_l2_sequential(const float* a, const float* b, int64_t N, int px, double* l2);
 

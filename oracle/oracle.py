@@ -51,6 +51,7 @@ def lib():
         L.orc_cluster_members.argtypes = [i32p, f32p, C.c_int64, C.c_int, C.c_int, f32p, C.c_int,
                                           i64p, i32p, f32p]
         L.orc_l2.argtypes = [f32p, f32p, C.c_int64, C.c_int, f64p]
+        L.orc_nearest_l2.argtypes = [f32p, C.c_int, f32p, C.c_int64, C.c_int, i64p, f64p]
         L.orc_l2_sequential.argtypes = [f32p, f32p, C.c_int64, C.c_int, f64p]
         L.orc_anomaly_flags.argtypes = [f64p, C.c_int64, C.c_int64, C.c_double, u8p, C.POINTER(C.c_double)]
         L.orc_num_threads.restype = C.c_int
@@ -160,6 +161,18 @@ def l2(a, b, sequential=False):
     fn = lib().orc_l2_sequential if sequential else lib().orc_l2
     _chk(fn(a2, b2, N, a2.shape[1], out), "l2")
     return out
+
+
+def nearest_l2(queries, images):
+    """sample.lua:128-148: per query the set image with the first strictly smallest torch.dist."""
+    q, x = _f32(queries), _f32(images)
+    Q, N = q.shape[0], x.shape[0]
+    q2 = q.reshape(Q, -1)
+    x2 = x.reshape(N, -1) if N else np.zeros((0, q2.shape[1]), np.float32)
+    ids = np.empty((Q,), np.int64)
+    dist = np.empty((Q,), np.float64)
+    _chk(lib().orc_nearest_l2(q2, Q, x2, N, q2.shape[1], ids, dist), "nearest_l2")
+    return ids, dist
 
 
 def anomaly_flags(l2v, n_calc, n_show, quantile):

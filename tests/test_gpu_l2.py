@@ -41,3 +41,54 @@ def test_anomaly_flags_exact(orc, ctx, n_calc, n_show, q):
 def test_anomaly_flags_bad_quantile(pkg, ctx):
     with pytest.raises(pkg.GanrevError):
         ctx.anomaly_flags(np.ones(5), 5, 5, 0.15)     # floor(5*0.15) = 0: Lua would index nil
+
+
+@pytest.mark.parametrize("Q,N,px", [(3, 1000, 1024), (8, 4096, 1024), (11, 700, 3072), (1, 5, 37), (20, 257, 100)])
+def test_nearest_l2_exact(orc, ctx, Q, N, px):
+    """SURVEY 8f rank 3 (sample.lua:128-148): ids and distances bit-exact against the oracle."""
+    rng = np.random.default_rng(Q * 7 + N)
+    ts = rng.random((N, px)).astype(np.float32)
+    q = (ts[rng.integers(0, N, size=Q)] + rng.normal(scale=0.02, size=(Q, px))).astype(np.float32)
+    if N > 60:
+        ts[50] = ts[3]; ts[N - 1] = ts[3]; q[0] = ts[3]                  # exact duplicates: distance 0 three times -> row 3
+    ids, dist = ctx.nearest_l2(q, ts)
+    oi, od = orc.nearest_l2(q, ts)
+    np.testing.assert_array_equal(ids, oi)
+    assert_bitexact(dist, od, "nearest_l2 distance")
+
+
+def test_nearest_l2_nan_and_empty(orc, ctx):
+    rng = np.random.default_rng(5)
+    ts = rng.random((600, 64)).astype(np.float32)
+    q = rng.random((9, 64)).astype(np.float32)
+    ts_a = ts.copy(); ts_a[0, 1] = np.nan                                # row 0 is taken unconditionally and then sticks
+    ids, dist = ctx.nearest_l2(q, ts_a)
+    assert np.all(ids == 0) and np.all(np.isnan(dist))
+    ts_b = ts.copy(); ts_b[77, 5] = np.nan                               # NaN rows elsewhere are never taken
+    ids_b, dist_b = ctx.nearest_l2(q, ts_b)
+    oi, od = orc.nearest_l2(q, ts_b)
+    np.testing.assert_array_equal(ids_b, oi)
+    assert_bitexact(dist_b, od)
+    ids_e, dist_e = ctx.nearest_l2(q, np.zeros((0, 64), np.float32))
+    assert np.all(ids_e == -1) and np.all(np.isinf(dist_e))
+
+
+def test_nearest_l2_resident_images_fullsize(pkg, orc, ctx):
+    """200k resident 32x32 faces (819 MB): the nearest neighbour of a face that IS in the set is itself at distance 0,
+    and a sampled check against the oracle on a slice."""
+    rng = np.random.default_rng(9)
+    N, px = 200000, 1024
+    imgs = rng.random((N, px), dtype=np.float32)
+    ctx.load_G(1, 32, 32, 100, pkg.weights.init_G(1, 32, 32, 100))     # resident buffers take their row shape from the loaded model
+    ctx.buffer_put(pkg._lib.BUF_IMAGES, imgs.reshape(N, 1, 32, 32))
+    rows = np.array([0, 1, 777, 123456, N - 1])
+    ids, dist = ctx.nearest_l2(imgs[rows], None, N=N)
+    np.testing.assert_array_equal(ids, rows)
+    assert np.all(dist == 0.0)
+    q = (imgs[rows] + rng.normal(scale=0.05, size=(5, px))).astype(np.float32)
+    ids2, dist2 = ctx.nearest_l2(q, None, N=N)
+    np.testing.assert_array_equal(ids2, rows)
+    sl = slice(123000, 124000)
+    oi, od = orc.nearest_l2(q[[3]], imgs[sl])
+    assert oi[0] + 123000 == ids2[3]
+    assert_bitexact(dist2[[3]], od)

@@ -150,3 +150,25 @@ def test_assign_min_members_l2_flags(orc):
     np.testing.assert_array_equal(flags.astype(bool), sims[:5] <= thr)
     with pytest.raises(RuntimeError):
         orc.anomaly_flags(d, 5, 5, 0.15)
+
+
+def test_nearest_l2_oracle(orc):
+    """sample.lua:128-148: first strictly smallest torch.dist; ties -> lowest row; row-0 NaN sticks; empty set."""
+    rng = np.random.default_rng(11)
+    ts = rng.random((300, 48)).astype(np.float32)
+    q = (ts[[5, 250, 17]] + rng.normal(scale=0.01, size=(3, 48))).astype(np.float32)
+    ids, dist = orc.nearest_l2(q, ts)
+    ref = np.sqrt(((ts[None].astype(np.float64) - q[:, None].astype(np.float64)) ** 2).sum(-1))
+    np.testing.assert_array_equal(ids, ref.argmin(1))
+    np.testing.assert_allclose(dist, ref.min(1), rtol=1e-6)
+    ts2 = ts.copy(); ts2[40] = ts2[7]; ts2[200] = ts2[7]                # exact duplicates: the first one wins
+    ids2, _ = orc.nearest_l2(ts2[[7]], ts2)
+    assert ids2[0] == 7
+    ts3 = ts.copy(); ts3[0, 3] = np.nan                                  # "closestDist == nil or dist < closestDist"
+    ids3, d3 = orc.nearest_l2(q, ts3)
+    assert np.all(ids3 == 0) and np.all(np.isnan(d3))
+    ts4 = ts.copy(); ts4[9, 0] = np.nan                                  # NaN elsewhere is never taken
+    ids4, _ = orc.nearest_l2(q, ts4)
+    np.testing.assert_array_equal(ids4, ids)
+    ids5, d5 = orc.nearest_l2(q, np.zeros((0, 48), np.float32))
+    assert np.all(ids5 == -1) and np.all(np.isinf(d5))
