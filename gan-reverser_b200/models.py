@@ -100,3 +100,20 @@ def create_R(dimensions, noiseDim, noiseMethod="normal", fixer=False, cuda=True,
     if slot is None:
         slot = 1 if fixer else 0
     return Reverser(ctx or default_context(), slot, dimensions, noiseDim, noiseMethod, fixer, blob)
+
+
+def load_G(path, ctx=None):
+    """`torch.load(OPT.G)` of apply_r.lua:62-69 without Torch7: parse the `.net` file (t7.py), take the
+    geometry from its `opt` table and load `ckpt.G`.  Returns (Generator, opt)."""
+    from . import t7
+    ckpt = t7.load(path)
+    C, H, W, nd, blob = t7.g_blob(ckpt)
+    return Generator(ctx or default_context(), (C, H, W), nd, blob), ckpt["opt"]
+
+
+def load_R(path, dimensions, noiseDim, noiseMethod="normal", fixer=False, ctx=None, slot=None):
+    """`torch.load(OPT.R).R` / `torch.load(OPT.R_fixer).R` of apply_r.lua:92-103 without Torch7."""
+    from . import t7
+    C, H, W = dimensions
+    blob = t7.r_blob(t7.load(path), C, H, W, noiseDim)
+    return create_R(dimensions, noiseDim, noiseMethod, fixer, blob=blob, ctx=ctx, slot=slot)

@@ -153,3 +153,31 @@ def test_errors(pkg, ctx):
         c2.geom = (1, 32, 32, 32)
         c2.forward_G(np.zeros((2, 32), np.float32))                  # nothing loaded
     c2.close()
+
+
+def test_t7_checkpoint_loads_like_blob(pkg, tmp_path):
+    """a Torch7 `.net` file written in the documented format drives the library exactly like
+    the blob it was made from (same bytes in -> same images / vectors out)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(__file__))
+    import t7_writer as tw
+    from test_t7_cpu import _seq, _bn, _conv
+    W = pkg.weights
+    C, H, Wd, nd = 1, 32, 32, 100
+    gb = W.init_G(C, H, Wd, nd, seed=3, stress=True)
+    p = W.unpack(gb, W.g_layout(C, H, Wd, nd))
+    G = _seq(tw.Module("nn.Linear", weight=p["lin.w"], bias=p["lin.b"]), _bn("bn0", p, False), _conv("c1", p, cudnn=True), _bn("bn1", p, True),
+             _conv("c2", p, cudnn=True), _bn("bn2", p, True), _conv("c3", p, cudnn=True))
+    opt = {"noiseDim": nd, "noiseMethod": "normal", "height": H, "width": Wd, "colorSpace": "y"}
+    path = tmp_path / "adversarial.net"
+    path.write_bytes(tw.dumps({"G": G, "opt": opt}, cuda=True))
+    ctx = pkg.Context(0)
+    try:
+        noise = np.random.default_rng(0).normal(size=(64, nd)).astype(np.float32)
+        g1, opt_out = pkg.models.load_G(str(path), ctx=ctx)
+        assert opt_out["noiseDim"] == nd
+        a = g1.forward(noise)
+        b = pkg.models.create_G((C, H, Wd), nd, blob=gb, ctx=ctx).forward(noise)
+        np.testing.assert_array_equal(a, b)
+    finally:
+        ctx.close()
