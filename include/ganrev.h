@@ -160,7 +160,7 @@ int ganrev_profile_get(ganrev_ctx* ctx, int idx, const char** name, uint64_t* la
 /* Debug: clock64 timeline of CTA 0 of the named tensor-core layer (roles x events, [8][256]). */
 int ganrev_debug_trace_arm(ganrev_ctx* ctx, const char* layer);
 int ganrev_debug_trace_read(ganrev_ctx* ctx, int64_t* out);
-/* Tuning / debugging knobs: "chunk" (images per pipeline chunk), "conv_impl"
+/* Tuning / debugging knobs: "chunk" (images per pipeline chunk; default = 8192 32x32 faces' worth of pixels), "conv_impl"
  * (0 = tcgen05 implicit GEMM, 1 = plain CUDA-core kernel kept for A/B debugging). */
 int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value);
 
