@@ -19,6 +19,8 @@ using namespace ganrev;
 // =================================================================================
 // context
 // =================================================================================
+constexpr int kMaxDevices = 64;   // per-device caches of kernel attributes
+
 struct TcLayer {
     std::string name;
     ConvGemm g{};
@@ -377,7 +379,8 @@ static int check_geom(ganrev_ctx* ctx, int C, int H, int W, int nd) {
 template <int NT, int MT, int NDY, bool BRES, int ACT, bool POOL, bool OUT_FP32, int CG>
 static int launch_tc(ganrev_ctx* ctx, const TcLayer& L, const CUtensorMap& tmA, const ConvGemm& g, int n_items) {
     auto kern = tc::conv_tc_kernel<NT, MT, NDY, BRES, ACT, POOL, OUT_FP32, CG>;
-    static size_t attr_max = 0;
+    static size_t attr_max_dev[kMaxDevices] = {};          // function attributes are per device
+    size_t& attr_max = attr_max_dev[ctx->device];
     if (L.smem_bytes > attr_max) {
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L.smem_bytes)));
         attr_max = L.smem_bytes;
@@ -699,8 +702,8 @@ static int forward_R_dev(ganrev_ctx* ctx, int slot, const float* d_images, const
                 const int n_tiles = static_cast<int>(blocks);
                 // resident CTAs per SM: bounded by registers (128 threads each) and 512 TMEM columns / 64; shared memory
                 // (26 KB each) is not the limit once the carve-out favours it.  One even wave of persistent CTAs.
-                static int occ1 = 0, occ3 = 0;
-                int& occ = R.C == 1 ? occ1 : occ3;
+                static int occ_dev[kMaxDevices][2] = {};
+                int& occ = occ_dev[ctx->device][R.C == 1 ? 0 : 1];
                 if (occ == 0) {
                     cudaFuncAttributes fa{};
                     if (R.C == 1) { CU_TRY(cudaFuncGetAttributes(&fa, tc::r_conv1_tc_kernel<1>)); CU_TRY(cudaFuncSetAttribute(tc::r_conv1_tc_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); }
@@ -755,7 +758,7 @@ int ganrev_create(ganrev_ctx** out, int device) {
     ganrev_ctx* ctx = c.get();
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return GANREV_ENODEV;
-    if (device < 0 || device >= count) return GANREV_ENODEV;
+    if (device < 0 || device >= count || device >= kMaxDevices) return GANREV_ENODEV;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GANREV_ENODEV;
     if (prop.major != 10) return GANREV_ENODEV;   // tcgen05 / TMEM kernels are sm_100a only; there is no fallback
@@ -1149,7 +1152,8 @@ static int launch_search_wide(ganrev_ctx* ctx, const scan::ScanParams& p, int sp
     constexpr int QT = 64, K2 = 32 * E;
     const size_t smem = sizeof(float) * (static_cast<size_t>(p.d) * scan::XS + static_cast<size_t>(p.d) * QT) +
                         sizeof(unsigned long long) * (QT * K2 + QT * scan::CAP + QT) + sizeof(int) * QT;
-    static size_t attr_max = 0;
+    static size_t attr_max_dev[kMaxDevices] = {};          // function attributes are per device
+    size_t& attr_max = attr_max_dev[ctx->device];
     if (smem > attr_max) {
         CU_TRY(cudaFuncSetAttribute(scan::search_kernel_wide<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         attr_max = smem;
@@ -1166,7 +1170,8 @@ static int launch_search_wide4(ganrev_ctx* ctx, const scan::ScanParams& p, int s
     const int S = scan::wide4_stride(p.d);
     const size_t smem = sizeof(float) * (static_cast<size_t>(scan::RT + QT) * S) +
                         sizeof(unsigned long long) * (QT * K2 + QT * scan::CAP + QT) + sizeof(int) * QT;
-    static size_t attr_max = 0;
+    static size_t attr_max_dev[kMaxDevices] = {};          // function attributes are per device
+    size_t& attr_max = attr_max_dev[ctx->device];
     if (smem > attr_max) {
         CU_TRY(cudaFuncSetAttribute(scan::search_kernel_wide4<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         attr_max = smem;
@@ -1199,7 +1204,8 @@ static bool stream_plan(ganrev_ctx* ctx, const scan::ScanParams& p, int NQ, int 
 }
 template <int NQ, int MODE, int E>
 static int launch_stream(ganrev_ctx* ctx, const scan::StreamParams& sp, size_t smem, int grid) {
-    static size_t attr_max = 0;
+    static size_t attr_max_dev[kMaxDevices] = {};          // function attributes are per device
+    size_t& attr_max = attr_max_dev[ctx->device];
     if (smem > attr_max) {
         CU_TRY(cudaFuncSetAttribute(scan::stream_kernel<NQ, MODE, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         attr_max = smem;
@@ -1360,7 +1366,8 @@ static int launch_assign(ganrev_ctx* ctx, const scan::ScanParams& p) {
     constexpr int QT = 16 * TQ;
     size_t smem = sizeof(float) * (scan::DK * scan::XS + scan::DK * QT + 16 * scan::RT) + sizeof(int) * (16 * scan::RT + scan::RT);
     if (MODE == 1 && p.smem_acc) smem += sizeof(unsigned long long) * (static_cast<size_t>(p.nq) * p.d + p.nq);
-    static size_t attr_max = 0;
+    static size_t attr_max_dev[kMaxDevices] = {};          // function attributes are per device
+    size_t& attr_max = attr_max_dev[ctx->device];
     if (smem > attr_max) {
         CU_TRY(cudaFuncSetAttribute(scan::assign_kernel<TQ, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         attr_max = smem;
