@@ -67,6 +67,7 @@ struct ganrev_ctx {
     std::string err;
     int64_t chunk = 0;            // images per pipeline chunk; 0 = auto (8192 32x32 faces' worth of pixels, see chunk_for)
     int conv_impl = 0;
+    int rtile = 1;                // register-tiled kmeans / cosine-min kernels for 9 <= k <= 32 (0 = the one-thread-per-row streaming kernels; A/B)
     int cta_pairs = 0x1f;     // which layers use tcgen05 cta_group::2 CTA pairs (bit0 G conv1, bit1 G conv2, bit2 R conv2/3,
                               // bit3 R conv4, bit4 R conv5/6); takes effect at the next ganrev_load_*.  Default = measured best.
     int dbg = 0;
@@ -1217,6 +1218,7 @@ static int launch_stream(ganrev_ctx* ctx, const scan::StreamParams& sp, size_t s
 template <int MODE, int E>
 static int dispatch_stream(ganrev_ctx* ctx, int NQ, const scan::StreamParams& sp, size_t smem, int grid) {
     switch (NQ) {
+        case 4: return launch_stream<4, MODE, E>(ctx, sp, smem, grid);
         case 8: return launch_stream<8, MODE, E>(ctx, sp, smem, grid);
         case 16: return launch_stream<16, MODE, E>(ctx, sp, smem, grid);
         case 24: return launch_stream<24, MODE, E>(ctx, sp, smem, grid);
@@ -1224,7 +1226,46 @@ static int dispatch_stream(ganrev_ctx* ctx, int NQ, const scan::StreamParams& sp
     }
     return fail(ctx, GANREV_EINVAL, "bad NQ %d", NQ);
 }
-static int stream_nq(int nq) { return nq <= 8 ? 8 : (nq <= 16 ? 16 : (nq <= 24 ? 24 : 32)); }
+static int stream_nq(int nq) { return nq <= 4 ? 4 : (nq <= 8 ? 8 : (nq <= 16 ? 16 : (nq <= 24 ? 24 : 32))); }
+
+// ---- register-tiled labelling kernels (kmeans / cosine-min, 9 <= nq <= 32, d % 4 == 0, d <= 128): plan + launch
+static bool rtile_plan(ganrev_ctx* ctx, const scan::ScanParams& p, int NQ, int mode, scan::StreamParams& sp, size_t& smem, int& grid) {
+    if (!ctx->rtile || p.nq <= 8 || p.nq > 32 || p.d % 4 != 0 || p.d > 128) return false;
+    const int T = NQ * 8, S = scan::wide4_stride(p.d), NW = NQ / 4;
+    sp.s = p;
+    sp.groups = mode == 1 ? std::max(1, T / (p.d / 4)) : 0;
+    smem = sizeof(float) * (static_cast<size_t>(scan::SR + NQ) * S + 2 * static_cast<size_t>(scan::SR) * NW + 2 * scan::SR + NQ + 2) +
+           (mode == 1 ? sizeof(unsigned long long) * (static_cast<size_t>(p.nq) * p.d + p.nq) : 0);
+    if (smem > 200 * 1024) return false;
+    const int per_sm = std::max<int>(1, std::min<int>({4, static_cast<int>((220 * 1024) / (smem + 1024)), 2048 / T}));
+    const long long n_tiles = (p.n_rows + scan::SR - 1) / scan::SR;
+    grid = static_cast<int>(std::max<long long>(1, std::min<long long>(n_tiles, static_cast<long long>(ctx->num_sms) * per_sm)));
+    sp.tiles_per_block = (n_tiles + grid - 1) / grid;
+    grid = static_cast<int>(std::max<long long>(1, (n_tiles + sp.tiles_per_block - 1) / sp.tiles_per_block));
+    return true;
+}
+template <int NQ, int MODE>
+static int launch_rtile(ganrev_ctx* ctx, const scan::StreamParams& sp, size_t smem, int grid) {
+    static size_t attr_max_dev[kMaxDevices] = {};          // function attributes are per device
+    size_t& attr_max = attr_max_dev[ctx->device];
+    if (smem > attr_max) {
+        CU_TRY(cudaFuncSetAttribute(scan::rtile_kernel<NQ, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        CU_TRY(cudaFuncSetAttribute(scan::rtile_kernel<NQ, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attr_max = smem;
+    }
+    scan::rtile_kernel<NQ, MODE><<<grid, NQ * 8, smem, ctx->stream>>>(sp);
+    CU_TRY(cudaGetLastError());
+    return GANREV_OK;
+}
+template <int MODE>
+static int dispatch_rtile(ganrev_ctx* ctx, int NQ, const scan::StreamParams& sp, size_t smem, int grid) {
+    switch (NQ) {
+        case 16: return launch_rtile<16, MODE>(ctx, sp, smem, grid);
+        case 24: return launch_rtile<24, MODE>(ctx, sp, smem, grid);
+        case 32: return launch_rtile<32, MODE>(ctx, sp, smem, grid);
+    }
+    return fail(ctx, GANREV_EINVAL, "bad NQ %d", NQ);
+}
 
 // merge the per-split lists, (multi-GPU) allgather + merge across ranks, copy results out
 static int search_finish(ganrev_ctx* ctx, const unsigned long long* partial, int splits, int Q, int k, int64_t* ids, float* scores) {
@@ -1424,7 +1465,8 @@ int ganrev_kmeans(ganrev_ctx* ctx, int k, int niter, const float* init_centroids
             scan::StreamParams sp{};
             size_t smem = 0;
             int grid = 0;
-            if (stream_plan(ctx, p, stream_nq(k), 1, 0, sp, smem, grid)) RC_TRY((dispatch_stream<1, 1>(ctx, stream_nq(k), sp, smem, grid)));
+            if (rtile_plan(ctx, p, stream_nq(k), 1, sp, smem, grid)) RC_TRY((dispatch_rtile<1>(ctx, stream_nq(k), sp, smem, grid)));
+            else if (stream_plan(ctx, p, stream_nq(k), 1, 0, sp, smem, grid)) RC_TRY((dispatch_stream<1, 1>(ctx, stream_nq(k), sp, smem, grid)));
             else if (k <= 16) RC_TRY((launch_assign<1, 1>(ctx, p)));
             else RC_TRY((launch_assign<4, 1>(ctx, p)));
         }
@@ -1468,7 +1510,8 @@ int ganrev_assign_cosine_min(ganrev_ctx* ctx, const float* centroids, int k, int
         scan::StreamParams sp{};
         size_t smem = 0;
         int grid = 0;
-        if (stream_plan(ctx, p, stream_nq(k), 2, 0, sp, smem, grid)) RC_TRY((dispatch_stream<2, 1>(ctx, stream_nq(k), sp, smem, grid)));
+        if (rtile_plan(ctx, p, stream_nq(k), 2, sp, smem, grid)) RC_TRY((dispatch_rtile<2>(ctx, stream_nq(k), sp, smem, grid)));
+        else if (stream_plan(ctx, p, stream_nq(k), 2, 0, sp, smem, grid)) RC_TRY((dispatch_stream<2, 1>(ctx, stream_nq(k), sp, smem, grid)));
         else if (k <= 16) RC_TRY((launch_assign<1, 2>(ctx, p)));
         else RC_TRY((launch_assign<4, 2>(ctx, p)));
     }
@@ -1575,6 +1618,7 @@ int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value) {
         ctx->chunk = value;
         return GANREV_OK;
     }
+    if (!strcmp(name, "rtile")) { ctx->rtile = value != 0; return GANREV_OK; }
     if (!strcmp(name, "conv_impl")) {
         if (value != 0 && value != 1) return fail(ctx, GANREV_EINVAL, "conv_impl must be 0 or 1");
         ctx->conv_impl = static_cast<int>(value);

@@ -591,6 +591,24 @@ __device__ __forceinline__ bool better(const Best a, const Best b) {   // is a s
     }
 }
 
+// kmeans fixed point: llrint(x * 2^shift).  With 2^shift >= 1 the product is exact in fp32 as well (a pure exponent
+// change that cannot overflow: |x| * 2^shift < 2^63 by the choice of shift), so one fp32 multiply + one F2I replaces
+// F2D + DMUL + D2I -- the conversion unit (16 lanes/clk/SM) is what bounds the centroid-update pass.
+struct FixScale {
+    double sc;
+    float scf;
+    bool f32;
+};
+__device__ __forceinline__ FixScale make_fix_scale(double sc) {
+    FixScale f;
+    f.sc = sc; f.scf = static_cast<float>(sc);
+    f.f32 = static_cast<double>(f.scf) == sc && f.scf >= 1.0f;
+    return f;
+}
+__device__ __forceinline__ long long fix64(float x, const FixScale& f) {
+    return f.f32 ? __float2ll_rn(__fmul_rn(x, f.scf)) : __double2ll_rn(static_cast<double>(x) * f.sc);
+}
+
 // ------------------------------------------------------------------ streaming kernels, nq <= 32
 // The HBM-bound regime (a handful of needles, k = 20 centroids): ONE THREAD PER ROW keeps all nq
 // accumulators in registers -- still one sequential fmaf chain per (query,row) pair -- while the
@@ -621,9 +639,10 @@ template <int NQ, int MODE, int E>
 __global__ void __launch_bounds__(kThreads)
 stream_kernel(const StreamParams sp) {
     const ScanParams& p = sp.s;
+    const FixScale fx = make_fix_scale(MODE == 1 ? p.sc : 1.0);
     constexpr int K2 = 32 * E;
     constexpr int NH = NQ / 2;                                // accumulators per thread
-    static_assert(NQ % 8 == 0, "NQ/2 must be a multiple of 4");
+    static_assert(NQ == 4 || NQ % 8 == 0, "NQ/2 is 2 (four needles: the BASELINE config-0 shape, no padded FMAs) or a multiple of 4");
     extern __shared__ __align__(16) uint8_t sm[];
     const int d = p.d, dc = sp.dc, dcp = sp.dc_pad;
     float* stage0 = reinterpret_cast<float*>(sm);             // [SSTAGES][SR][dc_pad]
@@ -715,20 +734,31 @@ stream_kernel(const StreamParams sp) {
         for (int i = 0; i < kk; i += 4) {
             const float4 x4 = *reinterpret_cast<const float4*>(xr + i);
             const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
-            float4 qv[4][NH / 4];                             // all operand loads first, then 4*NH independent-ish FMAs
+            if constexpr (NH == 2) {                           // two queries per thread: 8-byte operand loads
+                float2 q2[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
+                for (int e = 0; e < 4; ++e) q2[e] = *reinterpret_cast<const float2*>(qs + (c0 + i + e) * NQ + jbase);
 #pragma unroll
-                for (int v = 0; v < NH / 4; ++v) qv[e][v] = *reinterpret_cast<const float4*>(qs + (c0 + i + e) * NQ + jbase + 4 * v);
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-#pragma unroll
-                for (int v = 0; v < NH / 4; ++v) {
-                    acc[4 * v + 0] = __fmaf_rn(qv[e][v].x, xv[e], acc[4 * v + 0]);
-                    acc[4 * v + 1] = __fmaf_rn(qv[e][v].y, xv[e], acc[4 * v + 1]);
-                    acc[4 * v + 2] = __fmaf_rn(qv[e][v].z, xv[e], acc[4 * v + 2]);
-                    acc[4 * v + 3] = __fmaf_rn(qv[e][v].w, xv[e], acc[4 * v + 3]);
+                for (int e = 0; e < 4; ++e) {
+                    acc[0] = __fmaf_rn(q2[e].x, xv[e], acc[0]);
+                    acc[1] = __fmaf_rn(q2[e].y, xv[e], acc[1]);
                 }
+            } else {
+                float4 qv[4][(NH + 3) / 4];                   // all operand loads first, then 4*NH independent-ish FMAs
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int v = 0; v < NH / 4; ++v) qv[e][v] = *reinterpret_cast<const float4*>(qs + (c0 + i + e) * NQ + jbase + 4 * v);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int v = 0; v < NH / 4; ++v) {
+                        acc[4 * v + 0] = __fmaf_rn(qv[e][v].x, xv[e], acc[4 * v + 0]);
+                        acc[4 * v + 1] = __fmaf_rn(qv[e][v].y, xv[e], acc[4 * v + 1]);
+                        acc[4 * v + 2] = __fmaf_rn(qv[e][v].z, xv[e], acc[4 * v + 2]);
+                        acc[4 * v + 3] = __fmaf_rn(qv[e][v].w, xv[e], acc[4 * v + 3]);
+                    }
+            }
         }
         if (chunk != sp.n_chunks - 1) continue;
         // ---------------------------------------------------------------- row finished
@@ -836,10 +866,10 @@ stream_kernel(const StreamParams sp) {
                         if (lab < 0) continue;
                         if (lab != cur) { flush(); cur = lab; run0 = run1 = run2 = run3 = 0; cnt = 0; }
                         const float4 x4 = *reinterpret_cast<const float4*>(tilep + r * dcp + c);
-                        run0 += __double2ll_rn(static_cast<double>(x4.x) * p.sc);
-                        run1 += __double2ll_rn(static_cast<double>(x4.y) * p.sc);
-                        run2 += __double2ll_rn(static_cast<double>(x4.z) * p.sc);
-                        run3 += __double2ll_rn(static_cast<double>(x4.w) * p.sc);
+                        run0 += fix64(x4.x, fx);
+                        run1 += fix64(x4.y, fx);
+                        run2 += fix64(x4.z, fx);
+                        run3 += fix64(x4.w, fx);
                         ++cnt;
                     }
                     flush();
@@ -870,6 +900,187 @@ stream_kernel(const StreamParams sp) {
 // Merge [parts][nq][k] partial lists per query (one warp per query).
 //   mode 0: write ids (int64, + id_offset) and scores
 //   mode 1: write keys re-based to global ids (for the NCCL allgather)
+// ------------------------------------------------------------------ register-tiled labelling, 9 <= nq <= 32
+// kmeans (MODE 1) and cosine-min (MODE 2) at k = 20 perform 20+ FMAs per loaded float: an operand fetched
+// from shared memory for EVERY FMA caps the SM at 32 FMA lanes per clock (the 128 B/clk shared->register
+// path), which is where stream_kernel sits (0.7 TB/s).  Here each thread owns a 4-query x 4-row register
+// tile: a warp is one group of 4 queries (its query loads are warp-uniform broadcasts), its lanes are rows
+// (16-byte loads of 32 consecutive rows, stride S = 4 mod 32 floats: conflict-free), so 8 shared loads feed
+// 64 FMAs.  Every (query,row) accumulator is still one sequential fmaf chain over d.  The per-row winner is
+// the thread's best of its 4 queries (index order), then the NQ/4 warps' winners are merged in index order
+// with the same comparator -- the sequential scan of the reference.  Row tiles arrive by 16-byte cp.async
+// into ONE buffer; 2-3 blocks per SM overlap each other's loads.  MODE 1 then runs stream_kernel's
+// counting-sort / int64 run-sum update on the same row-major tile.
+template <int NQ, int MODE>
+__global__ void __launch_bounds__(NQ * 8)
+rtile_kernel(const StreamParams sp) {
+    static_assert(MODE == 1 || MODE == 2, "labelling modes only");
+    static_assert(NQ == 16 || NQ == 24 || NQ == 32, "NQ/4 warps, at least 128 threads");
+    const ScanParams& p = sp.s;
+    const FixScale fx = make_fix_scale(MODE == 1 ? p.sc : 1.0);
+    constexpr int T = NQ * 8, NW = NQ / 4;
+    extern __shared__ __align__(16) uint8_t sm[];
+    const int d = p.d, S = wide4_stride(d), d4 = d >> 2;
+    float* xs = reinterpret_cast<float*>(sm);                 // [SR][S]
+    float* qs = xs + SR * S;                                  // [NQ][S]
+    float* pv = qs + NQ * S;                                  // [SR][NW] best value per (row, warp)
+    int* pj = reinterpret_cast<int*>(pv + SR * NW);           // [SR][NW] best index
+    int* slab = pj + SR * NW;                                 // [SR] final labels of the tile
+    int* perm = slab + SR;                                    // [SR] rows grouped by label (MODE 1)
+    int* lstart = perm + SR;                                  // [NQ + 2] first sorted position of each label (MODE 1)
+    unsigned long long* sacc = reinterpret_cast<unsigned long long*>(lstart + NQ + 2);   // [nq*d + nq] (MODE 1; 8-byte aligned: all counts above are even)
+
+    const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
+    for (int g = tid; g < NQ * d4; g += T) {                  // centroids / queries, row-major, zero rows past nq
+        const int r = g / d4, c4 = g - r * d4;
+        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (r < p.nq) v = __ldg(reinterpret_cast<const float4*>(p.q + static_cast<long long>(r) * d) + c4);
+        *reinterpret_cast<float4*>(qs + r * S + 4 * c4) = v;
+    }
+    if (MODE == 1)
+        for (int i = tid; i < p.nq * d + p.nq; i += T) sacc[i] = 0ull;
+    float aux[4];                                             // c2 (MODE 1) or rq (MODE 2) of this warp's 4 queries
+#pragma unroll
+    for (int v = 0; v < 4; ++v) aux[v] = wq * 4 + v < p.nq ? __ldg((MODE == 1 ? p.c2 : p.rq) + wq * 4 + v) : 0.0f;
+
+    const long long tile_begin = static_cast<long long>(blockIdx.x) * sp.tiles_per_block;
+    const long long n_tiles_all = (p.n_rows + SR - 1) / SR;
+    const long long tile_end = min(n_tiles_all, tile_begin + sp.tiles_per_block);
+    for (long long tile = tile_begin; tile < tile_end; ++tile) {
+        const long long row0 = tile * SR;
+        __syncthreads();                                      // previous tile fully consumed (and the set-up above)
+        for (int g = tid; g < SR * d4; g += T) {
+            const int r = g / d4, c4 = g - r * d4;
+            const bool ok = row0 + r < p.n_rows;
+            cp_async16_zfill(xs + r * S + 4 * c4, p.db + (ok ? row0 + r : row0) * d + 4 * c4, ok);
+        }
+        cp_async_commit_group();
+        float rx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long row = row0 + u * 32 + lane;
+            rx[u] = (MODE == 2 && row < p.n_rows) ? __ldg(p.rdb + row) : 0.0f;
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        float acc[4][4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[v][u] = 0.0f;
+#pragma unroll 2
+        for (int i = 0; i < d; i += 4) {
+            float4 qv[4], xv[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) qv[v] = *reinterpret_cast<const float4*>(qs + (wq * 4 + v) * S + i);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xv[u] = *reinterpret_cast<const float4*>(xs + (u * 32 + lane) * S + i);
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float a = acc[v][u];
+                    a = __fmaf_rn(qv[v].x, xv[u].x, a);
+                    a = __fmaf_rn(qv[v].y, xv[u].y, a);
+                    a = __fmaf_rn(qv[v].z, xv[u].z, a);
+                    a = __fmaf_rn(qv[v].w, xv[u].w, a);
+                    acc[v][u] = a;
+                }
+        }
+        // this thread's winner per row among its 4 queries, in index order
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            Best b;
+            b.v = 0.0f; b.j = -1;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                if (wq * 4 + v < p.nq) {
+                    Best c;
+                    c.j = wq * 4 + v;
+                    c.v = MODE == 1 ? __fsub_rn(acc[v][u], aux[v]) : cos_from(acc[v][u], rx[u], aux[v]);
+                    if (better<MODE>(c, b)) b = c;
+                }
+            }
+            pv[(u * 32 + lane) * NW + wq] = b.v;
+            pj[(u * 32 + lane) * NW + wq] = b.j;
+        }
+        __syncthreads();
+        if (tid < SR) {                                       // merge the warps' winners in index order
+            Best b;
+            b.v = pv[tid * NW]; b.j = pj[tid * NW];
+#pragma unroll
+            for (int w = 1; w < NW; ++w) {
+                Best o;
+                o.v = pv[tid * NW + w]; o.j = pj[tid * NW + w];
+                if (better<MODE>(o, b)) b = o;
+            }
+            const long long row = row0 + tid;
+            const bool live = row < p.n_rows;
+            slab[tid] = live ? b.j : -1;
+            if (live) {
+                p.labels[row] = b.j;
+                if (MODE == 2) p.cosv[row] = b.v;
+            }
+        }
+        if (MODE == 1) {
+            // centroid sums.  (1) counting-sort the tile's rows by label (perm[] = rows grouped by label, lstart[L] =
+            // first position of label L).  (2) thread (g, c4) owns 4 columns of the labels L = g, g + groups, ...: it
+            // walks that label's rows with int64 run sums in registers and adds them to the block's accumulator with a
+            // plain read-modify-write -- every (label, column) has exactly one owner, so no atomics (64-bit shared
+            // atomics are CAS spin loops).  Integer adds are associative: neither order nor split changes the result.
+            __syncthreads();
+            if (tid < SR) {
+                const int mine = slab[tid];
+                int rank = 0;
+                for (int r = 0; r < SR; ++r) {
+                    const int o = slab[r];
+                    rank += (o < mine || (o == mine && r < tid)) ? 1 : 0;
+                }
+                perm[rank] = tid;                              // dead rows (label -1) sort first
+            }
+            if (tid <= p.nq) {                                 // lstart[L] = rows with a label < L (L = nq: all rows)
+                int c = 0;
+                for (int r = 0; r < SR; ++r) c += slab[r] < tid ? 1 : 0;
+                lstart[tid] = c;
+            }
+            __syncthreads();
+            const int tpg = d >> 2;                           // threads per group
+            const int g = tid / tpg, c = (tid - g * tpg) * 4;
+            if (g < sp.groups) {
+                for (int L = g; L < p.nq; L += sp.groups) {
+                    const int pos0 = lstart[L], pos1 = lstart[L + 1];
+                    if (pos0 == pos1) continue;
+                    long long run0 = 0, run1 = 0, run2 = 0, run3 = 0;
+                    for (int pos = pos0; pos < pos1; ++pos) {
+                        const float4 x4 = *reinterpret_cast<const float4*>(xs + perm[pos] * S + c);
+                        run0 += fix64(x4.x, fx);
+                        run1 += fix64(x4.y, fx);
+                        run2 += fix64(x4.z, fx);
+                        run3 += fix64(x4.w, fx);
+                    }
+                    unsigned long long* a = sacc + L * d + c;
+                    a[0] += static_cast<unsigned long long>(run0);
+                    a[1] += static_cast<unsigned long long>(run1);
+                    a[2] += static_cast<unsigned long long>(run2);
+                    a[3] += static_cast<unsigned long long>(run3);
+                    if (c == 0) sacc[p.nq * d + L] += static_cast<unsigned long long>(pos1 - pos0);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (MODE == 1) {
+        const int per = p.nq * d + p.nq;
+        for (int i = tid; i < per; i += T) {
+            const unsigned long long v = sacc[i];
+            if (v != 0ull) {
+                if (i < p.nq * d) atomicAdd(&p.acc[i], v);
+                else atomicAdd(&p.cnt[i - p.nq * d], v);
+            }
+        }
+    }
+}
+
 template <int E>
 __global__ void __launch_bounds__(kThreads)
 merge_kernel(const unsigned long long* __restrict__ partial, int parts, int nq, int k, long long id_offset, int mode,
@@ -925,6 +1136,7 @@ merge_kernel(const unsigned long long* __restrict__ partial, int parts, int nq, 
 template <int TQ, int MODE>
 __global__ void __launch_bounds__(kThreads)
 assign_kernel(const ScanParams p, const long long n_tiles) {
+    const FixScale fx = make_fix_scale(MODE == 1 ? p.sc : 1.0);
     constexpr int QT = 16 * TQ;
     extern __shared__ __align__(16) uint8_t sm[];
     float* xs = reinterpret_cast<float*>(sm);
@@ -999,7 +1211,7 @@ assign_kernel(const ScanParams p, const long long n_tiles) {
                 const int j = slab[rr];
                 const float* xrow = p.db + (row0 + rr) * p.d;
                 for (int c = lane; c < p.d; c += 32) {
-                    const long long qv = __double2ll_rn(static_cast<double>(__ldg(xrow + c)) * p.sc);
+                    const long long qv = fix64(__ldg(xrow + c), fx);
                     if (p.smem_acc) atomicAdd(&sacc[j * p.d + c], static_cast<unsigned long long>(qv));
                     else atomicAdd(&p.acc[static_cast<long long>(j) * p.d + c], static_cast<unsigned long long>(qv));
                 }
