@@ -217,3 +217,81 @@ def test_assign_cosine_min_and_members_exact(orc, ctx, case):
     ok = want_cnt > 0                                 # empty clusters: 0/0 = NaN on both sides
     assert_bitexact(mean[ok], want_mean[ok], "mean images")
     assert np.isnan(mean[~ok]).all()
+
+
+RTILE_CASES = [
+    # N, d, k : the register-tiled path (9 <= k <= 32, d % 4 == 0, d <= 128) at its boundaries
+    (5000, 100, 9), (5000, 100, 16), (5000, 100, 17), (4097, 100, 24), (5000, 100, 25), (5000, 100, 32),
+    (1000, 4, 20), (1000, 128, 20), (127, 32, 20), (128, 32, 20), (129, 32, 20), (1, 32, 20),
+]
+
+
+@pytest.mark.parametrize("case", RTILE_CASES, ids=lambda c: "N%d_d%d_k%d" % c)
+def test_rtile_kmeans_and_assign_exact(orc, ctx, case):
+    """kmeans labels/centroids/counts and cosine-min labels/values: bit-exact against the oracle, and identical with the
+    register-tiled kernels switched off (the one-thread-per-row streaming kernels)."""
+    N, d, k = case
+    x = _db(N, d, 31)
+    init = _init(k, d, seed=32)
+    want_c, want_t, want_l = orc.kmeans(x, k, 3, init)
+    ctx.db_set(x)
+    for rtile in (1, 0):
+        ctx.set_option("rtile", rtile)
+        cen, tot, lab = ctx.kmeans(k, 3, init)
+        np.testing.assert_array_equal(lab, want_l)
+        assert_bitexact(tot, want_t, "total counts")
+        assert_bitexact(cen, want_c, "centroids")
+    ctx.set_option("rtile", 1)
+    cenq = _db(k, d, 33)
+    if N > 9:
+        x2 = x.copy(); x2[7] = cenq[0]; x2[8] = cenq[k - 1]          # exact duplicates of the first / last centroid
+        ctx.db_set(x2)
+    else:
+        x2 = x
+    want_cl, want_cv = orc.assign_cosine_min(x2, cenq)
+    for rtile in (1, 0):
+        ctx.set_option("rtile", rtile)
+        cl, cv = ctx.assign_cosine_min(cenq)
+        np.testing.assert_array_equal(cl, want_cl)
+        assert_bitexact(cv, want_cv, "cos")
+    ctx.set_option("rtile", 1)
+
+
+def test_rtile_nan_and_tie_rules(orc, ctx):
+    """TH max scan (first NaN wins, else first maximum) and cosine-min (a NaN at j = 0 sticks, other NaNs never win,
+    lowest j on ties) across the warp-merge of the register-tiled kernels."""
+    rng = np.random.default_rng(41)
+    N, d, k = 1500, 32, 20
+    x = rng.normal(size=(N, d)).astype(np.float32)
+    cen = rng.normal(size=(k, d)).astype(np.float32)
+    cen[5] = cen[13]                                                   # two identical centroids in different warps: lowest j
+    cen[17, 3] = np.nan                                                # a NaN centroid in the last warp
+    x[100, 0] = np.nan                                                 # a NaN row: every score NaN
+    x[200] = 0.0                                                       # zero row: every cosine 0 -> j = 0
+    init = cen.copy()
+    want_c, want_t, want_l = orc.kmeans(x, k, 2, init)
+    ctx.db_set(x)
+    c, t, l = ctx.kmeans(k, 2, init)
+    np.testing.assert_array_equal(l, want_l)
+    assert_bitexact(t, want_t); assert_bitexact(c, want_c)
+    want_cl, want_cv = orc.assign_cosine_min(x, cen)
+    cl, cv = ctx.assign_cosine_min(cen)
+    np.testing.assert_array_equal(cl, want_cl)
+    assert_bitexact(cv, want_cv)
+    cen0 = cen.copy(); cen0[0, 1] = np.nan                            # NaN at j = 0 sticks for cosine-min
+    want_cl, want_cv = orc.assign_cosine_min(x, cen0)
+    cl, cv = ctx.assign_cosine_min(cen0)
+    np.testing.assert_array_equal(cl, want_cl)
+    assert_bitexact(cv, want_cv)
+
+
+def test_search_four_needles_variant(orc, ctx):
+    """Q <= 4 takes the unpadded 2-queries-per-thread streaming variant: exact at Q = 1..4, ragged N."""
+    x = _db(3001, 100, 51)
+    ctx.db_set(x)
+    for Q in (1, 2, 3, 4):
+        q = x[[5, 77, 1234, 3000][:Q]] + 0.01
+        ids, sc = ctx.search_cosine(q, 20)
+        wi, ws = orc.search_cosine(x, q, 20)
+        np.testing.assert_array_equal(ids, wi)
+        assert_bitexact(sc, ws)
