@@ -1051,7 +1051,20 @@ rtile_kernel(const StreamParams sp) {
                     const int pos0 = lstart[L], pos1 = lstart[L + 1];
                     if (pos0 == pos1) continue;
                     long long run0 = 0, run1 = 0, run2 = 0, run3 = 0;
-                    for (int pos = pos0; pos < pos1; ++pos) {
+                    int pos = pos0;
+                    for (; pos + 4 <= pos1; pos += 4) {       // four rows in flight: the perm -> row -> convert chain is latency-bound
+                        float4 x4[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) x4[e] = *reinterpret_cast<const float4*>(xs + perm[pos + e] * S + c);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            run0 += fix64(x4[e].x, fx);
+                            run1 += fix64(x4[e].y, fx);
+                            run2 += fix64(x4[e].z, fx);
+                            run3 += fix64(x4[e].w, fx);
+                        }
+                    }
+                    for (; pos < pos1; ++pos) {
                         const float4 x4 = *reinterpret_cast<const float4*>(xs + perm[pos] * S + c);
                         run0 += fix64(x4.x, fx);
                         run1 += fix64(x4.y, fx);
