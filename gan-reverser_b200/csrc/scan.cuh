@@ -420,6 +420,7 @@ search_kernel_wide4(const ScanParams p) {
     constexpr int TQ = 4, QT = 64, K2 = 32 * E;
     extern __shared__ __align__(16) uint8_t sm[];
     const int d = p.d, S = wide4_stride(d), d4 = d >> 2;
+    const unsigned d4magic = 0xFFFFFFFFu / static_cast<unsigned>(d4) + 1u;   // ceil(2^32 / d4)
     float* xs = reinterpret_cast<float*>(sm);                 // [RT][S]
     float* qs = xs + RT * S;                                  // [QT][S]
     unsigned long long* lists = reinterpret_cast<unsigned long long*>(qs + QT * S);
@@ -451,7 +452,7 @@ search_kernel_wide4(const ScanParams p) {
     const long long r_end = min(p.n_rows, r_begin + p.rows_per_split);
     auto issue = [&](long long row0, float* dst) {            // one row tile -> smem (rows past the end: zeros)
         for (int g = tid; g < RT * d4; g += kThreads) {
-            const int r = g / d4, c4 = g - r * d4;
+            const int r = d4 == 1 ? g : static_cast<int>(__umulhi(static_cast<unsigned>(g), d4magic)), c4 = g - r * d4;   // exact floor(g / d4) for g < 2^30
             const long long row = row0 + r;
             const bool ok = row < r_end;
             cp_async16_zfill(dst + r * S + 4 * c4, p.db + (ok ? row : r_begin) * d + 4 * c4, ok);
@@ -921,6 +922,7 @@ rtile_kernel(const StreamParams sp) {
     constexpr int T = NQ * 8, NW = NQ / 4;
     extern __shared__ __align__(16) uint8_t sm[];
     const int d = p.d, S = wide4_stride(d), d4 = d >> 2;
+    const unsigned d4magic = 0xFFFFFFFFu / static_cast<unsigned>(d4) + 1u;   // ceil(2^32 / d4)
     float* xs = reinterpret_cast<float*>(sm);                 // [SR][S]
     float* qs = xs + SR * S;                                  // [NQ][S]
     float* pv = qs + NQ * S;                                  // [SR][NW] best value per (row, warp)
@@ -950,7 +952,7 @@ rtile_kernel(const StreamParams sp) {
         const long long row0 = tile * SR;
         __syncthreads();                                      // previous tile fully consumed (and the set-up above)
         for (int g = tid; g < SR * d4; g += T) {
-            const int r = g / d4, c4 = g - r * d4;
+            const int r = d4 == 1 ? g : static_cast<int>(__umulhi(static_cast<unsigned>(g), d4magic)), c4 = g - r * d4;   // exact floor(g / d4) for g < 2^30
             const bool ok = row0 + r < p.n_rows;
             cp_async16_zfill(xs + r * S + 4 * c4, p.db + (ok ? row0 + r : row0) * d + 4 * c4, ok);
         }
