@@ -435,7 +435,8 @@ static int dispatch_tc(ganrev_ctx* ctx, const TcLayer& L, const CUtensorMap& tmA
     TC_CASE(128, 2, 3, false, ACT_ELU, true, false)        // Conv 128->128 + x0.75 + MaxPool
     TC_CASE(128, 2, 1, false, ACT_ELU, false, false)
     TC_CASE(128, 2, 1, false, ACT_ELU, true, false)
-    TC_CASE(64, 1, 1, false, ACT_ELU, false, false)        // Linear 8192->512
+    TC_CASE(64, 1, 1, false, ACT_ELU, false, false)
+    TC_CASE(256, 1, 1, false, ACT_ELU, false, false)       // Linear 8192->512
     TC_CASE(32, 1, 1, false, tc::ACT_RUNTIME, false, true) // Linear 512->nd (+Tanh)
     TC_CASE(64, 1, 1, false, tc::ACT_RUNTIME, false, true)
     TC_CASE(128, 1, 1, false, tc::ACT_RUNTIME, false, true)
@@ -611,7 +612,7 @@ static int load_R_impl(ganrev_ctx* ctx, int slot, int C, int H, int W, int nd, i
             for (int c = 0; c < 128; ++c)
                 for (int s = 0; s < HWq; ++s) wm[static_cast<size_t>(o) * F + s * 128 + c] = 0.75f * l1w[static_cast<size_t>(o) * F + c * HWq + s];
         BnFold bn = fold_bn(l1b, g7, be7, m7, v7, 512, 512);
-        const LayerDef d{"r_linear1", KIND_LINEAR, 64, 1, 1, false, 1, 1, F, 512, 8, 1, 1, 512, 0, ACT_ELU, 1.0f, 0, false};
+        const LayerDef d{"r_linear1", KIND_LINEAR, 256, 1, 1, false, 1, 1, F, 512, 2, 1, 1, 512, 0, ACT_ELU, 1.0f, 0, false};   // N = 256: the A tile is re-read twice, not 8 times
         RC_TRY(build_tc_layer(ctx, R.l1, d, wm.data(), bn));
     }
     {   // Linear(512 -> nd) [+ Tanh], fp32 output
