@@ -602,7 +602,8 @@ static int load_R_impl(ganrev_ctx* ctx, int slot, int C, int H, int W, int nd, i
     };
     RC_TRY(conv_layer(R.c2, "r_conv2", c2, 64, 64, H, W, 0, 1.0f, 2, true, (ctx->cta_pairs & 4) ? 2 : 1));
     RC_TRY(conv_layer(R.c3, "r_conv3_pool", c3, 64, 64, H, W, 1, 1.0f, 2, true, (ctx->cta_pairs & 4) ? 2 : 1));
-    RC_TRY(conv_layer(R.c4, "r_conv4", c4, 128, 64, Hh, Wh, 0, 1.0f, (ctx->cta_pairs & 8) ? 2 : 1, true, (ctx->cta_pairs & 8) ? 2 : 1));   // pairs: half of B per CTA leaves room for MT = 2
+    const bool c4_pairs = (ctx->cta_pairs & 8) && Hh * Wh >= 128 && Wh >= 8;   // CTA pairs exist for the halo-reuse tiling only
+    RC_TRY(conv_layer(R.c4, "r_conv4", c4, 128, 64, Hh, Wh, 0, 1.0f, c4_pairs ? 2 : 1, true, (ctx->cta_pairs & 8) ? 2 : 1));   // pairs: half of B per CTA leaves room for MT = 2
     RC_TRY(conv_layer(R.c5, "r_conv5", c5, 128, 128, Hh, Wh, 0, 1.0f, 2, false, (ctx->cta_pairs & 16) ? 2 : 1));
     RC_TRY(conv_layer(R.c6, "r_conv6_pool", c6, 128, 128, Hh, Wh, 1, 1.0f, 2, false, (ctx->cta_pairs & 16) ? 2 : 1));   // its SpatialDropout(0.25) x0.75 is folded into r_linear1
     {   // Linear(F -> 512) + BN1d + ELU; input columns re-ordered from View (NCHW flatten, models.lua:446) to NHWC.
