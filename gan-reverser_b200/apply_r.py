@@ -1,7 +1,8 @@
 """Host-side mirror of apply_r.lua's four analysis modes and helpers.  Same names and argument
-meaning as the reference; the inner loops are single calls into libganrev_cuda.so.  JPEG grid
-writing (image.toDisplayTensor / image.save) is presentation and out of scope (SURVEY.md
-section 8f): each function returns the data the reference would have drawn.
+meaning as the reference; the inner loops are single calls into libganrev_cuda.so.  Each function
+returns the data the reference would have drawn; present.py turns
+those results into the reference's JPEG grids (saveClusterImages, saveSimilaritySearchImages,
+saveFixedFaces, saveAnomalies).
 """
 import math
 
