@@ -181,3 +181,24 @@ def test_t7_checkpoint_loads_like_blob(pkg, tmp_path):
         np.testing.assert_array_equal(a, b)
     finally:
         ctx.close()
+
+
+def test_apply_r_main_end_to_end(pkg, tmp_path):
+    """apply_r.lua main() through the library (random-init nets, 1,200 faces so every mode's constants fit):
+    every artefact of the reference is written and the returned data is consistent."""
+    ctx = pkg.Context(0)
+    try:
+        out = pkg.apply_r.main(writeTo=str(tmp_path), nbImages=1200, ctx=ctx)
+    finally:
+        ctx.close()
+    names = sorted(os.path.basename(f) for f in out["files"])
+    assert "variations.jpg" in names and "anomalies.jpg" in names and "fixed_pairs.jpg" in names
+    assert "fixed_images_528.jpg" in names and "fixed_images_528_unfixed.jpg" in names
+    assert sum(n.startswith("similar_attributes_") for n in names) == 5 and sum(n.startswith("similar_pixelwise_") for n in names) == 5
+    nonempty = int((out["clusters"]["member_counts"] > 0).sum())
+    assert sum(n.startswith("cluster_") for n in names) == nonempty > 0
+    assert all(os.path.getsize(f) > 0 for f in out["files"])
+    ids, sc = out["similar"]["attributes"]
+    assert ids.shape == (5, 100) and np.array_equal(ids[:, 0], np.array([99, 199, 299, 399, 499]))   # a needle's best match is itself
+    assert out["anomalies"]["flags"].shape == (528,) and 0 < out["anomalies"]["flags"].sum() < 528
+    assert out["variations"].shape == (100 * 16, 1, 32, 32)
