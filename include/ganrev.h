@@ -160,8 +160,12 @@ int ganrev_profile_get(ganrev_ctx* ctx, int idx, const char** name, uint64_t* la
 /* Debug: clock64 timeline of CTA 0 of the named tensor-core layer (roles x events, [8][256]). */
 int ganrev_debug_trace_arm(ganrev_ctx* ctx, const char* layer);
 int ganrev_debug_trace_read(ganrev_ctx* ctx, int64_t* out);
-/* Tuning / debugging knobs: "chunk" (images per pipeline chunk; default = 8192 32x32 faces' worth of pixels), "conv_impl"
- * (0 = tcgen05 implicit GEMM, 1 = plain CUDA-core kernel kept for A/B debugging). */
+/* Tuning / debugging knobs (none changes results):
+ *   "chunk"     images per pipeline chunk; default = 8192 32x32 faces' worth of pixels
+ *   "conv_impl" 0 = tcgen05 implicit GEMM (default), 1 = plain CUDA-core kernels kept for on-device A/B checks
+ *   "cta_pairs" bit mask of the conv layers that run as tcgen05 cta_group::2 CTA pairs (default all; read at ganrev_load_*)
+ *   "rtile"     1 = register-tiled kmeans / cosine-min kernels for 9 <= k <= 32 (default), 0 = one-thread-per-row streaming kernels
+ *   "dbg"       timing experiments: bit 0 skip A loads, 1 skip B loads, 2 skip epilogue, 3 skip MMAs, 4 skip stores (results invalid) */
 int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value);
 
 #ifdef __cplusplus
