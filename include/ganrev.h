@@ -160,7 +160,7 @@ int ganrev_profile_get(ganrev_ctx* ctx, int idx, const char** name, uint64_t* la
 /* Debug: clock64 timeline of CTA 0 of the named tensor-core layer (roles x events, [8][256]). */
 int ganrev_debug_trace_arm(ganrev_ctx* ctx, const char* layer);
 int ganrev_debug_trace_read(ganrev_ctx* ctx, int64_t* out);
-/* Tuning / debugging knobs (none changes results):
+/* Tuning / debugging knobs (exact outputs are unaffected; conv_impl 1 differs within the conv tolerance; dbg invalidates results):
  *   "chunk"     images per pipeline chunk; default = 8192 32x32 faces' worth of pixels
  *   "conv_impl" 0 = tcgen05 implicit GEMM (default), 1 = plain CUDA-core kernels kept for on-device A/B checks
  *   "cta_pairs" bit mask of the conv layers that run as tcgen05 cta_group::2 CTA pairs (default all; read at ganrev_load_*)
