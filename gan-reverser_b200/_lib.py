@@ -97,6 +97,7 @@ class Context:
             raise GanrevError(rc, "ganrev_create failed (needs an sm_100 GPU; there is no CPU fallback)")
         self.device = int(device)
         self.geom = None       # (C, H, W, nd)
+        self.db_shape = None   # (N local rows, d) of the database set by db_set
         self.world, self.rank = 1, 0
 
     def close(self):
@@ -261,6 +262,8 @@ class Context:
 
     def kmeans(self, k, niter, init, want_labels=True):
         init = _arr(init, np.float32)
+        if self.db_shape is None:
+            raise GanrevError(ESTATE, "database not set (call db_set first)")
         N, d = self.db_shape
         assert init.shape == (k, d)
         cen = np.empty((k, d), np.float32)
@@ -271,6 +274,8 @@ class Context:
 
     def assign_cosine_min(self, centroids):
         centroids = _arr(centroids, np.float32)
+        if self.db_shape is None:
+            raise GanrevError(ESTATE, "database not set (call db_set first)")
         N, d = self.db_shape
         k = centroids.shape[0]
         cl = np.empty((N,), np.int32)

@@ -295,3 +295,25 @@ def test_search_four_needles_variant(orc, ctx):
         wi, ws = orc.search_cosine(x, q, 20)
         np.testing.assert_array_equal(ids, wi)
         assert_bitexact(sc, ws)
+
+
+def test_db_error_paths(pkg):
+    """Misuse fails with an error code and a message, never with a crash or a silent fallback."""
+    c = pkg.Context(0)
+    try:
+        q = np.zeros((2, 8), np.float32)
+        with pytest.raises(pkg.GanrevError):
+            c.search_cosine(q, 5)                                   # no database
+        with pytest.raises(pkg.GanrevError):
+            c.kmeans(3, 1, np.zeros((3, 8), np.float32))            # no database
+        c.db_set(np.random.default_rng(0).normal(size=(50, 8)).astype(np.float32))
+        with pytest.raises(pkg.GanrevError):
+            c.search_cosine(q, 129)                                 # k <= 128
+        with pytest.raises(pkg.GanrevError):
+            c.cluster_members(3, 5, np.zeros((50, 4), np.float32))  # assign_cosine_min has not run
+        with pytest.raises(pkg.GanrevError):
+            c.nearest_l2(np.zeros((1, 16), np.float32), None, N=10)  # no resident images
+        ids, sc = c.search_cosine(q, 5)                             # zero queries: every cosine is 0 -> lowest ids
+        assert ids.tolist() == [[0, 1, 2, 3, 4]] * 2 and np.all(sc == 0)
+    finally:
+        c.close()
