@@ -51,6 +51,7 @@ template <int NT, int MT, int CG = 1> struct Cfg {
     static constexpr int kTmemCols = kCols <= 32 ? 32 : (kCols <= 64 ? 64 : (kCols <= 128 ? 128 : (kCols <= 256 ? 256 : 512)));
     static constexpr int kChunk = NT < 32 ? NT : 32;                    // accumulator columns per tcgen05.ld
     static constexpr int kBarBytes = (2 * kMaxStages + 5) * 8 + 24;     // full/empty per stage, tfull/tempty x2, bres, tmem slot (16 B aligned)
+    static constexpr int kXposeOff = (kBarBytes + 2 * NT * 4 + 1023) / 1024 * 1024;   // store buffers start on a swizzle-pattern boundary (TMA store)
     static constexpr int kSsBytes = 2 * NT * 4;                         // double-buffered shift
     static constexpr int kXposeBytes = kEpiWarps * 32 * 64;             // per-warp 32 px x 64 B store-transpose buffers
 };
@@ -110,6 +111,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// TMA store of one 4-D box from shared memory (bulk async-group completion)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -304,7 +315,7 @@ __device__ __forceinline__ ItemCoord decode_item(const ConvGemm& p, int item) {
 template <int NT, int MT, int NDY, bool BRES, int ACT, bool POOL, bool OUT_FP32, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ ConvGemm p, const int n_items) {
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvGemm p, const int n_items) {
     using C = Cfg<NT, MT, CG>;
     constexpr int NACC = C::kNAcc;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;          // CG == 2: rank 0 is the leader (issues the MMAs)
@@ -490,8 +501,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int w_l = m & (BW - 1);
         const int h_l = (m >> p.lgBW) & ((1 << p.lgBH) - 1);
         const int n_l = m >> (p.lgBW + p.lgBH);
+        const int qw0 = (q * 32) & (BW - 1), qh0 = ((q * 32) >> p.lgBW) & ((1 << p.lgBH) - 1), qn0 = (q * 32) >> (p.lgBW + p.lgBH);   // first pixel of this warp's lane quarter
         float* ss_base = reinterpret_cast<float*>(smem + tail_off + C::kBarBytes);
-        uint4* xpose = reinterpret_cast<uint4*>(smem + tail_off + C::kBarBytes + C::kSsBytes) + (warp - 2) * 128;   // 2 KB per warp
+        uint4* xpose = reinterpret_cast<uint4*>(smem + tail_off + C::kXposeOff) + (warp - 2) * 128;   // 2 KB per warp
         constexpr int CW = C::kChunk;
         constexpr int kChunksPerTile = NT / CW;
         constexpr int kPairs = MT * kChunksPerTile;           // (sub-tile, column chunk) pairs per item
@@ -525,9 +537,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             long long offs[MT][4];
             size_t pix_off[MT];
             bool writer[MT];
+            TileCoord tco[MT];
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 const TileCoord t = decode_tile(p, (c.mgroup * CG + static_cast<int>(rank)) * MT + mt);
+                tco[mt] = t;
                 const int n = t.n0 + n_l, h = t.h0 + h_l, w = t.w0 + w_l;
                 int oh = h, ow = w;
                 writer[mt] = n < p.n_img;
@@ -579,10 +593,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 long long o4[4] = {-1, -1, -1, -1};
                 size_t po = 0;
                 bool wr = false;
+                TileCoord tt = tco[0];
 #pragma unroll
                 for (int m2 = 0; m2 < MT; ++m2)
                     if (m2 == mt) {
-                        po = pix_off[m2]; wr = writer[m2];
+                        po = pix_off[m2]; wr = writer[m2]; tt = tco[m2];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) o4[i] = offs[m2][i];
                     }
@@ -594,6 +609,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     constexpr int kPasses = (OUT_FP32 && NT == 32) ? 2 : 1;
 #pragma unroll
                     for (int hpass = 0; hpass < kPasses; ++hpass) {
+                        if (!OUT_FP32 && p.tma_store) tma_store_wait_read();   // the previous TMA store has read this buffer
                         __syncwarp();
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -608,6 +624,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 pk.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
                             }
                             xpose[lane * 4 + (j ^ ((lane >> 1) & 3))] = pk;
+                        }
+                        if (!OUT_FP32 && p.tma_store) {
+                            // The buffer is exactly a [32 pixels][32 channels] bf16 box in TMA's 64B-swizzle layout: one
+                            // bulk tensor store per chunk replaces the read-back, the address math and the predicated STGs
+                            // (pixels past the end of the batch are clipped by the tensor map).
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0 && !no_store)
+                                tma_store_4d(&tmO, smem_u32(xpose), cbase + c0, tt.w0 + qw0, tt.h0 + qh0, tt.n0 + qn0);
+                            continue;
                         }
                         __syncwarp();
 #pragma unroll
@@ -670,6 +696,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     }
 
+    if (p.tma_store) tma_store_wait_read();                  // pending bulk stores have read their shared-memory source
     tcgen05_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();   // the leader's MMAs read the peer's smem: nobody leaves early
     if (warp == 2) {

@@ -29,6 +29,7 @@ struct TcLayer {
     size_t smem_bytes = 0;
     DevBuf w, shift;
     CUtensorMap tmB{};
+    CUtensorMap tmO{};            // output map of the current launch (TMA-store layers)
     double flops_per_img = 0.0;   // executed MAC*2 per image (phase form counts the folded work)
     double bytes_per_img = 0.0;   // activation in + out per image
 };
@@ -67,6 +68,7 @@ struct ganrev_ctx {
     std::string err;
     int64_t chunk = 0;            // images per pipeline chunk; 0 = auto (8192 32x32 faces' worth of pixels, see chunk_for)
     int conv_impl = 0;
+    int tma_store = 1;            // TMA bulk tensor stores in the conv epilogue where the layer allows (0 = st.global everywhere; A/B)
     int rtile = 1;                // register-tiled kmeans / cosine-min kernels for 9 <= k <= 32 (0 = the one-thread-per-row streaming kernels; A/B)
     int cta_pairs = 0x1f;     // which layers use tcgen05 cta_group::2 CTA pairs (bit0 G conv1, bit1 G conv2, bit2 R conv2/3,
                               // bit3 R conv4, bit4 R conv5/6); takes effect at the next ganrev_load_*.  Default = measured best.
@@ -344,7 +346,7 @@ static int build_tc_layer(ganrev_ctx* ctx, TcLayer& L, const LayerDef& d, const 
     g.a_unit_bytes = (BH + g.ndy - 1) * BW * BN * 128;
     g.b_kb_bytes = (d.NT / L.CG) * 128;          // this CTA's share of a 64-wide weight tile
     g.dy_stride_bytes = BW * BN * 128;
-    const int tail = (2 * tc::kMaxStages + 5) * 8 + 24 + 2 * d.NT * 4 + tc::kEpiWarps * 32 * 64;   // barriers, shift (double-buffered), store-transpose buffers
+    const int tail = ((2 * tc::kMaxStages + 5) * 8 + 24 + 2 * d.NT * 4 + 1023) / 1024 * 1024 + tc::kEpiWarps * 32 * 64;   // barriers, shift (double-buffered), store-transpose buffers
     const int budget = tc::kSmemBudget - 1024 - tail;
     const size_t wbytes = static_cast<size_t>(g.units) * g.ndy * g.b_kb_bytes;
     L.bres = d.want_bres && g.nphase == 1 && g.n_tiles == 1 && wbytes + 2 * static_cast<size_t>(L.MT) * g.a_unit_bytes <= static_cast<size_t>(budget);
@@ -398,7 +400,7 @@ static int launch_tc(ganrev_ctx* ctx, const TcLayer& L, const CUtensorMap& tmA, 
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = CG == 2 ? 1 : 0;
-    CU_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, L.tmB, g, n_items));
+    CU_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, L.tmB, L.tmO, g, n_items));
     return GANREV_OK;
 }
 // The layer shapes of G3 / R_default map onto this fixed set of kernel variants
@@ -478,6 +480,20 @@ static int run_layer(ganrev_ctx* ctx, TcLayer& L, const void* in, void* out, int
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ctx, GANREV_ECUDA, "cuTensorMapEncodeTiled(A, %s) failed: %d", L.name.c_str(), (int)r);
+    // Output map for the TMA-store epilogue: plain (no pool / upsample) bf16 NHWC layers with whole 32-channel chunks.  A lane
+    // quarter's 32 pixels are one box {32 ch, bw, bh, bn} of the [n][Hout][Wout][channels] tensor; rows past n_img are clipped.
+    g.tma_store = (ctx->tma_store && !g.out_fp32 && !g.pool && g.up == 1 && g.out_sC == 1 && g.cout_real == g.cout_pad && L.NT % 32 == 0) ? 1 : 0;
+    L.tmO = tmA;
+    if (g.tma_store) {
+        const int BW = 1 << g.lgBW, BH = 1 << g.lgBH;
+        const int bw = std::min(BW, 32), bh = std::min(BH, 32 / bw), bn = 32 / (bw * bh);
+        const cuuint64_t odims[4] = {static_cast<cuuint64_t>(g.out_sP), static_cast<cuuint64_t>(g.Wout), static_cast<cuuint64_t>(g.Hout), static_cast<cuuint64_t>(n_img)};
+        const cuuint64_t ostr[3] = {static_cast<cuuint64_t>(g.out_sP) * 2, static_cast<cuuint64_t>(g.Wout) * g.out_sP * 2, static_cast<cuuint64_t>(g.out_sN) * 2};
+        const cuuint32_t obox[4] = {32u, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), static_cast<cuuint32_t>(bn)};
+        r = ctx->encode(&L.tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, odims, ostr, obox, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(ctx, GANREV_ECUDA, "cuTensorMapEncodeTiled(out, %s) failed: %d", L.name.c_str(), (int)r);
+    }
     return dispatch_tc(ctx, L, tmA, g, n_items);
 }
 
@@ -1622,6 +1638,7 @@ int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value) {
         return GANREV_OK;
     }
     if (!strcmp(name, "rtile")) { ctx->rtile = value != 0; return GANREV_OK; }
+    if (!strcmp(name, "tma_store")) { ctx->tma_store = value != 0; return GANREV_OK; }
     if (!strcmp(name, "conv_impl")) {
         if (value != 0 && value != 1) return fail(ctx, GANREV_EINVAL, "conv_impl must be 0 or 1");
         ctx->conv_impl = static_cast<int>(value);
