@@ -501,6 +501,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int w_l = m & (BW - 1);
         const int h_l = (m >> p.lgBW) & ((1 << p.lgBH) - 1);
         const int n_l = m >> (p.lgBW + p.lgBH);
+        // pooled TMA store: this lane's slot among the quarter's (bw/2) x (bh/2) pooled pixels (bw = min(BW, 32) columns per quarter row)
+        const int lg_bw = min(p.lgBW, 5);
+        const bool pool_writer = !(w_l & 1) && !(h_l & 1);
+        const int pool_row = ((lane >> lg_bw) >> 1) * ((1 << lg_bw) >> 1) + ((lane & ((1 << lg_bw) - 1)) >> 1);
         const int qw0 = (q * 32) & (BW - 1), qh0 = ((q * 32) >> p.lgBW) & ((1 << p.lgBH) - 1), qn0 = (q * 32) >> (p.lgBW + p.lgBH);   // first pixel of this warp's lane quarter
         float* ss_base = reinterpret_cast<float*>(smem + tail_off + C::kBarBytes);
         uint4* xpose = reinterpret_cast<uint4*>(smem + tail_off + C::kXposeOff) + (warp - 2) * 128;   // 2 KB per warp
@@ -623,7 +627,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 pk.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
                                 pk.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
                             }
-                            xpose[lane * 4 + (j ^ ((lane >> 1) & 3))] = pk;
+                            if (POOL && !OUT_FP32 && p.tma_store) {   // pooled: only the even-(h, w) lanes hold a result; pack them densely
+                                if (pool_writer) xpose[pool_row * 4 + (j ^ ((pool_row >> 1) & 3))] = pk;
+                            } else {
+                                xpose[lane * 4 + (j ^ ((lane >> 1) & 3))] = pk;
+                            }
                         }
                         if (!OUT_FP32 && p.tma_store) {
                             // The buffer is exactly a [32 pixels][32 channels] bf16 box in TMA's 64B-swizzle layout: one
@@ -631,8 +639,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             // (pixels past the end of the batch are clipped by the tensor map).
                             fence_proxy_async_smem();
                             __syncwarp();
-                            if (lane == 0 && !no_store)
-                                tma_store_4d(&tmO, smem_u32(xpose), cbase + c0, tt.w0 + qw0, tt.h0 + qh0, tt.n0 + qn0);
+                            if (lane == 0 && !no_store) {
+                                if (POOL) tma_store_4d(&tmO, smem_u32(xpose), cbase + c0, (tt.w0 + qw0) >> 1, (tt.h0 + qh0) >> 1, tt.n0 + qn0);
+                                else tma_store_4d(&tmO, smem_u32(xpose), cbase + c0, tt.w0 + qw0, tt.h0 + qh0, tt.n0 + qn0);
+                            }
                             continue;
                         }
                         __syncwarp();

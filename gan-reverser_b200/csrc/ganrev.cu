@@ -482,11 +482,17 @@ static int run_layer(ganrev_ctx* ctx, TcLayer& L, const void* in, void* out, int
     if (r != CUDA_SUCCESS) return fail(ctx, GANREV_ECUDA, "cuTensorMapEncodeTiled(A, %s) failed: %d", L.name.c_str(), (int)r);
     // Output map for the TMA-store epilogue: plain (no pool / upsample) bf16 NHWC layers with whole 32-channel chunks.  A lane
     // quarter's 32 pixels are one box {32 ch, bw, bh, bn} of the [n][Hout][Wout][channels] tensor; rows past n_img are clipped.
-    g.tma_store = (ctx->tma_store && !g.out_fp32 && !g.pool && g.up == 1 && g.out_sC == 1 && g.cout_real == g.cout_pad && L.NT % 32 == 0) ? 1 : 0;
+    g.tma_store = (ctx->tma_store && !g.out_fp32 && g.up == 1 && g.out_sC == 1 && g.cout_real == g.cout_pad && L.NT % 32 == 0) ? 1 : 0;
     L.tmO = tmA;
+    {
+        const int BW = 1 << g.lgBW, BH = 1 << g.lgBH;
+        if (g.pool && (std::min(BW, 32) < 2 || std::min(BH, 32 / std::min(BW, 32)) < 2)) g.tma_store = 0;   // a lane quarter must hold whole 2x2 windows
+    }
     if (g.tma_store) {
         const int BW = 1 << g.lgBW, BH = 1 << g.lgBH;
-        const int bw = std::min(BW, 32), bh = std::min(BH, 32 / bw), bn = 32 / (bw * bh);
+        int bw = std::min(BW, 32), bh = std::min(BH, 32 / bw);
+        const int bn = 32 / (bw * bh);
+        if (g.pool) { bw /= 2; bh /= 2; }                      // the pooled quarter: (bw/2) x (bh/2) pixels, packed densely by the epilogue
         const cuuint64_t odims[4] = {static_cast<cuuint64_t>(g.out_sP), static_cast<cuuint64_t>(g.Wout), static_cast<cuuint64_t>(g.Hout), static_cast<cuuint64_t>(n_img)};
         const cuuint64_t ostr[3] = {static_cast<cuuint64_t>(g.out_sP) * 2, static_cast<cuuint64_t>(g.Wout) * g.out_sP * 2, static_cast<cuuint64_t>(g.out_sN) * 2};
         const cuuint32_t obox[4] = {32u, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), static_cast<cuuint32_t>(bn)};
