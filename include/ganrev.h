@@ -164,7 +164,7 @@ int ganrev_debug_trace_read(ganrev_ctx* ctx, int64_t* out);
  *   "chunk"     images per pipeline chunk; default = 8192 32x32 faces' worth of pixels
  *   "conv_impl" 0 = tcgen05 implicit GEMM (default), 1 = plain CUDA-core kernels kept for on-device A/B checks
  *   "cta_pairs" bit mask of the conv layers that run as tcgen05 cta_group::2 CTA pairs (default all; read at ganrev_load_*)
- *   "tma_store" 1 = TMA bulk tensor stores in the conv epilogue where the layer allows (default), 0 = st.global everywhere
+ *   "tma_store" 1 = TMA bulk tensor stores in the conv epilogue of the plain layers (default), 2 = also the pooled layers, 0 = st.global everywhere
  *   "rtile"     1 = register-tiled kmeans / cosine-min kernels for 9 <= k <= 32 (default), 0 = one-thread-per-row streaming kernels
  *   "dbg"       timing experiments: bit 0 skip A loads, 1 skip B loads, 2 skip epilogue, 3 skip MMAs, 4 skip stores (results invalid) */
 int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value);
