@@ -113,3 +113,38 @@ def test_g_and_r_checkpoints_to_blobs(pkg, t7):
     bad = _seq(tw.Module("nn.Linear", weight=p["lin.w"], bias=p["lin.b"]), _conv("c1", p))
     with pytest.raises(t7.T7Error):
         t7.g_blob(t7.loads(tw.dumps({"G": bad, "opt": opt})))
+
+
+def test_round_trip_property(t7):
+    """Random nested tables / tensors survive writer -> reader unchanged (hypothesis)."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    leaves = st.one_of(
+        st.booleans(), st.integers(min_value=-2 ** 40, max_value=2 ** 40), st.floats(allow_nan=False, allow_infinity=False, width=64),
+        st.text(alphabet=st.characters(min_codepoint=32, max_codepoint=126), max_size=12),
+        st.lists(st.floats(allow_nan=False, width=32), min_size=0, max_size=6).map(lambda v: np.asarray(v, np.float32)),
+        st.lists(st.integers(-100, 100), min_size=1, max_size=6).map(lambda v: np.asarray(v, np.int64).reshape(1, -1)),
+    )
+    keys = st.one_of(st.integers(1, 50), st.text(alphabet="abcxyz_", min_size=1, max_size=6))
+    tables = st.recursive(leaves, lambda ch: st.dictionaries(keys, ch, max_size=4), max_leaves=12)
+
+    def same(a, b):
+        if isinstance(a, np.ndarray):
+            return isinstance(b, np.ndarray) and a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b)
+        if isinstance(a, dict):
+            return isinstance(b, dict) and a.keys() == b.keys() and all(same(a[k], b[k]) for k in a)
+        if isinstance(a, float):
+            return float(b) == a
+        return a == b and type(a) is type(b) or (isinstance(a, int) and not isinstance(a, bool) and b == a)
+
+    @settings(max_examples=150, deadline=None)
+    @given(tables, st.sampled_from([8, 4]), st.booleans())
+    def run(obj, long_size, legacy):
+        out = t7.loads(tw.dumps(obj, long_size=long_size, legacy=legacy), long_size=long_size)
+        if isinstance(obj, float) and obj == int(obj) and abs(obj) < 2 ** 53:
+            assert out == obj                                   # integral numbers come back as ints (Lua has one number type)
+        else:
+            assert same(obj, out), (obj, out)
+
+    run()
