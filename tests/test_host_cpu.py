@@ -124,3 +124,31 @@ def test_gloo_world2_plumbing():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours) needs no GPU: one JSON line with the
+    contract's keys, rank 0 only under torchrun."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-images", "32"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "g2r_images_per_sec" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--ref-images", "32"],
+                          capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert out1.returncode == 0 and out1.stdout.strip() == ""     # the other ranks exit 0 without work
+
+
+def test_integration_doc_lists_every_entry_point():
+    import os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = re.sub(r"/\*.*?\*/", " ", open(os.path.join(root, "include", "ganrev.h")).read(), flags=re.S)
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    names = set(re.findall(r"\b(ganrev_[a-z0-9_A-Z]+)\s*\(", hdr))
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, f"INTEGRATION.md does not mention {missing}"
