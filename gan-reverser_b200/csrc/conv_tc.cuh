@@ -15,11 +15,16 @@
 //  * MT accumulators per CTA: every weight tile feeds MT MMAs (M = 128*MT per item).
 //  * nearest-upsample + 3x3 conv (models.lua:121-122, 127-128) runs as four 2x2 phase
 //    convolutions on the low-res input (weights pre-summed per phase at load time).
-//  * tcgen05.mma (cta_group::1, kind::f16, bf16 x bf16 -> fp32) is issued by one elected thread;
-//    accumulators live in TMEM, double-buffered when 2*MT*NT <= 512 columns so the epilogue of
-//    item i overlaps the MMAs of item i+1.
-//  * epilogue: tcgen05.ld -> folded BatchNorm affine -> ReLU/ELU/tanh/sigmoid -> optional 2x2
-//    max-pool (warp shuffles) and x0.75 (SpatialDropout in eval) -> bf16 NHWC / fp32 store.
+//  * tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) is issued by one elected thread; accumulators
+//    live in TMEM, double-buffered when 2*MT*NT <= 512 columns.  CG = 2: cta_group::2 CTA pairs
+//    (M = 256 across the two SMs of a TPC, each CTA loads its own A tiles and half of every B
+//    tile, only the leader issues; commits are multicast to both CTAs).
+//  * epilogue: each warp loads TWO 32-column chunks per tcgen05.wait::ld, hands the accumulator
+//    stage back to the MMA warp at once (registers are the third buffer), then folded-BN shift
+//    (the BN scale is folded into the bf16 weights) -> ReLU/ELU/tanh/sigmoid -> optional 2x2
+//    max-pool (warp shuffles) -> bf16 NHWC / fp32.  The chunk is staged in an XOR-swizzled smem
+//    buffer that is TMA's 64B-swizzle layout: plain layers issue one cp.async.bulk.tensor store
+//    per chunk, the others read it back for coalesced 16-byte st.global.cg.
 //
 // Why this shape (measured): a B200 SM ingests ~128 B/clk through TMA with
 // ~1300 cycles of latency, and the mbarrier round trip per pipeline stage costs 300+ cycles; a
@@ -29,7 +34,8 @@
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread
 // each), warps 2..9 = epilogue (two warps per TMEM lane quarter; warp 2 owns the TMEM
 // allocation).  Only ONE lane ever polls an mbarrier: the other epilogue threads park on a
-// hardware named barrier, because spinning try_waits measurably slow the TMA / MMA handshakes.  Shape, activation, pooling and output type are template parameters.
+// hardware named barrier, because spinning try_waits measurably slow the TMA / MMA handshakes.
+// Shape, activation, pooling, output type and CTA-pair mode are template parameters.
 #pragma once
 #include "common.cuh"
 
