@@ -76,29 +76,44 @@ size_t orc_blob_floats_R(int C, int H, int W, int nd) {
 /* ------------------------------------------------------------------ */
 
 /* nn.SpatialConvolution / cudnn.SpatialConvolution 3x3, stride 1, pad 1. */
+/* Register-blocked direct form: 4 output channels share every loaded input row and one output row stays in
+ * registers across all Cin x 9 taps (the previous shift-and-accumulate form re-read and re-wrote the output plane
+ * for every tap and ran at ~10 % of the cores' FMA rate).  Per output element the terms are still added in the
+ * order ci ascending, ky, kx -- the same order as before, so results are unchanged up to FMA contraction. */
 FASTFP static void conv3x3(const float* in, int Cin, int H, int W,
                            const float* w, const float* b, int Cout, float* out) {
-    for (int co = 0; co < Cout; ++co) {
-        float* o = out + (size_t)co * H * W;
-        for (int i = 0; i < H * W; ++i) o[i] = b[co];
-        for (int ci = 0; ci < Cin; ++ci) {
-            const float* ip = in + (size_t)ci * H * W;
-            const float* wp = w + ((size_t)co * Cin + ci) * 9;
-            for (int ky = 0; ky < 3; ++ky) {
-                for (int kx = 0; kx < 3; ++kx) {
-                    const float wv = wp[ky * 3 + kx];
-                    const int dy = ky - 1, dx = kx - 1;
-                    const int y0 = dy < 0 ? 1 : 0, y1 = dy > 0 ? H - 1 : H;
-                    const int x0 = dx < 0 ? 1 : 0, x1 = dx > 0 ? W - 1 : W;
-                    for (int y = y0; y < y1; ++y) {
-                        float* orow = o + (size_t)y * W;
-                        const float* irow = ip + (size_t)(y + dy) * W + dx;
-                        for (int x = x0; x < x1; ++x) orow[x] += wv * irow[x];
+    const int Wp = W + 2;
+    float* pad = (float*)calloc((size_t)Cin * (H + 2) * Wp, sizeof(float));   /* zero border = the conv's padding */
+    if (!pad) abort();
+    for (int ci = 0; ci < Cin; ++ci)
+        for (int y = 0; y < H; ++y)
+            memcpy(pad + ((size_t)ci * (H + 2) + y + 1) * Wp + 1, in + ((size_t)ci * H + y) * W, sizeof(float) * W);
+    enum { CB = 4, XB = 64 };
+    for (int co0 = 0; co0 < Cout; co0 += CB) {
+        const int nc = Cout - co0 < CB ? Cout - co0 : CB;
+        for (int y = 0; y < H; ++y) {
+            for (int x0 = 0; x0 < W; x0 += XB) {
+                const int nx = W - x0 < XB ? W - x0 : XB;
+                float acc[CB][XB];
+                for (int c = 0; c < CB; ++c)
+                    for (int x = 0; x < nx; ++x) acc[c][x] = c < nc ? b[co0 + c] : 0.0f;
+                for (int ci = 0; ci < Cin; ++ci) {
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const float* r = pad + ((size_t)ci * (H + 2) + y + ky) * Wp + x0;
+                        for (int kx = 0; kx < 3; ++kx) {
+                            float wv[CB];
+                            for (int c = 0; c < CB; ++c) wv[c] = c < nc ? w[((size_t)(co0 + c) * Cin + ci) * 9 + ky * 3 + kx] : 0.0f;
+                            for (int c = 0; c < CB; ++c)
+                                for (int x = 0; x < nx; ++x) acc[c][x] += wv[c] * r[x + kx];
+                        }
                     }
                 }
+                for (int c = 0; c < nc; ++c)
+                    memcpy(out + ((size_t)(co0 + c) * H + y) * W + x0, acc[c], sizeof(float) * nx);
             }
         }
     }
+    free(pad);
 }
 
 /* nn.(Spatial)BatchNormalization in evaluate() mode: running stats, affine. */
