@@ -196,8 +196,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=1_000_000, help="faces per GPU per step")
     ap.add_argument("--chunk", type=int, default=0, help="pipeline chunk (0 = library default)")
-    ap.add_argument("--ref-images", type=int, default=384, help="CPU-arm sample size per step")
-    ap.add_argument("--cpu-images", type=int, default=512, help="cpu_baseline sample size")
+    ap.add_argument("--ref-images", type=int, default=1536, help="CPU-arm sample size per step (~8 s of 16-thread CPU work)")
+    ap.add_argument("--cpu-images", type=int, default=2048, help="cpu_baseline sample size (~10 s of 16-thread CPU work)")
     ap.add_argument("--geom", default="", help="C,H,W,nd of another geometry (e.g. 3,64,64,256 = BASELINE configs[4]'s G/R); default configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm-kernels", action="store_true", help="skip the L2 / kmeans / small-Q search bandwidth rooflines")
