@@ -142,9 +142,8 @@ def hbm_kernels(ctx, pkg, peak_gbs):
     out["l2_pairs"] = timed("l2_pairs", lambda: ctx.l2(a, b), 8.0 * n * 1024, 2)
     out["l2_pairs"]["workload"] = f"{n} pairs of 32x32 fp32 faces, 8*C*H*W algorithmic bytes per pair"
     # nearest training image by torch.dist for 8 query faces (sample.lua:128-148): the set is read once
-    ctx.buffer_put(pkg._lib.BUF_IMAGES, a.reshape(n, 1, 32, 32))
-    out["nearest_l2_q8"] = timed("nearest_l2", lambda: ctx.nearest_l2(b[:8], None, N=n), 4.0 * n * 1024, 3)
-    out["nearest_l2_q8"]["workload"] = (f"8 query faces against {n} resident 32x32 fp32 faces, 4*C*H*W algorithmic bytes per set row; "
+    out["nearest_l2_q8"] = timed("nearest_l2", lambda: ctx.nearest_l2(b[:8], a), 4.0 * n * 1024, 3)   # explicit set: independent of --geom
+    out["nearest_l2_q8"]["workload"] = (f"8 query faces against {n} 32x32 fp32 faces, 4*C*H*W algorithmic bytes per set row; "
                                         "the canonical fp32-square / fp64-sum arithmetic needs one fp32->fp64 conversion per (query, element), "
                                         "so with 8 queries per pass the conversion unit (16 lanes/clk/SM), not HBM, is the nearer bound")
     # kmeans k=20 over 4M x 100 rows (recovered-vector shape): 4*N*d algorithmic bytes per iteration
