@@ -135,7 +135,7 @@ class Context:
     def load_R(self, slot, Cc, H, W, nd, blob, tanh_out=False):
         blob = _arr(blob, np.float32)
         self._chk(lib().ganrev_load_R(self._h, slot, Cc, H, W, nd, int(bool(tanh_out)), _ptr(blob), blob.size))
-        self.geom = self.geom or (Cc, H, W, nd)
+        self.geom = (Cc, H, W, nd)     # one geometry per context (ganrev.h): a different one unloaded the old models
 
     def forward_G(self, noise, N=None, want_images=True, out=None):
         Cc, H, W, nd = self.geom

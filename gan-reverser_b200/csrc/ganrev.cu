@@ -90,10 +90,15 @@ struct ganrev_ctx {
     // resident buffers + activation arena
     DevBuf buf[GANREV_BUF_COUNT];
     int64_t buf_rows[GANREV_BUF_COUNT] = {0, 0, 0, 0, 0, 0};
+    int gC = 0, gH = 0, gW = 0, gnd = 0;   // the one geometry every loaded model and resident buffer shares (0 = none yet)
     DevBuf arena[2], noise_bf16, stage_a, stage_b, l2buf, thr, flags;
-    DevBuf nn_partial, nn_ids, nn_dist, nn_flag;   // ganrev_nearest_l2 scratch
+    int64_t l2_valid = 0;                  // entries of l2buf written by the last fix_l2 / l2 / anomaly_flags call
+    DevBuf nn_partial, nn_ids, nn_dist, nn_flag, nn_all;   // ganrev_nearest_l2 scratch
+    DevBuf qsel, shard;                    // radix-select state + histogram; row-shard bookkeeping (world + 2 int64)
     // database
     DevBuf db, rdb, maxabs;
+    const float* db_ptr = nullptr;         // rows of the database: db.p (own copy) or the resident ATTRS0 buffer (alias)
+    bool db_alias = false;
     int64_t db_n = 0, db_offset = 0, db_total = 0;
     int db_d = 0;
     float db_maxabs = 0.0f;
@@ -509,12 +514,26 @@ static int run_layer(ganrev_ctx* ctx, TcLayer& L, const void* in, void* out, int
 // =================================================================================
 static void release_layer(TcLayer& L) { release(L.w); release(L.shift); }
 
+// One geometry per context: G, R and R_fixer of apply_r.lua share {C, H, W, noiseDim} (apply_r.lua:65-79), and the resident
+// buffers are sized by it.  Loading a model of a DIFFERENT geometry therefore unloads the models of the old one and empties
+// every resident buffer (and a database aliasing ATTRS0) -- nothing sized for the old geometry can be read or written afterwards.
+static void adopt_geometry(ganrev_ctx* ctx, int C, int H, int W, int nd) {
+    if (ctx->gC == C && ctx->gH == H && ctx->gW == W && ctx->gnd == nd) return;
+    ctx->G.loaded = false;
+    ctx->R[0].loaded = ctx->R[1].loaded = false;
+    for (int b = 0; b < GANREV_BUF_COUNT; ++b) ctx->buf_rows[b] = 0;
+    if (ctx->db_alias) { ctx->db_ptr = nullptr; ctx->db_alias = false; ctx->db_n = 0; ctx->assigned = false; }
+    ctx->l2_valid = 0;
+    ctx->gC = C; ctx->gH = H; ctx->gW = W; ctx->gnd = nd;
+}
+
 static int load_G_impl(ganrev_ctx* ctx, int C, int H, int W, int nd, const float* blob, size_t n_floats) {
     RC_TRY(check_geom(ctx, C, H, W, nd));
     const int sH = H / 4, sW = W / 4, HW0 = sH * sW, F = 512 * HW0;
     const size_t need = static_cast<size_t>(F) * nd + 5 * static_cast<size_t>(F) + 256u * 512 * 9 + 5 * 256 + 128u * 256 * 9 + 5 * 128 +
                         static_cast<size_t>(C) * 128 * 9 + C;
     if (n_floats != need) return fail(ctx, GANREV_EINVAL, "G blob has %zu floats, expected %zu", n_floats, need);
+    adopt_geometry(ctx, C, H, W, nd);
     GModel& G = ctx->G;
     G.loaded = false;
     const float* p = blob;
@@ -581,6 +600,7 @@ static int load_R_impl(ganrev_ctx* ctx, int slot, int C, int H, int W, int nd, i
     const size_t need = static_cast<size_t>(64) * C * 9 + 5 * 64 + 2 * (64u * 64 * 9 + 5 * 64) + (128u * 64 * 9 + 5 * 128) +
                         2 * (128u * 128 * 9 + 5 * 128) + 512 * static_cast<size_t>(F) + 5 * 512 + static_cast<size_t>(nd) * 512 + nd;
     if (n_floats != need) return fail(ctx, GANREV_EINVAL, "R blob has %zu floats, expected %zu", n_floats, need);
+    adopt_geometry(ctx, C, H, W, nd);
     RModel& R = ctx->R[slot];
     R.loaded = false;
     R.C = C; R.H = H; R.W = W; R.nd = nd; R.tanh_out = tanh_out;
@@ -781,25 +801,31 @@ int ganrev_version(void) { return 100; }
 int ganrev_create(ganrev_ctx** out, int device) {
     if (!out) return GANREV_EINVAL;
     *out = nullptr;
-    std::unique_ptr<ganrev_ctx> c(new ganrev_ctx());
-    ganrev_ctx* ctx = c.get();
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return GANREV_ENODEV;
     if (device < 0 || device >= count || device >= kMaxDevices) return GANREV_ENODEV;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GANREV_ENODEV;
     if (prop.major != 10) return GANREV_ENODEV;   // tcgen05 / TMEM kernels are sm_100a only; there is no fallback
+    if (cudaSetDevice(device) != cudaSuccess) return GANREV_ECUDA;
+    ganrev_ctx* ctx = new ganrev_ctx();
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
-    if (cudaSetDevice(device) != cudaSuccess) return GANREV_ECUDA;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return GANREV_ECUDA;
-    if (cudaMalloc(&ctx->d_err_flag, sizeof(int)) != cudaSuccess) return GANREV_ENOMEM;
-    cudaMemset(ctx->d_err_flag, 0, sizeof(int));
+    int rc = GANREV_OK;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return GANREV_ECUDA;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->stream = nullptr; rc = GANREV_ECUDA; }
+    else if (cudaMalloc(&ctx->d_err_flag, sizeof(int)) != cudaSuccess) { ctx->d_err_flag = nullptr; rc = GANREV_ENOMEM; }
+    else if (cudaMemset(ctx->d_err_flag, 0, sizeof(int)) != cudaSuccess) rc = GANREV_ECUDA;
+    else if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) rc = GANREV_ECUDA;
+    if (rc != GANREV_OK) {   // nothing created above outlives a failed create
+        if (ctx->d_err_flag) cudaFree(ctx->d_err_flag);
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return rc;
+    }
     ctx->encode = reinterpret_cast<EncodeTiledFn>(fn);
-    *out = c.release();
+    *out = ctx;
     return GANREV_OK;
 }
 
@@ -818,7 +844,7 @@ void ganrev_destroy(ganrev_ctx* ctx) {
         for (TcLayer* L : {&R.c2, &R.c3, &R.c4, &R.c5, &R.c6, &R.l1, &R.l2}) release_layer(*L);
     }
     for (auto& b : ctx->buf) release(b);
-    for (DevBuf* b : {&ctx->nn_partial, &ctx->nn_ids, &ctx->nn_dist, &ctx->nn_flag}) release(*b);
+    for (DevBuf* b : {&ctx->nn_partial, &ctx->nn_ids, &ctx->nn_dist, &ctx->nn_flag, &ctx->nn_all, &ctx->qsel, &ctx->shard}) release(*b);
     for (DevBuf* b : {&ctx->arena[0], &ctx->arena[1], &ctx->noise_bf16, &ctx->stage_a, &ctx->stage_b, &ctx->l2buf, &ctx->thr, &ctx->flags,
                       &ctx->db, &ctx->rdb, &ctx->maxabs, &ctx->q, &ctx->rq, &ctx->c2, &ctx->partial, &ctx->keys, &ctx->keys_all, &ctx->ids,
                       &ctx->scores, &ctx->cen, &ctx->acc, &ctx->cnt, &ctx->total, &ctx->labels, &ctx->cosv, &ctx->tcounts, &ctx->mids,
@@ -893,9 +919,7 @@ int ganrev_load_R(ganrev_ctx* ctx, int slot, int C, int H, int W, int noise_dim,
 
 // ---------------------------------------------------------------- resident buffers
 static size_t buf_row_bytes(ganrev_ctx* ctx, int which) {
-    int C = 0, H = 0, W = 0, nd = 0;
-    if (ctx->G.loaded) { C = ctx->G.C; H = ctx->G.H; W = ctx->G.W; nd = ctx->G.nd; }
-    else for (int s = 0; s < 2; ++s) if (ctx->R[s].loaded) { C = ctx->R[s].C; H = ctx->R[s].H; W = ctx->R[s].W; nd = ctx->R[s].nd; break; }
+    const int C = ctx->gC, H = ctx->gH, W = ctx->gW, nd = ctx->gnd;   // 0 until a model is loaded
     switch (which) {
         case GANREV_BUF_NOISE: case GANREV_BUF_ATTRS0: case GANREV_BUF_ATTRS1: return static_cast<size_t>(nd) * 4;
         case GANREV_BUF_IMAGES: case GANREV_BUF_FIXED: return static_cast<size_t>(C) * H * W * 4;
@@ -903,9 +927,14 @@ static size_t buf_row_bytes(ganrev_ctx* ctx, int which) {
     }
     return 0;
 }
+// A resident buffer is about to be overwritten or reallocated: a database that aliases it is no longer set.
+static void buf_touch(ganrev_ctx* ctx, int which) {
+    if (which == GANREV_BUF_ATTRS0 && ctx->db_alias) { ctx->db_ptr = nullptr; ctx->db_alias = false; ctx->db_n = 0; ctx->assigned = false; }
+}
 static int buf_reserve(ganrev_ctx* ctx, int which, int64_t rows) {
     const size_t rb = buf_row_bytes(ctx, which);
     if (rb == 0) return fail(ctx, GANREV_ESTATE, "load a model before using resident buffers");
+    buf_touch(ctx, which);
     RC_TRY(ensure(ctx, ctx->buf[which], rb * static_cast<size_t>(std::max<int64_t>(rows, 1))));
     return GANREV_OK;
 }
@@ -929,7 +958,7 @@ int ganrev_buffer_get(ganrev_ctx* ctx, int which, void* host, int64_t row0, int6
 // input helper: host pointer -> upload into resident buffer; NULL -> resident buffer must hold >= N rows
 static int stage_input(ganrev_ctx* ctx, int which, const void* host, int64_t N) {
     if (host) {
-        RC_TRY(buf_reserve(ctx, which, N));
+        RC_TRY(buf_reserve(ctx, which, N));   // (also un-sets a database aliasing this buffer)
         CU_TRY(cudaMemcpyAsync(ctx->buf[which].p, host, buf_row_bytes(ctx, which) * N, cudaMemcpyHostToDevice, ctx->stream));
         ctx->buf_rows[which] = N;
     } else if (ctx->buf_rows[which] < N || !ctx->buf[which].p) {
@@ -988,6 +1017,7 @@ int ganrev_fix_l2(ganrev_ctx* ctx, int slot, const float* images, const uint8_t*
     const int ob = slot == 0 ? GANREV_BUF_ATTRS0 : GANREV_BUF_ATTRS1;
     RC_TRY(buf_reserve(ctx, ob, N));
     RC_TRY(buf_reserve(ctx, GANREV_BUF_FIXED, N));
+    ctx->l2_valid = 0;
     RC_TRY(ensure(ctx, ctx->l2buf, sizeof(double) * static_cast<size_t>(std::max<int64_t>(N, 1))));
     const float* d_img = static_cast<const float*>(ctx->buf[GANREV_BUF_IMAGES].p);
     float* d_att = static_cast<float*>(ctx->buf[ob].p);
@@ -997,6 +1027,7 @@ int ganrev_fix_l2(ganrev_ctx* ctx, int slot, const float* images, const uint8_t*
     RC_TRY(forward_G_dev(ctx, d_att, N, d_fix));
     ctx->buf_rows[GANREV_BUF_FIXED] = N;
     RC_TRY(l2_dev(ctx, d_img, d_fix, N, ctx->G.C * ctx->G.H * ctx->G.W, static_cast<double*>(ctx->l2buf.p)));
+    ctx->l2_valid = N;
     RC_TRY(fetch_output(ctx, ob, attrs, N));
     RC_TRY(fetch_output(ctx, GANREV_BUF_FIXED, fixed, N));
     if (l2) CU_TRY(cudaMemcpyAsync(l2, ctx->l2buf.p, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1009,10 +1040,12 @@ int ganrev_l2(ganrev_ctx* ctx, const float* a, const float* b, int64_t N, int px
     const size_t bytes = sizeof(float) * static_cast<size_t>(N) * px;
     RC_TRY(ensure(ctx, ctx->stage_a, bytes));
     RC_TRY(ensure(ctx, ctx->stage_b, bytes));
+    ctx->l2_valid = 0;
     RC_TRY(ensure(ctx, ctx->l2buf, sizeof(double) * static_cast<size_t>(std::max<int64_t>(N, 1))));
     CU_TRY(cudaMemcpyAsync(ctx->stage_a.p, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(cudaMemcpyAsync(ctx->stage_b.p, b, bytes, cudaMemcpyHostToDevice, ctx->stream));
     RC_TRY(l2_dev(ctx, static_cast<const float*>(ctx->stage_a.p), static_cast<const float*>(ctx->stage_b.p), N, px, static_cast<double*>(ctx->l2buf.p)));
+    ctx->l2_valid = N;
     CU_TRY(cudaMemcpyAsync(l2, ctx->l2buf.p, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
     return finish(ctx);
 }
@@ -1053,9 +1086,34 @@ int ganrev_nearest_l2(ganrev_ctx* ctx, const float* queries, int Q, const float*
         {
             ProfScope ps(ctx, "nearest_l2_merge", 0.0, 16.0 * n_warps * nq);
             nearest_l2_merge_kernel<<<nq, 32, 0, ctx->stream>>>(static_cast<const NearestRec*>(ctx->nn_partial.p), n_warps, Q, q0, N,
-                                                               static_cast<const unsigned char*>(ctx->nn_flag.p), static_cast<long long*>(ctx->nn_ids.p), static_cast<double*>(ctx->nn_dist.p));
+                                                               static_cast<const unsigned char*>(ctx->nn_flag.p), ctx->world == 1 ? 1 : 0,
+                                                               static_cast<long long*>(ctx->nn_ids.p), static_cast<double*>(ctx->nn_dist.p));
             CU_TRY(cudaGetLastError());
         }
+    }
+    if (ctx->world > 1) {
+        // row-sharded set (each rank passes its own shard): global row = local row + the lower ranks' N; one allgather of
+        // Q records, merged identically on every rank; the "row 0 sticks" quirk belongs to the rank that owns global row 0
+        RC_TRY(ensure(ctx, ctx->shard, sizeof(long long) * (ctx->world + 2)));
+        long long* d_all = static_cast<long long*>(ctx->shard.p);
+        const long long mine = N;
+        std::vector<long long> all(ctx->world, 0);
+        CU_TRY(cudaMemcpyAsync(d_all + ctx->world, &mine, sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        NCCL_TRY(ctx->nccl.AllGather(d_all + ctx->world, d_all, 1, ncclInt64, ctx->comm, ctx->stream));
+        CU_TRY(cudaMemcpyAsync(all.data(), d_all, sizeof(long long) * ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
+        RC_TRY(finish(ctx));
+        long long offset = 0, total = 0;
+        for (int r = 0; r < ctx->world; ++r) { if (r < ctx->rank) offset += all[r]; total += all[r]; }
+        RC_TRY(ensure(ctx, ctx->nn_all, sizeof(NearestRankRec) * static_cast<size_t>(Q) * (ctx->world + 1)));
+        NearestRankRec* rec_all = static_cast<NearestRankRec*>(ctx->nn_all.p);
+        NearestRankRec* rec_mine = rec_all + static_cast<size_t>(Q) * ctx->world;
+        ProfScope ps(ctx, "nearest_l2_ranks", 0.0, 32.0 * Q * ctx->world);
+        nearest_l2_pack_kernel<<<(Q + 127) / 128, 128, 0, ctx->stream>>>(static_cast<const long long*>(ctx->nn_ids.p), static_cast<const double*>(ctx->nn_dist.p),
+            static_cast<const unsigned char*>(ctx->nn_flag.p), Q, offset, (offset == 0 && N > 0) ? 1 : 0, rec_mine);
+        NCCL_TRY(ctx->nccl.AllGather(rec_mine, rec_all, sizeof(NearestRankRec) * static_cast<size_t>(Q), ncclUint8, ctx->comm, ctx->stream));
+        nearest_l2_ranks_kernel<<<(Q + 127) / 128, 128, 0, ctx->stream>>>(rec_all, ctx->world, Q, total, static_cast<long long*>(ctx->nn_ids.p), static_cast<double*>(ctx->nn_dist.p));
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
     }
     static_assert(sizeof(long long) == sizeof(int64_t), "ids are copied out as int64");
     CU_TRY(cudaMemcpyAsync(ids, ctx->nn_ids.p, sizeof(int64_t) * Q, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1064,17 +1122,39 @@ int ganrev_nearest_l2(ganrev_ctx* ctx, const float* queries, int Q, const float*
 }
 
 int ganrev_anomaly_flags(ganrev_ctx* ctx, const double* l2, int64_t n_calc, int64_t n_show, double quantile, uint8_t* flags, double* thr) {
-    if (!ctx || n_calc < 1 || n_show < 0 || n_show > n_calc || !flags) return ctx ? fail(ctx, GANREV_EINVAL, "bad anomaly_flags arguments") : GANREV_EINVAL;
-    const int64_t r = static_cast<int64_t>(std::floor(static_cast<double>(n_calc) * quantile));   // math.floor(#distancesForSort*threshold)
-    if (r < 1 || r > n_calc) return fail(ctx, GANREV_EINVAL, "floor(n_calc*quantile)=%lld is not a valid 1-based index", (long long)r);
+    if (!ctx || n_calc < 0 || n_show < 0 || n_show > n_calc || (!flags && n_show > 0)) return ctx ? fail(ctx, GANREV_EINVAL, "bad anomaly_flags arguments") : GANREV_EINVAL;
+    if (ctx->world == 1 && n_calc < 1) return fail(ctx, GANREV_EINVAL, "bad anomaly_flags arguments");
+    if (!l2 && ctx->l2_valid < n_calc) return fail(ctx, GANREV_ESTATE, "l2 == NULL needs %lld resident distances, the last fix_l2 / l2 call left %lld", (long long)n_calc, (long long)ctx->l2_valid);
     CU_TRY(cudaSetDevice(ctx->device));
-    RC_TRY(ensure(ctx, ctx->l2buf, sizeof(double) * static_cast<size_t>(n_calc)));
+    RC_TRY(ensure(ctx, ctx->qsel, sizeof(unsigned long long) * (4 + 256)));
+    unsigned long long* state = static_cast<unsigned long long*>(ctx->qsel.p);
+    unsigned long long* hist = state + 4;
+    int64_t n_total = n_calc;
+    if (ctx->world > 1) {   // the distances are sharded like the images: the order statistic is over all ranks' n_calc values
+        const unsigned long long mine = static_cast<unsigned long long>(n_calc);
+        CU_TRY(cudaMemcpyAsync(state + 2, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+        NCCL_TRY(ctx->nccl.AllReduce(state + 2, state + 2, 1, ncclUint64, ncclSum, ctx->comm, ctx->stream));
+        unsigned long long tot = 0;
+        CU_TRY(cudaMemcpyAsync(&tot, state + 2, sizeof(tot), cudaMemcpyDeviceToHost, ctx->stream));
+        RC_TRY(finish(ctx));
+        n_total = static_cast<int64_t>(tot);
+    }
+    const int64_t r = static_cast<int64_t>(std::floor(static_cast<double>(n_total) * quantile));   // math.floor(#distancesForSort*threshold)
+    if (r < 1 || r > n_total) return fail(ctx, GANREV_EINVAL, "floor(n_calc*quantile)=%lld is not a valid 1-based index", (long long)r);
+    if (l2 || n_calc == 0) RC_TRY(ensure(ctx, ctx->l2buf, sizeof(double) * static_cast<size_t>(std::max<int64_t>(n_calc, 1))));
     RC_TRY(ensure(ctx, ctx->thr, sizeof(double)));
     RC_TRY(ensure(ctx, ctx->flags, static_cast<size_t>(std::max<int64_t>(n_show, 1))));
-    if (l2) CU_TRY(cudaMemcpyAsync(ctx->l2buf.p, l2, sizeof(double) * n_calc, cudaMemcpyHostToDevice, ctx->stream));
+    if (l2 && n_calc > 0) { CU_TRY(cudaMemcpyAsync(ctx->l2buf.p, l2, sizeof(double) * n_calc, cudaMemcpyHostToDevice, ctx->stream)); ctx->l2_valid = n_calc; }
     {
         ProfScope ps(ctx, "quantile_select", 0.0, 8.0 * 8.0 * n_calc);
-        quantile_select_kernel<<<1, 1024, 0, ctx->stream>>>(static_cast<const double*>(ctx->l2buf.p), n_calc, r - 1, static_cast<double*>(ctx->thr.p));
+        ctx->launches += 16;
+        quantile_init_kernel<<<1, 256, 0, ctx->stream>>>(state, hist, r - 1, quantile);
+        const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n_calc + 4095) / 4096, 4LL * ctx->num_sms)));
+        for (int pass = 0; pass < 8; ++pass) {
+            quantile_hist_kernel<<<blocks, 256, 0, ctx->stream>>>(static_cast<const double*>(ctx->l2buf.p), n_calc, state, pass, hist);
+            if (ctx->world > 1) NCCL_TRY(ctx->nccl.AllReduce(hist, hist, 256, ncclUint64, ncclSum, ctx->comm, ctx->stream));
+            quantile_pick_kernel<<<1, 256, 0, ctx->stream>>>(state, hist, pass, static_cast<double*>(ctx->thr.p));
+        }
         CU_TRY(cudaGetLastError());
     }
     if (n_show > 0) {
@@ -1100,43 +1180,45 @@ int ganrev_db_set(ganrev_ctx* ctx, const float* vecs, int64_t N, int d) {
     if (!ctx || N < 0 || d < 1 || N > 0xFFFFFFF0ll) return ctx ? fail(ctx, GANREV_EINVAL, "bad db_set arguments") : GANREV_EINVAL;
     CU_TRY(cudaSetDevice(ctx->device));
     const size_t bytes = sizeof(float) * static_cast<size_t>(N) * d;
-    RC_TRY(ensure(ctx, ctx->db, bytes));
+    ctx->db_ptr = nullptr; ctx->db_alias = false; ctx->db_n = 0; ctx->assigned = false;
     RC_TRY(ensure(ctx, ctx->rdb, sizeof(float) * static_cast<size_t>(std::max<int64_t>(N, 1))));
     RC_TRY(ensure(ctx, ctx->maxabs, 3 * sizeof(long long)));
+    RC_TRY(ensure(ctx, ctx->shard, sizeof(long long) * (ctx->world + 2)));
+    const float* rows = nullptr;
     if (vecs) {
+        RC_TRY(ensure(ctx, ctx->db, bytes));
         CU_TRY(cudaMemcpyAsync(ctx->db.p, vecs, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        rows = static_cast<const float*>(ctx->db.p);
     } else {
-        if (ctx->buf_rows[GANREV_BUF_ATTRS0] < N || buf_row_bytes(ctx, GANREV_BUF_ATTRS0) != sizeof(float) * static_cast<size_t>(d))
+        // the recovered vectors stay where R left them: the database ALIASES the resident ATTRS0 buffer (no copy);
+        // overwriting ATTRS0 afterwards (forward_R / fix_l2 slot 0, buffer_put) un-sets the database
+        if (ctx->buf_rows[GANREV_BUF_ATTRS0] < N || !ctx->buf[GANREV_BUF_ATTRS0].p || buf_row_bytes(ctx, GANREV_BUF_ATTRS0) != sizeof(float) * static_cast<size_t>(d))
             return fail(ctx, GANREV_ESTATE, "resident ATTRS0 does not hold %lld x %d", (long long)N, d);
-        CU_TRY(cudaMemcpyAsync(ctx->db.p, ctx->buf[GANREV_BUF_ATTRS0].p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        rows = static_cast<const float*>(ctx->buf[GANREV_BUF_ATTRS0].p);
     }
     CU_TRY(cudaMemsetAsync(ctx->maxabs.p, 0, 3 * sizeof(long long), ctx->stream));
-    RC_TRY(vec_prep(ctx, static_cast<const float*>(ctx->db.p), N, d, static_cast<float*>(ctx->rdb.p), nullptr, static_cast<unsigned int*>(ctx->maxabs.p)));
-    ctx->db_n = N; ctx->db_d = d; ctx->assigned = false;
+    RC_TRY(vec_prep(ctx, rows, N, d, static_cast<float*>(ctx->rdb.p), nullptr, static_cast<unsigned int*>(ctx->maxabs.p)));
     unsigned int mb = 0;
+    std::vector<long long> all(ctx->world, 0);
+    if (ctx->world > 1) {
+        // row-shard bookkeeping: global offset = sum of the lower ranks' N; global max|x| (one allgather + one allreduce, no allocation)
+        long long* d_all = static_cast<long long*>(ctx->shard.p);
+        const long long mine = N;
+        CU_TRY(cudaMemcpyAsync(d_all + ctx->world, &mine, sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        NCCL_TRY(ctx->nccl.AllGather(d_all + ctx->world, d_all, 1, ncclInt64, ctx->comm, ctx->stream));
+        NCCL_TRY(ctx->nccl.AllReduce(ctx->maxabs.p, ctx->maxabs.p, 1, ncclUint32, ncclMax, ctx->comm, ctx->stream));
+        CU_TRY(cudaMemcpyAsync(all.data(), d_all, sizeof(long long) * ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CU_TRY(cudaMemcpyAsync(&mb, ctx->maxabs.p, sizeof(mb), cudaMemcpyDeviceToHost, ctx->stream));
     RC_TRY(finish(ctx));
     memcpy(&ctx->db_maxabs, &mb, 4);
     ctx->db_offset = 0; ctx->db_total = N;
     if (ctx->world > 1) {
-        // row-shard bookkeeping: global offset = sum of the lower ranks' N; global max|x|
-        std::vector<long long> all(ctx->world);
-        long long* d_all = nullptr;
-        CU_TRY(cudaMalloc(&d_all, sizeof(long long) * (ctx->world + 1)));
-        long long mine = N;
-        CU_TRY(cudaMemcpyAsync(d_all + ctx->world, &mine, sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-        NCCL_TRY(ctx->nccl.AllGather(d_all + ctx->world, d_all, 1, ncclInt64, ctx->comm, ctx->stream));
-        NCCL_TRY(ctx->nccl.AllReduce(ctx->maxabs.p, ctx->maxabs.p, 1, ncclUint32, ncclMax, ctx->comm, ctx->stream));
-        CU_TRY(cudaMemcpyAsync(all.data(), d_all, sizeof(long long) * ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
-        CU_TRY(cudaMemcpyAsync(&mb, ctx->maxabs.p, sizeof(mb), cudaMemcpyDeviceToHost, ctx->stream));
-        int rc = finish(ctx);
-        cudaFree(d_all);
-        RC_TRY(rc);
-        memcpy(&ctx->db_maxabs, &mb, 4);
-        ctx->db_offset = 0; ctx->db_total = 0;
+        ctx->db_total = 0;
         for (int r = 0; r < ctx->world; ++r) { if (r < ctx->rank) ctx->db_offset += all[r]; ctx->db_total += all[r]; }
         if (ctx->db_total > 0xFFFFFFF0ll) return fail(ctx, GANREV_EINVAL, "global database exceeds 2^32 rows");
     }
+    ctx->db_ptr = rows; ctx->db_alias = vecs == nullptr; ctx->db_n = N; ctx->db_d = d;
     return GANREV_OK;
 }
 
@@ -1161,10 +1243,11 @@ template <int TQ, int E>
 static int launch_search(ganrev_ctx* ctx, const scan::ScanParams& p, int splits) {
     constexpr int QT = 16 * TQ, K2 = 32 * E;
     const size_t smem = sizeof(float) * (scan::DK * scan::XS + scan::DK * QT) + sizeof(unsigned long long) * (QT * K2 + QT * scan::CAP + QT) + sizeof(int) * QT;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static size_t attr_max_dev[kMaxDevices] = {};          // function attributes are per device
+    size_t& attr_max = attr_max_dev[ctx->device];
+    if (smem > attr_max) {
         CU_TRY(cudaFuncSetAttribute(scan::search_kernel<TQ, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        attr_set = true;
+        attr_max = smem;
     }
     dim3 grid(splits, (p.nq + QT - 1) / QT);
     scan::search_kernel<TQ, E><<<grid, scan::kThreads, smem, ctx->stream>>>(p);
@@ -1337,7 +1420,7 @@ static int search_dev(ganrev_ctx* ctx, int Q, int k, int64_t* ids, float* scores
     RC_TRY(vec_prep(ctx, static_cast<const float*>(ctx->q.p), Q, d, static_cast<float*>(ctx->rq.p), nullptr, nullptr));
     if (Q <= 16 && d % 4 == 0) {   // HBM-bound regime: stream the database once
         scan::ScanParams p{};
-        p.db = static_cast<const float*>(ctx->db.p); p.rdb = static_cast<const float*>(ctx->rdb.p); p.n_rows = N; p.d = d;
+        p.db = ctx->db_ptr; p.rdb = static_cast<const float*>(ctx->rdb.p); p.n_rows = N; p.d = d;
         p.q = static_cast<const float*>(ctx->q.p); p.rq = static_cast<const float*>(ctx->rq.p); p.nq = Q; p.k = k;
         scan::StreamParams sp{};
         size_t smem = 0;
@@ -1380,7 +1463,7 @@ static int search_dev(ganrev_ctx* ctx, int Q, int k, int64_t* ids, float* scores
     RC_TRY(ensure(ctx, ctx->ids, sizeof(long long) * static_cast<size_t>(Q) * k));
     RC_TRY(ensure(ctx, ctx->scores, sizeof(float) * static_cast<size_t>(Q) * k));
     scan::ScanParams p{};
-    p.db = static_cast<const float*>(ctx->db.p); p.rdb = static_cast<const float*>(ctx->rdb.p); p.n_rows = N; p.d = d;
+    p.db = ctx->db_ptr; p.rdb = static_cast<const float*>(ctx->rdb.p); p.n_rows = N; p.d = d;
     p.q = static_cast<const float*>(ctx->q.p); p.rq = static_cast<const float*>(ctx->rq.p); p.nq = Q; p.k = k;
     p.partial = static_cast<unsigned long long*>(ctx->partial.p); p.rows_per_split = rows_per_split;
     {
@@ -1397,7 +1480,7 @@ static int search_dev(ganrev_ctx* ctx, int Q, int k, int64_t* ids, float* scores
 extern "C" {
 int ganrev_search_cosine(ganrev_ctx* ctx, const float* queries, int Q, int k, int64_t* ids, float* scores) {
     if (!ctx || !queries || Q < 0 || k < 1 || k > 128 || !ids || !scores) return ctx ? fail(ctx, GANREV_EINVAL, "bad search arguments (k must be 1..128)") : GANREV_EINVAL;
-    if (!ctx->db.p) return fail(ctx, GANREV_ESTATE, "database not set");
+    if (!ctx->db_ptr) return fail(ctx, GANREV_ESTATE, "database not set");
     if (Q == 0) return GANREV_OK;
     CU_TRY(cudaSetDevice(ctx->device));
     RC_TRY(ensure(ctx, ctx->q, sizeof(float) * static_cast<size_t>(Q) * ctx->db_d));
@@ -1407,7 +1490,7 @@ int ganrev_search_cosine(ganrev_ctx* ctx, const float* queries, int Q, int k, in
 
 int ganrev_search_rows(ganrev_ctx* ctx, const int64_t* rows, int Q, int k, int64_t* ids, float* scores) {
     if (!ctx || !rows || Q < 0 || k < 1 || k > 128 || !ids || !scores) return ctx ? fail(ctx, GANREV_EINVAL, "bad search_rows arguments (k must be 1..128)") : GANREV_EINVAL;
-    if (!ctx->db.p) return fail(ctx, GANREV_ESTATE, "database not set");
+    if (!ctx->db_ptr) return fail(ctx, GANREV_ESTATE, "database not set");
     if (Q == 0) return GANREV_OK;
     for (int i = 0; i < Q; ++i)
         if (rows[i] < 0 || rows[i] >= ctx->db_total) return fail(ctx, GANREV_EINVAL, "row id %lld outside the database", (long long)rows[i]);
@@ -1420,7 +1503,7 @@ int ganrev_search_rows(ganrev_ctx* ctx, const int64_t* rows, int Q, int k, int64
         ProfScope ps(ctx, "gather_rows", 0.0, 8.0 * Q * d);
         const long long tot = static_cast<long long>(Q) * d;
         scan::gather_rows_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ctx->stream>>>(
-            static_cast<const float*>(ctx->db.p), ctx->db_n, d, ctx->db_offset, static_cast<const long long*>(ctx->stage_b.p), Q, static_cast<float*>(ctx->q.p));
+            ctx->db_ptr, ctx->db_n, d, ctx->db_offset, static_cast<const long long*>(ctx->stage_b.p), Q, static_cast<float*>(ctx->q.p));
         CU_TRY(cudaGetLastError());
     }
     if (ctx->world > 1)   // exactly one rank holds each row; the others contribute +0.0f (all-zero bits)
@@ -1459,7 +1542,7 @@ static int kmeans_shift_of(float maxabs, int64_t n_total) {
 
 int ganrev_kmeans(ganrev_ctx* ctx, int k, int niter, const float* init_centroids, float* centroids, float* total_counts, int32_t* last_labels) {
     if (!ctx || k < 1 || niter < 0 || !init_centroids || !centroids || !total_counts) return ctx ? fail(ctx, GANREV_EINVAL, "bad kmeans arguments") : GANREV_EINVAL;
-    if (!ctx->db.p) return fail(ctx, GANREV_ESTATE, "database not set");
+    if (!ctx->db_ptr) return fail(ctx, GANREV_ESTATE, "database not set");
     CU_TRY(cudaSetDevice(ctx->device));
     const int d = ctx->db_d;
     const int64_t N = ctx->db_n;
@@ -1480,7 +1563,7 @@ int ganrev_kmeans(ganrev_ctx* ctx, int k, int niter, const float* init_centroids
     CU_TRY(cudaMemsetAsync(ctx->total.p, 0, sizeof(unsigned long long) * k, ctx->stream));
     if (niter == 0) CU_TRY(cudaMemsetAsync(ctx->labels.p, 0xFF, sizeof(int) * static_cast<size_t>(std::max<int64_t>(N, 1)), ctx->stream));
     scan::ScanParams p{};
-    p.db = static_cast<const float*>(ctx->db.p); p.rdb = static_cast<const float*>(ctx->rdb.p); p.n_rows = N; p.d = d;
+    p.db = ctx->db_ptr; p.rdb = static_cast<const float*>(ctx->rdb.p); p.n_rows = N; p.d = d;
     p.q = static_cast<const float*>(ctx->cen.p); p.c2 = static_cast<const float*>(ctx->c2.p); p.rq = nullptr; p.nq = k;
     p.labels = static_cast<int*>(ctx->labels.p); p.acc = d_acc; p.cnt = d_cnt; p.sc = sc;
     p.smem_acc = (kd + k) * sizeof(unsigned long long) <= 96 * 1024 ? 1 : 0;
@@ -1516,7 +1599,7 @@ int ganrev_kmeans(ganrev_ctx* ctx, int k, int niter, const float* init_centroids
 
 int ganrev_assign_cosine_min(ganrev_ctx* ctx, const float* centroids, int k, int32_t* cluster, float* cosv) {
     if (!ctx || !centroids || k < 1) return ctx ? fail(ctx, GANREV_EINVAL, "bad assign arguments") : GANREV_EINVAL;
-    if (!ctx->db.p) return fail(ctx, GANREV_ESTATE, "database not set");
+    if (!ctx->db_ptr) return fail(ctx, GANREV_ESTATE, "database not set");
     CU_TRY(cudaSetDevice(ctx->device));
     const int d = ctx->db_d;
     const int64_t N = ctx->db_n;
@@ -1528,7 +1611,7 @@ int ganrev_assign_cosine_min(ganrev_ctx* ctx, const float* centroids, int k, int
     CU_TRY(cudaMemcpyAsync(ctx->q.p, centroids, sizeof(float) * kd, cudaMemcpyHostToDevice, ctx->stream));
     RC_TRY(vec_prep(ctx, static_cast<const float*>(ctx->q.p), k, d, static_cast<float*>(ctx->rq.p), nullptr, nullptr));
     scan::ScanParams p{};
-    p.db = static_cast<const float*>(ctx->db.p); p.rdb = static_cast<const float*>(ctx->rdb.p); p.n_rows = N; p.d = d;
+    p.db = ctx->db_ptr; p.rdb = static_cast<const float*>(ctx->rdb.p); p.n_rows = N; p.d = d;
     p.q = static_cast<const float*>(ctx->q.p); p.rq = static_cast<const float*>(ctx->rq.p); p.nq = k;
     p.labels = static_cast<int*>(ctx->labels.p); p.cosv = static_cast<float*>(ctx->cosv.p);
     {
@@ -1550,22 +1633,43 @@ int ganrev_assign_cosine_min(ganrev_ctx* ctx, const float* centroids, int k, int
 int ganrev_cluster_members(ganrev_ctx* ctx, int k, int m, const float* images, int px, int64_t* member_ids, int32_t* member_counts, float* mean_images) {
     if (!ctx || k < 1 || m < 1 || m > 128 || !member_ids || !member_counts) return ctx ? fail(ctx, GANREV_EINVAL, "bad cluster_members arguments (m must be 1..128)") : GANREV_EINVAL;
     if (!ctx->assigned || ctx->assigned_k != k) return fail(ctx, GANREV_ESTATE, "call ganrev_assign_cosine_min with k=%d first", k);
-    if (ctx->world > 1) return fail(ctx, GANREV_ESTATE, "cluster_members is single-rank");
     CU_TRY(cudaSetDevice(ctx->device));
     const int64_t N = ctx->db_n;
-    RC_TRY(ensure(ctx, ctx->mids, sizeof(long long) * static_cast<size_t>(k) * m));
+    const bool multi = ctx->world > 1;
+    const size_t km = static_cast<size_t>(k) * m;
+    RC_TRY(ensure(ctx, ctx->mids, sizeof(long long) * km));
     RC_TRY(ensure(ctx, ctx->mcnt, sizeof(int) * k));
+    if (multi) {
+        RC_TRY(ensure(ctx, ctx->keys, sizeof(unsigned long long) * (km + k)));                     // local keys, then the unclipped counts
+        RC_TRY(ensure(ctx, ctx->keys_all, sizeof(unsigned long long) * km * ctx->world));
+        RC_TRY(ensure(ctx, ctx->scores, sizeof(float) * km));
+    }
+    unsigned long long* d_keys = multi ? static_cast<unsigned long long*>(ctx->keys.p) : nullptr;
+    unsigned long long* d_raw = multi ? d_keys + km : nullptr;
     {
         ProfScope ps(ctx, "cluster_members", 0.0, 8.0 * N * k);
-        scan::cluster_members_kernel<<<k, 32, 0, ctx->stream>>>(static_cast<const int*>(ctx->labels.p), static_cast<const float*>(ctx->cosv.p), N, m,
-                                                               static_cast<long long*>(ctx->mids.p), static_cast<int*>(ctx->mcnt.p));
+        scan::cluster_members_kernel<<<k, 32, 0, ctx->stream>>>(static_cast<const int*>(ctx->labels.p), static_cast<const float*>(ctx->cosv.p), N, m, ctx->db_offset,
+                                                               static_cast<long long*>(ctx->mids.p), static_cast<int*>(ctx->mcnt.p), d_keys, d_raw);
+        CU_TRY(cudaGetLastError());
+    }
+    if (multi) {
+        // per-cluster top-m across the row shards = the search merge with Q = k clusters: one allgather of the
+        // local (cos, global id) keys, one allreduce of the member counts
+        NCCL_TRY(ctx->nccl.AllGather(d_keys, ctx->keys_all.p, km, ncclUint64, ctx->comm, ctx->stream));
+        NCCL_TRY(ctx->nccl.AllReduce(d_raw, d_raw, k, ncclUint64, ncclSum, ctx->comm, ctx->stream));
+        ProfScope ps(ctx, "cluster_members_merge", 0.0, 8.0 * ctx->world * km);
+        const unsigned mblocks = static_cast<unsigned>((static_cast<long long>(k) * 32 + scan::kThreads - 1) / scan::kThreads);
+        scan::merge_kernel<4><<<mblocks, scan::kThreads, 0, ctx->stream>>>(static_cast<const unsigned long long*>(ctx->keys_all.p), ctx->world, k, m, 0, 0,
+            static_cast<long long*>(ctx->mids.p), static_cast<float*>(ctx->scores.p), nullptr);
+        scan::cluster_keep_kernel<<<(k + 127) / 128, 128, 0, ctx->stream>>>(d_raw, k, m, static_cast<int*>(ctx->mcnt.p));
+        ctx->launches++;
         CU_TRY(cudaGetLastError());
     }
     if (mean_images) {
         if (px < 1) return fail(ctx, GANREV_EINVAL, "px must be positive");
         const float* d_img = nullptr;
         if (images) {
-            RC_TRY(ensure(ctx, ctx->stage_a, sizeof(float) * static_cast<size_t>(N) * px));
+            RC_TRY(ensure(ctx, ctx->stage_a, sizeof(float) * static_cast<size_t>(std::max<int64_t>(N, 1)) * px));
             CU_TRY(cudaMemcpyAsync(ctx->stage_a.p, images, sizeof(float) * static_cast<size_t>(N) * px, cudaMemcpyHostToDevice, ctx->stream));
             d_img = static_cast<const float*>(ctx->stage_a.p);
         } else {
@@ -1574,14 +1678,34 @@ int ganrev_cluster_members(ganrev_ctx* ctx, int k, int m, const float* images, i
             d_img = static_cast<const float*>(ctx->buf[GANREV_BUF_IMAGES].p);
         }
         RC_TRY(ensure(ctx, ctx->mmean, sizeof(float) * static_cast<size_t>(k) * px));
-        ProfScope ps(ctx, "cluster_mean", 1.0 * k * m * px, 4.0 * k * m * px);
-        dim3 grid((px + 255) / 256, k);
-        scan::cluster_mean_kernel<<<grid, 256, 0, ctx->stream>>>(d_img, px, static_cast<const long long*>(ctx->mids.p), static_cast<const int*>(ctx->mcnt.p), m,
-                                                                static_cast<float*>(ctx->mmean.p));
-        CU_TRY(cudaGetLastError());
+        if (!multi) {
+            ProfScope ps(ctx, "cluster_mean", 1.0 * k * m * px, 4.0 * k * m * px);
+            dim3 grid((px + 255) / 256, k);
+            scan::cluster_mean_kernel<<<grid, 256, 0, ctx->stream>>>(d_img, px, static_cast<const long long*>(ctx->mids.p), static_cast<const int*>(ctx->mcnt.p), m,
+                                                                    static_cast<float*>(ctx->mmean.p));
+            CU_TRY(cudaGetLastError());
+        } else {
+            // the kept images live on whichever rank owns their rows: stage them (a bounded number of clusters at a time),
+            // assemble with one integer max-allreduce (every slot has one owner, the others hold zero bits), average in member order
+            const int jstep = static_cast<int>(std::max<size_t>(1, std::min<size_t>(k, (size_t(64) << 20) / (static_cast<size_t>(m) * px * 4))));
+            RC_TRY(ensure(ctx, ctx->stage_b, sizeof(float) * static_cast<size_t>(jstep) * m * px));
+            for (int j0 = 0; j0 < k; j0 += jstep) {
+                const int nj = std::min(jstep, k - j0);
+                const long long tot = static_cast<long long>(nj) * m * px;
+                ProfScope ps(ctx, "cluster_mean", 1.0 * nj * m * px, 8.0 * nj * m * px);
+                scan::cluster_stage_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ctx->stream>>>(d_img, N, ctx->db_offset, px,
+                    static_cast<const long long*>(ctx->mids.p), m, j0, nj, static_cast<float*>(ctx->stage_b.p));
+                NCCL_TRY(ctx->nccl.AllReduce(ctx->stage_b.p, ctx->stage_b.p, static_cast<size_t>(tot), ncclUint32, ncclMax, ctx->comm, ctx->stream));
+                dim3 grid((px + 255) / 256, nj);
+                scan::cluster_mean_staged_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const float*>(ctx->stage_b.p), px, static_cast<const int*>(ctx->mcnt.p), m, j0,
+                                                                               static_cast<float*>(ctx->mmean.p));
+                ctx->launches++;
+                CU_TRY(cudaGetLastError());
+            }
+        }
         CU_TRY(cudaMemcpyAsync(mean_images, ctx->mmean.p, sizeof(float) * static_cast<size_t>(k) * px, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    CU_TRY(cudaMemcpyAsync(member_ids, ctx->mids.p, sizeof(long long) * static_cast<size_t>(k) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(member_ids, ctx->mids.p, sizeof(long long) * km, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(cudaMemcpyAsync(member_counts, ctx->mcnt.p, sizeof(int) * k, cudaMemcpyDeviceToHost, ctx->stream));
     return finish(ctx);
 }
@@ -1640,7 +1764,7 @@ int ganrev_debug_trace_read(ganrev_ctx* ctx, int64_t* out) {
 int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return GANREV_EINVAL;
     if (!strcmp(name, "chunk")) {
-        if (value < 1 || value > (1 << 20)) return fail(ctx, GANREV_EINVAL, "chunk out of range");
+        if (value < 0 || value > (1 << 20)) return fail(ctx, GANREV_EINVAL, "chunk out of range");   // 0 = automatic
         ctx->chunk = value;
         return GANREV_OK;
     }

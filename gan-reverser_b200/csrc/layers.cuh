@@ -260,9 +260,10 @@ nearest_l2_kernel(const float* __restrict__ q, int Q, int q0, const float* __res
     }
 }
 
-// one warp per query of the pass: min over the per-warp records by (distance, row)
+// one warp per query of the pass: min over the per-warp records by (distance, row).  quirk = 1 applies the reference's
+// "row 0 is taken unconditionally" rule here (single rank); quirk = 0 leaves it to nearest_l2_ranks_kernel.
 __global__ void nearest_l2_merge_kernel(const NearestRec* __restrict__ partial, long long n_warps, int Q, int q0, long long N,
-                                        const unsigned char* __restrict__ row0_nan, long long* __restrict__ ids, double* __restrict__ dist) {
+                                        const unsigned char* __restrict__ row0_nan, int quirk, long long* __restrict__ ids, double* __restrict__ dist) {
     const int v = blockIdx.x, lane = threadIdx.x;
     if (q0 + v >= Q) return;
     double bd = 0.0;
@@ -278,7 +279,7 @@ __global__ void nearest_l2_merge_kernel(const NearestRec* __restrict__ partial, 
         if (oi >= 0 && (bi < 0 || od < bd || (od == bd && oi < bi))) { bd = od; bi = oi; }
     }
     if (lane == 0) {
-        if (N > 0 && (row0_nan[q0 + v] || bi < 0)) {      // row 0 was NaN (it sticks), or every distance was NaN (row 0 again)
+        if (quirk && N > 0 && (row0_nan[q0 + v] || bi < 0)) {      // row 0 was NaN (it sticks), or every distance was NaN (row 0 again)
             ids[q0 + v] = 0;
             dist[q0 + v] = __longlong_as_double(0x7ff8000000000000ll);
         } else {
@@ -286,6 +287,32 @@ __global__ void nearest_l2_merge_kernel(const NearestRec* __restrict__ partial, 
             dist[q0 + v] = bi < 0 ? __longlong_as_double(0x7ff0000000000000ll) : bd;   // empty set: -1, +inf
         }
     }
+}
+// Row-sharded set: rec[r][q] = {distance, global row or -1, row0-was-NaN flag of the rank that owns global row 0}; every rank
+// merges the allgathered records identically.
+struct NearestRankRec { double d; long long id; long long row0_nan; long long pad; };
+__global__ void nearest_l2_pack_kernel(const long long* __restrict__ ids, const double* __restrict__ dist, const unsigned char* __restrict__ row0_nan,
+                                       int Q, long long offset, int owns_row0, NearestRankRec* __restrict__ out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    NearestRankRec r;
+    r.d = dist[q]; r.id = ids[q] < 0 ? -1 : ids[q] + offset; r.row0_nan = owns_row0 ? row0_nan[q] : 0; r.pad = 0;
+    out[q] = r;
+}
+__global__ void nearest_l2_ranks_kernel(const NearestRankRec* __restrict__ all, int world, int Q, long long n_total,
+                                        long long* __restrict__ ids, double* __restrict__ dist) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    double bd = 0.0;
+    long long bi = -1;
+    bool stick = false;
+    for (int r = 0; r < world; ++r) {
+        const NearestRankRec c = all[static_cast<long long>(r) * Q + q];
+        stick |= c.row0_nan != 0;
+        if (c.id >= 0 && (bi < 0 || c.d < bd || (c.d == bd && c.id < bi))) { bd = c.d; bi = c.id; }
+    }
+    if (n_total > 0 && (stick || bi < 0)) { ids[q] = 0; dist[q] = __longlong_as_double(0x7ff8000000000000ll); }
+    else { ids[q] = bi; dist[q] = bi < 0 ? __longlong_as_double(0x7ff0000000000000ll) : bd; }
 }
 
 // ------------------------------------------------------------------ quantile threshold + flags
@@ -297,38 +324,52 @@ __device__ __forceinline__ double f64_unkey(unsigned long long k) {
     const unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
     return __longlong_as_double(static_cast<long long>(b));
 }
-// Single-block MSB radix select of the rank-th smallest (0-based) of sims = 1 - l2.
-__global__ void __launch_bounds__(1024)
-quantile_select_kernel(const double* __restrict__ l2, long long n, long long rank, double* __restrict__ thr_out) {
-    __shared__ unsigned int hist[256];
-    __shared__ unsigned long long s_prefix;
-    __shared__ long long s_rank;
-    if (threadIdx.x == 0) { s_prefix = 0ull; s_rank = rank; }
-    __syncthreads();
-    for (int pass = 0; pass < 8; ++pass) {
-        const int shift = 56 - 8 * pass;
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
-        __syncthreads();
-        const unsigned long long prefix = s_prefix;
-        const unsigned long long himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
-        for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-            const unsigned long long k = f64_key(1.0 - l2[i]);
-            if ((k & himask) == prefix) atomicAdd(&hist[(k >> shift) & 0xFF], 1u);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            long long r = s_rank;
-            int bin = 0;
-            for (; bin < 256; ++bin) {
-                if (r < static_cast<long long>(hist[bin])) break;
-                r -= hist[bin];
-            }
-            s_rank = r;
-            s_prefix = prefix | (static_cast<unsigned long long>(bin) << shift);
-        }
-        __syncthreads();
+// MSB radix select of the rank-th smallest (0-based) of sims = 1 - l2, 8 bits per pass, any number of blocks and
+// (with one 256-bin integer allreduce per pass between the two kernels) any number of ranks: every rank sees the same
+// global histogram, so every rank walks the same prefix.  state = {prefix, rank, n_total}, hist = 256 bins (uint64).
+__global__ void quantile_init_kernel(unsigned long long* __restrict__ state, unsigned long long* __restrict__ hist, long long rank_or_neg,
+                                     double quantile) {
+    hist[threadIdx.x] = 0ull;
+    if (threadIdx.x == 0) {
+        state[0] = 0ull;
+        // multi-rank: state[2] holds the allreduced n_calc; rank = floor(n_total * quantile) - 1 (apply_r.lua:371, 1-based index)
+        state[1] = rank_or_neg >= 0 ? static_cast<unsigned long long>(rank_or_neg)
+                                    : static_cast<unsigned long long>(static_cast<long long>(floor(static_cast<double>(static_cast<long long>(state[2])) * quantile)) - 1);
     }
-    if (threadIdx.x == 0) *thr_out = f64_unkey(s_prefix);
+}
+__global__ void __launch_bounds__(256)
+quantile_hist_kernel(const double* __restrict__ l2, long long n, const unsigned long long* __restrict__ state, int pass,
+                     unsigned long long* __restrict__ hist) {
+    __shared__ unsigned int sh[256];
+    sh[threadIdx.x] = 0u;
+    __syncthreads();
+    const int shift = 56 - 8 * pass;
+    const unsigned long long prefix = state[0];
+    const unsigned long long himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const unsigned long long k = f64_key(1.0 - l2[i]);
+        if ((k & himask) == prefix) atomicAdd(&sh[(k >> shift) & 0xFF], 1u);
+    }
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], static_cast<unsigned long long>(sh[threadIdx.x]));
+}
+__global__ void quantile_pick_kernel(unsigned long long* __restrict__ state, unsigned long long* __restrict__ hist, int pass,
+                                     double* __restrict__ thr_out) {
+    __shared__ unsigned long long h[256];
+    h[threadIdx.x] = hist[threadIdx.x];
+    hist[threadIdx.x] = 0ull;                                  // ready for the next pass
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long r = state[1];
+        int bin = 0;
+        for (; bin < 255; ++bin) {
+            if (r < h[bin]) break;
+            r -= h[bin];
+        }
+        state[1] = r;
+        state[0] |= static_cast<unsigned long long>(bin) << (56 - 8 * pass);
+        if (pass == 7) *thr_out = f64_unkey(state[0]);
+    }
 }
 __global__ void anomaly_flags_kernel(const double* __restrict__ l2, long long n_show, const double* __restrict__ thr, uint8_t* __restrict__ flags) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;

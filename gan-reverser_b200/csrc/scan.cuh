@@ -1308,16 +1308,18 @@ __global__ void cosine_pair_kernel(const float* __restrict__ a, const float* __r
 
 // ------------------------------------------------------------------ cluster members + mean image
 // One warp per cluster scans all rows; keeps the best m by (cos desc, id asc).  K2 = 128.
+// keys_out (row-sharded database): the kept keys re-based to global ids, for the allgather + merge_kernel; raw_counts: unclipped.
 __global__ void __launch_bounds__(32)
-cluster_members_kernel(const int* __restrict__ cluster, const float* __restrict__ cosv, long long n, int m,
-                       long long* __restrict__ member_ids, int* __restrict__ member_counts) {
+cluster_members_kernel(const int* __restrict__ cluster, const float* __restrict__ cosv, long long n, int m, long long id_offset,
+                       long long* __restrict__ member_ids, int* __restrict__ member_counts,
+                       unsigned long long* __restrict__ keys_out, unsigned long long* __restrict__ raw_counts) {
     constexpr int E = 4;
     const int j = blockIdx.x, lane = threadIdx.x;
     unsigned long long L[E];
 #pragma unroll
     for (int t = 0; t < E; ++t) L[t] = 0ull;
     unsigned long long kth = 0ull;
-    int count = 0;
+    long long count = 0;
     for (long long base = 0; base < n; base += 32) {
         const long long i = base + lane;
         unsigned long long c = 0ull;
@@ -1334,17 +1336,28 @@ cluster_members_kernel(const int* __restrict__ cluster, const float* __restrict_
             }
         }
     }
-    const int keep = min(count, m);
-    if (lane == 0) member_counts[j] = keep;
+    const int keep = static_cast<int>(min(count, static_cast<long long>(m)));
+    if (lane == 0) {
+        member_counts[j] = keep;
+        if (raw_counts) raw_counts[j] = static_cast<unsigned long long>(count);
+    }
 #pragma unroll
     for (int t = 0; t < E; ++t) {
         const int r = lane * E + t;
         if (r < m) {
             const unsigned long long key = L[t];
-            member_ids[static_cast<long long>(j) * m + r] =
-                (r < keep) ? static_cast<long long>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull)) : -1;
+            const uint32_t lid = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
+            member_ids[static_cast<long long>(j) * m + r] = (r < keep) ? id_offset + static_cast<long long>(lid) : -1;
+            if (keys_out)
+                keys_out[static_cast<long long>(j) * m + r] =
+                    (r < keep) ? ((key & 0xFFFFFFFF00000000ull) | static_cast<unsigned long long>(0xFFFFFFFFu - (static_cast<uint32_t>(id_offset) + lid))) : 0ull;
         }
     }
+}
+// keep = min(global count, m) after the count allreduce
+__global__ void cluster_keep_kernel(const unsigned long long* __restrict__ raw_counts, int k, int m, int* __restrict__ member_counts) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < k) member_counts[j] = static_cast<int>(min(raw_counts[j], static_cast<unsigned long long>(m)));
 }
 // face = zeros; face:add(img) in member order; face:div(count)   (apply_r.lua:236-242)
 __global__ void cluster_mean_kernel(const float* __restrict__ images, int px, const long long* __restrict__ member_ids,
@@ -1356,6 +1369,29 @@ __global__ void cluster_mean_kernel(const float* __restrict__ images, int px, co
     float s = 0.0f;
     for (int r = 0; r < keep; ++r) s = __fadd_rn(s, images[member_ids[static_cast<long long>(j) * m + r] * px + pidx]);
     mean[static_cast<long long>(j) * px + pidx] = __fdiv_rn(s, static_cast<float>(keep));
+}
+// Row-sharded images: each rank copies the member images it owns into staged[(j - j0)*m + r][px] (zero bits elsewhere; one
+// integer max-allreduce assembles them exactly), then every rank averages the staged rows in member order.
+__global__ void cluster_stage_kernel(const float* __restrict__ images, long long n_local, long long id_offset, int px,
+                                     const long long* __restrict__ member_ids, int m, int j0, int nj, float* __restrict__ staged) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(nj) * m * px;
+    if (idx >= total) return;
+    const long long slot = idx / px;
+    const int pidx = static_cast<int>(idx - slot * px);
+    const long long gid = member_ids[static_cast<long long>(j0) * m + slot];
+    const long long lid = gid - id_offset;
+    staged[idx] = (gid >= 0 && lid >= 0 && lid < n_local) ? images[lid * px + pidx] : 0.0f;
+}
+__global__ void cluster_mean_staged_kernel(const float* __restrict__ staged, int px, const int* __restrict__ member_counts, int m, int j0,
+                                           float* __restrict__ mean) {
+    const int jj = blockIdx.y;
+    const int pidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pidx >= px) return;
+    const int keep = member_counts[j0 + jj];
+    float s = 0.0f;
+    for (int r = 0; r < keep; ++r) s = __fadd_rn(s, staged[(static_cast<long long>(jj) * m + r) * px + pidx]);
+    mean[static_cast<long long>(j0 + jj) * px + pidx] = __fdiv_rn(s, static_cast<float>(keep));
 }
 
 }  // namespace scan

@@ -32,3 +32,33 @@ def init_comm(ctx):
     uid = ctx.comm_unique_id() if rank == 0 else None
     uid = broadcast_bytes(uid, src=0)
     ctx.comm_init(world, rank, uid)
+
+
+def file_unique_id(ctx, world, rank, path, timeout_s=120.0):
+    """The NCCL unique-id hand-off without torch.distributed (what `lua/ganrev.lua` comm_init_file does for one
+    `th apply_r.lua` per GPU): rank 0 writes the id to `path + '.tmp'` and renames it (atomic), the others poll."""
+    import time
+    if rank == 0:
+        uid = ctx.comm_unique_id()
+        with open(path + ".tmp", "wb") as f:
+            f.write(uid)
+        os.replace(path + ".tmp", path)
+        return uid
+    t0 = time.time()
+    while True:
+        try:
+            with open(path, "rb") as f:
+                uid = f.read()
+            if uid:
+                return uid
+        except FileNotFoundError:
+            pass
+        if time.time() - t0 > timeout_s:
+            raise TimeoutError(f"no NCCL unique id at {path}")
+        time.sleep(0.02)
+
+
+def init_comm_file(ctx, world, rank, path, timeout_s=120.0):
+    if world == 1:
+        return
+    ctx.comm_init(world, rank, file_unique_id(ctx, world, rank, path, timeout_s))

@@ -17,6 +17,7 @@ local ffi = require 'ffi'
 require 'torch'
 
 ffi.cdef[[
+int usleep(unsigned int usec);
 typedef struct ganrev_ctx ganrev_ctx;
 int         ganrev_version(void);
 int         ganrev_create(ganrev_ctx** out, int device);
@@ -69,6 +70,31 @@ end
 function M.comm_init(ctx, world, rank, id)
     check(ctx, lib.ganrev_comm_init(ctx, world, rank, id, #id))
 end
+-- The hand-off as code: one `th apply_r.lua` process per GPU (RANK / WORLD_SIZE in the environment), a path on
+-- a file system all of them see.  Rank 0 writes the id to `path .. '.tmp'` and renames it (atomic on POSIX), the
+-- others poll for `path`; every rank then joins the communicator.  gan-reverser_b200/dist.py has the same protocol.
+function M.comm_init_file(ctx, world, rank, path, timeout_s)
+    if world == 1 then return end
+    local id
+    if rank == 0 then
+        id = M.unique_id(ctx)
+        local f = assert(io.open(path .. '.tmp', 'wb'))
+        f:write(id); f:close()
+        assert(os.rename(path .. '.tmp', path))
+    else
+        local t0 = os.time()
+        while true do
+            local f = io.open(path, 'rb')
+            if f then
+                id = f:read('*a'); f:close()
+                if #id > 0 then break end
+            end
+            if os.time() - t0 > (timeout_s or 120) then error('no NCCL unique id at ' .. path) end
+            ffi.C.usleep(20000)
+        end
+    end
+    M.comm_init(ctx, world, rank, id)
+end
 
 -- Flatten a trained nn.Sequential into the weight blob of include/ganrev.h: every Linear /
 -- (cudnn.)SpatialConvolution as weight then bias, every (Spatial)BatchNormalization as
@@ -92,10 +118,56 @@ function M.flatten(model)
     return blob
 end
 
--- MODELS.create_G(dimensions, noiseDim, cuda) replacement: object with the nn.Module protocol
--- apply_r.lua uses (:forward, :evaluate, :training, :float).
+-- Weight blobs without nn / cudnn -----------------------------------------------------------
+-- Layout of include/ganrev.h ("Weight blob"), as {kind, n_out, fan_in} records in models.lua module order.
+local function g_layout(C, H, W, nd)
+    local F = 512 * (H / 4) * (W / 4)
+    return {{'w', F, nd}, {'bn', F}, {'w', 256, 512 * 9}, {'bn', 256}, {'w', 128, 256 * 9}, {'bn', 128}, {'w', C, 128 * 9}}
+end
+local function r_layout(C, H, W, nd)
+    local F = 128 * (H / 4) * (W / 4)
+    return {{'w', 64, C * 9}, {'bn', 64}, {'w', 64, 64 * 9}, {'bn', 64}, {'w', 64, 64 * 9}, {'bn', 64}, {'w', 128, 64 * 9}, {'bn', 128},
+            {'w', 128, 128 * 9}, {'bn', 128}, {'w', 128, 128 * 9}, {'bn', 128}, {'w', 512, F}, {'bn', 512}, {'w', nd, 512}}
+end
+-- Random init = what models.lua + w_init(net, 'heuristic') leave behind (weight-init.lua:14-16, 52-73): weights
+-- U(+-1/sqrt(fan_in)), every bias (BN beta included) zero, BN gamma U(0,1), running mean 0 / var 1.  Drawn from
+-- torch's global generator, so torch.manualSeed(OPT.seed) (apply_r.lua:35) makes it reproducible.
+local function init_blob(layout)
+    local n = 0
+    for _, l in ipairs(layout) do n = n + (l[1] == 'w' and l[2] * l[3] + l[2] or 4 * l[2]) end
+    local blob, o = torch.FloatTensor(n):zero(), 1
+    for _, l in ipairs(layout) do
+        if l[1] == 'w' then
+            local bound = 1 / math.sqrt(l[3])
+            blob:narrow(1, o, l[2] * l[3]):uniform(-bound, bound); o = o + l[2] * l[3] + l[2]      -- bias stays zero
+        else
+            blob:narrow(1, o, l[2]):uniform(0, 1)                                                -- gamma
+            blob:narrow(1, o + 3 * l[2], l[2]):fill(1); o = o + 4 * l[2]                          -- running_var
+        end
+    end
+    return blob
+end
+function M.init_blob_G(dimensions, noiseDim) return init_blob(g_layout(dimensions[1], dimensions[2], dimensions[3], noiseDim)) end
+function M.init_blob_R(dimensions, noiseDim) return init_blob(r_layout(dimensions[1], dimensions[2], dimensions[3], noiseDim)) end
+-- A trained checkpoint converted offline by `python tools/net2blob.py logs/adversarial.net` (Torch7 .net -> raw float32
+-- blob + a .json with the geometry): the Lua process then needs neither nn nor cudnn to deserialise it.
+function M.read_blob(path)
+    return torch.FloatTensor(torch.FloatStorage(path))
+end
+
+-- MODELS.create_G(dimensions, noiseDim, cuda)   models.lua:201-203: random-init G3 living in the library
+function M.create_G(ctx, dimensions, noiseDim, blob)
+    return M.wrap_G(ctx, blob or M.init_blob_G(dimensions, noiseDim), dimensions, noiseDim)
+end
+-- MODELS.create_R(dimensions, noiseDim, noiseMethod, fixer, cuda)   models.lua:385-387
+function M.create_R(ctx, dimensions, noiseDim, noiseMethod, fixer, blob)
+    return M.wrap_R(ctx, blob or M.init_blob_R(dimensions, noiseDim), fixer and 1 or 0, dimensions, noiseDim, noiseMethod, fixer)
+end
+
+-- Object with the nn.Module protocol apply_r.lua uses (:forward, :evaluate, :training, :float) over a trained
+-- nn.Sequential (flattened here) or a ready weight blob (a torch.FloatTensor).
 function M.wrap_G(ctx, model, dimensions, noiseDim)
-    local blob = M.flatten(model)
+    local blob = torch.isTensor(model) and model:float():contiguous() or M.flatten(model)
     check(ctx, lib.ganrev_load_G(ctx, dimensions[1], dimensions[2], dimensions[3], noiseDim, blob:data(), blob:nElement()))
     local G = {ctx = ctx, dimensions = dimensions, noiseDim = noiseDim}
     function G:forward(noise)                                  -- utils/nn_utils.lua:5-33 batches; the library chunks internally
@@ -119,7 +191,7 @@ end
 -- here with torch.bernoulli and passed down as an explicit mask (x*mask, no rescale).
 function M.wrap_R(ctx, model, slot, dimensions, noiseDim, noiseMethod, fixer)
     assert(noiseMethod == 'normal' or noiseMethod == 'uniform')          -- models.lua:390
-    local blob = M.flatten(model)
+    local blob = torch.isTensor(model) and model:float():contiguous() or M.flatten(model)
     check(ctx, lib.ganrev_load_R(ctx, slot, dimensions[1], dimensions[2], dimensions[3], noiseDim,
                                  noiseMethod ~= 'normal' and 1 or 0, blob:data(), blob:nElement()))
     local R = {ctx = ctx, slot = slot, fixer = fixer, noiseDim = noiseDim}

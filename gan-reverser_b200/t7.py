@@ -113,7 +113,12 @@ class Reader:
             return self.int32() == 1
         if t == TYPE_STRING:
             return self.string()
-        if t in (TYPE_TABLE, TYPE_TORCH, TYPE_FUNCTION, TYPE_LEGACY_RECUR_FUNCTION, TYPE_RECUR_FUNCTION):
+        if t == TYPE_FUNCTION:
+            # legacy function record (torch7 File.lua readObject): NO object index and no memoisation --
+            # int32 size, the dumped chunk, then the upvalues object
+            dumped = bytes(self._take(self.int32()))
+            return LuaFunction(dumped, self.obj())
+        if t in (TYPE_TABLE, TYPE_TORCH, TYPE_LEGACY_RECUR_FUNCTION, TYPE_RECUR_FUNCTION):
             index = self.int32()
             if index in self.memo:
                 return self.memo[index]

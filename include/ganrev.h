@@ -31,6 +31,11 @@
  *                           Conv 256->128, BN, Conv 128->C.
  *   R (models.lua:409-451): 6 x (Conv, BN) with channels C->64->64->64->128->128->128,
  *                           Linear(128*H/4*W/4 -> 512), BN, Linear(512 -> nd).
+ *
+ * One geometry per context: G, R and R_fixer of apply_r.lua share {C, H, W, noiseDim}
+ * (apply_r.lua:65-79) and the resident buffers are sized by it.  Loading a model with a
+ * DIFFERENT geometry unloads the models of the old geometry and empties every resident
+ * buffer, so nothing sized for the old geometry can be read or written afterwards.
  */
 #ifndef GANREV_H
 #define GANREV_H
@@ -104,11 +109,15 @@ int ganrev_l2(ganrev_ctx* ctx, const float* a, const float* b, int64_t N, int px
 /* SURVEY 8(f) rank 3 -- findClosestNeighboursOf   sample.lua:128-148: for each of Q query images [Q x px] the
  * row of `set` [N x px] (NULL = the first N resident IMAGES) with the smallest torch.dist, first strict minimum
  * in row order (row 0 is always taken first, so a NaN there sticks, as in the Lua loop).  ids [Q] 0-based
- * (-1 when N == 0), dist [Q] (+inf when N == 0).  Single-rank. */
+ * (-1 when N == 0), dist [Q] (+inf when N == 0).  After ganrev_comm_init each rank passes ITS row shard of the set
+ * (shards in rank order); ids are then global rows and every rank returns the same answer (one allgather of Q records). */
 int ganrev_nearest_l2(ganrev_ctx* ctx, const float* queries, int Q, const float* set, int64_t N, int px,
                       int64_t* ids, double* dist);
 /* apply_r.lua:370-378: sims = 1 - l2; thr = ascending sims[floor(n_calc*quantile)] (1-based);
- * flags[i] = sims[i] <= thr, i < n_show.  thr may be NULL. */
+ * flags[i] = sims[i] <= thr, i < n_show.  thr may be NULL.  l2 == NULL reuses the distances the last ganrev_fix_l2 /
+ * ganrev_l2 call left on the device (GANREV_ESTATE if it left fewer than n_calc).  After ganrev_comm_init l2 / n_calc /
+ * n_show describe this rank's shard (n_calc may be 0): the order statistic is taken over all ranks' n_calc values by a
+ * device radix select with one 256-bin allreduce per pass; flags are this rank's first n_show. */
 int ganrev_anomaly_flags(ganrev_ctx* ctx, const double* l2, int64_t n_calc, int64_t n_show,
                          double quantile, uint8_t* flags, double* thr);
 
@@ -117,7 +126,9 @@ int ganrev_buffer_put(ganrev_ctx* ctx, int which, const void* host, int64_t rows
 int ganrev_buffer_get(ganrev_ctx* ctx, int which, void* host, int64_t row0, int64_t rows);
 
 /* ---- recovered-vector database --------------------------------------------------
- * vecs [N x d] (NULL = copy the resident ATTRS0 rows) becomes this rank's row shard. */
+ * vecs [N x d] becomes this rank's row shard.  vecs == NULL: the first N resident ATTRS0 rows ARE the shard -- the
+ * database aliases that buffer (the recovered vectors stay where R left them, no copy); overwriting ATTRS0 afterwards
+ * (ganrev_forward_R / ganrev_fix_l2 with slot 0, ganrev_buffer_put) un-sets the database. */
 int ganrev_db_set(ganrev_ctx* ctx, const float* vecs, int64_t N, int d);
 /* cosineSimilarity(v1, v2)   apply_r.lua:396-400 (nn.CosineDistance). */
 int ganrev_cosine(ganrev_ctx* ctx, const float* a, const float* b, int d, float* out);
@@ -143,7 +154,9 @@ int ganrev_assign_cosine_min(ganrev_ctx* ctx, const float* centroids, int k,
 /* apply_r.lua:222-243: per cluster keep <= m members by (cos desc, id asc) and average
  * their images (images NULL = resident IMAGES; px = C*H*W).  member_ids [k x m] (-1
  * padded), member_counts [k], mean_images [k x px] (NULL to skip).  m <= 128.
- * Uses the result of the last ganrev_assign_cosine_min.  Single-rank only. */
+ * Uses the result of the last ganrev_assign_cosine_min.  After ganrev_comm_init the database and `images` are this rank's
+ * row shards: member ids are global rows, merged like the search (one allgather of k*m keys, one allreduce of k counts);
+ * the kept images are assembled across ranks with an integer allreduce and every rank returns the same lists and means. */
 int ganrev_cluster_members(ganrev_ctx* ctx, int k, int m, const float* images, int px,
                            int64_t* member_ids, int32_t* member_counts, float* mean_images);
 
@@ -161,7 +174,7 @@ int ganrev_profile_get(ganrev_ctx* ctx, int idx, const char** name, uint64_t* la
 int ganrev_debug_trace_arm(ganrev_ctx* ctx, const char* layer);
 int ganrev_debug_trace_read(ganrev_ctx* ctx, int64_t* out);
 /* Tuning / debugging knobs (exact outputs are unaffected; conv_impl 1 differs within the conv tolerance; dbg invalidates results):
- *   "chunk"     images per pipeline chunk; default = 8192 32x32 faces' worth of pixels
+ *   "chunk"     images per pipeline chunk; 0 = default = 8192 32x32 faces' worth of pixels
  *   "conv_impl" 0 = tcgen05 implicit GEMM (default), 1 = plain CUDA-core kernels kept for on-device A/B checks
  *   "cta_pairs" bit mask of the conv layers that run as tcgen05 cta_group::2 CTA pairs (default all; read at ganrev_load_*)
  *   "tma_store" 1 = TMA bulk tensor stores in the conv epilogue of the plain layers (default), 2 = also the pooled layers, 0 = st.global everywhere

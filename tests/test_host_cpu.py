@@ -152,3 +152,23 @@ def test_integration_doc_lists_every_entry_point():
     names = set(re.findall(r"\b(ganrev_[a-z0-9_A-Z]+)\s*\(", hdr))
     missing = sorted(n for n in names if n not in doc)
     assert not missing, f"INTEGRATION.md does not mention {missing}"
+
+
+def test_file_unique_id_handoff(pkg, tmp_path):
+    """The NCCL unique-id hand-off without torch.distributed (mirrored by lua/ganrev.lua
+    comm_init_file): rank 0 publishes the id atomically, later ranks poll for it, a missing file times out."""
+    import threading
+
+    class FakeCtx:
+        def comm_unique_id(self):
+            return bytes(range(128))
+
+    path = str(tmp_path / "uid")
+    got = {}
+    t = threading.Thread(target=lambda: got.setdefault("r1", pkg.dist.file_unique_id(None, 2, 1, path, timeout_s=10)))
+    t.start()
+    assert pkg.dist.file_unique_id(FakeCtx(), 2, 0, path) == bytes(range(128))
+    t.join()
+    assert got["r1"] == bytes(range(128)) and not os.path.exists(path + ".tmp")
+    with pytest.raises(TimeoutError):
+        pkg.dist.file_unique_id(None, 2, 1, str(tmp_path / "never"), timeout_s=0.1)

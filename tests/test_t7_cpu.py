@@ -36,6 +36,30 @@ def test_known_answer_bytes(t7):
         t7.loads(i32(99))                                     # unknown tag
 
 
+def test_function_records_known_answer(t7):
+    """Serialized Lua functions (a fixer checkpoint holds one: models.lua:404 sets drop.evaluate = function() end).
+    Bytes assembled by hand from torch7 File.lua's readObject, not from the test writer: tag 6 (TYPE_FUNCTION, legacy)
+    is int32 size + dumped chunk + upvalues object with NO object index; tag 8 (TYPE_RECUR_FUNCTION) and 7 (its legacy
+    twin) carry an index first and are memoised like tables."""
+    i32 = lambda v: struct.pack("<i", v)
+    chunk = b"\x1bLJ\x02\x00dummy"
+    upv = i32(3) + i32(5) + i32(0)                              # upvalues: empty table with object index 5
+    f6 = t7.loads(i32(6) + i32(len(chunk)) + chunk + upv)
+    assert f6.dumped == chunk and f6.upvalues == {}
+    for tag in (8, 7):
+        f = t7.loads(i32(tag) + i32(2) + i32(len(chunk)) + chunk + upv)
+        assert f.dumped == chunk and f.upvalues == {}
+    # {f = <tag-8 function, index 2>, g = <the same function by index>, h = <tag-6 function>, n = 4}
+    s = lambda x: i32(2) + i32(len(x)) + x
+    tbl = (i32(3) + i32(1) + i32(4)
+           + s(b"f") + i32(8) + i32(2) + i32(len(chunk)) + chunk + i32(3) + i32(3) + i32(0)
+           + s(b"g") + i32(8) + i32(2)
+           + s(b"h") + i32(6) + i32(len(chunk)) + chunk + i32(0)
+           + s(b"n") + i32(1) + struct.pack("<d", 4.0))
+    out = t7.loads(tbl)
+    assert out["f"] is out["g"] and out["f"].upvalues == {} and out["h"].upvalues is None and out["n"] == 4
+
+
 @pytest.mark.parametrize("kw", [{}, {"legacy": True}, {"long_size": 4}, {"cuda": True}])
 def test_round_trip_structures(t7, kw):
     rng = np.random.default_rng(0)
