@@ -55,6 +55,8 @@ _SIGS = {
     "ganrev_profile_get": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.POINTER(C.c_double),
                                 C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ganrev_set_option": (_i, [_vp, C.c_char_p, _i64]),
+    "ganrev_debug_db_synthetic": (_i, [_vp, _i64, _i, C.c_uint64, _i64]),
+    "ganrev_debug_fma_peak": (_i, [_vp, C.POINTER(C.c_double)]),
     "ganrev_debug_trace_arm": (_i, [_vp, C.c_char_p]),
     "ganrev_debug_trace_read": (_i, [_vp, _vp]),
 }
@@ -237,6 +239,16 @@ class Context:
             N, d = vecs.shape
         self._chk(lib().ganrev_db_set(self._h, _ptr(vecs), N, d))
         self.db_shape = (N, d)
+
+    def db_synthetic(self, N, d, seed=8, global_row0=0):
+        """bench.py: N(0,1) rows generated on the device and adopted as the database."""
+        self._chk(lib().ganrev_debug_db_synthetic(self._h, int(N), int(d), int(seed), int(global_row0)))
+        self.db_shape = (int(N), int(d))
+
+    def fma_peak(self):
+        out = C.c_double(0.0)
+        self._chk(lib().ganrev_debug_fma_peak(self._h, C.byref(out)))
+        return out.value
 
     def cosine(self, a, b):
         a, b = _arr(a, np.float32).ravel(), _arr(b, np.float32).ravel()

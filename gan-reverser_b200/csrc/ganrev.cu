@@ -152,8 +152,9 @@ struct ProfScope {
     ganrev_ctx* ctx;
     ProfPending pp{};
     bool on;
-    ProfScope(ganrev_ctx* c, const std::string& name, double flops, double bytes) : ctx(c), on(c->prof_on) {
-        ctx->launches++;
+    // count = false: a library (NCCL) call, timed but not one of OUR kernel launches
+    ProfScope(ganrev_ctx* c, const std::string& name, double flops, double bytes, bool count = true) : ctx(c), on(c->prof_on) {
+        if (count) ctx->launches++;
         if (!on) return;
         auto it = ctx->prof_idx.find(name);
         int idx;
@@ -1176,7 +1177,11 @@ static int vec_prep(ganrev_ctx* ctx, const float* x, int64_t n, int d, float* rn
     return GANREV_OK;
 }
 
-int ganrev_db_set(ganrev_ctx* ctx, const float* vecs, int64_t N, int d) {
+static int db_set_impl(ganrev_ctx* ctx, const float* vecs, int64_t N, int d, bool own_resident);
+int ganrev_db_set(ganrev_ctx* ctx, const float* vecs, int64_t N, int d) { return db_set_impl(ctx, vecs, N, d, false); }
+static int ganrev_db_adopt_own(ganrev_ctx* ctx, int64_t N, int d) { return db_set_impl(ctx, nullptr, N, d, true); }
+// own_resident: ctx->db already holds the rows on the device (ganrev_debug_db_synthetic)
+static int db_set_impl(ganrev_ctx* ctx, const float* vecs, int64_t N, int d, bool own_resident) {
     if (!ctx || N < 0 || d < 1 || N > 0xFFFFFFF0ll) return ctx ? fail(ctx, GANREV_EINVAL, "bad db_set arguments") : GANREV_EINVAL;
     CU_TRY(cudaSetDevice(ctx->device));
     const size_t bytes = sizeof(float) * static_cast<size_t>(N) * d;
@@ -1185,7 +1190,9 @@ int ganrev_db_set(ganrev_ctx* ctx, const float* vecs, int64_t N, int d) {
     RC_TRY(ensure(ctx, ctx->maxabs, 3 * sizeof(long long)));
     RC_TRY(ensure(ctx, ctx->shard, sizeof(long long) * (ctx->world + 2)));
     const float* rows = nullptr;
-    if (vecs) {
+    if (own_resident) {
+        rows = static_cast<const float*>(ctx->db.p);
+    } else if (vecs) {
         RC_TRY(ensure(ctx, ctx->db, bytes));
         CU_TRY(cudaMemcpyAsync(ctx->db.p, vecs, bytes, cudaMemcpyHostToDevice, ctx->stream));
         rows = static_cast<const float*>(ctx->db.p);
@@ -1205,8 +1212,11 @@ int ganrev_db_set(ganrev_ctx* ctx, const float* vecs, int64_t N, int d) {
         long long* d_all = static_cast<long long*>(ctx->shard.p);
         const long long mine = N;
         CU_TRY(cudaMemcpyAsync(d_all + ctx->world, &mine, sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-        NCCL_TRY(ctx->nccl.AllGather(d_all + ctx->world, d_all, 1, ncclInt64, ctx->comm, ctx->stream));
-        NCCL_TRY(ctx->nccl.AllReduce(ctx->maxabs.p, ctx->maxabs.p, 1, ncclUint32, ncclMax, ctx->comm, ctx->stream));
+        {
+            ProfScope pc(ctx, "nccl_shard_bookkeeping", 0.0, 12.0 * ctx->world, false);
+            NCCL_TRY(ctx->nccl.AllGather(d_all + ctx->world, d_all, 1, ncclInt64, ctx->comm, ctx->stream));
+            NCCL_TRY(ctx->nccl.AllReduce(ctx->maxabs.p, ctx->maxabs.p, 1, ncclUint32, ncclMax, ctx->comm, ctx->stream));
+        }
         CU_TRY(cudaMemcpyAsync(all.data(), d_all, sizeof(long long) * ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CU_TRY(cudaMemcpyAsync(&mb, ctx->maxabs.p, sizeof(mb), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1218,7 +1228,7 @@ int ganrev_db_set(ganrev_ctx* ctx, const float* vecs, int64_t N, int d) {
         for (int r = 0; r < ctx->world; ++r) { if (r < ctx->rank) ctx->db_offset += all[r]; ctx->db_total += all[r]; }
         if (ctx->db_total > 0xFFFFFFF0ll) return fail(ctx, GANREV_EINVAL, "global database exceeds 2^32 rows");
     }
-    ctx->db_ptr = rows; ctx->db_alias = vecs == nullptr; ctx->db_n = N; ctx->db_d = d;
+    ctx->db_ptr = rows; ctx->db_alias = vecs == nullptr && !own_resident; ctx->db_n = N; ctx->db_d = d;
     return GANREV_OK;
 }
 
@@ -1396,7 +1406,10 @@ static int search_finish(ganrev_ctx* ctx, const unsigned long long* partial, int
     }
     if (multi) {
         // per-query top-k allgather (Q*k*8 B per rank), then the same merge over `world` partial lists
-        NCCL_TRY(ctx->nccl.AllGather(ctx->keys.p, ctx->keys_all.p, static_cast<size_t>(Q) * k, ncclUint64, ctx->comm, ctx->stream));
+        {
+            ProfScope pc(ctx, "nccl_allgather_topk", 0.0, 8.0 * ctx->world * Q * k, false);
+            NCCL_TRY(ctx->nccl.AllGather(ctx->keys.p, ctx->keys_all.p, static_cast<size_t>(Q) * k, ncclUint64, ctx->comm, ctx->stream));
+        }
         ProfScope ps(ctx, "search_merge_global", 0.0, 8.0 * ctx->world * Q * k + 12.0 * Q * k);
         if (k <= 32)
             scan::merge_kernel<1><<<mblocks, scan::kThreads, 0, ctx->stream>>>(static_cast<const unsigned long long*>(ctx->keys_all.p), ctx->world, Q, k, 0, 0,
@@ -1506,8 +1519,10 @@ int ganrev_search_rows(ganrev_ctx* ctx, const int64_t* rows, int Q, int k, int64
             ctx->db_ptr, ctx->db_n, d, ctx->db_offset, static_cast<const long long*>(ctx->stage_b.p), Q, static_cast<float*>(ctx->q.p));
         CU_TRY(cudaGetLastError());
     }
-    if (ctx->world > 1)   // exactly one rank holds each row; the others contribute +0.0f (all-zero bits)
+    if (ctx->world > 1) {   // exactly one rank holds each row; the others contribute +0.0f (all-zero bits)
+        ProfScope pc(ctx, "nccl_allreduce_queries", 0.0, 4.0 * Q * d, false);
         NCCL_TRY(ctx->nccl.AllReduce(ctx->q.p, ctx->q.p, static_cast<size_t>(Q) * d, ncclUint32, ncclMax, ctx->comm, ctx->stream));
+    }
     return search_dev(ctx, Q, k, ids, scores);
 }
 }  // extern "C"
@@ -1579,8 +1594,10 @@ int ganrev_kmeans(ganrev_ctx* ctx, int k, int niter, const float* init_centroids
             else if (k <= 16) RC_TRY((launch_assign<1, 1>(ctx, p)));
             else RC_TRY((launch_assign<4, 1>(ctx, p)));
         }
-        if (ctx->world > 1)   // centroid sums + counts: one order-free int64 allreduce per iteration
+        if (ctx->world > 1) {   // centroid sums + counts: one order-free int64 allreduce per iteration
+            ProfScope pc(ctx, "nccl_allreduce_centroids", 0.0, 8.0 * (kd + k), false);
             NCCL_TRY(ctx->nccl.AllReduce(ctx->acc.p, ctx->acc.p, kd + k, ncclUint64, ncclSum, ctx->comm, ctx->stream));
+        }
         {
             ProfScope ps(ctx, "kmeans_finalize", 0.0, 12.0 * kd);
             scan::kmeans_finalize_kernel<<<k, 128, 0, ctx->stream>>>(static_cast<float*>(ctx->cen.p), d_acc, d_cnt,
@@ -1745,6 +1762,48 @@ int ganrev_profile_get(ganrev_ctx* ctx, int idx, const char** name, uint64_t* la
     if (flops) *flops = e.flops;
     if (bytes) *bytes = e.bytes;
     return GANREV_OK;
+}
+// bench.py --config 5: a synthetic N(0,1) database generated on the device ("generated on device" so that
+// no 10 GB host upload is timed); counter-based, so any sharding of the rows gives the same values for the same global row.
+int ganrev_debug_db_synthetic(ganrev_ctx* ctx, int64_t N, int d, uint64_t seed, int64_t global_row0) {
+    if (!ctx || N < 0 || d < 1) return ctx ? fail(ctx, GANREV_EINVAL, "bad db_synthetic arguments") : GANREV_EINVAL;
+    CU_TRY(cudaSetDevice(ctx->device));
+    ctx->db_ptr = nullptr; ctx->db_n = 0;
+    RC_TRY(ensure(ctx, ctx->db, sizeof(float) * static_cast<size_t>(std::max<int64_t>(N, 1)) * d));
+    const long long tot = static_cast<long long>(N) * d;
+    synthetic_normal_kernel<<<static_cast<unsigned>(std::min<long long>((tot + 255) / 256, 1 << 20)), 256, 0, ctx->stream>>>(
+        static_cast<float*>(ctx->db.p), tot, seed, static_cast<unsigned long long>(global_row0) * d);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    RC_TRY(finish(ctx));
+    // adopt it as the database through the normal path (device-to-device "upload" of itself is skipped: db.p already holds it)
+    return ganrev_db_adopt_own(ctx, N, d);
+}
+// Measured fp32 FMA throughput of this GPU at its current clocks (the roof the exact fmaf-chain kernels are graded against;
+// MEASURED_PEAKS.json has no fp32 figure): 8 independent chains per thread, all SMs, ~50 ms.
+int ganrev_debug_fma_peak(ganrev_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return GANREV_EINVAL;
+    CU_TRY(cudaSetDevice(ctx->device));
+    RC_TRY(ensure(ctx, ctx->thr, sizeof(double)));
+    const int iters = 1 << 16, blocks = ctx->num_sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0)); CU_TRY(cudaEventCreate(&e1));
+    fma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(static_cast<float*>(ctx->thr.p), 1024, 1.0f);   // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0, ctx->stream);
+        fma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(static_cast<float*>(ctx->thr.p), iters, 1.0f);
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = 2.0 * 16.0 * iters * static_cast<double>(blocks) * threads;
+        best = std::max(best, fl / (ms * 1e-3) * 1e-12);
+    }
+    ctx->launches += 4;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops = best;
+    return finish(ctx);
 }
 // Debug: arm a clock64 timeline of CTA 0 for the named tensor-core layer / read it back ([8][256] int64).
 int ganrev_debug_trace_arm(ganrev_ctx* ctx, const char* layer) {

@@ -376,4 +376,33 @@ __global__ void anomaly_flags_kernel(const double* __restrict__ l2, long long n_
     if (i < n_show) flags[i] = ((1.0 - l2[i]) <= *thr) ? 1 : 0;
 }
 
+// ------------------------------------------------------------------ measurement helpers (bench.py)
+// counter-based N(0,1): splitmix64 of (seed, global element index) -> two uniforms -> Box-Muller
+__global__ void synthetic_normal_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long elem0) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        unsigned long long z = seed * 0x9E3779B97F4A7C15ull + (elem0 + static_cast<unsigned long long>(i)) * 0xD1B54A32D192ED03ull + 0x632BE59BD9B4E019ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        const float u1 = (static_cast<float>(static_cast<unsigned>(z >> 40)) + 1.0f) * (1.0f / 16777217.0f);   // (0, 1)
+        const float u2 = static_cast<float>(static_cast<unsigned>(z) >> 8) * (1.0f / 16777216.0f);
+        out[i] = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+    }
+}
+// fp32 FMA roof: 16 independent fmaf chains per thread
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* __restrict__ sink, int iters, float seed) {
+    float a[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = seed + 0.001f * j + 1e-6f * threadIdx.x;
+    const float m = 0.9999f, c = 1e-4f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = __fmaf_rn(a[j], m, c);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += a[j];
+    if (s == 123.456f) *sink = s;      // never true: keeps the chains alive
+}
+
 }  // namespace ganrev

@@ -170,6 +170,10 @@ int ganrev_profile_reset(ganrev_ctx* ctx);
 int ganrev_profile_count(ganrev_ctx* ctx);
 int ganrev_profile_get(ganrev_ctx* ctx, int idx, const char** name, uint64_t* launches,
                        double* total_ms, double* flops, double* bytes);
+/* bench.py: a synthetic N(0,1) [N x d] database generated on the device (counter-based on seed and GLOBAL element index:
+ * global_row0 = this shard's first global row) and adopted as by ganrev_db_set; the measured fp32 FMA roof of this GPU. */
+int ganrev_debug_db_synthetic(ganrev_ctx* ctx, int64_t N, int d, uint64_t seed, int64_t global_row0);
+int ganrev_debug_fma_peak(ganrev_ctx* ctx, double* tflops);
 /* Debug: clock64 timeline of CTA 0 of the named tensor-core layer (roles x events, [8][256]). */
 int ganrev_debug_trace_arm(ganrev_ctx* ctx, const char* layer);
 int ganrev_debug_trace_read(ganrev_ctx* ctx, int64_t* out);

@@ -45,6 +45,65 @@ def test_search_exact(orc, ctx, case):
     assert_bitexact(sc, want_sc, "scores")
 
 
+CONFIG5_SEARCH = [
+    # BASELINE configs[4] shapes (d = 256, top-100) at sizes the oracle finishes in seconds
+    (50000, 256, 70, 100),     # many queries, d > 128
+    (30000, 256, 4096, 100),   # the full query batch
+    (20000, 256, 17, 100),     # 17 queries: first size past the streaming family
+]
+
+
+@pytest.mark.parametrize("case", CONFIG5_SEARCH, ids=lambda c: "N%d_d%d_Q%d_k%d" % c)
+def test_search_config5_shapes_exact(orc, ctx, case):
+    N, d, Q, k = case
+    db = _db(N, d, 61)
+    rows = np.random.default_rng(62).choice(N, size=Q // 2, replace=False)
+    q = np.concatenate([db[rows], _db(Q - Q // 2, d, 63)])
+    want_ids, want_sc = orc.search_cosine(db, q, k)
+    ctx.db_set(db)
+    ids, sc = ctx.search_cosine(q, k)
+    np.testing.assert_array_equal(ids, want_ids)
+    assert_bitexact(sc, want_sc, "scores")
+
+
+def test_kmeans_config5_shape_exact(orc, ctx):
+    """k = 1024 centroids over d = 256 rows (BASELINE configs[4]), 2 iterations."""
+    N, d, k = 20000, 256, 1024
+    x = _db(N, d, 64)
+    init = _init(k, d, seed=65)
+    want_c, want_t, want_l = orc.kmeans(x, k, 2, init)
+    ctx.db_set(x)
+    cen, tot, lab = ctx.kmeans(k, 2, init)
+    np.testing.assert_array_equal(lab, want_l)
+    assert_bitexact(tot, want_t, "total counts")
+    assert_bitexact(cen, want_c, "centroids")
+
+
+def test_db_aliases_resident_attrs(pkg, orc, ctx):
+    """ganrev_db_set(NULL): the database IS the resident ATTRS0 buffer (no copy); overwriting ATTRS0 un-sets it."""
+    C, H, W, nd, N = 1, 32, 32, 32, 300
+    c = pkg.Context(0)
+    try:
+        c.load_G(C, H, W, nd, pkg.weights.init_G(C, H, W, nd, stress=True))
+        c.load_R(0, C, H, W, nd, pkg.weights.init_R(C, H, W, nd, stress=True))
+        img = c.forward_G(np.random.default_rng(1).normal(size=(N, nd)).astype(np.float32))
+        att = c.forward_R(0, img)
+        c.db_set(None, N=N, d=nd)
+        ids, sc = c.search_rows(np.array([5, 17], np.int64), 10)
+        want_ids, want_sc = orc.search_cosine(att, att[[5, 17]], 10)
+        np.testing.assert_array_equal(ids, want_ids)
+        assert_bitexact(sc, want_sc)
+        c.forward_R(0, img[:10])                                  # ATTRS0 overwritten
+        with pytest.raises(pkg.GanrevError):
+            c.search_rows(np.array([5], np.int64), 10)
+        c.db_set(att)                                             # an own copy survives
+        c.forward_R(0, img[:10])
+        ids2, _ = c.search_rows(np.array([5, 17], np.int64), 10)
+        np.testing.assert_array_equal(ids2, want_ids)
+    finally:
+        c.close()
+
+
 def test_search_rows_equals_search_by_vector(orc, ctx):
     """apply_r.lua:268: needles are rows i*100 of the searched tensor."""
     db = _db(10000, 32, 5)

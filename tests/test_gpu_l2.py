@@ -38,6 +38,32 @@ def test_anomaly_flags_exact(orc, ctx, n_calc, n_show, q):
     np.testing.assert_array_equal(flags, want_flags)
 
 
+def test_anomaly_flags_full_size(ctx):
+    """1M distances (BASELINE configs[3] size): the multi-block radix select returns the exact order statistic."""
+    rng = np.random.default_rng(77)
+    n = 1_000_000
+    l2 = np.abs(rng.normal(size=n)) * 2.0
+    l2[::1000] = l2[7]                                              # a run of duplicates
+    flags, thr = ctx.anomaly_flags(l2, n, n, 0.15)
+    sims = 1.0 - l2
+    want_thr = np.partition(sims, int(np.floor(n * 0.15)) - 1)[int(np.floor(n * 0.15)) - 1]
+    assert np.float64(thr).view(np.uint64) == np.float64(want_thr).view(np.uint64)
+    np.testing.assert_array_equal(flags, (sims <= want_thr).astype(np.uint8))
+
+
+def test_anomaly_flags_resident_distances(pkg, orc, ctx):
+    """l2 == NULL reuses the distances of the last l2 / fix_l2 call; fewer than n_calc resident is an error."""
+    rng = np.random.default_rng(3)
+    a, b = rng.random((64, 100)).astype(np.float32), rng.random((64, 100)).astype(np.float32)
+    l2 = ctx.l2(a, b)
+    flags, thr = ctx.anomaly_flags(None, 64, 40, 0.15)
+    want_flags, want_thr = orc.anomaly_flags(l2, 64, 40, 0.15)
+    np.testing.assert_array_equal(flags, want_flags)
+    assert np.float64(thr).view(np.uint64) == np.float64(want_thr).view(np.uint64)
+    with pytest.raises(pkg.GanrevError):
+        ctx.anomaly_flags(None, 65, 40, 0.15)
+
+
 def test_anomaly_flags_bad_quantile(pkg, ctx):
     with pytest.raises(pkg.GanrevError):
         ctx.anomaly_flags(np.ones(5), 5, 5, 0.15)     # floor(5*0.15) = 0: Lua would index nil

@@ -79,6 +79,76 @@ def test_R_matches_oracle(pkg, orc, ctx, geom, impl):
     assert rel_l2(got_f, want) > 10 * REL_TOL, "mask must change the result"
 
 
+BENCH_SHAPES = [
+    # C, H, W, nd, N, rows checked against the oracle: BASELINE configs[3] and configs[4] geometries at the DEFAULT chunk
+    (1, 32, 32, 100, 20000, 1000),
+    (3, 64, 64, 256, 5000, 256),
+]
+
+
+@pytest.mark.parametrize("shape", BENCH_SHAPES, ids=lambda g: "C%dx%dx%d_nd%d_N%d_check%d" % g)
+def test_benchmark_launch_shape_matches_oracle(pkg, orc, ctx, shape):
+    """The launch shape bench.py times: default chunk (8192 32x32 faces' worth of pixels, ~55 items per persistent CTA per
+    layer, accumulator / smem-ring / transpose-buffer wrap-around at depth), several chunks with a ragged last one.
+    Sampled rows of G and of R against the oracle within north_star's tolerances, and the device-resident chain
+    (NULL pointers, what bench.py's `value` times) equal to the host-pointer chain bit for bit."""
+    C, H, W, nd, N, n_check = shape
+    ctx.set_option("conv_impl", 0)
+    ctx.set_option("cta_pairs", 31)
+    ctx.set_option("chunk", 0)                                  # library default
+    gb = pkg.weights.init_G(C, H, W, nd, seed=1, stress=True)
+    rb = pkg.weights.init_R(C, H, W, nd, seed=2, stress=True)
+    ctx.load_G(C, H, W, nd, gb)
+    ctx.load_R(0, C, H, W, nd, rb)
+    rng = np.random.default_rng(17)
+    noise = rng.standard_normal(size=(N, nd), dtype=np.float32)
+    img = ctx.forward_G(noise)
+    att = ctx.forward_R(0, img)
+    # rows spread over every chunk, always including the first / last rows of the batch and of a chunk boundary
+    chunk = max(256, 8192 * 1024 // (H * W))
+    rows = np.unique(np.concatenate([rng.choice(N, size=n_check - 8, replace=False),
+                                     [0, 1, chunk - 1, chunk, min(N - 1, 2 * chunk), N - 2, N - 1, N // 2]]))
+    want_img = orc.forward_G(gb, C, H, W, nd, noise[rows])
+    err = np.abs(img[rows] - want_img).max()
+    assert err <= PIX_TOL, f"max |pixel diff| {err}"
+    want_att = orc.forward_R(rb, C, H, W, nd, img[rows])           # identical inputs for both sides
+    assert row_cosine(att[rows], want_att).min() >= COS_TOL
+    assert rel_l2(att[rows], want_att) <= REL_TOL, rel_l2(att[rows], want_att)
+    # resident chain == host-pointer chain, bit for bit, over ALL rows
+    ctx.buffer_put(pkg._lib.BUF_NOISE, noise)
+    ctx.forward_G(None, N=N, want_images=False)
+    att2 = ctx.forward_R(0, None, N=N)
+    np.testing.assert_array_equal(att2, att)
+    for r0 in (0, chunk - 4, N - 8):
+        np.testing.assert_array_equal(ctx.buffer_get(pkg._lib.BUF_IMAGES, r0, 8), img[r0:r0 + 8])
+    # determinism at depth: a second pass over the same input is identical
+    np.testing.assert_array_equal(ctx.forward_R(0, None, N=N), att)
+    ctx.set_option("chunk", 16)
+
+
+def test_one_geometry_per_context(pkg, ctx):
+    """include/ganrev.h: loading a model of a different geometry unloads the old models and empties the resident buffers
+    (R.nd > G.nd wrote past ATTRS; a reload kept stale row counts)."""
+    W_ = pkg.weights
+    ctx.load_G(1, 32, 32, 32, W_.init_G(1, 32, 32, 32))
+    ctx.load_R(0, 1, 32, 32, 32, W_.init_R(1, 32, 32, 32))
+    noise = np.zeros((4, 32), np.float32)
+    ctx.forward_G(noise)
+    ctx.forward_R(0, None, N=4)
+    ctx.load_R(1, 1, 32, 32, 100, W_.init_R(1, 32, 32, 100))      # another noise_dim: G and R slot 0 are gone
+    with pytest.raises(pkg.GanrevError):
+        ctx.forward_R(0, None, N=4)
+    with pytest.raises(pkg.GanrevError):
+        ctx.forward_G(None, N=4, want_images=False)
+    with pytest.raises(pkg.GanrevError):
+        ctx.forward_R(1, None, N=4)                               # the resident images were emptied too
+    with pytest.raises(pkg.GanrevError):
+        ctx.buffer_get(pkg._lib.BUF_IMAGES, 0, 1)
+    ctx.load_G(1, 32, 32, 100, W_.init_G(1, 32, 32, 100))
+    img = ctx.forward_G(np.zeros((4, 100), np.float32))
+    assert ctx.forward_R(1, img).shape == (4, 100)
+
+
 def test_tanh_output(pkg, orc, ctx):
     C, H, W, nd, N = 1, 32, 32, 32, 8
     ctx.set_option("conv_impl", 0)
