@@ -57,6 +57,8 @@ _SIGS = {
     "ganrev_set_option": (_i, [_vp, C.c_char_p, _i64]),
     "ganrev_debug_db_synthetic": (_i, [_vp, _i64, _i, C.c_uint64, _i64]),
     "ganrev_debug_fma_peak": (_i, [_vp, C.POINTER(C.c_double)]),
+    "ganrev_debug_tc_scores": (_i, [_vp, _vp, _i, _vp, C.POINTER(C.c_float)]),
+    "ganrev_debug_tc_counters": (_i, [_vp, _vp]),
     "ganrev_debug_trace_arm": (_i, [_vp, C.c_char_p]),
     "ganrev_debug_trace_read": (_i, [_vp, _vp]),
 }
@@ -244,6 +246,19 @@ class Context:
         """bench.py: N(0,1) rows generated on the device and adopted as the database."""
         self._chk(lib().ganrev_debug_db_synthetic(self._h, int(N), int(d), int(seed), int(global_row0)))
         self.db_shape = (int(N), int(d))
+
+    def tc_scores(self, queries):
+        """Tests: approximate cosines of the tensor-core filter for every (query, row) pair, and the assumed bound eps(d)."""
+        q = _arr(queries, np.float32)
+        out = np.empty((q.shape[0], self.db_shape[0]), np.float32)
+        eps = C.c_float(0.0)
+        self._chk(lib().ganrev_debug_tc_scores(self._h, _ptr(q), q.shape[0], _ptr(out), C.byref(eps)))
+        return out, eps.value
+
+    def tc_counters(self):
+        out = np.zeros((2,), np.uint64)
+        self._chk(lib().ganrev_debug_tc_counters(self._h, _ptr(out)))
+        return int(out[0]), int(out[1])
 
     def fma_peak(self):
         out = C.c_double(0.0)

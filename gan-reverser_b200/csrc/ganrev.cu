@@ -13,6 +13,7 @@
 #include "conv1_tc.cuh"
 #include "layers.cuh"
 #include "scan.cuh"
+#include "search_tc.cuh"
 
 using namespace ganrev;
 
@@ -69,6 +70,8 @@ struct ganrev_ctx {
     int64_t chunk = 0;            // images per pipeline chunk; 0 = auto (8192 32x32 faces' worth of pixels, see chunk_for)
     int conv_impl = 0;
     int tma_store = 1;            // TMA bulk tensor stores in the conv epilogue where the layer allows (0 = st.global everywhere; A/B)
+    int search_tc = 1;            // tensor-core candidate filter + exact re-score for many-query searches (0 = fmaf-chain kernels only; A/B)
+    uint64_t tc_searches = 0, tc_fallbacks = 0;   // searches served by the tensor-core path / re-run on the fmaf-chain kernels
     int rtile = 1;                // register-tiled kmeans / cosine-min kernels for 9 <= k <= 32 (0 = the one-thread-per-row streaming kernels; A/B)
     int cta_pairs = 0x1f;     // which layers use tcgen05 cta_group::2 CTA pairs (bit0 G conv1, bit1 G conv2, bit2 R conv2/3,
                               // bit3 R conv4, bit4 R conv5/6); takes effect at the next ganrev_load_*.  Default = measured best.
@@ -94,6 +97,8 @@ struct ganrev_ctx {
     DevBuf arena[2], noise_bf16, stage_a, stage_b, l2buf, thr, flags;
     int64_t l2_valid = 0;                  // entries of l2buf written by the last fix_l2 / l2 / anomaly_flags call
     DevBuf nn_partial, nn_ids, nn_dist, nn_flag, nn_all;   // ganrev_nearest_l2 scratch
+    DevBuf pdb, pq, tc_thr, tc_cnt, tc_cand, tc_pairs, tc_keys, tc_special, tc_flags, tc_dump;   // search_tc.cuh: packed split-bf16 operands, candidates
+    bool pdb_valid = false;                // pdb / tc_special describe the current database
     DevBuf qsel, shard;                    // radix-select state + histogram; row-shard bookkeeping (world + 2 int64)
     // database
     DevBuf db, rdb, maxabs;
@@ -845,7 +850,8 @@ void ganrev_destroy(ganrev_ctx* ctx) {
         for (TcLayer* L : {&R.c2, &R.c3, &R.c4, &R.c5, &R.c6, &R.l1, &R.l2}) release_layer(*L);
     }
     for (auto& b : ctx->buf) release(b);
-    for (DevBuf* b : {&ctx->nn_partial, &ctx->nn_ids, &ctx->nn_dist, &ctx->nn_flag, &ctx->nn_all, &ctx->qsel, &ctx->shard}) release(*b);
+    for (DevBuf* b : {&ctx->nn_partial, &ctx->nn_ids, &ctx->nn_dist, &ctx->nn_flag, &ctx->nn_all, &ctx->qsel, &ctx->shard, &ctx->pdb, &ctx->pq, &ctx->tc_thr,
+                      &ctx->tc_cnt, &ctx->tc_cand, &ctx->tc_pairs, &ctx->tc_keys, &ctx->tc_special, &ctx->tc_flags, &ctx->tc_dump}) release(*b);
     for (DevBuf* b : {&ctx->arena[0], &ctx->arena[1], &ctx->noise_bf16, &ctx->stage_a, &ctx->stage_b, &ctx->l2buf, &ctx->thr, &ctx->flags,
                       &ctx->db, &ctx->rdb, &ctx->maxabs, &ctx->q, &ctx->rq, &ctx->c2, &ctx->partial, &ctx->keys, &ctx->keys_all, &ctx->ids,
                       &ctx->scores, &ctx->cen, &ctx->acc, &ctx->cnt, &ctx->total, &ctx->labels, &ctx->cosv, &ctx->tcounts, &ctx->mids,
@@ -1185,7 +1191,7 @@ static int db_set_impl(ganrev_ctx* ctx, const float* vecs, int64_t N, int d, boo
     if (!ctx || N < 0 || d < 1 || N > 0xFFFFFFF0ll) return ctx ? fail(ctx, GANREV_EINVAL, "bad db_set arguments") : GANREV_EINVAL;
     CU_TRY(cudaSetDevice(ctx->device));
     const size_t bytes = sizeof(float) * static_cast<size_t>(N) * d;
-    ctx->db_ptr = nullptr; ctx->db_alias = false; ctx->db_n = 0; ctx->assigned = false;
+    ctx->db_ptr = nullptr; ctx->db_alias = false; ctx->db_n = 0; ctx->assigned = false; ctx->pdb_valid = false;
     RC_TRY(ensure(ctx, ctx->rdb, sizeof(float) * static_cast<size_t>(std::max<int64_t>(N, 1))));
     RC_TRY(ensure(ctx, ctx->maxabs, 3 * sizeof(long long)));
     RC_TRY(ensure(ctx, ctx->shard, sizeof(long long) * (ctx->world + 2)));
@@ -1425,12 +1431,10 @@ static int search_finish(ganrev_ctx* ctx, const unsigned long long* partial, int
 }
 
 
-// queries already on the device in ctx->q (Q x d)
-static int search_dev(ganrev_ctx* ctx, int Q, int k, int64_t* ids, float* scores) {
+// queries already on the device in ctx->q (Q x d), their 1/(|q|^2+eps) in ctx->rq: the fmaf-chain kernels
+static int search_exact_dev(ganrev_ctx* ctx, int Q, int k, int64_t* ids, float* scores) {
     const int d = ctx->db_d;
     const int64_t N = ctx->db_n;
-    RC_TRY(ensure(ctx, ctx->rq, sizeof(float) * Q));
-    RC_TRY(vec_prep(ctx, static_cast<const float*>(ctx->q.p), Q, d, static_cast<float*>(ctx->rq.p), nullptr, nullptr));
     if (Q <= 16 && d % 4 == 0) {   // HBM-bound regime: stream the database once
         scan::ScanParams p{};
         p.db = ctx->db_ptr; p.rdb = static_cast<const float*>(ctx->rdb.p); p.n_rows = N; p.d = d;
@@ -1488,6 +1492,177 @@ static int search_dev(ganrev_ctx* ctx, int Q, int k, int64_t* ids, float* scores
         else           { if (k <= 32) RC_TRY((launch_search<4, 1>(ctx, p, splits))); else RC_TRY((launch_search<4, 4>(ctx, p, splits))); }
     }
     return search_finish(ctx, p.partial, splits, Q, k, ids, scores);
+}
+
+// ---- tensor-core candidate filter + exact re-score (search_tc.cuh)
+static int tc_make_map(ganrev_ctx* ctx, CUtensorMap* m, const void* base, int kp, long long rows, long long row_pitch_elems, int box_rows) {
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kp), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(row_pitch_elems) * 2};
+    const cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+    const cuuint32_t es[2] = {1u, 1u};
+    CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, GANREV_ECUDA, "cuTensorMapEncodeTiled(search operand) failed: %d", (int)r);
+    return GANREV_OK;
+}
+static int tc_pack(ganrev_ctx* ctx, const char* name, const float* x, const float* rn, int64_t n, int d, DevBuf& out, bool is_query) {
+    const int kp = stc::packed_cols(d);
+    RC_TRY(ensure(ctx, out, sizeof(bf16) * static_cast<size_t>(std::max<int64_t>(n, 1)) * kp));
+    RC_TRY(ensure(ctx, ctx->tc_special, sizeof(unsigned) * (stc::kMaxSpecial + 4)));
+    RC_TRY(ensure(ctx, ctx->tc_flags, 4 * sizeof(int)));
+    unsigned* sp_rows = static_cast<unsigned*>(ctx->tc_special.p);
+    unsigned* sp_count = sp_rows + stc::kMaxSpecial;
+    int* flags = static_cast<int*>(ctx->tc_flags.p);           // [0] this search, [1] the database
+    if (!is_query) { CU_TRY(cudaMemsetAsync(sp_count, 0, sizeof(unsigned), ctx->stream)); CU_TRY(cudaMemsetAsync(flags + 1, 0, sizeof(int), ctx->stream)); }
+    ProfScope ps(ctx, name, 2.0 * n * d, n * (4.0 * d + 2.0 * kp));
+    const long long tot = n * (kp / 4);
+    if (tot > 0) stc::pack_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, ctx->stream>>>(x, rn, n, d, static_cast<bf16*>(out.p), is_query ? 1 : 0,
+                                                                                                 sp_rows, sp_count, is_query ? flags : flags + 1);
+    CU_TRY(cudaGetLastError());
+    return GANREV_OK;
+}
+struct TcPlan { int levels; int stride[8]; int cap; };
+__global__ void tc_combine_flags_kernel(int* flags, int extra) { flags[2] = flags[0] | flags[1] | extra; }
+static bool tc_plan(const ganrev_ctx* ctx, int Q, int k, TcPlan& pl) {
+    const int64_t N = ctx->db_n;
+    if (N < 8192) return false;
+    const int64_t n_t = std::max<int64_t>(1024, 8LL * k);      // rows of the coarsest (exhaustively re-scored) sample
+    const int64_t sL = N / n_t;                                 // >= 8
+    const int L = std::max(1, static_cast<int>(std::ceil(std::log(static_cast<double>(sL)) / std::log(32.0) - 1e-9)));
+    if (L > 6) return false;
+    const double r = std::pow(static_cast<double>(sL), 1.0 / L);
+    pl.levels = L;
+    pl.stride[0] = 1;
+    for (int i = 1; i <= L; ++i) {
+        int s = i == L ? static_cast<int>(sL) : static_cast<int>(std::llround(std::pow(r, i)));
+        pl.stride[i] = std::max(s, pl.stride[i - 1] + 1);
+    }
+    pl.cap = std::max(2048, 64 * k);
+    return true;
+}
+// Runs the levels on this rank's shard: leaves the shard's top-k keys in ctx->partial and the flags on the device.
+static int search_tc_local(ganrev_ctx* ctx, const TcPlan& pl, int Q, int k) {
+    const int d = ctx->db_d, kp = stc::packed_cols(d);
+    const int64_t N = ctx->db_n;
+    int* d_flags = static_cast<int*>(ctx->tc_flags.p);
+    if (!ctx->pdb_valid) {
+        RC_TRY(tc_pack(ctx, "search_tc_pack_db", ctx->db_ptr, static_cast<const float*>(ctx->rdb.p), N, d, ctx->pdb, false));
+        ctx->pdb_valid = true;
+    }
+    RC_TRY(tc_pack(ctx, "search_tc_pack_q", static_cast<const float*>(ctx->q.p), static_cast<const float*>(ctx->rq.p), Q, d, ctx->pq, true));
+    RC_TRY(ensure(ctx, ctx->tc_thr, sizeof(float) * Q));
+    // per level: cnt[Q] | offsets[Q] | cursor[Q] | total; pairs in arrival order, then candidates grouped by query
+    const size_t pair_cap = static_cast<size_t>(Q) * std::max(2048, 100 * k);
+    RC_TRY(ensure(ctx, ctx->tc_cnt, sizeof(unsigned) * (3 * static_cast<size_t>(Q) + 4)));
+    RC_TRY(ensure(ctx, ctx->tc_pairs, sizeof(uint2) * pair_cap));
+    RC_TRY(ensure(ctx, ctx->tc_cand, sizeof(unsigned) * pair_cap));
+    RC_TRY(ensure(ctx, ctx->tc_keys, sizeof(unsigned long long) * static_cast<size_t>(Q) * k));
+    unsigned* d_cnt = static_cast<unsigned*>(ctx->tc_cnt.p);
+    unsigned* d_off = d_cnt + Q;
+    unsigned* d_cur = d_off + Q;
+    unsigned* d_total = d_cur + Q;
+    unsigned* sp_rows = static_cast<unsigned*>(ctx->tc_special.p);
+    static size_t attr_dev[kMaxDevices][2] = {};
+    if (!attr_dev[ctx->device][0]) {
+        CU_TRY(cudaFuncSetAttribute(stc::filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, stc::kSmem));
+        CU_TRY(cudaFuncSetAttribute(stc::filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stc::kSmem));
+        attr_dev[ctx->device][0] = 1;
+    }
+    const int64_t nL = (N + pl.stride[pl.levels] - 1) / pl.stride[pl.levels];
+    const size_t rs_smem = 8 * (static_cast<size_t>(std::max<int64_t>(pl.cap + stc::kMaxSpecial, nL)) + 2) + 4 * static_cast<size_t>(d) + 16;
+    if (rs_smem > attr_dev[ctx->device][1]) {
+        CU_TRY(cudaFuncSetAttribute(stc::rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rs_smem)));
+        attr_dev[ctx->device][1] = rs_smem;
+    }
+    stc::RescoreParams rp{};
+    rp.db = ctx->db_ptr; rp.rdb = static_cast<const float*>(ctx->rdb.p); rp.n = N; rp.d = d;
+    rp.q = static_cast<const float*>(ctx->q.p); rp.rq = static_cast<const float*>(ctx->rq.p); rp.nq = Q; rp.k = k;
+    rp.cnt = d_cnt; rp.offsets = d_off; rp.cand = static_cast<const unsigned*>(ctx->tc_cand.p); rp.cap = pl.cap;
+    rp.special_rows = sp_rows; rp.special_count = sp_rows + stc::kMaxSpecial; rp.eps = stc::tc_eps(d); rp.flags = d_flags;
+    CUtensorMap tmQ, tmX;
+    RC_TRY(tc_make_map(ctx, &tmQ, ctx->pq.p, kp, Q, kp, stc::QM));
+    for (int lvl = pl.levels; lvl >= 0; --lvl) {
+        const int stride = pl.stride[lvl];
+        const int64_t n_l = (N + stride - 1) / stride;
+        const bool coarsest = lvl == pl.levels, final_level = lvl == 0;
+        if (!coarsest) {
+            CU_TRY(cudaMemsetAsync(ctx->tc_cnt.p, 0, sizeof(unsigned) * (3 * static_cast<size_t>(Q) + 4), ctx->stream));
+            RC_TRY(tc_make_map(ctx, &tmX, ctx->pdb.p, kp, n_l, static_cast<long long>(stride) * kp, stc::RN));
+            stc::FilterParams fp{};
+            fp.nq = Q; fp.n_rows = n_l; fp.stride = stride; fp.d = d; fp.nslices = kp / 128;
+            fp.q_tiles = (Q + stc::QM - 1) / stc::QM;
+            fp.items = static_cast<long long>(fp.q_tiles) * ((n_l + stc::RN - 1) / stc::RN);
+            fp.thr = static_cast<const float*>(ctx->tc_thr.p); fp.cnt = d_cnt;
+            fp.pairs = static_cast<uint2*>(ctx->tc_pairs.p); fp.total = d_total; fp.pair_cap = static_cast<unsigned>(pair_cap);
+            fp.flags = d_flags; fp.err_flag = ctx->d_err_flag; fp.dump = nullptr;
+            // executed work: three bf16 product chains over the 16-padded columns; bytes: the packed rows once (L2 serves the other query tiles)
+            ProfScope ps(ctx, "search_tc_filter", 3.0 * 2.0 * n_l * Q * ((d + 15) / 16 * 16), 2.0 * kp * (static_cast<double>(n_l) + Q));
+            const int grid = static_cast<int>(std::min<long long>(fp.items, ctx->num_sms));
+            stc::filter_kernel<false><<<grid, stc::kThr, stc::kSmem, ctx->stream>>>(tmQ, tmX, fp);
+            CU_TRY(cudaGetLastError());
+        }
+        if (!coarsest) {
+            ProfScope ps(ctx, "search_tc_group", 0.0, 20.0 * Q * 32.0 * k);
+            ctx->launches++;
+            stc::offsets_kernel<<<1, 1024, 0, ctx->stream>>>(d_cnt, Q, static_cast<unsigned>(pl.cap), d_off, d_cur, d_flags);
+            stc::scatter_kernel<<<4 * ctx->num_sms, 256, 0, ctx->stream>>>(static_cast<const uint2*>(ctx->tc_pairs.p), d_total, static_cast<unsigned>(pair_cap), d_off, d_cur,
+                                                                          static_cast<unsigned*>(ctx->tc_cand.p), d_flags);
+            CU_TRY(cudaGetLastError());
+        }
+        rp.implicit_stride = coarsest ? stride : 0;
+        rp.n_implicit = coarsest ? static_cast<int>(n_l) : 0;
+        rp.use_special = final_level ? 1 : 0;
+        rp.next_ratio = final_level ? 1.0f : static_cast<float>(stride) / static_cast<float>(pl.stride[lvl - 1]);
+        rp.keys_out = static_cast<unsigned long long*>(final_level ? ctx->partial.p : ctx->tc_keys.p);
+        rp.thr_out = final_level ? nullptr : static_cast<float*>(ctx->tc_thr.p);
+        ProfScope ps(ctx, "search_tc_rescore", 2.0 * Q * d * (coarsest ? static_cast<double>(n_l) : 32.0 * k), 0.0);
+        stc::rescore_kernel<<<Q, 256, rs_smem, ctx->stream>>>(rp);
+        CU_TRY(cudaGetLastError());
+    }
+    return GANREV_OK;
+}
+// *served = true: ids / scores are final.  *served = false: the caller runs the fmaf-chain kernels (on every rank alike).
+static int search_tc_dev(ganrev_ctx* ctx, int Q, int k, int64_t* ids, float* scores, bool* served) {
+    *served = false;
+    // eligibility from quantities every rank agrees on (the branches below contain collectives)
+    if (!ctx->search_tc || Q < 48 || k > 128 || ctx->db_d > 1024 || ctx->db_total < 8192LL * ctx->world) return GANREV_OK;
+    TcPlan pl;
+    const bool local_ok = tc_plan(ctx, Q, k, pl);
+    RC_TRY(ensure(ctx, ctx->tc_flags, 4 * sizeof(int)));
+    RC_TRY(ensure(ctx, ctx->partial, sizeof(unsigned long long) * static_cast<size_t>(Q) * k));
+    RC_TRY(ensure(ctx, ctx->ids, sizeof(long long) * static_cast<size_t>(Q) * k));
+    RC_TRY(ensure(ctx, ctx->scores, sizeof(float) * static_cast<size_t>(Q) * k));
+    int* d_flags = static_cast<int*>(ctx->tc_flags.p);           // [0] this search, [1] the database, [2] combined over ranks
+    CU_TRY(cudaMemsetAsync(d_flags, 0, sizeof(int), ctx->stream));
+    if (local_ok) RC_TRY(search_tc_local(ctx, pl, Q, k));
+    int h_flags[2] = {0, 0};
+    if (ctx->world == 1) {
+        if (!local_ok) return GANREV_OK;
+        // optimistic: merge and copy the result out, then look at the flags (no extra synchronisation on the common path)
+        RC_TRY(search_finish(ctx, static_cast<const unsigned long long*>(ctx->partial.p), 1, Q, k, ids, scores));
+        CU_TRY(cudaMemcpy(h_flags, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+    } else {
+        // every rank must take the same branch: combine the flags first (a shard too small for the levels votes for the fallback)
+        tc_combine_flags_kernel<<<1, 1, 0, ctx->stream>>>(d_flags, local_ok ? 0 : stc::FLAG_OVERFLOW);
+        ctx->launches++;
+        NCCL_TRY(ctx->nccl.AllReduce(d_flags + 2, d_flags + 2, 1, ncclInt32, ncclMax, ctx->comm, ctx->stream));
+        CU_TRY(cudaMemcpyAsync(h_flags, d_flags + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        RC_TRY(finish(ctx));
+        if (h_flags[0] == 0) RC_TRY(search_finish(ctx, static_cast<const unsigned long long*>(ctx->partial.p), 1, Q, k, ids, scores));
+    }
+    if (h_flags[0] | h_flags[1]) { ctx->tc_fallbacks++; return GANREV_OK; }   // overflow / special vectors: the fmaf-chain kernels decide
+    ctx->tc_searches++;
+    *served = true;
+    return GANREV_OK;
+}
+
+static int search_dev(ganrev_ctx* ctx, int Q, int k, int64_t* ids, float* scores) {
+    RC_TRY(ensure(ctx, ctx->rq, sizeof(float) * Q));
+    RC_TRY(vec_prep(ctx, static_cast<const float*>(ctx->q.p), Q, ctx->db_d, static_cast<float*>(ctx->rq.p), nullptr, nullptr));
+    bool served = false;
+    RC_TRY(search_tc_dev(ctx, Q, k, ids, scores, &served));
+    if (served) return GANREV_OK;
+    return search_exact_dev(ctx, Q, k, ids, scores);
 }
 
 extern "C" {
@@ -1779,6 +1954,60 @@ int ganrev_debug_db_synthetic(ganrev_ctx* ctx, int64_t N, int d, uint64_t seed, 
     // adopt it as the database through the normal path (device-to-device "upload" of itself is skipped: db.p already holds it)
     return ganrev_db_adopt_own(ctx, N, d);
 }
+// The approximate cosines of the tensor-core filter for every (query, row) pair of a SMALL database, so that tests can measure
+// |approximate - exact| against the bound eps(d) the filter relies on (search_tc.cuh).  out [Q x N]; eps_out = eps(d).
+int ganrev_debug_tc_scores(ganrev_ctx* ctx, const float* queries, int Q, float* out, float* eps_out) {
+    if (!ctx || !queries || Q < 1 || !out) return ctx ? fail(ctx, GANREV_EINVAL, "bad tc_scores arguments") : GANREV_EINVAL;
+    if (!ctx->db_ptr) return fail(ctx, GANREV_ESTATE, "database not set");
+    const int d = ctx->db_d, kp = stc::packed_cols(d);
+    const int64_t N = ctx->db_n;
+    if (d > 1024 || static_cast<double>(N) * Q > 1.0e8) return fail(ctx, GANREV_EINVAL, "tc_scores is a debug hook for small problems");
+    CU_TRY(cudaSetDevice(ctx->device));
+    RC_TRY(ensure(ctx, ctx->q, sizeof(float) * static_cast<size_t>(Q) * d));
+    RC_TRY(ensure(ctx, ctx->rq, sizeof(float) * Q));
+    CU_TRY(cudaMemcpyAsync(ctx->q.p, queries, sizeof(float) * static_cast<size_t>(Q) * d, cudaMemcpyHostToDevice, ctx->stream));
+    RC_TRY(vec_prep(ctx, static_cast<const float*>(ctx->q.p), Q, d, static_cast<float*>(ctx->rq.p), nullptr, nullptr));
+    RC_TRY(ensure(ctx, ctx->tc_flags, 4 * sizeof(int)));
+    CU_TRY(cudaMemsetAsync(ctx->tc_flags.p, 0, 4 * sizeof(int), ctx->stream));
+    if (!ctx->pdb_valid) {
+        RC_TRY(tc_pack(ctx, "search_tc_pack_db", ctx->db_ptr, static_cast<const float*>(ctx->rdb.p), N, d, ctx->pdb, false));
+        ctx->pdb_valid = true;
+    }
+    RC_TRY(tc_pack(ctx, "search_tc_pack_q", static_cast<const float*>(ctx->q.p), static_cast<const float*>(ctx->rq.p), Q, d, ctx->pq, true));
+    RC_TRY(ensure(ctx, ctx->tc_thr, sizeof(float) * Q));
+    RC_TRY(ensure(ctx, ctx->tc_cnt, sizeof(unsigned) * (3 * static_cast<size_t>(Q) + 4)));
+    RC_TRY(ensure(ctx, ctx->tc_pairs, sizeof(uint2) * 16));
+    RC_TRY(ensure(ctx, ctx->tc_dump, sizeof(float) * static_cast<size_t>(Q) * N));
+    CU_TRY(cudaMemsetAsync(ctx->tc_thr.p, 0x7f, sizeof(float) * Q, ctx->stream));     // 0x7f7f7f7f = 3.39e38: nothing passes
+    CU_TRY(cudaMemsetAsync(ctx->tc_cnt.p, 0, sizeof(unsigned) * (3 * static_cast<size_t>(Q) + 4), ctx->stream));
+    CU_TRY(cudaMemsetAsync(ctx->tc_dump.p, 0, sizeof(float) * static_cast<size_t>(Q) * N, ctx->stream));
+    CU_TRY(cudaFuncSetAttribute(stc::filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, stc::kSmem));
+    CUtensorMap tmQ, tmX;
+    RC_TRY(tc_make_map(ctx, &tmQ, ctx->pq.p, kp, Q, kp, stc::QM));
+    RC_TRY(tc_make_map(ctx, &tmX, ctx->pdb.p, kp, N, kp, stc::RN));
+    stc::FilterParams fp{};
+    fp.nq = Q; fp.n_rows = N; fp.stride = 1; fp.d = d; fp.nslices = kp / 128;
+    fp.q_tiles = (Q + stc::QM - 1) / stc::QM;
+    fp.items = static_cast<long long>(fp.q_tiles) * ((N + stc::RN - 1) / stc::RN);
+    fp.thr = static_cast<const float*>(ctx->tc_thr.p); fp.cnt = static_cast<unsigned*>(ctx->tc_cnt.p);
+    fp.pairs = static_cast<uint2*>(ctx->tc_pairs.p); fp.total = static_cast<unsigned*>(ctx->tc_cnt.p) + 3 * Q; fp.pair_cap = 0;
+    fp.flags = static_cast<int*>(ctx->tc_flags.p) + 3; fp.err_flag = ctx->d_err_flag;
+    fp.dump = static_cast<float*>(ctx->tc_dump.p);
+    {
+        ProfScope ps(ctx, "search_tc_filter_dump", 0.0, 0.0);
+        stc::filter_kernel<true><<<static_cast<int>(std::min<long long>(fp.items, ctx->num_sms)), stc::kThr, stc::kSmem, ctx->stream>>>(tmQ, tmX, fp);
+        CU_TRY(cudaGetLastError());
+    }
+    CU_TRY(cudaMemcpyAsync(out, ctx->tc_dump.p, sizeof(float) * static_cast<size_t>(Q) * N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (eps_out) *eps_out = stc::tc_eps(d);
+    return finish(ctx);
+}
+// [0] searches answered by the tensor-core path, [1] searches re-run on the fmaf-chain kernels (flags raised)
+int ganrev_debug_tc_counters(ganrev_ctx* ctx, uint64_t* out2) {
+    if (!ctx || !out2) return GANREV_EINVAL;
+    out2[0] = ctx->tc_searches; out2[1] = ctx->tc_fallbacks;
+    return GANREV_OK;
+}
 // Measured fp32 FMA throughput of this GPU at its current clocks (the roof the exact fmaf-chain kernels are graded against;
 // MEASURED_PEAKS.json has no fp32 figure): 8 independent chains per thread, all SMs, ~50 ms.
 int ganrev_debug_fma_peak(ganrev_ctx* ctx, double* tflops) {
@@ -1828,6 +2057,7 @@ int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value) {
         return GANREV_OK;
     }
     if (!strcmp(name, "rtile")) { ctx->rtile = value != 0; return GANREV_OK; }
+    if (!strcmp(name, "search_tc")) { ctx->search_tc = value != 0; return GANREV_OK; }
     if (!strcmp(name, "tma_store")) { ctx->tma_store = value < 0 ? 0 : (value > 2 ? 2 : static_cast<int>(value)); return GANREV_OK; }
     if (!strcmp(name, "conv_impl")) {
         if (value != 0 && value != 1) return fail(ctx, GANREV_EINVAL, "conv_impl must be 0 or 1");

@@ -174,6 +174,11 @@ int ganrev_profile_get(ganrev_ctx* ctx, int idx, const char** name, uint64_t* la
  * global_row0 = this shard's first global row) and adopted as by ganrev_db_set; the measured fp32 FMA roof of this GPU. */
 int ganrev_debug_db_synthetic(ganrev_ctx* ctx, int64_t N, int d, uint64_t seed, int64_t global_row0);
 int ganrev_debug_fma_peak(ganrev_ctx* ctx, double* tflops);
+/* Tests: the tensor-core filter's approximate cosine of every (query, row) pair of a small database, out [Q x N], and the
+ * error bound eps(d) the filter assumes (search_tc.cuh); how many searches the tensor-core path served [0] / handed to the
+ * fmaf-chain kernels after raising a flag [1]. */
+int ganrev_debug_tc_scores(ganrev_ctx* ctx, const float* queries, int Q, float* out, float* eps_out);
+int ganrev_debug_tc_counters(ganrev_ctx* ctx, uint64_t* out2);
 /* Debug: clock64 timeline of CTA 0 of the named tensor-core layer (roles x events, [8][256]). */
 int ganrev_debug_trace_arm(ganrev_ctx* ctx, const char* layer);
 int ganrev_debug_trace_read(ganrev_ctx* ctx, int64_t* out);
@@ -182,6 +187,8 @@ int ganrev_debug_trace_read(ganrev_ctx* ctx, int64_t* out);
  *   "conv_impl" 0 = tcgen05 implicit GEMM (default), 1 = plain CUDA-core kernels kept for on-device A/B checks
  *   "cta_pairs" bit mask of the conv layers that run as tcgen05 cta_group::2 CTA pairs (default all; read at ganrev_load_*)
  *   "tma_store" 1 = TMA bulk tensor stores in the conv epilogue of the plain layers (default), 2 = also the pooled layers, 0 = st.global everywhere
+ *   "search_tc" 1 = many-query searches (Q >= 48, >= 8192 rows per rank) run as tensor-core candidate filter + exact re-score (default;
+ *               results are bit-identical), 0 = fmaf-chain kernels only
  *   "rtile"     1 = register-tiled kmeans / cosine-min kernels for 9 <= k <= 32 (default), 0 = one-thread-per-row streaming kernels
  *   "dbg"       timing experiments: bit 0 skip A loads, 1 skip B loads, 2 skip epilogue, 3 skip MMAs, 4 skip stores (results invalid) */
 int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value);

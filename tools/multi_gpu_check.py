@@ -39,7 +39,8 @@ def run_checks(pkg, ctx, world, rank, seed=11):
     want_ids, want_sc = orc.search_cosine(db, q, k)
     res["search_ids"] = bool((ids == want_ids).all())
     res["search_scores"] = bool((bits(sc) == bits(want_sc)).all())
-    rows = np.array([7, 12000, N - 1, lo, max(lo, hi - 1)], np.int64)
+    bounds = [pkg.dist.shard_range(N, world, r) for r in range(world)]                 # the same needle list on every rank
+    rows = np.array([7, 12000, N - 1] + [b[0] for b in bounds] + [b[1] - 1 for b in bounds], np.int64)
     ids_r, sc_r = ctx.search_rows(rows, k)
     wi, ws = orc.search_cosine(db, db[rows], k)
     res["search_rows"] = bool((ids_r == wi).all() and (bits(sc_r) == bits(ws)).all())
