@@ -428,6 +428,8 @@ static int dispatch_tc(ganrev_ctx* ctx, const TcLayer& L, const CUtensorMap& tmA
     TC_CASE_CG(128, 2, 2, false, ACT_RELU, false, false, 2)   // G Up+Conv 256->128
     TC_CASE_CG(64, 2, 3, true, ACT_ELU, false, false, 2)      // R Conv 64->64
     TC_CASE_CG(64, 2, 3, true, ACT_ELU, true, false, 2)
+    TC_CASE_CG(64, 4, 3, true, ACT_ELU, false, false, 2)      // ... four sub-tiles per item (8 x 64 = 512 TMEM columns, double-buffered)
+    TC_CASE_CG(64, 4, 3, true, ACT_ELU, true, false, 2)
     TC_CASE_CG(128, 1, 3, true, ACT_ELU, false, false, 2)     // R Conv 64->128
     TC_CASE_CG(128, 2, 3, true, ACT_ELU, false, false, 2)
     TC_CASE_CG(128, 2, 3, false, ACT_ELU, false, false, 2)    // R Conv 128->128
@@ -649,8 +651,11 @@ static int load_R_impl(ganrev_ctx* ctx, int slot, int C, int H, int W, int nd, i
         const LayerDef d{name, KIND_CONV3, co, MT, pairs, bres, Hin, Win, ci, co, 1, Ho, Wo, co, pool, ACT_ELU, post, 0, false};
         return build_tc_layer(ctx, L, d, c.w, bn);
     };
-    RC_TRY(conv_layer(R.c2, "r_conv2", c2, 64, 64, H, W, 0, 1.0f, 2, true, (ctx->cta_pairs & 4) ? 2 : 1));
-    RC_TRY(conv_layer(R.c3, "r_conv3_pool", c3, 64, 64, H, W, 1, 1.0f, 2, true, (ctx->cta_pairs & 4) ? 2 : 1));
+    // 64-channel layers: an item of MT = 2 sub-tiles is 72 MMAs (~2900 cycles) against ~900 cycles of accumulator / stage hand-off
+    // (DESIGN section 6 finding 9); MT = 4 (cta_pairs bit 5, CTA pairs only: half of B per CTA leaves the room) amortises it over 144
+    const int mt64 = ((ctx->cta_pairs & 4) && (ctx->cta_pairs & 32) && H * W >= 128 && W >= 8) ? 4 : 2;
+    RC_TRY(conv_layer(R.c2, "r_conv2", c2, 64, 64, H, W, 0, 1.0f, mt64, true, (ctx->cta_pairs & 4) ? 2 : 1));
+    RC_TRY(conv_layer(R.c3, "r_conv3_pool", c3, 64, 64, H, W, 1, 1.0f, mt64, true, (ctx->cta_pairs & 4) ? 2 : 1));
     const bool c4_pairs = (ctx->cta_pairs & 8) && Hh * Wh >= 128 && Wh >= 8;   // CTA pairs exist for the halo-reuse tiling only
     RC_TRY(conv_layer(R.c4, "r_conv4", c4, 128, 64, Hh, Wh, 0, 1.0f, c4_pairs ? 2 : 1, true, (ctx->cta_pairs & 8) ? 2 : 1));   // pairs: half of B per CTA leaves room for MT = 2
     RC_TRY(conv_layer(R.c5, "r_conv5", c5, 128, 128, Hh, Wh, 0, 1.0f, 2, false, (ctx->cta_pairs & 16) ? 2 : 1));
@@ -1528,7 +1533,7 @@ static bool tc_plan(const ganrev_ctx* ctx, int Q, int k, TcPlan& pl) {
     if (N < 8192) return false;
     const int64_t n_t = std::max<int64_t>(1024, 8LL * k);      // rows of the coarsest (exhaustively re-scored) sample
     const int64_t sL = N / n_t;                                 // >= 8
-    const int L = std::max(1, static_cast<int>(std::ceil(std::log(static_cast<double>(sL)) / std::log(32.0) - 1e-9)));
+    const int L = std::max(1, static_cast<int>(std::ceil(std::log(static_cast<double>(sL)) / std::log(24.0) - 1e-9)));   // levels at most 24x apart: ~24 k candidates per query against lists of >= 64 k
     if (L > 6) return false;
     const double r = std::pow(static_cast<double>(sL), 1.0 / L);
     pl.levels = L;
@@ -1554,8 +1559,8 @@ static int search_tc_local(ganrev_ctx* ctx, const TcPlan& pl, int Q, int k) {
     // per level: cnt[Q] | offsets[Q] | cursor[Q] | total; pairs in arrival order, then candidates grouped by query
     const size_t pair_cap = static_cast<size_t>(Q) * std::max(2048, 100 * k);
     RC_TRY(ensure(ctx, ctx->tc_cnt, sizeof(unsigned) * (3 * static_cast<size_t>(Q) + 4)));
-    RC_TRY(ensure(ctx, ctx->tc_pairs, sizeof(uint2) * pair_cap));
-    RC_TRY(ensure(ctx, ctx->tc_cand, sizeof(unsigned) * pair_cap));
+    RC_TRY(ensure(ctx, ctx->tc_pairs, sizeof(uint4) * pair_cap));
+    RC_TRY(ensure(ctx, ctx->tc_cand, 2 * sizeof(unsigned) * pair_cap));          // rows, then their approximate scores
     RC_TRY(ensure(ctx, ctx->tc_keys, sizeof(unsigned long long) * static_cast<size_t>(Q) * k));
     unsigned* d_cnt = static_cast<unsigned*>(ctx->tc_cnt.p);
     unsigned* d_off = d_cnt + Q;
@@ -1569,7 +1574,7 @@ static int search_tc_local(ganrev_ctx* ctx, const TcPlan& pl, int Q, int k) {
         attr_dev[ctx->device][0] = 1;
     }
     const int64_t nL = (N + pl.stride[pl.levels] - 1) / pl.stride[pl.levels];
-    const size_t rs_smem = 8 * (static_cast<size_t>(std::max<int64_t>(pl.cap + stc::kMaxSpecial, nL)) + 2) + 4 * static_cast<size_t>(d) + 16;
+    const size_t rs_smem = 12 * (static_cast<size_t>(std::max<int64_t>(pl.cap, nL)) + stc::kMaxSpecial + 8) + 4 * static_cast<size_t>(d) + 64;
     if (rs_smem > attr_dev[ctx->device][1]) {
         CU_TRY(cudaFuncSetAttribute(stc::rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(rs_smem)));
         attr_dev[ctx->device][1] = rs_smem;
@@ -1577,45 +1582,53 @@ static int search_tc_local(ganrev_ctx* ctx, const TcPlan& pl, int Q, int k) {
     stc::RescoreParams rp{};
     rp.db = ctx->db_ptr; rp.rdb = static_cast<const float*>(ctx->rdb.p); rp.n = N; rp.d = d;
     rp.q = static_cast<const float*>(ctx->q.p); rp.rq = static_cast<const float*>(ctx->rq.p); rp.nq = Q; rp.k = k;
-    rp.cnt = d_cnt; rp.offsets = d_off; rp.cand = static_cast<const unsigned*>(ctx->tc_cand.p); rp.cap = pl.cap;
+    rp.cnt = d_cnt; rp.offsets = d_off; rp.cand = static_cast<const unsigned*>(ctx->tc_cand.p);
+    rp.cand_score = reinterpret_cast<const float*>(static_cast<const unsigned*>(ctx->tc_cand.p) + pair_cap); rp.cap = pl.cap;
     rp.special_rows = sp_rows; rp.special_count = sp_rows + stc::kMaxSpecial; rp.eps = stc::tc_eps(d); rp.flags = d_flags;
     CUtensorMap tmQ, tmX;
     RC_TRY(tc_make_map(ctx, &tmQ, ctx->pq.p, kp, Q, kp, stc::QM));
+    const float* d_cscore = reinterpret_cast<const float*>(static_cast<const unsigned*>(ctx->tc_cand.p) + pair_cap);
     for (int lvl = pl.levels; lvl >= 0; --lvl) {
         const int stride = pl.stride[lvl];
         const int64_t n_l = (N + stride - 1) / stride;
         const bool coarsest = lvl == pl.levels, final_level = lvl == 0;
-        if (!coarsest) {
-            CU_TRY(cudaMemsetAsync(ctx->tc_cnt.p, 0, sizeof(unsigned) * (3 * static_cast<size_t>(Q) + 4), ctx->stream));
-            RC_TRY(tc_make_map(ctx, &tmX, ctx->pdb.p, kp, n_l, static_cast<long long>(stride) * kp, stc::RN));
-            stc::FilterParams fp{};
-            fp.nq = Q; fp.n_rows = n_l; fp.stride = stride; fp.d = d; fp.nslices = kp / 128;
-            fp.q_tiles = (Q + stc::QM - 1) / stc::QM;
-            fp.items = static_cast<long long>(fp.q_tiles) * ((n_l + stc::RN - 1) / stc::RN);
-            fp.thr = static_cast<const float*>(ctx->tc_thr.p); fp.cnt = d_cnt;
-            fp.pairs = static_cast<uint2*>(ctx->tc_pairs.p); fp.total = d_total; fp.pair_cap = static_cast<unsigned>(pair_cap);
-            fp.flags = d_flags; fp.err_flag = ctx->d_err_flag; fp.dump = nullptr;
+        CU_TRY(cudaMemsetAsync(ctx->tc_cnt.p, 0, sizeof(unsigned) * (3 * static_cast<size_t>(Q) + 4), ctx->stream));
+        if (coarsest) {   // every pair of the coarsest sample is kept: dense approximate scores, no pair passes the (infinite) threshold
+            RC_TRY(ensure(ctx, ctx->tc_dump, sizeof(float) * static_cast<size_t>(Q) * n_l));
+            CU_TRY(cudaMemsetAsync(ctx->tc_thr.p, 0x7f, sizeof(float) * Q, ctx->stream));
+        }
+        RC_TRY(tc_make_map(ctx, &tmX, ctx->pdb.p, kp, n_l, static_cast<long long>(stride) * kp, stc::RN));
+        stc::FilterParams fp{};
+        fp.nq = Q; fp.n_rows = n_l; fp.stride = stride; fp.d = d; fp.nslices = kp / 128;
+        fp.q_tiles = (Q + stc::QM - 1) / stc::QM;
+        fp.items = static_cast<long long>(fp.q_tiles) * ((n_l + stc::RN - 1) / stc::RN);
+        fp.thr = static_cast<const float*>(ctx->tc_thr.p); fp.cnt = d_cnt;
+        fp.pairs = static_cast<uint4*>(ctx->tc_pairs.p); fp.total = d_total; fp.pair_cap = static_cast<unsigned>(pair_cap);
+        fp.flags = d_flags; fp.err_flag = ctx->d_err_flag; fp.dump = coarsest ? static_cast<float*>(ctx->tc_dump.p) : nullptr;
+        {
             // executed work: three bf16 product chains over the 16-padded columns; bytes: the packed rows once (L2 serves the other query tiles)
             ProfScope ps(ctx, "search_tc_filter", 3.0 * 2.0 * n_l * Q * ((d + 15) / 16 * 16), 2.0 * kp * (static_cast<double>(n_l) + Q));
             const int grid = static_cast<int>(std::min<long long>(fp.items, ctx->num_sms));
-            stc::filter_kernel<false><<<grid, stc::kThr, stc::kSmem, ctx->stream>>>(tmQ, tmX, fp);
+            if (coarsest) stc::filter_kernel<true><<<grid, stc::kThr, stc::kSmem, ctx->stream>>>(tmQ, tmX, fp);
+            else stc::filter_kernel<false><<<grid, stc::kThr, stc::kSmem, ctx->stream>>>(tmQ, tmX, fp);
             CU_TRY(cudaGetLastError());
         }
         if (!coarsest) {
             ProfScope ps(ctx, "search_tc_group", 0.0, 20.0 * Q * 32.0 * k);
             ctx->launches++;
             stc::offsets_kernel<<<1, 1024, 0, ctx->stream>>>(d_cnt, Q, static_cast<unsigned>(pl.cap), d_off, d_cur, d_flags);
-            stc::scatter_kernel<<<4 * ctx->num_sms, 256, 0, ctx->stream>>>(static_cast<const uint2*>(ctx->tc_pairs.p), d_total, static_cast<unsigned>(pair_cap), d_off, d_cur,
-                                                                          static_cast<unsigned*>(ctx->tc_cand.p), d_flags);
+            stc::scatter_kernel<<<4 * ctx->num_sms, 256, 0, ctx->stream>>>(static_cast<const uint4*>(ctx->tc_pairs.p), d_total, static_cast<unsigned>(pair_cap), d_off, d_cur,
+                                                                          static_cast<unsigned*>(ctx->tc_cand.p), const_cast<float*>(d_cscore), d_flags);
             CU_TRY(cudaGetLastError());
         }
         rp.implicit_stride = coarsest ? stride : 0;
         rp.n_implicit = coarsest ? static_cast<int>(n_l) : 0;
-        rp.use_special = final_level ? 1 : 0;
+        rp.cand_score = coarsest ? static_cast<const float*>(ctx->tc_dump.p) : d_cscore;
+        rp.final_level = final_level ? 1 : 0;
         rp.next_ratio = final_level ? 1.0f : static_cast<float>(stride) / static_cast<float>(pl.stride[lvl - 1]);
-        rp.keys_out = static_cast<unsigned long long*>(final_level ? ctx->partial.p : ctx->tc_keys.p);
+        rp.keys_out = static_cast<unsigned long long*>(ctx->partial.p);
         rp.thr_out = final_level ? nullptr : static_cast<float*>(ctx->tc_thr.p);
-        ProfScope ps(ctx, "search_tc_rescore", 2.0 * Q * d * (coarsest ? static_cast<double>(n_l) : 32.0 * k), 0.0);
+        ProfScope ps(ctx, final_level ? "search_tc_rescore" : "search_tc_select", final_level ? 2.0 * Q * d * 1.5 * k : 0.0, 0.0);
         stc::rescore_kernel<<<Q, 256, rs_smem, ctx->stream>>>(rp);
         CU_TRY(cudaGetLastError());
     }
@@ -1976,7 +1989,7 @@ int ganrev_debug_tc_scores(ganrev_ctx* ctx, const float* queries, int Q, float* 
     RC_TRY(tc_pack(ctx, "search_tc_pack_q", static_cast<const float*>(ctx->q.p), static_cast<const float*>(ctx->rq.p), Q, d, ctx->pq, true));
     RC_TRY(ensure(ctx, ctx->tc_thr, sizeof(float) * Q));
     RC_TRY(ensure(ctx, ctx->tc_cnt, sizeof(unsigned) * (3 * static_cast<size_t>(Q) + 4)));
-    RC_TRY(ensure(ctx, ctx->tc_pairs, sizeof(uint2) * 16));
+    RC_TRY(ensure(ctx, ctx->tc_pairs, sizeof(uint4) * 16));
     RC_TRY(ensure(ctx, ctx->tc_dump, sizeof(float) * static_cast<size_t>(Q) * N));
     CU_TRY(cudaMemsetAsync(ctx->tc_thr.p, 0x7f, sizeof(float) * Q, ctx->stream));     // 0x7f7f7f7f = 3.39e38: nothing passes
     CU_TRY(cudaMemsetAsync(ctx->tc_cnt.p, 0, sizeof(unsigned) * (3 * static_cast<size_t>(Q) + 4), ctx->stream));
@@ -1990,7 +2003,7 @@ int ganrev_debug_tc_scores(ganrev_ctx* ctx, const float* queries, int Q, float* 
     fp.q_tiles = (Q + stc::QM - 1) / stc::QM;
     fp.items = static_cast<long long>(fp.q_tiles) * ((N + stc::RN - 1) / stc::RN);
     fp.thr = static_cast<const float*>(ctx->tc_thr.p); fp.cnt = static_cast<unsigned*>(ctx->tc_cnt.p);
-    fp.pairs = static_cast<uint2*>(ctx->tc_pairs.p); fp.total = static_cast<unsigned*>(ctx->tc_cnt.p) + 3 * Q; fp.pair_cap = 0;
+    fp.pairs = static_cast<uint4*>(ctx->tc_pairs.p); fp.total = static_cast<unsigned*>(ctx->tc_cnt.p) + 3 * Q; fp.pair_cap = 0;
     fp.flags = static_cast<int*>(ctx->tc_flags.p) + 3; fp.err_flag = ctx->d_err_flag;
     fp.dump = static_cast<float*>(ctx->tc_dump.p);
     {

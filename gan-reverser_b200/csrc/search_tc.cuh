@@ -17,14 +17,16 @@
 //      fmaf-chain score vs the true cosine      <= (4d + 12) * 2^-24               (dot product, two norms, sqrt, product)
 //    (sum < eps(d) for every d; tests/test_gpu_search_tc.py measures the observed maximum on the device: <= eps/8).
 // 3. THRESHOLDS without a sequential dependency: levels of strided samples of the database (stride s_L > ... > s_1 > 1 =
-//    s_0, about 32x apart, the coarsest ~1024 rows).  The exact k-th best score tau over a SUBSET of the rows is a lower
-//    bound of the k-th best over all rows, so thr_q = tau_q(level l+1) - eps can never drop a top-k member of level l;
-//    it passes ~ k * s_{l+1}/s_l candidates per query.  The coarsest level is re-scored exhaustively.  The strided
-//    sample is a TMA tensor map with a larger row pitch: no copy.
-// 4. RESCORE + SELECT (rescore_kernel, one block per query): every candidate gets the exact score (one thread = one
-//    sequential fmaf chain), keys (score desc, NaN last, lowest id) go through the same warp-level sorted-list insertion
-//    as merge_kernel.  Output: the level's top-k keys (final level: the `partial` list search_finish merges, also across
-//    ranks) and the next level's thresholds.
+//    s_0, at most 24x apart, the coarsest ~1024 rows).  The exact k-th best score over a SUBSET of the rows is a lower
+//    bound of the k-th best over all rows, so a threshold derived from level l+1 (see 4.) can never drop a top-k member of
+//    level l; it passes ~ k * s_{l+1}/s_l candidates per query.  The coarsest level keeps every pair (its approximate scores
+//    are written densely).  The strided sample is a TMA tensor map with a larger row pitch: no copy.
+// 4. SELECT + RESCORE (rescore_kernel, one block per query).  The pairs carry their approximate scores.  With a_k = the k-th
+//    largest approximate score among a query's candidates, the exact k-th best is >= a_k - eps, so only candidates with
+//    approx >= a_k - 2 eps can be in the top-k: about k of the ~32 k candidates.  Intermediate levels therefore re-score
+//    nothing (next threshold = a_k - 2 eps); the final level runs the exact chain (one thread = one sequential fmaf chain)
+//    on the survivors and the special rows, and their total-order keys (score desc, NaN last, lowest id) go through the same
+//    warp-level sorted-list insertion as merge_kernel into the `partial` list search_finish merges (also across ranks).
 // Rows whose norm is not a positive finite number (NaN / inf entries) are "special": packed as zeros and appended to
 // every query's candidates at the final level.  Candidate-list overflow (adversarial duplicates), special queries or
 // too many special rows raise a flag and the caller re-runs the search with the fmaf-chain kernels: never a wrong
@@ -49,7 +51,7 @@ constexpr int kBB = RN * 128;                  // bytes of one row block    [256
 constexpr int kStage = 2 * kAB + 2 * kBB;      // q_hi, q_lo, x_hi, x_lo of one slice: 96 KB
 constexpr int kStages = 2;
 constexpr int kWB = 128;                       // candidate pairs staged per epilogue warp before one global reservation
-constexpr int kSmem = kStages * kStage + 1024 /*barriers*/ + kEpi * kWB * 8 /*pair staging*/ + 1024 /*alignment*/;
+constexpr int kSmem = kStages * kStage + 1024 /*barriers*/ + kEpi * kWB * 16 /*pair staging*/ + 1024 /*alignment*/;
 constexpr int kMaxSpecial = 1024;              // special rows handled exactly; more -> the fmaf-chain kernels take over
 constexpr int FLAG_OVERFLOW = 1, FLAG_SPECIAL_QUERY = 2, FLAG_SPECIAL_ROWS = 4;
 
@@ -104,7 +106,7 @@ struct FilterParams {
     long long items;           // q_tiles * ceil(n_rows / RN)
     const float* thr;          // [nq] pass iff approx >= thr
     unsigned* cnt;             // [nq] candidates per query (fire-and-forget REDs)
-    uint2* pairs;              // [pair_cap] (query, global row) in arrival order; grouped by query afterwards (group_kernel)
+    uint4* pairs;              // [pair_cap] (query, global row, approximate score bits, 0) in arrival order; grouped by query afterwards
     unsigned* total;           // pairs written so far
     unsigned pair_cap;
     int* flags;
@@ -201,7 +203,7 @@ filter_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const int etid = threadIdx.x - 64;
         const int ew = warp - 2;
         const float pinf = __uint_as_float(0x7f800000u);
-        uint2* wbuf = reinterpret_cast<uint2*>(smem + kStages * kStage + 1024) + ew * kWB;
+        uint4* wbuf = reinterpret_cast<uint4*>(smem + kStages * kStage + 1024) + ew * kWB;
         unsigned* wcnt = reinterpret_cast<unsigned*>(smem + kStages * kStage + 512) + ew;
         if (lane == 0) *wcnt = 0u;
         __syncwarp();
@@ -258,7 +260,16 @@ filter_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                     const long long r = row_base + c2 * 64 + j;
                     if (r < p.n_rows) {
                         atomicAdd(p.cnt + qidx, 1u);                       // result unused: a RED, no round trip
-                        const uint2 pr = make_uint2(static_cast<unsigned>(qidx), static_cast<unsigned>(r * p.stride));
+                        // the approximate score of column j travels with the pair (it selects what gets re-scored exactly):
+                        // a 6-level select tree over the 64 registers, ~63 SELs, only on this rare path
+                        uint32_t t[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) t[i] = (j & 32) ? rb[i] : ra[i];
+#pragma unroll
+                        for (int w = 16; w >= 1; w >>= 1)
+#pragma unroll
+                            for (int i = 0; i < w; ++i) t[i] = (j & w) ? t[i + w] : t[i];
+                        const uint4 pr = make_uint4(static_cast<unsigned>(qidx), static_cast<unsigned>(r * p.stride), t[0], 0u);
                         const unsigned slot = atomicAdd(wcnt, 1u);         // shared memory
                         if (slot < static_cast<unsigned>(kWB)) wbuf[slot] = pr;
                         else {                                             // staging full (a burst): straight to the global list
@@ -322,14 +333,14 @@ offsets_kernel(const unsigned* __restrict__ cnt, int nq, unsigned cap, unsigned*
         if (q < nq) { offsets[q] = run; run += cnt[q]; }
     }
 }
-__global__ void scatter_kernel(const uint2* __restrict__ pairs, const unsigned* __restrict__ total, unsigned pair_cap, const unsigned* __restrict__ offsets,
-                               unsigned* __restrict__ cursor, unsigned* __restrict__ cand, const int* __restrict__ flags) {
+__global__ void scatter_kernel(const uint4* __restrict__ pairs, const unsigned* __restrict__ total, unsigned pair_cap, const unsigned* __restrict__ offsets,
+                               unsigned* __restrict__ cursor, unsigned* __restrict__ cand, float* __restrict__ cand_score, const int* __restrict__ flags) {
     if (*reinterpret_cast<const volatile int*>(flags) != 0) return;
     const unsigned n = min(*total, pair_cap);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint2 pr = pairs[i];
+        const uint4 pr = pairs[i];
         const unsigned pos = offsets[pr.x] + atomicAdd(cursor + pr.x, 1u);
-        if (pos < pair_cap) cand[pos] = pr.y;
+        if (pos < pair_cap) { cand[pos] = pr.y; cand_score[pos] = __uint_as_float(pr.z); }
     }
 }
 
@@ -342,47 +353,148 @@ struct RescoreParams {
     const float* q;            // [nq][d]
     const float* rq;           // [nq]
     int nq, k;
-    // candidates: either the implicit strided sample (stride > 0: rows i*stride, i < n_implicit) or the per-query lists
+    // candidates: the whole strided sample of the coarsest level (implicit_stride > 0: cand_score is the dense [nq][n_implicit]
+    // matrix filter_kernel<true> wrote), or the per-query lists of the filter with their approximate scores
     int implicit_stride;
     int n_implicit;
     const unsigned* cnt;       // [nq]
     const unsigned* offsets;   // [nq] first candidate of each query in cand
     const unsigned* cand;      // candidates grouped by query (global row ids)
+    const float* cand_score;   // their approximate scores
     int cap;                   // most candidates one query may have
     const unsigned* special_rows;    // final level: appended to every query's candidates
     const unsigned* special_count;
-    int use_special;
+    int final_level;
     float eps;
     int* flags;
     float next_ratio;                // rows of the next (finer) level per row of this one
-    unsigned long long* keys_out;    // [nq][k] sorted descending (the `partial` list of the final level)
-    float* thr_out;                  // [nq] next (finer) level's threshold, or nullptr
+    unsigned long long* keys_out;    // [nq][k] sorted descending: the `partial` list of the final level
+    float* thr_out;                  // [nq] next (finer) level's threshold (not final)
 };
 
+// k-th largest of n keys held in shared memory (one warp; the sorted-list insertion of merge_kernel); returns the list too
+template <int E>
+__device__ __forceinline__ unsigned long long warp_topk(const unsigned long long* keys, int n, int k, int lane, unsigned long long (&L)[E]) {
+#pragma unroll
+    for (int j = 0; j < E; ++j) L[j] = 0ull;
+    unsigned long long kth = 0ull;
+    for (int base = 0; base < n; base += 32) {
+        const unsigned long long c = base + lane < n ? keys[base + lane] : 0ull;
+        unsigned hit = __ballot_sync(0xffffffffu, c > kth);
+        while (hit) {
+            const int t = __ffs(hit) - 1;
+            hit &= hit - 1;
+            const unsigned long long cc = __shfl_sync(0xffffffffu, c, t);
+            if (cc > kth) {                                       // warp-uniform (kth may have risen since the ballot)
+                scan::list_insert<E>(L, cc, lane);
+                kth = scan::list_kth<E>(L, k);
+            }
+        }
+    }
+    return kth;
+}
+
+// k-th largest (1-based) of n 32-bit order-preserving keys in shared memory, whole block of 256 threads: MSB radix select,
+// four 8-bit passes over a shared histogram.  Returns 0 when n < k.  Every thread gets the result.
+__device__ __forceinline__ uint32_t block_kth_largest(const uint32_t* keys, int n, int k, unsigned* hist /*[256]*/, unsigned* state /*[2]*/) {
+    const int tid = threadIdx.x;
+    if (n < k) return 0u;
+    if (tid == 0) { state[0] = 0u; state[1] = static_cast<unsigned>(k); }
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        hist[tid] = 0u;
+        __syncthreads();
+        const uint32_t prefix = state[0];
+        const uint32_t himask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+        for (int i = tid; i < n; i += 256) {
+            const uint32_t v = keys[i];
+            if ((v & himask) == prefix) atomicAdd(&hist[(v >> shift) & 0xFFu], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned r = state[1];
+            int bin = 255;
+            for (; bin > 0; --bin) {
+                if (r <= hist[bin]) break;
+                r -= hist[bin];
+            }
+            state[1] = r;
+            state[0] = prefix | (static_cast<uint32_t>(bin) << shift);
+        }
+        __syncthreads();
+    }
+    return state[0];
+}
+
+// One block per query.  a_k = the k-th largest APPROXIMATE score among the query's candidates (coarsest level: every row of
+// the strided sample, scores written densely by filter_kernel<true>; other levels: the filter's candidate list).  Each of those
+// k rows has an exact score >= a_k - eps, so the exact k-th best of the level is >= a_k - eps, and a row that reaches the top-k
+// of this (or any finer) level has an approximate score >= a_k - 2 eps.  Hence
+//   not final: thr_out = a_k - 2 eps, nothing is scored exactly;
+//   final    : only the candidates with approx >= a_k - 2 eps (about k, not k * 32) and the special rows get the exact fmaf
+//              chain (one thread = one sequential chain, oracle orc_search_cosine); their total-order keys give the answer.
 __global__ void __launch_bounds__(256)
 rescore_kernel(const RescoreParams p) {
     constexpr int E = 4;                                          // k <= 128
     extern __shared__ __align__(16) uint8_t sm[];
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(sm);
     const int q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (*reinterpret_cast<const volatile int*>(p.flags) != 0) return;   // raised by an earlier kernel: the fmaf-chain kernels will answer
-    const int n_list = p.implicit_stride > 0 ? p.n_implicit : static_cast<int>(min(p.cnt[q], static_cast<unsigned>(p.cap)));
-    const int n_sp = p.use_special ? static_cast<int>(min(*p.special_count, static_cast<unsigned>(kMaxSpecial))) : 0;
-    const int n_c = n_list + n_sp;
-    float* qs = reinterpret_cast<float*>(keys + ((n_c + 1) & ~1));
+    const bool dense = p.implicit_stride > 0;
+    const int n_list = dense ? p.n_implicit : static_cast<int>(min(p.cnt[q], static_cast<unsigned>(p.cap)));
+    const int n_sp = p.final_level ? static_cast<int>(min(*p.special_count, static_cast<unsigned>(kMaxSpecial))) : 0;
+    const int n_max = max(n_list, 1) + n_sp;
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(sm);                  // [n_list] approximate keys, later [n_sel + n_sp] exact keys
+    unsigned* sel = reinterpret_cast<unsigned*>(keys + ((n_max + 2) & ~1));            // even key count: everything behind stays 16-byte aligned
+    float* qs = reinterpret_cast<float*>(sel + ((n_max + 3) & ~3));
+    __shared__ int s_nsel;
+    const float ninf = __uint_as_float(0xff800000u);
+    // ---- phase A: the k-th largest approximate score (block radix select on order-preserving 32-bit keys)
+    const float* ascore = dense ? p.cand_score + static_cast<long long>(q) * p.n_implicit : p.cand_score + p.offsets[q];
+    uint32_t* akeys = reinterpret_cast<uint32_t*>(keys);
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned s_state[2];
+    for (int i = tid; i < n_list; i += 256) akeys[i] = scan::score_key32(ascore[i]);
+    if (tid == 0) s_nsel = 0;
+    __syncthreads();
+    const uint32_t hi = block_kth_largest(akeys, n_list, p.k, s_hist, s_state);
+    __syncthreads();
+    const float a_k = scan::score_unkey32(hi);
+    const bool usable = hi != 0u && fabsf(a_k) < 3.0e38f;         // else fewer than k candidates: no bound
+    const float cut = usable ? a_k - 2.0f * p.eps : ninf;
+    if (!p.final_level) {
+        // The next level's threshold, and a prediction of its candidate count from THIS level's scores: every row within
+        // 4*eps of a_k stands for next_ratio rows that will pass the next filter.  Scores packed closer than the filter's
+        // resolution (e.g. the recovered vectors of an untrained R: all cosines within 1e-5 of 1) cannot be pruned by any
+        // approximation -- say so now, before the expensive levels run, and let the fmaf-chain kernels answer.
+        const float band = usable ? a_k - 4.0f * p.eps : ninf;
+        int mine = 0;
+        for (int i = tid; i < n_list; i += 256) mine += ascore[i] >= band ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if (lane == 0 && mine) atomicAdd(&s_nsel, mine);
+        __syncthreads();
+        if (tid == 0) {
+            p.thr_out[q] = cut;
+            if (!usable || static_cast<float>(s_nsel) * p.next_ratio > 0.75f * static_cast<float>(p.cap)) atomicOr(p.flags, FLAG_OVERFLOW);
+        }
+        return;
+    }
+    // ---- final level: compact the candidates that can still reach the top-k
+    const unsigned* crow = p.cand + p.offsets[q];
+    for (int i = tid; i < n_list; i += 256)
+        if (ascore[i] >= cut) sel[atomicAdd(&s_nsel, 1)] = crow[i];
     for (int i = tid; i < p.d; i += 256) qs[i] = __ldg(p.q + static_cast<long long>(q) * p.d + i);
     __syncthreads();
+    const int n_sel = s_nsel;
+    // ---- exact scores
     const float rqv = __ldg(p.rq + q);
     const bool vec = (p.d & 3) == 0;
+    const int n_c = n_sel + n_sp;
     for (int i = tid; i < n_c; i += 256) {
-        long long row;
-        bool dup = false;
-        if (i >= n_list) row = p.special_rows[i - n_list];
-        else if (p.implicit_stride > 0) row = static_cast<long long>(i) * p.implicit_stride;
-        else row = p.cand[p.offsets[q] + i];
+        const long long row = i >= n_sel ? p.special_rows[i - n_sel] : sel[i];
         const float rx = __ldg(p.rdb + row);
-        if (p.use_special && i < n_list && (!(rx > 0.0f) || !(rx < 3.0e38f))) dup = true;   // a special row: scored once, through the special list
+        const bool dup = i < n_sel && (!(rx > 0.0f) || !(rx < 3.0e38f));   // a special row: scored once, through the special list
         const float* xr = p.db + row * p.d;
         float acc = 0.0f;
         if (vec) {
@@ -402,44 +514,11 @@ rescore_kernel(const RescoreParams p) {
     __syncthreads();
     if (warp != 0) return;
     unsigned long long L[E];
-#pragma unroll
-    for (int j = 0; j < E; ++j) L[j] = 0ull;
-    unsigned long long kth = 0ull;
-    for (int base = 0; base < n_c; base += 32) {
-        const unsigned long long c = base + lane < n_c ? keys[base + lane] : 0ull;
-        unsigned hit = __ballot_sync(0xffffffffu, c > kth);
-        while (hit) {
-            const int t = __ffs(hit) - 1;
-            hit &= hit - 1;
-            const unsigned long long cc = __shfl_sync(0xffffffffu, c, t);
-            if (cc > kth) {                                       // warp-uniform (kth may have risen since the ballot)
-                scan::list_insert<E>(L, cc, lane);
-                kth = scan::list_kth<E>(L, p.k);
-            }
-        }
-    }
+    warp_topk<E>(keys, n_c, p.k, lane, L);
 #pragma unroll
     for (int j = 0; j < E; ++j) {
         const int t = lane * E + j;
         if (t < p.k) p.keys_out[static_cast<long long>(q) * p.k + t] = L[j];
-    }
-    if (p.thr_out) {
-        const uint32_t hi = static_cast<uint32_t>(kth >> 32);
-        const float tau = scan::score_unkey32(hi);
-        const bool usable = hi != 0u && fabsf(tau) < 3.0e38f;     // else: list not full, or its k-th entry NaN / infinite
-        // Predict the next level's candidate count from THIS level's exact scores: every row within 2*eps of tau stands
-        // for next_ratio rows that will pass the filter.  Scores packed closer than the filter's resolution (e.g. recovered
-        // vectors of an untrained R: all cosines within 1e-5 of 1) cannot be pruned by any approximation -- say so now,
-        // before the expensive levels run, and let the fmaf-chain kernels answer.
-        const uint32_t lo_key = usable ? scan::score_key32(tau - 2.0f * p.eps) : 0u;
-        int near = 0;
-        for (int i = lane; i < n_c; i += 32) near += (static_cast<uint32_t>(keys[i] >> 32) >= lo_key && keys[i] != 0ull) ? 1 : 0;
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) near += __shfl_xor_sync(0xffffffffu, near, off);
-        if (lane == 0) {
-            p.thr_out[q] = usable ? tau - p.eps : __uint_as_float(0xff800000u);
-            if (!usable || static_cast<float>(near) * p.next_ratio > 0.5f * static_cast<float>(p.cap)) atomicOr(p.flags, FLAG_OVERFLOW);
-        }
     }
 }
 
