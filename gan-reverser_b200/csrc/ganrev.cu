@@ -14,6 +14,8 @@
 #include "layers.cuh"
 #include "scan.cuh"
 #include "search_tc.cuh"
+#include "label_tc.cuh"
+#include "kmeans_tc.cuh"
 
 using namespace ganrev;
 
@@ -72,6 +74,8 @@ struct ganrev_ctx {
     int tma_store = 1;            // TMA bulk tensor stores in the conv epilogue where the layer allows (0 = st.global everywhere; A/B)
     int search_tc = 1;            // tensor-core candidate filter + exact re-score for many-query searches (0 = fmaf-chain kernels only; A/B)
     uint64_t tc_searches = 0, tc_fallbacks = 0;   // searches served by the tensor-core path / re-run on the fmaf-chain kernels
+    int label_tc = 0;             // 1 = tensor-core labelling for k <= 32, d <= 128 (label_tc.cuh; bit-exact, measured no faster than rtile_kernel yet: off)
+    int kmeans_tc = 1;            // tensor-core labelling for 32 < k (kmeans_tc.cuh): approximate scores, exact chains only for near-ties
     int rtile = 1;                // register-tiled kmeans / cosine-min kernels for 9 <= k <= 32 (0 = the one-thread-per-row streaming kernels; A/B)
     int cta_pairs = 0x1f;     // which layers use tcgen05 cta_group::2 CTA pairs (bit0 G conv1, bit1 G conv2, bit2 R conv2/3,
                               // bit3 R conv4, bit4 R conv5/6); takes effect at the next ganrev_load_*.  Default = measured best.
@@ -97,7 +101,7 @@ struct ganrev_ctx {
     DevBuf arena[2], noise_bf16, stage_a, stage_b, l2buf, thr, flags;
     int64_t l2_valid = 0;                  // entries of l2buf written by the last fix_l2 / l2 / anomaly_flags call
     DevBuf nn_partial, nn_ids, nn_dist, nn_flag, nn_all;   // ganrev_nearest_l2 scratch
-    DevBuf pdb, pq, tc_thr, tc_cnt, tc_cand, tc_pairs, tc_keys, tc_special, tc_flags, tc_dump;   // search_tc.cuh: packed split-bf16 operands, candidates
+    DevBuf amb, pdb, pq, tc_thr, tc_cnt, tc_cand, tc_pairs, tc_keys, tc_special, tc_flags, tc_dump;   // search_tc.cuh: packed split-bf16 operands, candidates
     bool pdb_valid = false;                // pdb / tc_special describe the current database
     DevBuf qsel, shard;                    // radix-select state + histogram; row-shard bookkeeping (world + 2 int64)
     // database
@@ -855,7 +859,7 @@ void ganrev_destroy(ganrev_ctx* ctx) {
         for (TcLayer* L : {&R.c2, &R.c3, &R.c4, &R.c5, &R.c6, &R.l1, &R.l2}) release_layer(*L);
     }
     for (auto& b : ctx->buf) release(b);
-    for (DevBuf* b : {&ctx->nn_partial, &ctx->nn_ids, &ctx->nn_dist, &ctx->nn_flag, &ctx->nn_all, &ctx->qsel, &ctx->shard, &ctx->pdb, &ctx->pq, &ctx->tc_thr,
+    for (DevBuf* b : {&ctx->nn_partial, &ctx->nn_ids, &ctx->nn_dist, &ctx->nn_flag, &ctx->nn_all, &ctx->qsel, &ctx->shard, &ctx->amb, &ctx->pdb, &ctx->pq, &ctx->tc_thr,
                       &ctx->tc_cnt, &ctx->tc_cand, &ctx->tc_pairs, &ctx->tc_keys, &ctx->tc_special, &ctx->tc_flags, &ctx->tc_dump}) release(*b);
     for (DevBuf* b : {&ctx->arena[0], &ctx->arena[1], &ctx->noise_bf16, &ctx->stage_a, &ctx->stage_b, &ctx->l2buf, &ctx->thr, &ctx->flags,
                       &ctx->db, &ctx->rdb, &ctx->maxabs, &ctx->q, &ctx->rq, &ctx->c2, &ctx->partial, &ctx->keys, &ctx->keys_all, &ctx->ids,
@@ -1397,6 +1401,39 @@ static int dispatch_rtile(ganrev_ctx* ctx, int NQ, const scan::StreamParams& sp,
     return fail(ctx, GANREV_EINVAL, "bad NQ %d", NQ);
 }
 
+// ---- tensor-core labelling (label_tc.cuh): kmeans (MODE 1) / cosine-min (MODE 2) for k <= 32, d % 4 == 0, d <= 128
+static size_t label_tc_smem(const scan::ScanParams& p, int mode) {
+    const int d = p.d, nsl = (d + 63) / 64;
+    return static_cast<size_t>(nsl) * 2 * ltc::kABlk + static_cast<size_t>(nsl) * 2 * ltc::kBBlk + 2 * static_cast<size_t>(ltc::LR) * scan::wide4_stride(d) * 4 + 32 + 64 * 4 +
+           (3 * ltc::LR + 36 + 128) * 4 + 16 + ltc::kAmbStage * 4 + (mode == 2 ? ltc::LN * (d | 1) * 4 : 0) + 8 + (mode == 1 ? (static_cast<size_t>(p.nq) * d + p.nq) * 8 : 0) + 1024 + 64;
+}
+static bool label_tc_ok(const ganrev_ctx* ctx, const scan::ScanParams& p, int mode) {
+    return ctx->label_tc && p.nq >= 1 && p.nq <= 32 && p.d % 4 == 0 && p.d <= 128 && p.n_rows > 0 && label_tc_smem(p, mode) <= 227 * 1024;
+}
+template <int MODE>
+static int launch_label_tc(ganrev_ctx* ctx, const scan::ScanParams& p) {
+    RC_TRY(ensure(ctx, ctx->amb, sizeof(unsigned) * (static_cast<size_t>(p.n_rows) + 4)));
+    unsigned* d_count = static_cast<unsigned*>(ctx->amb.p);
+    unsigned* d_rows = d_count + 4;
+    CU_TRY(cudaMemsetAsync(d_count, 0, sizeof(unsigned), ctx->stream));
+    ltc::LabelParams lp{};
+    lp.s = p; lp.n_tiles = (p.n_rows + ltc::LR - 1) / ltc::LR; lp.amb_rows = d_rows; lp.amb_count = d_count; lp.err_flag = ctx->d_err_flag; lp.dbg = ctx->dbg >> 8;
+    const size_t smem = label_tc_smem(p, MODE);
+    static size_t attr_max_dev[kMaxDevices] = {};
+    size_t& attr_max = attr_max_dev[ctx->device];
+    if (smem > attr_max) {
+        CU_TRY(cudaFuncSetAttribute(ltc::label_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr_max = smem;
+    }
+    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(lp.n_tiles, static_cast<long long>(ctx->num_sms) * per_sm)));
+    ltc::label_tc_kernel<MODE><<<grid, ltc::kThreads, smem, ctx->stream>>>(lp);
+    ltc::label_exact_list_kernel<MODE><<<2 * ctx->num_sms, 256, 0, ctx->stream>>>(p, d_rows, d_count);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return GANREV_OK;
+}
+
 // merge the per-split lists, (multi-GPU) allgather + merge across ranks, copy results out
 static int search_finish(ganrev_ctx* ctx, const unsigned long long* partial, int splits, int Q, int k, int64_t* ids, float* scores) {
     const unsigned mblocks = static_cast<unsigned>((static_cast<long long>(Q) * 32 + scan::kThreads - 1) / scan::kThreads);
@@ -1732,6 +1769,62 @@ static int launch_assign(ganrev_ctx* ctx, const scan::ScanParams& p) {
     return GANREV_OK;
 }
 
+// ---- kmeans labelling for k > 32 on the tensor cores (kmeans_tc.cuh)
+static bool kmeans_tc_ok(const ganrev_ctx* ctx, int k) {
+    return ctx->kmeans_tc && k > 32 && ctx->db_d <= 1024 && ctx->db_n >= 1 && ctx->db_ptr != nullptr;
+}
+static int kmeans_tc_iteration(ganrev_ctx* ctx, const scan::ScanParams& p) {
+    const int d = p.d, k = p.nq, kp = stc::packed_cols(d);
+    const int64_t N = p.n_rows;
+    if (!ctx->pdb_valid) {
+        RC_TRY(tc_pack(ctx, "search_tc_pack_db", ctx->db_ptr, static_cast<const float*>(ctx->rdb.p), N, d, ctx->pdb, false));
+        ctx->pdb_valid = true;
+    }
+    RC_TRY(tc_pack(ctx, "kmeans_tc_pack_c", p.q, nullptr, k, d, ctx->pq, true));
+    // [count2 | cm2 | pad] | near-tie entries uint4[N] | full rows u32[N] | full keys u64[N]
+    const size_t amb_bytes = 32 + sizeof(uint4) * static_cast<size_t>(N) + 4 * static_cast<size_t>(N) + 8 * static_cast<size_t>(N) + 64;
+    RC_TRY(ensure(ctx, ctx->amb, amb_bytes));
+    unsigned* d_count = static_cast<unsigned*>(ctx->amb.p);
+    float* d_cm = reinterpret_cast<float*>(d_count + 2);
+    uint4* d_rows = reinterpret_cast<uint4*>(d_count + 8);
+    unsigned long long* d_keys = reinterpret_cast<unsigned long long*>(d_rows + N);
+    unsigned* d_full = reinterpret_cast<unsigned*>(d_keys + N);
+    CU_TRY(cudaMemsetAsync(d_keys, 0, 8 * static_cast<size_t>(N), ctx->stream));   // (the layout depends on N and the buffer is shared: clear every time, 8 bytes per row)
+    CU_TRY(cudaMemsetAsync(d_count, 0, 2 * sizeof(unsigned), ctx->stream));
+    ktc::cmax_kernel<<<1, 32, 0, ctx->stream>>>(p.c2, k, stc::tc_eps(d), d_cm);
+    static bool attr_dev[kMaxDevices] = {};
+    if (!attr_dev[ctx->device]) {
+        CU_TRY(cudaFuncSetAttribute(ktc::label_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ktc::kSmem));
+        attr_dev[ctx->device] = true;
+    }
+    CUtensorMap tmX, tmC;
+    RC_TRY(tc_make_map(ctx, &tmX, ctx->pdb.p, kp, N, kp, stc::QM));
+    RC_TRY(tc_make_map(ctx, &tmC, ctx->pq.p, kp, k, kp, stc::RN));
+    ktc::KParams kp_{};
+    kp_.n_rows = N; kp_.d = d; kp_.nslices = kp / 128; kp_.k = k; kp_.nchunks = (k + stc::RN - 1) / stc::RN;
+    kp_.r_tiles = (N + stc::QM - 1) / stc::QM;
+    kp_.rdb = p.rdb; kp_.c2 = p.c2; kp_.cm = d_cm; kp_.labels = p.labels; kp_.amb_rows = d_rows; kp_.full_rows = d_full; kp_.amb_count = d_count; kp_.err_flag = ctx->d_err_flag;
+    const int grid = static_cast<int>(std::min<long long>(kp_.r_tiles, ctx->num_sms));
+    {
+        ProfScope ps(ctx, "kmeans_tc_label", 3.0 * 2.0 * N * k * ((d + 15) / 16 * 16), 2.0 * kp * (static_cast<double>(N) + k));
+        ktc::label_kernel<<<grid, stc::kThr, ktc::kSmem, ctx->stream>>>(tmX, tmC, kp_);
+    }
+    {
+        ProfScope ps(ctx, "kmeans_tc_update", 1.0 * N * d, 4.0 * N * d + 4.0 * N);
+        ktc::update_kernel<<<8 * ctx->num_sms, 256, 0, ctx->stream>>>(p.db, N, d, p.labels, p.sc, p.acc, p.cnt);
+    }
+    {
+        ProfScope ps(ctx, "kmeans_tc_exact", 0.0, 0.0);
+        ktc::exact_two_kernel<<<4 * ctx->num_sms, 256, 0, ctx->stream>>>(p, d_rows, d_count);
+        ktc::full_scan_kernel<<<4 * ctx->num_sms, 256, 0, ctx->stream>>>(p, d_full, d_count + 1, d_keys);
+        ktc::full_finalize_kernel<<<ctx->num_sms, 256, 0, ctx->stream>>>(p, d_full, d_count + 1, d_keys);
+        ctx->launches += 2;
+    }
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return GANREV_OK;
+}
+
 extern "C" {
 static int kmeans_shift_of(float maxabs, int64_t n_total) {
     if (!(maxabs <= 3.0e38f)) return -1;
@@ -1739,8 +1832,9 @@ static int kmeans_shift_of(float maxabs, int64_t n_total) {
     if (maxabs > 0.0f) (void)std::frexp(maxabs, &e);
     int n = 0;
     while ((static_cast<int64_t>(1) << n) < n_total) ++n;
-    int s = 62 - n - e;
-    return std::max(0, std::min(60, s));
+    const int s = 62 - n - e;
+    if (s < 0) return -1;               // llrint(x * 2^0) summed over the rows would leave int64
+    return std::min(60, s);
 }
 
 int ganrev_kmeans(ganrev_ctx* ctx, int k, int niter, const float* init_centroids, float* centroids, float* total_counts, int32_t* last_labels) {
@@ -1750,7 +1844,7 @@ int ganrev_kmeans(ganrev_ctx* ctx, int k, int niter, const float* init_centroids
     const int d = ctx->db_d;
     const int64_t N = ctx->db_n;
     const int shift = kmeans_shift_of(ctx->db_maxabs, ctx->db_total);
-    if (shift < 0) return fail(ctx, GANREV_EINVAL, "database contains non-finite values");
+    if (shift < 0) return fail(ctx, GANREV_EINVAL, "database contains non-finite values, or values too large for the 64-bit fixed-point centroid sums (max|x| * rows >= 2^62)");
     const double sc = std::ldexp(1.0, shift);
     const size_t kd = static_cast<size_t>(k) * d;
     RC_TRY(ensure(ctx, ctx->cen, sizeof(float) * kd));
@@ -1777,7 +1871,9 @@ int ganrev_kmeans(ganrev_ctx* ctx, int k, int niter, const float* init_centroids
             scan::StreamParams sp{};
             size_t smem = 0;
             int grid = 0;
-            if (rtile_plan(ctx, p, stream_nq(k), 1, sp, smem, grid)) RC_TRY((dispatch_rtile<1>(ctx, stream_nq(k), sp, smem, grid)));
+            if (kmeans_tc_ok(ctx, k)) RC_TRY(kmeans_tc_iteration(ctx, p));
+            else if (label_tc_ok(ctx, p, 1)) RC_TRY((launch_label_tc<1>(ctx, p)));
+            else if (rtile_plan(ctx, p, stream_nq(k), 1, sp, smem, grid)) RC_TRY((dispatch_rtile<1>(ctx, stream_nq(k), sp, smem, grid)));
             else if (stream_plan(ctx, p, stream_nq(k), 1, 0, sp, smem, grid)) RC_TRY((dispatch_stream<1, 1>(ctx, stream_nq(k), sp, smem, grid)));
             else if (k <= 16) RC_TRY((launch_assign<1, 1>(ctx, p)));
             else RC_TRY((launch_assign<4, 1>(ctx, p)));
@@ -1824,7 +1920,8 @@ int ganrev_assign_cosine_min(ganrev_ctx* ctx, const float* centroids, int k, int
         scan::StreamParams sp{};
         size_t smem = 0;
         int grid = 0;
-        if (rtile_plan(ctx, p, stream_nq(k), 2, sp, smem, grid)) RC_TRY((dispatch_rtile<2>(ctx, stream_nq(k), sp, smem, grid)));
+        if (label_tc_ok(ctx, p, 2)) RC_TRY((launch_label_tc<2>(ctx, p)));
+        else if (rtile_plan(ctx, p, stream_nq(k), 2, sp, smem, grid)) RC_TRY((dispatch_rtile<2>(ctx, stream_nq(k), sp, smem, grid)));
         else if (stream_plan(ctx, p, stream_nq(k), 2, 0, sp, smem, grid)) RC_TRY((dispatch_stream<2, 1>(ctx, stream_nq(k), sp, smem, grid)));
         else if (k <= 16) RC_TRY((launch_assign<1, 2>(ctx, p)));
         else RC_TRY((launch_assign<4, 2>(ctx, p)));
@@ -2071,6 +2168,8 @@ int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value) {
     }
     if (!strcmp(name, "rtile")) { ctx->rtile = value != 0; return GANREV_OK; }
     if (!strcmp(name, "search_tc")) { ctx->search_tc = value != 0; return GANREV_OK; }
+    if (!strcmp(name, "label_tc")) { ctx->label_tc = value != 0; return GANREV_OK; }
+    if (!strcmp(name, "kmeans_tc")) { ctx->kmeans_tc = value != 0; return GANREV_OK; }
     if (!strcmp(name, "tma_store")) { ctx->tma_store = value < 0 ? 0 : (value > 2 ? 2 : static_cast<int>(value)); return GANREV_OK; }
     if (!strcmp(name, "conv_impl")) {
         if (value != 0 && value != 1) return fail(ctx, GANREV_EINVAL, "conv_impl must be 0 or 1");

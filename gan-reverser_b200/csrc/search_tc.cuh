@@ -68,7 +68,8 @@ __global__ void pack_kernel(const float* __restrict__ x, const float* __restrict
     if (idx >= n * half) return;
     const long long row = idx / half;
     const int c = static_cast<int>(idx - row * half) * 2;
-    const float rn = rnorm[row];
+    const bool noscale = rnorm == nullptr;                            // kmeans centroids (kmeans_tc.cuh): split as they are
+    const float rn = noscale ? 1.0f : rnorm[row];
     const bool special = !(rn > 0.0f) || !(rn < 3.0e38f);            // NaN / zero (|x|^2 overflowed) / inf
     if (special && c == 0) {
         if (is_query) atomicOr(flags, FLAG_SPECIAL_QUERY);
@@ -83,8 +84,8 @@ __global__ void pack_kernel(const float* __restrict__ x, const float* __restrict
     if (!special) {
         if (c < d) v0 = __fmul_rn(x[row * d + c], s);
         if (c + 1 < d) v1 = __fmul_rn(x[row * d + c + 1], s);
-        if (!(fabsf(v0) <= 2.0f)) v0 = 0.0f;                         // an inf / NaN entry under a finite norm cannot happen; belt and braces
-        if (!(fabsf(v1) <= 2.0f)) v1 = 0.0f;
+        if (!noscale && !(fabsf(v0) <= 2.0f)) v0 = 0.0f;             // an inf / NaN entry under a finite norm cannot happen; belt and braces
+        if (!noscale && !(fabsf(v1) <= 2.0f)) v1 = 0.0f;
     }
     const bf16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
     const bf16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));

@@ -189,6 +189,9 @@ int ganrev_debug_trace_read(ganrev_ctx* ctx, int64_t* out);
  *   "tma_store" 1 = TMA bulk tensor stores in the conv epilogue of the plain layers (default), 2 = also the pooled layers, 0 = st.global everywhere
  *   "search_tc" 1 = many-query searches (Q >= 48, >= 8192 rows per rank) run as tensor-core candidate filter + exact re-score (default;
  *               results are bit-identical), 0 = fmaf-chain kernels only
+ *   "label_tc"  1 = kmeans / cosine-min labelling for k <= 32, d % 4 == 0, d <= 128 on the tensor cores, exact chains only for near-ties
+ *               (results are bit-identical; measured no faster than the register-tiled kernels yet), 0 = fmaf-chain kernels (default)
+ *   "kmeans_tc" 1 = kmeans labelling for k > 32 on the tensor cores with exact chains only for near-ties (default; bit-identical), 0 = off
  *   "rtile"     1 = register-tiled kmeans / cosine-min kernels for 9 <= k <= 32 (default), 0 = one-thread-per-row streaming kernels
  *   "dbg"       timing experiments: bit 0 skip A loads, 1 skip B loads, 2 skip epilogue, 3 skip MMAs, 4 skip stores (results invalid) */
 int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value);

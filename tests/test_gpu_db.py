@@ -79,6 +79,39 @@ def test_kmeans_config5_shape_exact(orc, ctx):
     assert_bitexact(cen, want_c, "centroids")
 
 
+def test_kmeans_tc_large_k_adversarial(orc, ctx):
+    """k > 32 runs on the tensor cores (kmeans_tc.cuh): duplicate centroids, a NaN centroid, NaN / zero / huge rows, a tight cluster
+    of rows -- labels, counts and centroids stay bit-exact (near-ties and special values go to the exact chains), and the
+    fmaf-chain kernels alone (kmeans_tc = 0) give the same bits."""
+    rng = np.random.default_rng(66)
+    N, d, k = 12000, 100, 150
+    x = rng.standard_normal(size=(N, d), dtype=np.float32)
+    x[:3000] = x[1] + np.float32(1e-3) * rng.standard_normal(size=(3000, d), dtype=np.float32)
+    x[3000:5000] *= np.exp(rng.uniform(-12, 12, size=(2000, 1))).astype(np.float32)
+    x[7000] = 0.0
+    x[7001, 5] = np.nan
+    x[7002] = 1e12
+    init = _init(k, d, seed=67)
+    init[77] = init[3]; init[149] = init[3]                       # exact ties: lowest index
+    for nan_centroid in (False, True):
+        ini = init.copy()
+        if nan_centroid:
+            ini[100, 7] = np.nan                                  # TH's max scan: the first NaN wins every row
+        want_c, want_t, want_l = orc.kmeans(x, k, 2, ini)
+        ctx.db_set(x)
+        for tc in (1, 0):
+            ctx.set_option("kmeans_tc", tc)
+            cen, tot, lab = ctx.kmeans(k, 2, ini)
+            np.testing.assert_array_equal(lab, want_l)
+            assert_bitexact(tot, want_t, "total counts")
+            assert_bitexact(cen, want_c, "centroids")
+    ctx.set_option("kmeans_tc", 1)
+    big = x.copy(); big[7002] = 1e30                              # |x| * N >= 2^62: the fixed-point sums cannot hold it -> refused, not wrapped
+    ctx.db_set(big)
+    with pytest.raises(Exception):
+        ctx.kmeans(k, 1, init)
+
+
 def test_db_aliases_resident_attrs(pkg, orc, ctx):
     """ganrev_db_set(NULL): the database IS the resident ATTRS0 buffer (no copy); overwriting ATTRS0 un-sets it."""
     C, H, W, nd, N = 1, 32, 32, 32, 300
@@ -294,13 +327,15 @@ def test_rtile_kmeans_and_assign_exact(orc, ctx, case):
     init = _init(k, d, seed=32)
     want_c, want_t, want_l = orc.kmeans(x, k, 3, init)
     ctx.db_set(x)
-    for rtile in (1, 0):
+    for label_tc, rtile in ((1, 1), (0, 1), (0, 0)):              # tensor-core labelling, register-tiled chains, streaming chains
+        ctx.set_option("label_tc", label_tc)
         ctx.set_option("rtile", rtile)
         cen, tot, lab = ctx.kmeans(k, 3, init)
         np.testing.assert_array_equal(lab, want_l)
         assert_bitexact(tot, want_t, "total counts")
         assert_bitexact(cen, want_c, "centroids")
     ctx.set_option("rtile", 1)
+    ctx.set_option("label_tc", 0)
     cenq = _db(k, d, 33)
     if N > 9:
         x2 = x.copy(); x2[7] = cenq[0]; x2[8] = cenq[k - 1]          # exact duplicates of the first / last centroid
@@ -308,12 +343,14 @@ def test_rtile_kmeans_and_assign_exact(orc, ctx, case):
     else:
         x2 = x
     want_cl, want_cv = orc.assign_cosine_min(x2, cenq)
-    for rtile in (1, 0):
+    for label_tc, rtile in ((1, 1), (0, 1), (0, 0)):
+        ctx.set_option("label_tc", label_tc)
         ctx.set_option("rtile", rtile)
         cl, cv = ctx.assign_cosine_min(cenq)
         np.testing.assert_array_equal(cl, want_cl)
         assert_bitexact(cv, want_cv, "cos")
     ctx.set_option("rtile", 1)
+    ctx.set_option("label_tc", 0)
 
 
 def test_rtile_nan_and_tie_rules(orc, ctx):
@@ -342,6 +379,45 @@ def test_rtile_nan_and_tie_rules(orc, ctx):
     cl, cv = ctx.assign_cosine_min(cen0)
     np.testing.assert_array_equal(cl, want_cl)
     assert_bitexact(cv, want_cv)
+
+
+def test_label_tc_adversarial(orc, ctx):
+    """Tensor-core labelling under stress: duplicate centroids (every row a tie), rows equal to centroids, clustered data with tiny
+    gaps, a huge dynamic range, a zero row and a zero centroid -- labels, centroids, counts and cosines stay bit-exact because every
+    near-tie goes to the exact chains."""
+    rng = np.random.default_rng(55)
+    N, d, k = 20000, 100, 20
+    x = rng.standard_normal(size=(N, d), dtype=np.float32)
+    x[:5000] = x[0] + np.float32(1e-4) * rng.standard_normal(size=(5000, d), dtype=np.float32)   # a tight cluster
+    x[5000:10000] *= np.exp(rng.uniform(-15, 15, size=(5000, 1))).astype(np.float32)
+    x[12345] = 0.0
+    init = _init(k, d, seed=56)
+    init[7] = init[3]                                             # duplicate centroids: exact ties, lowest index wins
+    init[9] = 0.0                                                 # a zero centroid
+    x[100] = init[5]; x[101] = init[19]
+    want_c, want_t, want_l = orc.kmeans(x, k, 3, init)
+    ctx.set_option("label_tc", 1)
+    ctx.db_set(x)
+    cen, tot, lab = ctx.kmeans(k, 3, init)
+    np.testing.assert_array_equal(lab, want_l)
+    assert_bitexact(tot, want_t); assert_bitexact(cen, want_c)
+    want_cl, want_cv = orc.assign_cosine_min(x, init)
+    cl, cv = ctx.assign_cosine_min(init)
+    np.testing.assert_array_equal(cl, want_cl)
+    assert_bitexact(cv, want_cv)
+    for kk, dd in ((1, 32), (2, 4), (32, 128), (31, 64), (20, 68)):   # shapes at the limits of the kernel
+        xs = rng.standard_normal(size=(3001, dd), dtype=np.float32)
+        ini = _init(kk, dd, seed=57)
+        w_c, w_t, w_l = orc.kmeans(xs, kk, 2, ini)
+        ctx.db_set(xs)
+        c2, t2, l2 = ctx.kmeans(kk, 2, ini)
+        np.testing.assert_array_equal(l2, w_l)
+        assert_bitexact(t2, w_t); assert_bitexact(c2, w_c)
+        w_cl, w_cv = orc.assign_cosine_min(xs, ini)
+        cl2, cv2 = ctx.assign_cosine_min(ini)
+        np.testing.assert_array_equal(cl2, w_cl)
+        assert_bitexact(cv2, w_cv)
+    ctx.set_option("label_tc", 0)
 
 
 def test_search_four_needles_variant(orc, ctx):
