@@ -2140,8 +2140,22 @@ int ganrev_debug_fma_peak(ganrev_ctx* ctx, double* tflops) {
         best = std::max(best, fl / (ms * 1e-3) * 1e-12);
     }
     ctx->launches += 4;
+    double best2 = 0.0;
+    fma2_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(static_cast<float*>(ctx->thr.p), 1024, 1.0f);
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0, ctx->stream);
+        fma2_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(static_cast<float*>(ctx->thr.p), iters, 1.0f);
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = 2.0 * 16.0 * iters * static_cast<double>(blocks) * threads;
+        best2 = std::max(best2, fl / (ms * 1e-3) * 1e-12);
+    }
+    ctx->launches += 4;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *tflops = best;
+    if (getenv("GANREV_PRINT_FMA2")) fprintf(stderr, "fp32 FFMA %.1f TFLOP/s, FFMA2 (fma.rn.f32x2) %.1f TFLOP/s\n", best, best2);
     return finish(ctx);
 }
 // Debug: arm a clock64 timeline of CTA 0 for the named tensor-core layer / read it back ([8][256] int64).

@@ -235,6 +235,23 @@ update_kernel(const float* __restrict__ db, long long n_rows, int d, const int* 
     }
 }
 
+// one sequential fmaf chain over d (index order), 16-byte loads eight columns ahead when the rows allow it
+__device__ __forceinline__ float chain_dot(const float* __restrict__ cr, const float* __restrict__ xr, int d) {
+    float acc = 0.0f;
+    if ((d & 7) == 0 && ((reinterpret_cast<uintptr_t>(cr) | reinterpret_cast<uintptr_t>(xr)) & 15) == 0) {
+        const float4* c4 = reinterpret_cast<const float4*>(cr);
+        const float4* x4 = reinterpret_cast<const float4*>(xr);
+        for (int i = 0; i < (d >> 2); i += 2) {
+            const float4 ca = __ldg(c4 + i), cb = __ldg(c4 + i + 1), xa = __ldg(x4 + i), xb = __ldg(x4 + i + 1);
+            acc = __fmaf_rn(ca.x, xa.x, acc); acc = __fmaf_rn(ca.y, xa.y, acc); acc = __fmaf_rn(ca.z, xa.z, acc); acc = __fmaf_rn(ca.w, xa.w, acc);
+            acc = __fmaf_rn(cb.x, xb.x, acc); acc = __fmaf_rn(cb.y, xb.y, acc); acc = __fmaf_rn(cb.z, xb.z, acc); acc = __fmaf_rn(cb.w, xb.w, acc);
+        }
+    } else {
+        for (int c = 0; c < d; ++c) acc = __fmaf_rn(__ldg(cr + c), __ldg(xr + c), acc);
+    }
+    return acc;
+}
+
 // Near-ties between two centroids: two exact sequential fmaf chains (lanes 0 and 1), TH's comparator, the row's sums.  One warp per row.
 __global__ void __launch_bounds__(256)
 exact_two_kernel(const scan::ScanParams p, const uint4* __restrict__ rows, const unsigned* __restrict__ count) {
@@ -251,9 +268,7 @@ exact_two_kernel(const scan::ScanParams p, const uint4* __restrict__ rows, const
         b.v = 0.0f; b.j = -1;
         if (lane < 2 && (lane == 0 || e.z != e.y)) {
             const int j = static_cast<int>(lane == 0 ? e.y : e.z);
-            const float* cr = p.q + static_cast<long long>(j) * p.d;
-            float acc = 0.0f;
-            for (int c = 0; c < p.d; ++c) acc = __fmaf_rn(__ldg(cr + c), __ldg(xr + c), acc);
+            const float acc = chain_dot(p.q + static_cast<long long>(j) * p.d, xr, p.d);
             b.j = j; b.v = __fsub_rn(acc, __ldg(p.c2 + j));
         }
         scan::Best ob;
@@ -287,9 +302,7 @@ full_scan_kernel(const scan::ScanParams p, const unsigned* __restrict__ rows, co
         const float* xr = p.db + static_cast<long long>(rows[slot]) * p.d;
         unsigned long long key = 0ull;
         if (j < p.nq) {
-            const float* cr = p.q + static_cast<long long>(j) * p.d;
-            float acc = 0.0f;
-            for (int c = 0; c < p.d; ++c) acc = __fmaf_rn(__ldg(cr + c), __ldg(xr + c), acc);
+            const float acc = chain_dot(p.q + static_cast<long long>(j) * p.d, xr, p.d);
             key = th_key(__fsub_rn(acc, __ldg(p.c2 + j)), j);
         }
 #pragma unroll

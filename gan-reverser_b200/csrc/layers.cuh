@@ -405,4 +405,24 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float* __restrict__ sink,
     if (s == 123.456f) *sink = s;      // never true: keeps the chains alive
 }
 
+// the same with packed fma.rn.f32x2 (FFMA2: two IEEE fp32 FMAs per instruction)
+__global__ void __launch_bounds__(256) fma2_peak_kernel(float* __restrict__ sink, int iters, float seed) {
+    unsigned long long a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float2 v = make_float2(seed + 0.001f * j + 1e-6f * threadIdx.x, seed + 0.002f * j);
+        a[j] = *reinterpret_cast<unsigned long long*>(&v);
+    }
+    float2 mv = make_float2(0.9999f, 0.9999f), cv = make_float2(1e-4f, 1e-4f);
+    const unsigned long long m = *reinterpret_cast<unsigned long long*>(&mv), c = *reinterpret_cast<unsigned long long*>(&cv);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[j]) : "l"(m), "l"(c));
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { float2 v = *reinterpret_cast<float2*>(&a[j]); s += v.x + v.y; }
+    if (s == 123.456f) *sink = s;
+}
+
 }  // namespace ganrev

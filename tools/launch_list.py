@@ -9,7 +9,7 @@ from collections import OrderedDict
 def short(name):
     name = name.replace("(int)", "").replace("(bool)", "")
     name = name.split(">(")[0] + ">" if ">(" in name else re.sub(r"\(.*$", "", name)   # drop the argument list
-    name = name.replace("void ", "").replace("ganrev::", "").replace("tc::", "").replace("scan::", "").replace("conv_tc_kernel", "conv_tc")
+    name = name.replace("void ", "").replace("stc::", "search_tc::").replace("ktc::", "kmeans_tc::").replace("ltc::", "label_tc::").replace("ganrev::", "").replace("tc::", "").replace("scan::", "").replace("conv_tc_kernel", "conv_tc")
     return name
 
 

@@ -14,6 +14,11 @@ METRICS = [
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_%"),
     ("dram__bytes_read.sum", "dram_rd_MB"),
     ("dram__bytes_write.sum", "dram_wr_MB"),
+    ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma_pipe_%"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu_pipe_%"),
+    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu_pipe_%"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed", "smem_wavefronts_%"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_%"),
     ("launch__registers_per_thread", "regs"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy_%"),
 ]
@@ -30,7 +35,7 @@ def main(rep):
     for k, r in enumerate(data):
         name = r[ci["Kernel Name"]]
         m = re.search(r"conv_tc_kernel<(.*?)>", name)
-        short = ("conv_tc<" + m.group(1).replace("(int)", "").replace("(bool)", "") + ">") if m else name.split("(")[0][-40:]
+        short = ("conv_tc<" + m.group(1).replace("(int)", "").replace("(bool)", "") + ">") if m else re.sub(r"\(.*", "", name).replace("void ", "").replace("ganrev::", "")[-48:]
         vals = []
         for mname, _ in cols:
             v = r[ci[mname]]

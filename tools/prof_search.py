@@ -1,6 +1,7 @@
 """Profiling driver for the database kernels: python tools/prof_search.py <case> (run under ncu, see profiles/r02/README).
-cases: tc (4096-needle search over 1M x 100 N(0,1) rows, tensor-core path), exact (same, fmaf-chain kernels),
-       kmeans20 / assign20 (k = 20 over 4M x 100), search4 (4 needles over 4M x 100), l2 (200k pairs), nearest (8 queries)."""
+cases: tc (4096-needle search over 1M x 100 N(0,1) rows, tensor-core path), exact (same, fmaf-chain kernels), tc256 (configs[4]: 1.25M x 256,
+       top-100), kmeans20 / assign20 (k = 20 over 4M x 100), labeltc20 (the same through label_tc.cuh), kmeans1024 (k = 1024 over 1.25M x 256),
+       search4 (4 needles over 4M x 100), l2 (200k pairs), nearest (8 queries)."""
 import os
 import sys
 
@@ -34,6 +35,37 @@ elif case in ("kmeans20", "assign20", "search4"):
             ctx.assign_cosine_min(init)
         else:
             ctx.search_rows(np.array([99, 199, 299, 399], np.int64), 20)
+elif case == "gr":
+    C, H, W, ND, N = 1, 32, 32, 100, 8192                     # one default chunk of G and of R
+    ctx.load_G(C, H, W, ND, pkg.weights.init_G(C, H, W, ND))
+    ctx.load_R(0, C, H, W, ND, pkg.weights.init_R(C, H, W, ND))
+    ctx.buffer_put(pkg._lib.BUF_NOISE, rng.standard_normal(size=(N, ND), dtype=np.float32))
+    for _ in range(reps + 1):
+        ctx.forward_G(None, N=N, want_images=False)
+        ctx.forward_R(0, None, N=N, want_attrs=False)
+elif case == "kmeans1024":
+    N, d, k = 1_250_000, 256, 1024
+    ctx.db_synthetic(N, d, seed=8)
+    init = rng.standard_normal(size=(k, d), dtype=np.float32)
+    init /= np.linalg.norm(init, axis=1, keepdims=True)
+    for _ in range(reps):
+        ctx.kmeans(k, 1, init, want_labels=False)
+elif case == "tc256":
+    N, d, Q, k = 1_250_000, 256, 4096, 100
+    ctx.db_synthetic(N, d, seed=8)
+    rows = np.arange(1, Q + 1, dtype=np.int64) * 300
+    for _ in range(reps):
+        ids, sc = ctx.search_rows(rows, k)
+    print(case, "self first:", bool((ids[:, 0] == rows).all()), "tc counters", ctx.tc_counters())
+elif case == "labeltc20":
+    N, d, k = 4_000_000, 100, 20
+    ctx.db_synthetic(N, d, seed=11)
+    ctx.set_option("label_tc", 1)
+    init = rng.standard_normal(size=(k, d), dtype=np.float32)
+    init /= np.linalg.norm(init, axis=1, keepdims=True)
+    for _ in range(reps):
+        ctx.kmeans(k, 2, init, want_labels=False)
+        ctx.assign_cosine_min(init)
 elif case in ("l2", "nearest"):
     n = 200_000
     a = rng.random((n, 1024), dtype=np.float32)
