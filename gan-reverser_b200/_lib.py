@@ -59,6 +59,7 @@ _SIGS = {
     "ganrev_debug_fma_peak": (_i, [_vp, C.POINTER(C.c_double)]),
     "ganrev_debug_tc_scores": (_i, [_vp, _vp, _i, _vp, C.POINTER(C.c_float)]),
     "ganrev_debug_tc_counters": (_i, [_vp, _vp]),
+    "ganrev_debug_tfs_stats": (_i, [_vp, _vp]),
     "ganrev_debug_trace_arm": (_i, [_vp, C.c_char_p]),
     "ganrev_debug_trace_read": (_i, [_vp, _vp]),
 }
@@ -259,6 +260,14 @@ class Context:
         out = np.zeros((2,), np.uint64)
         self._chk(lib().ganrev_debug_tc_counters(self._h, _ptr(out)))
         return int(out[0]), int(out[1])
+
+    def tfs_stats(self):
+        """Counters of the tf32 filter pipeline since the last call: chains on top of the filter, rows sent to the list
+        kernel, largest observed error / bound (measured under dbg bit 18), launches."""
+        out = np.zeros((4,), np.uint64)
+        self._chk(lib().ganrev_debug_tfs_stats(self._h, _ptr(out)))
+        return {"chains": int(out[0]), "listed_rows": int(out[1]),
+                "max_error_over_bound": float(np.array([int(out[2]) & 0xFFFFFFFF], np.uint32).view(np.float32)[0]), "launches": int(out[3])}
 
     def fma_peak(self):
         out = C.c_double(0.0)

@@ -15,6 +15,7 @@
 #include "scan.cuh"
 #include "search_tc.cuh"
 #include "label_tc.cuh"
+#include "stream_tc.cuh"
 #include "kmeans_tc.cuh"
 
 using namespace ganrev;
@@ -75,6 +76,7 @@ struct ganrev_ctx {
     int search_tc = 1;            // tensor-core candidate filter + exact re-score for many-query searches (0 = fmaf-chain kernels only; A/B)
     uint64_t tc_searches = 0, tc_fallbacks = 0;   // searches served by the tensor-core path / re-run on the fmaf-chain kernels
     int label_tc = 0;             // 1 = tensor-core labelling for k <= 32, d <= 128 (label_tc.cuh; bit-exact, measured no faster than rtile_kernel yet: off)
+    int stream_tc = 1;            // TMA -> tf32 tcgen05 filter pipeline for <= 32 needles / centroids (stream_tc.cuh; 0 = the fmaf-chain streaming kernels; A/B)
     int kmeans_tc = 1;            // tensor-core labelling for 32 < k (kmeans_tc.cuh): approximate scores, exact chains only for near-ties
     int rtile = 1;                // register-tiled kmeans / cosine-min kernels for 9 <= k <= 32 (0 = the one-thread-per-row streaming kernels; A/B)
     int cta_pairs = 0x1f;     // which layers use tcgen05 cta_group::2 CTA pairs (bit0 G conv1, bit1 G conv2, bit2 R conv2/3,
@@ -103,6 +105,8 @@ struct ganrev_ctx {
     DevBuf nn_partial, nn_ids, nn_dist, nn_flag, nn_all;   // ganrev_nearest_l2 scratch
     DevBuf amb, pdb, pq, tc_thr, tc_cnt, tc_cand, tc_pairs, tc_keys, tc_special, tc_flags, tc_dump;   // search_tc.cuh: packed split-bf16 operands, candidates
     bool pdb_valid = false;                // pdb / tc_special describe the current database
+    DevBuf tfs_aux;                        // stream_tc.cuh: published k-th scores [32 u32] | stats [4 u64]
+    uint64_t tfs_launches = 0;
     DevBuf qsel, shard;                    // radix-select state + histogram; row-shard bookkeeping (world + 2 int64)
     // database
     DevBuf db, rdb, maxabs;
@@ -859,7 +863,7 @@ void ganrev_destroy(ganrev_ctx* ctx) {
         for (TcLayer* L : {&R.c2, &R.c3, &R.c4, &R.c5, &R.c6, &R.l1, &R.l2}) release_layer(*L);
     }
     for (auto& b : ctx->buf) release(b);
-    for (DevBuf* b : {&ctx->nn_partial, &ctx->nn_ids, &ctx->nn_dist, &ctx->nn_flag, &ctx->nn_all, &ctx->qsel, &ctx->shard, &ctx->amb, &ctx->pdb, &ctx->pq, &ctx->tc_thr,
+    for (DevBuf* b : {&ctx->nn_partial, &ctx->nn_ids, &ctx->nn_dist, &ctx->nn_flag, &ctx->nn_all, &ctx->qsel, &ctx->shard, &ctx->tfs_aux, &ctx->amb, &ctx->pdb, &ctx->pq, &ctx->tc_thr,
                       &ctx->tc_cnt, &ctx->tc_cand, &ctx->tc_pairs, &ctx->tc_keys, &ctx->tc_special, &ctx->tc_flags, &ctx->tc_dump}) release(*b);
     for (DevBuf* b : {&ctx->arena[0], &ctx->arena[1], &ctx->noise_bf16, &ctx->stage_a, &ctx->stage_b, &ctx->l2buf, &ctx->thr, &ctx->flags,
                       &ctx->db, &ctx->rdb, &ctx->maxabs, &ctx->q, &ctx->rq, &ctx->c2, &ctx->partial, &ctx->keys, &ctx->keys_all, &ctx->ids,
@@ -1434,6 +1438,85 @@ static int launch_label_tc(ganrev_ctx* ctx, const scan::ScanParams& p) {
     return GANREV_OK;
 }
 
+// ---- TMA -> tf32 tcgen05 filter pipeline (stream_tc.cuh): search (MODE 0), kmeans (MODE 1), cosine-min (MODE 2) for nq <= 32, d % 4 == 0
+static int tfs_nqp(int nq) { return nq <= 16 ? 16 : 32; }
+static bool tfs_plan(const ganrev_ctx* ctx, const scan::ScanParams& p, int mode, int K2, tfs::TfsParams& tp, size_t& smem, int& grid) {
+    if (!ctx->stream_tc || p.nq < 1 || p.nq > 32 || p.d % 4 != 0 || p.d < 4 || p.n_rows < 1 || p.n_rows > 0x7fffff00LL) return false;
+    if ((reinterpret_cast<uintptr_t>(p.db) & 15) != 0) return false;
+    const int NQP = tfs_nqp(p.nq);
+    const int nbox = (p.d + tfs::kBoxCols - 1) / tfs::kBoxCols;
+    const size_t budget = 227 * 1024;
+    // the chains' fp32 centroid copy lives in shared memory unless that leaves fewer than three tiles of ring slots
+    bool cen_global = false;
+    size_t fixed = tfs::tfs_fixed_bytes(mode, NQP, K2, p.nq, p.d, false) + 1024;
+    if (fixed > budget || (budget - fixed) / tfs::kSlotBytes < static_cast<size_t>(std::min(mode == 0 ? 8 : 3 * nbox, tfs::kMaxSlots))) {
+        cen_global = true;
+        fixed = tfs::tfs_fixed_bytes(mode, NQP, K2, p.nq, p.d, true) + 1024;
+    }
+    if (fixed + 4 * static_cast<size_t>(tfs::kSlotBytes) > budget) return false;
+    int nslots = static_cast<int>(std::min<size_t>(tfs::kMaxSlots, (budget - fixed) / tfs::kSlotBytes));
+    tp.cen_global = cen_global ? 1 : 0;
+    if (mode != 0 && nslots < nbox + 1) return false;            // a tile stays resident until its rows were consumed
+    if (mode != 0 && nslots >= 2 * nbox) nslots = std::min(nslots, 3 * nbox);   // three tiles in flight are plenty
+    tp.s = p;
+    tp.n_tiles = (p.n_rows + tfs::kRows - 1) / tfs::kRows;
+    tp.nbox = nbox; tp.nslots = nslots; tp.err_flag = ctx->d_err_flag; tp.dbg = ctx->dbg >> 16;
+    tp.trace = (ctx->trace.p && ctx->trace_layer == "tfs") ? static_cast<long long*>(ctx->trace.p) : nullptr;
+    smem = fixed + static_cast<size_t>(nslots) * tfs::kSlotBytes;
+    grid = static_cast<int>(std::max<long long>(1, std::min<long long>(tp.n_tiles, ctx->num_sms)));
+    return true;
+}
+static int tfs_make_map(ganrev_ctx* ctx, CUtensorMap* m, const float* base, int d, long long rows) {
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(d), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(d) * 4};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(tfs::kBoxCols), static_cast<cuuint32_t>(tfs::kRows)};
+    const cuuint32_t es[2] = {1u, 1u};
+    CUresult r = ctx->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, GANREV_ECUDA, "cuTensorMapEncodeTiled(database rows) failed: %d", (int)r);
+    return GANREV_OK;
+}
+template <int MODE, int NQP, int E>
+static int launch_tfs_one(ganrev_ctx* ctx, const CUtensorMap& tm, const tfs::TfsParams& tp, size_t smem, int grid) {
+    static size_t attr_max_dev[kMaxDevices] = {};
+    size_t& attr_max = attr_max_dev[ctx->device];
+    if (smem > attr_max) {
+        CU_TRY(cudaFuncSetAttribute(tfs::tfs_kernel<MODE, NQP, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr_max = smem;
+    }
+    tfs::tfs_kernel<MODE, NQP, E><<<grid, tfs::threads_of<MODE>(), smem, ctx->stream>>>(tm, tp);
+    CU_TRY(cudaGetLastError());
+    return GANREV_OK;
+}
+template <int MODE, int E>
+static int launch_tfs(ganrev_ctx* ctx, tfs::TfsParams& tp, size_t smem, int grid) {
+    const scan::ScanParams& p = tp.s;
+    CUtensorMap tm;
+    RC_TRY(tfs_make_map(ctx, &tm, p.db, p.d, p.n_rows));
+    if (!ctx->tfs_aux.p) {
+        RC_TRY(ensure(ctx, ctx->tfs_aux, 32 * sizeof(unsigned) + 4 * sizeof(unsigned long long)));
+        CU_TRY(cudaMemsetAsync(ctx->tfs_aux.p, 0, 32 * sizeof(unsigned) + 4 * sizeof(unsigned long long), ctx->stream));
+    }
+    tp.gthr = static_cast<unsigned*>(ctx->tfs_aux.p);
+    tp.stats = reinterpret_cast<unsigned long long*>(tp.gthr + 32);
+    if (MODE == 0) CU_TRY(cudaMemsetAsync(tp.gthr, 0, 32 * sizeof(unsigned), ctx->stream));
+    if (MODE != 0) {
+        RC_TRY(ensure(ctx, ctx->amb, sizeof(unsigned) * (static_cast<size_t>(p.n_rows) + 4)));
+        tp.amb_count = static_cast<unsigned*>(ctx->amb.p);
+        tp.amb_rows = tp.amb_count + 4;
+        CU_TRY(cudaMemsetAsync(tp.amb_count, 0, sizeof(unsigned), ctx->stream));
+    }
+    ctx->tfs_launches++;
+    if (tfs_nqp(p.nq) == 16) RC_TRY((launch_tfs_one<MODE, 16, E>(ctx, tm, tp, smem, grid)));
+    else RC_TRY((launch_tfs_one<MODE, 32, E>(ctx, tm, tp, smem, grid)));
+    if (MODE != 0) {
+        ltc::label_exact_list_kernel<(MODE == 0 ? 1 : MODE)><<<2 * ctx->num_sms, 256, 0, ctx->stream>>>(p, tp.amb_rows, tp.amb_count);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+    }
+    return GANREV_OK;
+}
+
 // merge the per-split lists, (multi-GPU) allgather + merge across ranks, copy results out
 static int search_finish(ganrev_ctx* ctx, const unsigned long long* partial, int splits, int Q, int k, int64_t* ids, float* scores) {
     const unsigned mblocks = static_cast<unsigned>((static_cast<long long>(Q) * 32 + scan::kThreads - 1) / scan::kThreads);
@@ -1477,6 +1560,25 @@ static int search_finish(ganrev_ctx* ctx, const unsigned long long* partial, int
 static int search_exact_dev(ganrev_ctx* ctx, int Q, int k, int64_t* ids, float* scores) {
     const int d = ctx->db_d;
     const int64_t N = ctx->db_n;
+    if (Q <= 32 && k <= 128) {     // HBM-bound regime, tensor-core filter: the database streams once through TMA, chains only for candidates
+        scan::ScanParams p{};
+        p.db = ctx->db_ptr; p.rdb = static_cast<const float*>(ctx->rdb.p); p.n_rows = N; p.d = d;
+        p.q = static_cast<const float*>(ctx->q.p); p.rq = static_cast<const float*>(ctx->rq.p); p.nq = Q; p.k = k;
+        tfs::TfsParams tp{};
+        size_t smem = 0;
+        int grid = 0;
+        if (tfs_plan(ctx, p, 0, k <= 32 ? 32 : 128, tp, smem, grid)) {
+            RC_TRY(ensure(ctx, ctx->partial, sizeof(unsigned long long) * static_cast<size_t>(grid) * Q * k));
+            RC_TRY(ensure(ctx, ctx->ids, sizeof(long long) * static_cast<size_t>(Q) * k));
+            RC_TRY(ensure(ctx, ctx->scores, sizeof(float) * static_cast<size_t>(Q) * k));
+            tp.s.partial = static_cast<unsigned long long*>(ctx->partial.p);
+            {
+                ProfScope ps(ctx, "search_scan", 2.0 * N * Q * d, 4.0 * N * d + 4.0 * Q * d + 8.0 * grid * Q * k);
+                if (k <= 32) RC_TRY((launch_tfs<0, 1>(ctx, tp, smem, grid))); else RC_TRY((launch_tfs<0, 4>(ctx, tp, smem, grid)));
+            }
+            return search_finish(ctx, tp.s.partial, grid, Q, k, ids, scores);
+        }
+    }
     if (Q <= 16 && d % 4 == 0) {   // HBM-bound regime: stream the database once
         scan::ScanParams p{};
         p.db = ctx->db_ptr; p.rdb = static_cast<const float*>(ctx->rdb.p); p.n_rows = N; p.d = d;
@@ -1871,7 +1973,9 @@ int ganrev_kmeans(ganrev_ctx* ctx, int k, int niter, const float* init_centroids
             scan::StreamParams sp{};
             size_t smem = 0;
             int grid = 0;
+            tfs::TfsParams tp{};
             if (kmeans_tc_ok(ctx, k)) RC_TRY(kmeans_tc_iteration(ctx, p));
+            else if (tfs_plan(ctx, p, 1, 0, tp, smem, grid)) RC_TRY((launch_tfs<1, 1>(ctx, tp, smem, grid)));
             else if (label_tc_ok(ctx, p, 1)) RC_TRY((launch_label_tc<1>(ctx, p)));
             else if (rtile_plan(ctx, p, stream_nq(k), 1, sp, smem, grid)) RC_TRY((dispatch_rtile<1>(ctx, stream_nq(k), sp, smem, grid)));
             else if (stream_plan(ctx, p, stream_nq(k), 1, 0, sp, smem, grid)) RC_TRY((dispatch_stream<1, 1>(ctx, stream_nq(k), sp, smem, grid)));
@@ -1920,7 +2024,9 @@ int ganrev_assign_cosine_min(ganrev_ctx* ctx, const float* centroids, int k, int
         scan::StreamParams sp{};
         size_t smem = 0;
         int grid = 0;
-        if (label_tc_ok(ctx, p, 2)) RC_TRY((launch_label_tc<2>(ctx, p)));
+        tfs::TfsParams tp{};
+        if (tfs_plan(ctx, p, 2, 0, tp, smem, grid)) RC_TRY((launch_tfs<2, 1>(ctx, tp, smem, grid)));
+        else if (label_tc_ok(ctx, p, 2)) RC_TRY((launch_label_tc<2>(ctx, p)));
         else if (rtile_plan(ctx, p, stream_nq(k), 2, sp, smem, grid)) RC_TRY((dispatch_rtile<2>(ctx, stream_nq(k), sp, smem, grid)));
         else if (stream_plan(ctx, p, stream_nq(k), 2, 0, sp, smem, grid)) RC_TRY((dispatch_stream<2, 1>(ctx, stream_nq(k), sp, smem, grid)));
         else if (k <= 16) RC_TRY((launch_assign<1, 2>(ctx, p)));
@@ -2118,6 +2224,19 @@ int ganrev_debug_tc_counters(ganrev_ctx* ctx, uint64_t* out2) {
     out2[0] = ctx->tc_searches; out2[1] = ctx->tc_fallbacks;
     return GANREV_OK;
 }
+int ganrev_debug_tfs_stats(ganrev_ctx* ctx, uint64_t* out4) {
+    if (!ctx || !out4) return GANREV_EINVAL;
+    CU_TRY(cudaSetDevice(ctx->device));
+    out4[0] = out4[1] = out4[2] = 0; out4[3] = ctx->tfs_launches;
+    ctx->tfs_launches = 0;
+    if (ctx->tfs_aux.p) {
+        unsigned long long* st = reinterpret_cast<unsigned long long*>(static_cast<unsigned*>(ctx->tfs_aux.p) + 32);
+        CU_TRY(cudaMemcpyAsync(out4, st, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(cudaMemsetAsync(st, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        return finish(ctx);
+    }
+    return GANREV_OK;
+}
 // Measured fp32 FMA throughput of this GPU at its current clocks (the roof the exact fmaf-chain kernels are graded against;
 // MEASURED_PEAKS.json has no fp32 figure): 8 independent chains per thread, all SMs, ~50 ms.
 int ganrev_debug_fma_peak(ganrev_ctx* ctx, double* tflops) {
@@ -2183,6 +2302,7 @@ int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "rtile")) { ctx->rtile = value != 0; return GANREV_OK; }
     if (!strcmp(name, "search_tc")) { ctx->search_tc = value != 0; return GANREV_OK; }
     if (!strcmp(name, "label_tc")) { ctx->label_tc = value != 0; return GANREV_OK; }
+    if (!strcmp(name, "stream_tc")) { ctx->stream_tc = value != 0; return GANREV_OK; }
     if (!strcmp(name, "kmeans_tc")) { ctx->kmeans_tc = value != 0; return GANREV_OK; }
     if (!strcmp(name, "tma_store")) { ctx->tma_store = value < 0 ? 0 : (value > 2 ? 2 : static_cast<int>(value)); return GANREV_OK; }
     if (!strcmp(name, "conv_impl")) {

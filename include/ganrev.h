@@ -179,6 +179,10 @@ int ganrev_debug_fma_peak(ganrev_ctx* ctx, double* tflops);
  * fmaf-chain kernels after raising a flag [1]. */
 int ganrev_debug_tc_scores(ganrev_ctx* ctx, const float* queries, int Q, float* out, float* eps_out);
 int ganrev_debug_tc_counters(ganrev_ctx* ctx, uint64_t* out2);
+/* Tests / bench: counters of the TMA -> tf32 filter pipeline (stream_tc.cuh) since the last call, then reset: [0] (row, needle /
+ * centroid) pairs that needed an exact chain on top of the filter, [1] rows handed to the every-chain list kernel, [2] the
+ * largest observed |approximate - exact| over the assumed bound (float bits; only measured under "dbg" bit 18), [3] launches. */
+int ganrev_debug_tfs_stats(ganrev_ctx* ctx, uint64_t* out4);
 /* Debug: clock64 timeline of CTA 0 of the named tensor-core layer (roles x events, [8][256]). */
 int ganrev_debug_trace_arm(ganrev_ctx* ctx, const char* layer);
 int ganrev_debug_trace_read(ganrev_ctx* ctx, int64_t* out);
@@ -189,6 +193,8 @@ int ganrev_debug_trace_read(ganrev_ctx* ctx, int64_t* out);
  *   "tma_store" 1 = TMA bulk tensor stores in the conv epilogue of the plain layers (default), 2 = also the pooled layers, 0 = st.global everywhere
  *   "search_tc" 1 = many-query searches (Q >= 48, >= 8192 rows per rank) run as tensor-core candidate filter + exact re-score (default;
  *               results are bit-identical), 0 = fmaf-chain kernels only
+ *   "stream_tc" 1 = searches with <= 32 needles, kmeans with k <= 32 and the cosine-min assignment (d % 4 == 0) run as TMA -> tf32
+ *               tcgen05 filter + exact chains for the candidates / near-ties only (default; results are bit-identical), 0 = fmaf-chain kernels
  *   "label_tc"  1 = kmeans / cosine-min labelling for k <= 32, d % 4 == 0, d <= 128 on the tensor cores, exact chains only for near-ties
  *               (results are bit-identical; measured no faster than the register-tiled kernels yet), 0 = fmaf-chain kernels (default)
  *   "kmeans_tc" 1 = kmeans labelling for k > 32 on the tensor cores with exact chains only for near-ties (default; bit-identical), 0 = off

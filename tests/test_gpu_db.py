@@ -318,6 +318,17 @@ RTILE_CASES = [
 ]
 
 
+# (stream_tc, label_tc, rtile): the TMA -> tf32 filter pipeline (default), the split-bf16 labelling kernel, the register-tiled
+# chains, the one-thread-per-row streaming chains
+PATHS = ((1, 0, 1), (0, 1, 1), (0, 0, 1), (0, 0, 0))
+
+
+def _default_paths(ctx):
+    ctx.set_option("stream_tc", 1)
+    ctx.set_option("label_tc", 0)
+    ctx.set_option("rtile", 1)
+
+
 @pytest.mark.parametrize("case", RTILE_CASES, ids=lambda c: "N%d_d%d_k%d" % c)
 def test_rtile_kmeans_and_assign_exact(orc, ctx, case):
     """kmeans labels/centroids/counts and cosine-min labels/values: bit-exact against the oracle, and identical with the
@@ -327,15 +338,15 @@ def test_rtile_kmeans_and_assign_exact(orc, ctx, case):
     init = _init(k, d, seed=32)
     want_c, want_t, want_l = orc.kmeans(x, k, 3, init)
     ctx.db_set(x)
-    for label_tc, rtile in ((1, 1), (0, 1), (0, 0)):              # tensor-core labelling, register-tiled chains, streaming chains
+    for stream_tc, label_tc, rtile in PATHS:
+        ctx.set_option("stream_tc", stream_tc)
         ctx.set_option("label_tc", label_tc)
         ctx.set_option("rtile", rtile)
         cen, tot, lab = ctx.kmeans(k, 3, init)
         np.testing.assert_array_equal(lab, want_l)
         assert_bitexact(tot, want_t, "total counts")
         assert_bitexact(cen, want_c, "centroids")
-    ctx.set_option("rtile", 1)
-    ctx.set_option("label_tc", 0)
+    _default_paths(ctx)
     cenq = _db(k, d, 33)
     if N > 9:
         x2 = x.copy(); x2[7] = cenq[0]; x2[8] = cenq[k - 1]          # exact duplicates of the first / last centroid
@@ -343,14 +354,14 @@ def test_rtile_kmeans_and_assign_exact(orc, ctx, case):
     else:
         x2 = x
     want_cl, want_cv = orc.assign_cosine_min(x2, cenq)
-    for label_tc, rtile in ((1, 1), (0, 1), (0, 0)):
+    for stream_tc, label_tc, rtile in PATHS:
+        ctx.set_option("stream_tc", stream_tc)
         ctx.set_option("label_tc", label_tc)
         ctx.set_option("rtile", rtile)
         cl, cv = ctx.assign_cosine_min(cenq)
         np.testing.assert_array_equal(cl, want_cl)
         assert_bitexact(cv, want_cv, "cos")
-    ctx.set_option("rtile", 1)
-    ctx.set_option("label_tc", 0)
+    _default_paths(ctx)
 
 
 def test_rtile_nan_and_tie_rules(orc, ctx):
@@ -396,15 +407,17 @@ def test_label_tc_adversarial(orc, ctx):
     init[9] = 0.0                                                 # a zero centroid
     x[100] = init[5]; x[101] = init[19]
     want_c, want_t, want_l = orc.kmeans(x, k, 3, init)
-    ctx.set_option("label_tc", 1)
-    ctx.db_set(x)
-    cen, tot, lab = ctx.kmeans(k, 3, init)
-    np.testing.assert_array_equal(lab, want_l)
-    assert_bitexact(tot, want_t); assert_bitexact(cen, want_c)
     want_cl, want_cv = orc.assign_cosine_min(x, init)
-    cl, cv = ctx.assign_cosine_min(init)
-    np.testing.assert_array_equal(cl, want_cl)
-    assert_bitexact(cv, want_cv)
+    ctx.db_set(x)
+    for stream_tc in (1, 0):                                      # the tf32 pipeline, then the split-bf16 labelling kernel
+        ctx.set_option("stream_tc", stream_tc)
+        ctx.set_option("label_tc", 1)
+        cen, tot, lab = ctx.kmeans(k, 3, init)
+        np.testing.assert_array_equal(lab, want_l)
+        assert_bitexact(tot, want_t); assert_bitexact(cen, want_c)
+        cl, cv = ctx.assign_cosine_min(init)
+        np.testing.assert_array_equal(cl, want_cl)
+        assert_bitexact(cv, want_cv)
     for kk, dd in ((1, 32), (2, 4), (32, 128), (31, 64), (20, 68)):   # shapes at the limits of the kernel
         xs = rng.standard_normal(size=(3001, dd), dtype=np.float32)
         ini = _init(kk, dd, seed=57)
@@ -417,19 +430,21 @@ def test_label_tc_adversarial(orc, ctx):
         cl2, cv2 = ctx.assign_cosine_min(ini)
         np.testing.assert_array_equal(cl2, w_cl)
         assert_bitexact(cv2, w_cv)
-    ctx.set_option("label_tc", 0)
+    _default_paths(ctx)
 
 
 def test_search_four_needles_variant(orc, ctx):
     """Q <= 4 takes the unpadded 2-queries-per-thread streaming variant: exact at Q = 1..4, ragged N."""
     x = _db(3001, 100, 51)
     ctx.db_set(x)
-    for Q in (1, 2, 3, 4):
-        q = x[[5, 77, 1234, 3000][:Q]] + 0.01
-        ids, sc = ctx.search_cosine(q, 20)
-        wi, ws = orc.search_cosine(x, q, 20)
-        np.testing.assert_array_equal(ids, wi)
-        assert_bitexact(sc, ws)
+    for stream_tc in (0, 1):
+        ctx.set_option("stream_tc", stream_tc)
+        for Q in (1, 2, 3, 4):
+            q = x[[5, 77, 1234, 3000][:Q]] + 0.01
+            ids, sc = ctx.search_cosine(q, 20)
+            wi, ws = orc.search_cosine(x, q, 20)
+            np.testing.assert_array_equal(ids, wi)
+            assert_bitexact(sc, ws)
 
 
 def test_db_error_paths(pkg):
