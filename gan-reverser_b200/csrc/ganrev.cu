@@ -1457,6 +1457,7 @@ static bool tfs_plan(const ganrev_ctx* ctx, const scan::ScanParams& p, int mode,
     int nslots = static_cast<int>(std::min<size_t>(tfs::kMaxSlots, (budget - fixed) / tfs::kSlotBytes));
     tp.cen_global = cen_global ? 1 : 0;
     if (mode != 0 && nslots < nbox + 1) return false;            // a tile stays resident until its rows were consumed
+    if (mode == 1 && (p.d / 4 > tfs::kSumThreads || p.nq > tfs::kLPT * (tfs::kSumThreads / (p.d / 4)))) return false;   // the sums live in registers: kLPT labels per thread
     if (mode != 0 && nslots >= 2 * nbox) nslots = std::min(nslots, 3 * nbox);   // three tiles in flight are plenty
     tp.s = p;
     tp.n_tiles = (p.n_rows + tfs::kRows - 1) / tfs::kRows;

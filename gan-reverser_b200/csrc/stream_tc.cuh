@@ -54,13 +54,14 @@ constexpr int kSlotBytes = kRows * 128;         // 16 KB
 constexpr int kMaxSlots = 14;
 constexpr int kAcc = 4;                         // TMEM accumulator stages: the MMA warp runs up to four tiles ahead of the epilogue
 constexpr int kGroupThreads = 128;              // one epilogue group: 4 warps = the 4 TMEM lane quarters
-constexpr int kSumThreads = 256;                // (512 measured no faster: the kernel is instruction-issue bound, not latency bound)
-constexpr int kAmbWarpBuf = 64;                 // rows for the global list staged per epilogue warp
-constexpr int kPairCap = 64;                    // (row, centroid) pairs per warp and tile
+constexpr int kSumThreads = 512;                // 16 warps: halves the sums latency per tile, which (with 2.5 tiles of ring slots) sets the tile period
+constexpr int kAmbWarpBuf = 32;                 // rows for the global list staged per epilogue warp
+constexpr int kPairCap = 32;                    // (row, centroid) pairs per warp and tile
 constexpr int kBarBytes = 512;
+constexpr int kLPT = 2;                         // MODE 1: labels per sums thread (host-checked: nq <= kLPT * (kSumThreads / (d/4)))
 constexpr int kQCap = 1024;                     // MODE 0: queued (row, needle) candidates per block
 constexpr int kQTrig = 192;                     //         a batch of chains runs once this many are waiting
-constexpr int kRxDepth = 8;                     // tiles of row norms in flight per epilogue thread
+constexpr int kRxDepth = 4;                     // tiles of row norms in flight per epilogue thread
 
 struct TfsParams {
     scan::ScanParams s;
@@ -278,9 +279,8 @@ tfs_kernel(const __grid_constant__ CUtensorMap tmX, const TfsParams tp) {
     unsigned* pairs = ambw + 8 * kAmbWarpBuf;                  // [8 warps][kPairCap] (owner lane | centroid << 5)
     float* pvals = reinterpret_cast<float*>(pairs + 8 * kPairCap);   // [8 warps][kPairCap] exact objective of the pair
     float* cen12 = pvals + 8 * kPairCap;                       // [NQP][cstride] fp32 centroids for the chains (or in global memory)
-    int* bcnt = reinterpret_cast<int*>(cen12 + (tp.cen_global ? 0 : NQP * cstride));   // MODE 1: [2][32] rows per label of the tile
-    uint8_t* bucket = reinterpret_cast<uint8_t*>(bcnt + 64);   // [2][32][128] the tile's rows grouped by label
-    unsigned long long* sacc = reinterpret_cast<unsigned long long*>(bucket + 2 * 32 * kRows);   // [nq*d + nq]
+    int* bcnt = reinterpret_cast<int*>(cen12 + (tp.cen_global ? 0 : ((p.nq + 3) & ~3) * cstride));   // MODE 1: [2][32] rows per label of the tile
+    uint16_t* bucket = reinterpret_cast<uint16_t*>(bcnt + 64); // [2][32][128] the tile's rows grouped by label, as byte offsets r*128 | (r&7)<<4 into a box
     float* cen = MODE == 0 ? cen0 : cen12;
     const float* cenp = tp.cen_global ? p.q : cen;
 
@@ -333,7 +333,6 @@ tfs_kernel(const __grid_constant__ CUtensorMap tmX, const TfsParams tp) {
         if (tid < 4) qn[tid] = 0;
     }
     if (MODE == 1) {
-        for (int i = tid; i < p.nq * d + p.nq; i += nthreads) sacc[i] = 0ull;
         if (tid < 64) bcnt[tid] = 0;
     }
     fence_proxy_async_smem();                                  // generic-proxy writes of B -> visible to the tensor core
@@ -521,6 +520,7 @@ tfs_kernel(const __grid_constant__ CUtensorMap tmX, const TfsParams tp) {
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acce + 8 * a);      // accumulator stage back to the MMA warp
+            if (MODE != 0 && grp == 0 && gtid == 0) TFS_TR(6, 8 * nloc + 0);
             // |x| <= 1e15 (and every |c| <= 1e15, qbad / the margin test): no product or partial sum can overflow in either arithmetic
             const bool rx_ok = (rx >= 1.0e-30f) && (rx < 3.0e38f);
 
@@ -618,6 +618,7 @@ tfs_kernel(const __grid_constant__ CUtensorMap tmX, const TfsParams tp) {
                 if (!fin || (tp.dbg & 1)) m = 0u;              // (dbg 1: test hook, every row through the global list)
                 if (!live) m = 1u;                             // dead rows: nothing to decide
                 const int nc = __popc(m);
+                if (MODE != 0 && grp == 0 && gtid == 0) TFS_TR(6, 8 * nloc + 1);
                 // pairs of this warp: every candidate of a row with several
                 const unsigned extra = nc > 1 ? m : 0u;
                 const int cnt = nc > 1 ? nc : 0;
@@ -635,6 +636,7 @@ tfs_kernel(const __grid_constant__ CUtensorMap tmX, const TfsParams tp) {
                 }
                 const int npairs = min(kPairCap, total);       // (ranges that did not fit are not written: stale entries are harmless)
                 __syncwarp();
+                if (MODE != 0 && grp == 0 && gtid == 0) TFS_TR(6, 8 * nloc + 2);
                 scan::Best win;
                 win.j = __ffs(m) - 1; win.v = 0.0f;
                 if constexpr (MODE == 2) {
@@ -660,6 +662,7 @@ tfs_kernel(const __grid_constant__ CUtensorMap tmX, const TfsParams tp) {
                     }
                 }
                 __syncwarp();
+                if (MODE != 0 && grp == 0 && gtid == 0) TFS_TR(6, 8 * nloc + 3);
                 if (cnt && fits) {
                     // owner: the reference's comparator over its candidates, ascending index
                     unsigned e = extra;
@@ -699,10 +702,12 @@ tfs_kernel(const __grid_constant__ CUtensorMap tmX, const TfsParams tp) {
                     }
                 } else {
                     // the row joins its label's bucket (order inside a bucket is irrelevant: integer sums); the sums group releases the slots
+                    if (grp == 0 && gtid == 0) TFS_TR(6, 8 * nloc + 4);
                     warp_mbar_wait(bar_labe + 8 * t2, par2 ^ 1u, lane, tp.err_flag, 405);
+                    if (grp == 0 && gtid == 0) TFS_TR(6, 8 * nloc + 5);
                     if (live && !listed) {
                         const int pos = atomicAdd(bcnt + t2 * 32 + win.j, 1);
-                        bucket[(t2 * 32 + win.j) * kRows + pos] = static_cast<uint8_t>(rit);
+                        bucket[(t2 * 32 + win.j) * kRows + pos] = static_cast<uint16_t>((rit << 7) | ((rit & 7) << 4));
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_labf + 8 * t2);
@@ -744,55 +749,54 @@ tfs_kernel(const __grid_constant__ CUtensorMap tmX, const TfsParams tp) {
             const int d4 = d >> 2;
             const int groups = max(1, kSumThreads / d4);
             const int g = stid / d4, c = (stid - g * d4) * 4;
-            const int cbox = c >> 5, cin = c & 31;
+            const int cbox = c >> 5;
+            const unsigned cp16 = static_cast<unsigned>(((c & 31) >> 2) << 4);
+            // thread (g, c4) owns labels g, g + groups, ... (at most kLPT, host-checked) x 4 columns: the int64 sums live in
+            // registers for the whole kernel
+            long long acc[kLPT][4];
+            unsigned long long cntl[kLPT];
+#pragma unroll
+            for (int u = 0; u < kLPT; ++u) { acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0; cntl[u] = 0ull; }
             int slot0 = 0;
             int it = 0;
             for (long long tile = first; tile < tp.n_tiles; tile += step, ++it) {
                 const int t2 = it & 1;
                 warp_mbar_wait(bar_labf + 8 * t2, (static_cast<uint32_t>(it) >> 1) & 1u, lane, tp.err_flag, 406);
-                if (stid == 0) { TFS_TR(4, 2 * it); TFS_TR(5, 16 * it + 9); }
+                if (stid == 0) TFS_TR(4, 2 * it);
                 if (g < groups && !(tp.dbg & 2)) {
                     int sl = slot0 + cbox;
                     if (sl >= nslots) sl -= nslots;
                     const uint8_t* xcol = smem + sl * kSlotBytes;
-                    const int cpiece = cin >> 2;
-                    for (int L = g; L < p.nq; L += groups) {
-                        const int n = bcnt[t2 * 32 + L];
-                        if (n == 0) continue;
-                        const uint8_t* bk = bucket + (t2 * 32 + L) * kRows;
-                        long long run0 = 0, run1 = 0, run2 = 0, run3 = 0;
-                        int pos = 0;
-                        for (; pos + 4 <= n; pos += 4) {
-                            const unsigned r4 = *reinterpret_cast<const unsigned*>(bk + pos);   // four row indices
-                            float4 x4[4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int r = (r4 >> (8 * e)) & 255;
-                                x4[e] = *reinterpret_cast<const float4*>(xcol + r * 128 + ((cpiece ^ (r & 7)) << 4));
-                            }
+                    for (int u = 0; u < kLPT; ++u) {
+                        const int L = g + u * groups;
+                        if (L < p.nq) {
+                            const int n = bcnt[t2 * 32 + L];
+                            const uint16_t* bk = bucket + (t2 * 32 + L) * kRows;
+                            int pos = 0;
+                            for (; pos + 4 <= n; pos += 4) {
+                                const uint2 r4 = *reinterpret_cast<const uint2*>(bk + pos);   // four row offsets
+                                float4 x4[4];
+                                x4[0] = *reinterpret_cast<const float4*>(xcol + ((r4.x & 0xffffu) ^ cp16));
+                                x4[1] = *reinterpret_cast<const float4*>(xcol + ((r4.x >> 16) ^ cp16));
+                                x4[2] = *reinterpret_cast<const float4*>(xcol + ((r4.y & 0xffffu) ^ cp16));
+                                x4[3] = *reinterpret_cast<const float4*>(xcol + ((r4.y >> 16) ^ cp16));
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                run0 += TFS_FIX(x4[e].x, fx); run1 += TFS_FIX(x4[e].y, fx);
-                                run2 += TFS_FIX(x4[e].z, fx); run3 += TFS_FIX(x4[e].w, fx);
+                                for (int e = 0; e < 4; ++e) {
+                                    acc[u][0] += TFS_FIX(x4[e].x, fx); acc[u][1] += TFS_FIX(x4[e].y, fx);
+                                    acc[u][2] += TFS_FIX(x4[e].z, fx); acc[u][3] += TFS_FIX(x4[e].w, fx);
+                                }
                             }
+                            for (; pos < n; ++pos) {
+                                const float4 x4 = *reinterpret_cast<const float4*>(xcol + (static_cast<unsigned>(bk[pos]) ^ cp16));
+                                acc[u][0] += TFS_FIX(x4.x, fx); acc[u][1] += TFS_FIX(x4.y, fx);
+                                acc[u][2] += TFS_FIX(x4.z, fx); acc[u][3] += TFS_FIX(x4.w, fx);
+                            }
+                            cntl[u] += static_cast<unsigned long long>(n);
                         }
-                        for (; pos < n; ++pos) {
-                            const int r = bk[pos];
-                            const float4 x4 = *reinterpret_cast<const float4*>(xcol + r * 128 + ((cpiece ^ (r & 7)) << 4));
-                            run0 += TFS_FIX(x4.x, fx); run1 += TFS_FIX(x4.y, fx);
-                            run2 += TFS_FIX(x4.z, fx); run3 += TFS_FIX(x4.w, fx);
-                        }
-                        unsigned long long* acc = sacc + L * d + c;
-                        acc[0] += static_cast<unsigned long long>(run0);
-                        acc[1] += static_cast<unsigned long long>(run1);
-                        acc[2] += static_cast<unsigned long long>(run2);
-                        acc[3] += static_cast<unsigned long long>(run3);
-                        if (c == 0) sacc[p.nq * d + L] += static_cast<unsigned long long>(n);
                     }
                 }
-                if ((stid & 31) == 0) TFS_TR(5, 16 * it + (stid >> 5));          // each sums warp: its rows are summed
                 named_bar_sync(2, kSumThreads);                // the tile's rows and buckets have been read
-                if (stid == 0) TFS_TR(5, 16 * it + 8);
                 if (stid < 32) {
                     bcnt[t2 * 32 + stid] = 0;
                     __syncwarp();
@@ -806,12 +810,16 @@ tfs_kernel(const __grid_constant__ CUtensorMap tmX, const TfsParams tp) {
                 slot0 += nbox;
                 if (slot0 >= nslots) slot0 -= nslots;
             }
-            const int per = p.nq * d + p.nq;
-            for (int i = stid; i < per; i += kSumThreads) {
-                const unsigned long long v = sacc[i];
-                if (v != 0ull) {
-                    if (i < p.nq * d) atomicAdd(&p.acc[i], v);
-                    else atomicAdd(&p.cnt[i - p.nq * d], v);
+            if (g < groups) {
+#pragma unroll
+                for (int u = 0; u < kLPT; ++u) {
+                    const int L = g + u * groups;
+                    if (L < p.nq) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (acc[u][e] != 0) atomicAdd(&p.acc[static_cast<long long>(L) * d + c + e], static_cast<unsigned long long>(acc[u][e]));
+                        if (c == 0 && cntl[u] != 0ull) atomicAdd(&p.cnt[L], cntl[u]);
+                    }
                 }
             }
         }
@@ -825,9 +833,9 @@ tfs_kernel(const __grid_constant__ CUtensorMap tmX, const TfsParams tp) {
 inline size_t tfs_fixed_bytes(int mode, int NQP, int K2, int nq, int d, bool cen_global) {
     const int nbox = (d + kBoxCols - 1) / kBoxCols;
     size_t b = static_cast<size_t>(nbox) * NQP * 128 + kBarBytes + 128 * 4 + 16 + 64 + static_cast<size_t>(mode == 0 ? 1 : 2) * kRxDepth * kRows * 4;
-    if (mode == 0) return b + static_cast<size_t>(NQP) * (K2 + scan::CAP + 1) * 8 + NQP * 4 + 16 + kQCap * 4 + (cen_global ? 0 : static_cast<size_t>(NQP) * cen_stride(d) * 4);
-    b += 8 * kAmbWarpBuf * 4 + 8 * kPairCap * 8 + (cen_global ? 0 : static_cast<size_t>(NQP) * cen_stride(d) * 4);
-    if (mode == 1) b += 64 * 4 + 2 * 32 * kRows + (static_cast<size_t>(nq) * d + nq) * 8;
+    if (mode == 0) return b + static_cast<size_t>(NQP) * (K2 + scan::CAP + 1) * 8 + NQP * 4 + 16 + kQCap * 4 + (cen_global ? 0 : static_cast<size_t>((nq + 3) & ~3) * cen_stride(d) * 4);
+    b += 8 * kAmbWarpBuf * 4 + 8 * kPairCap * 8 + (cen_global ? 0 : static_cast<size_t>((nq + 3) & ~3) * cen_stride(d) * 4);
+    if (mode == 1) b += 64 * 4 + 2 * 32 * kRows * 2;
     return b;
 }
 

@@ -49,3 +49,9 @@ if (rel[5] >= 0).sum() > 64:
     print("S per warp: cycles from 'labels seen' to 'my rows are summed' (warps 0..7), then to 'barrier passed'")
     for n in range(4, 16):
         print("   tile", n, " ".join("%6d" % (ph[n, w] - ph[n, 9]) for w in range(8)), "| %6d" % (ph[n, 8] - ph[n, 9]))
+
+if (rel[6] >= 0).sum() > 64:
+    ph = rel[6][:256].reshape(32, 8)
+    print("E0 phases, cycles since the accumulator was released: candidates known, pairs listed, chains done, labels out, bucket buffer free")
+    for n in range(6, 18):
+        print("   tile", n, " ".join("%6d" % (ph[n, e] - ph[n, 0] if ph[n, e] >= 0 else -1) for e in range(1, 6)), "  (acc seen -> released %d)" % (ph[n, 0] - rel[2][2 * n]))
