@@ -16,6 +16,7 @@
 #include "search_tc.cuh"
 #include "label_tc.cuh"
 #include "stream_tc.cuh"
+#include "nearest_tc.cuh"
 #include "kmeans_tc.cuh"
 
 using namespace ganrev;
@@ -1070,6 +1071,9 @@ int ganrev_l2(ganrev_ctx* ctx, const float* a, const float* b, int64_t N, int px
     return finish(ctx);
 }
 
+}  // extern "C"
+static int tfs_make_map(ganrev_ctx* ctx, CUtensorMap* m, const float* base, int d, long long rows);
+extern "C" {
 int ganrev_nearest_l2(ganrev_ctx* ctx, const float* queries, int Q, const float* set, int64_t N, int px, int64_t* ids, double* dist) {
     if (!ctx || !queries || Q < 0 || N < 0 || px < 1 || !ids || !dist) return ctx ? fail(ctx, GANREV_EINVAL, "bad nearest_l2 arguments") : GANREV_EINVAL;
     if (Q == 0) return GANREV_OK;
@@ -1095,7 +1099,56 @@ int ganrev_nearest_l2(ganrev_ctx* ctx, const float* queries, int Q, const float*
     RC_TRY(ensure(ctx, ctx->nn_dist, sizeof(double) * static_cast<size_t>(Q)));
     RC_TRY(ensure(ctx, ctx->nn_flag, static_cast<size_t>(Q)));
     CU_TRY(cudaMemsetAsync(ctx->nn_flag.p, 0, static_cast<size_t>(Q), ctx->stream));
-    for (int q0 = 0; q0 < Q; q0 += NL2_QB) {
+    // tensor-core filter + canonical evaluation of the candidates (nearest_tc.cuh) where the shape allows, else the exact kernel for every pair
+    const int tc_nbox = (px + tfs::kBoxCols - 1) / tfs::kBoxCols;
+    const size_t tc_fixed = ntc::nearest_fixed_bytes(px) + 1024;
+    const bool use_tc = ctx->stream_tc && N >= 1 && N <= 0x7fffff00LL && px % 4 == 0 && (reinterpret_cast<uintptr_t>(d_set) & 15) == 0 &&
+                        tc_fixed + 4 * static_cast<size_t>(tfs::kSlotBytes) <= 227 * 1024;
+    if (use_tc) {
+        const int nslots = static_cast<int>(std::min<size_t>(tfs::kMaxSlots, (227 * 1024 - tc_fixed) / tfs::kSlotBytes));
+        const size_t smem = tc_fixed + static_cast<size_t>(nslots) * tfs::kSlotBytes;
+        const long long n_tiles = (N + tfs::kRows - 1) / tfs::kRows;
+        const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(n_tiles, ctx->num_sms)));
+        const long long tc_warps = 4LL * grid;
+        RC_TRY(ensure(ctx, ctx->nn_partial, sizeof(NearestRec) * static_cast<size_t>(std::max(n_warps, tc_warps)) * NL2_QB));
+        if (!ctx->tfs_aux.p) {
+            RC_TRY(ensure(ctx, ctx->tfs_aux, 32 * sizeof(unsigned) + 4 * sizeof(unsigned long long)));
+            CU_TRY(cudaMemsetAsync(ctx->tfs_aux.p, 0, 32 * sizeof(unsigned) + 4 * sizeof(unsigned long long), ctx->stream));
+        }
+        static size_t attr_max_dev[kMaxDevices] = {};
+        size_t& attr_max = attr_max_dev[ctx->device];
+        if (smem > attr_max) {
+            CU_TRY(cudaFuncSetAttribute(ntc::nearest_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            attr_max = smem;
+        }
+        CUtensorMap tm;
+        RC_TRY(tfs_make_map(ctx, &tm, d_set, px, N));
+        for (int q0 = 0; q0 < Q; q0 += NL2_QB) {
+            const int nq = std::min(NL2_QB, Q - q0);
+            ntc::NParams np{};
+            np.set = d_set; np.n_rows = N; np.px = px; np.q = static_cast<const float*>(ctx->stage_b.p); np.q0 = q0; np.nq = nq;
+            np.partial = static_cast<NearestRec*>(ctx->nn_partial.p); np.row0_nan = static_cast<unsigned char*>(ctx->nn_flag.p);
+            np.gthr = static_cast<unsigned*>(ctx->tfs_aux.p);
+            np.stats = reinterpret_cast<unsigned long long*>(np.gthr + 32);
+            np.n_tiles = n_tiles; np.nbox = tc_nbox; np.nslots = nslots; np.err_flag = ctx->d_err_flag;
+            {
+                ProfScope ps(ctx, "nearest_l2", 3.0 * N * px * nq, 4.0 * N * px);
+                ntc::nearest_init_kernel<<<1, 32, 0, ctx->stream>>>(np.gthr);
+                ntc::nearest_tc_kernel<<<grid, ntc::kThreads, smem, ctx->stream>>>(tm, np);
+                ctx->launches++;
+                ctx->tfs_launches++;
+                CU_TRY(cudaGetLastError());
+            }
+            {
+                ProfScope ps(ctx, "nearest_l2_merge", 0.0, 16.0 * tc_warps * nq);
+                nearest_l2_merge_kernel<<<nq, 32, 0, ctx->stream>>>(static_cast<const NearestRec*>(ctx->nn_partial.p), tc_warps, Q, q0, N,
+                                                                   static_cast<const unsigned char*>(ctx->nn_flag.p), ctx->world == 1 ? 1 : 0,
+                                                                   static_cast<long long*>(ctx->nn_ids.p), static_cast<double*>(ctx->nn_dist.p));
+                CU_TRY(cudaGetLastError());
+            }
+        }
+    }
+    for (int q0 = 0; q0 < Q && !use_tc; q0 += NL2_QB) {
         const int nq = std::min(NL2_QB, Q - q0);
         {
             ProfScope ps(ctx, "nearest_l2", 3.0 * N * px * nq, 4.0 * N * px);

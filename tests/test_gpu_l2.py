@@ -77,10 +77,13 @@ def test_nearest_l2_exact(orc, ctx, Q, N, px):
     q = (ts[rng.integers(0, N, size=Q)] + rng.normal(scale=0.02, size=(Q, px))).astype(np.float32)
     if N > 60:
         ts[50] = ts[3]; ts[N - 1] = ts[3]; q[0] = ts[3]                  # exact duplicates: distance 0 three times -> row 3
-    ids, dist = ctx.nearest_l2(q, ts)
     oi, od = orc.nearest_l2(q, ts)
-    np.testing.assert_array_equal(ids, oi)
-    assert_bitexact(dist, od, "nearest_l2 distance")
+    for stream_tc in (1, 0):                                             # tensor-core filter + canonical candidates; every pair canonically
+        ctx.set_option("stream_tc", stream_tc)
+        ids, dist = ctx.nearest_l2(q, ts)
+        np.testing.assert_array_equal(ids, oi)
+        assert_bitexact(dist, od, "nearest_l2 distance")
+    ctx.set_option("stream_tc", 1)
 
 
 def test_nearest_l2_nan_and_empty(orc, ctx):
@@ -118,3 +121,24 @@ def test_nearest_l2_resident_images_fullsize(pkg, orc, ctx):
     oi, od = orc.nearest_l2(q[[3]], imgs[sl])
     assert oi[0] + 123000 == ids2[3]
     assert_bitexact(dist2[[3]], od)
+
+
+def test_nearest_l2_filter_adversarial(orc, ctx):
+    """The tensor-core filter of nearest_l2 may only pass extra rows: sets whose rows are all within the tf32 resolution of each
+    other, many exact ties (lowest row wins), a huge dynamic range, zero rows / zero queries, inf and NaN entries away from row 0,
+    and a set smaller than one tile."""
+    rng = np.random.default_rng(17)
+    px = 256
+    base = rng.random((1, px)).astype(np.float32)
+    ts = (base + np.float32(1e-6) * rng.standard_normal((9000, px))).astype(np.float32)       # distances differ in the 1e-5s
+    ts[4000:6000] = rng.random((2000, px)).astype(np.float32) * np.exp(rng.uniform(-12, 12, size=(2000, 1))).astype(np.float32)
+    ts[10] = ts[7]; ts[8999] = ts[7]; ts[123] = 0.0
+    ts[200, 3] = np.inf; ts[201, 5] = np.nan
+    q = np.stack([ts[7], base[0], ts[4100], np.zeros(px, np.float32), ts[5000] * np.float32(1.0001), ts[123] + np.float32(1e-20)]).astype(np.float32)
+    for sub in (ts, ts[:100], ts[:129]):
+        oi, od = orc.nearest_l2(q, sub)
+        ids, dist = ctx.nearest_l2(q, sub)
+        np.testing.assert_array_equal(ids, oi)
+        assert_bitexact(dist, od)
+    st = ctx.tfs_stats()
+    assert st["launches"] >= 3
