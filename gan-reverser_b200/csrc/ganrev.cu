@@ -1510,7 +1510,7 @@ static bool tfs_plan(const ganrev_ctx* ctx, const scan::ScanParams& p, int mode,
     int nslots = static_cast<int>(std::min<size_t>(tfs::kMaxSlots, (budget - fixed) / tfs::kSlotBytes));
     tp.cen_global = cen_global ? 1 : 0;
     if (mode != 0 && nslots < nbox + 1) return false;            // a tile stays resident until its rows were consumed
-    if (mode == 1 && (p.d / 4 > tfs::kSumThreads || p.nq > tfs::kLPT * (tfs::kSumThreads / (p.d / 4)))) return false;   // the sums live in registers: kLPT labels per thread
+    if (mode == 1 && (p.d / 4 > tfs::kSumThreads || p.nq > 2 * tfs::kLPT * (tfs::kSumThreads / (p.d / 4)))) return false;   // the sums live in registers: kLPT (or 2 kLPT) labels per thread
     if (mode != 0 && nslots >= 2 * nbox) nslots = std::min(nslots, 3 * nbox);   // three tiles in flight are plenty
     tp.s = p;
     tp.n_tiles = (p.n_rows + tfs::kRows - 1) / tfs::kRows;
@@ -2029,7 +2029,10 @@ int ganrev_kmeans(ganrev_ctx* ctx, int k, int niter, const float* init_centroids
             int grid = 0;
             tfs::TfsParams tp{};
             if (kmeans_tc_ok(ctx, k)) RC_TRY(kmeans_tc_iteration(ctx, p));
-            else if (tfs_plan(ctx, p, 1, 0, tp, smem, grid)) RC_TRY((launch_tfs<1, 1>(ctx, tp, smem, grid)));
+            else if (tfs_plan(ctx, p, 1, 0, tp, smem, grid)) {
+                if (p.nq > tfs::kLPT * (tfs::kSumThreads / (p.d / 4))) RC_TRY((launch_tfs<1, 4>(ctx, tp, smem, grid)));   // more labels per sums thread
+                else RC_TRY((launch_tfs<1, 1>(ctx, tp, smem, grid)));
+            }
             else if (label_tc_ok(ctx, p, 1)) RC_TRY((launch_label_tc<1>(ctx, p)));
             else if (rtile_plan(ctx, p, stream_nq(k), 1, sp, smem, grid)) RC_TRY((dispatch_rtile<1>(ctx, stream_nq(k), sp, smem, grid)));
             else if (stream_plan(ctx, p, stream_nq(k), 1, 0, sp, smem, grid)) RC_TRY((dispatch_stream<1, 1>(ctx, stream_nq(k), sp, smem, grid)));

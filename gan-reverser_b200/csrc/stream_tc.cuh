@@ -753,10 +753,11 @@ tfs_kernel(const __grid_constant__ CUtensorMap tmX, const TfsParams tp) {
             const unsigned cp16 = static_cast<unsigned>(((c & 31) >> 2) << 4);
             // thread (g, c4) owns labels g, g + groups, ... (at most kLPT, host-checked) x 4 columns: the int64 sums live in
             // registers for the whole kernel
-            long long acc[kLPT][4];
-            unsigned long long cntl[kLPT];
+            constexpr int LPT = E == 4 ? 2 * kLPT : kLPT;      // (MODE 1 reuses the list-length parameter: E = 4 = wide rows / many labels per thread)
+            long long acc[LPT][4];
+            unsigned long long cntl[LPT];
 #pragma unroll
-            for (int u = 0; u < kLPT; ++u) { acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0; cntl[u] = 0ull; }
+            for (int u = 0; u < LPT; ++u) { acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0; cntl[u] = 0ull; }
             int slot0 = 0;
             int it = 0;
             for (long long tile = first; tile < tp.n_tiles; tile += step, ++it) {
@@ -768,7 +769,7 @@ tfs_kernel(const __grid_constant__ CUtensorMap tmX, const TfsParams tp) {
                     if (sl >= nslots) sl -= nslots;
                     const uint8_t* xcol = smem + sl * kSlotBytes;
 #pragma unroll
-                    for (int u = 0; u < kLPT; ++u) {
+                    for (int u = 0; u < LPT; ++u) {
                         const int L = g + u * groups;
                         if (L < p.nq) {
                             const int n = bcnt[t2 * 32 + L];
@@ -812,7 +813,7 @@ tfs_kernel(const __grid_constant__ CUtensorMap tmX, const TfsParams tp) {
             }
             if (g < groups) {
 #pragma unroll
-                for (int u = 0; u < kLPT; ++u) {
+                for (int u = 0; u < LPT; ++u) {
                     const int L = g + u * groups;
                     if (L < p.nq) {
 #pragma unroll

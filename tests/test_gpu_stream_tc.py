@@ -80,7 +80,7 @@ def test_search_near_ties_duplicates_and_specials(orc, ctx):
 LABEL = [
     # N, d, k
     (5000, 100, 20), (5000, 100, 1), (5000, 100, 2), (5000, 100, 8), (5000, 100, 9), (4097, 100, 16), (5000, 100, 17), (5000, 100, 32),
-    (3000, 32, 20), (3000, 4, 20), (3000, 20, 5), (3000, 128, 20), (3001, 256, 20), (2000, 288, 8), (127, 32, 20), (128, 32, 20),
+    (3000, 32, 20), (3000, 4, 20), (3000, 20, 5), (3000, 128, 20), (3001, 256, 20), (3001, 256, 32), (2000, 288, 8), (2000, 192, 24), (127, 32, 20), (128, 32, 20),
     (129, 32, 20), (1, 32, 20), (60000, 68, 20),
 ]
 
