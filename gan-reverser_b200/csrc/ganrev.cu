@@ -70,6 +70,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct ganrev_ctx {
     int device = 0, num_sms = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host <-> device copies of forward_G / forward_R run chunk by chunk beside the kernels (created on first use)
+    std::vector<cudaEvent_t> io_events;
+    bool copies_pending = false;
     std::string err;
     int64_t chunk = 0;            // images per pipeline chunk; 0 = auto (8192 32x32 faces' worth of pixels, see chunk_for)
     int conv_impl = 0;
@@ -208,6 +211,11 @@ static void prof_resolve(ganrev_ctx* ctx) {
 
 static int finish(ganrev_ctx* ctx) {
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (ctx->copies_pending) {
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->copy_in);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->copy_out);
+        ctx->copies_pending = false;
+    }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         int flag = 0;
@@ -711,15 +719,66 @@ static int ensure_arena(ganrev_ctx* ctx, size_t per_img_bytes, int64_t chunk) {
     return GANREV_OK;
 }
 
-static int forward_G_dev(ganrev_ctx* ctx, const float* d_noise, int64_t N, float* d_images) {
+// Host <-> device copies of a chunked forward pass, overlapped with the kernels: every input chunk is copied on `copy_in` (an event
+// per chunk, the compute stream waits for its chunk only), every output chunk goes back on `copy_out` as soon as its last kernel has
+// finished.  With pageable host memory the copies are staged by the driver and simply do not overlap; results are identical.
+struct ChunkIO {
+    const uint8_t* h_in = nullptr;  uint8_t* d_in = nullptr;        size_t in_row = 0;    // one row = one image / noise vector
+    uint8_t* h_out = nullptr;       const uint8_t* d_out = nullptr; size_t out_row = 0;
+    int first_event = 0;
+};
+static int chunk_io_begin(ganrev_ctx* ctx, ChunkIO* io, int64_t N, int64_t CH) {
+    if (!io || (!io->h_in && !io->h_out) || N <= 0) return GANREV_OK;
+    if (!ctx->copy_in) {
+        CU_TRY(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+    }
+    const int64_t chunks = (N + CH - 1) / CH;
+    while (static_cast<int64_t>(ctx->io_events.size()) < 2 * chunks + 1) {   // [0, chunks) inputs landed, [chunks, 2 chunks) outputs ready, [2 chunks] start
+        cudaEvent_t e;
+        CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->io_events.push_back(e);
+    }
+    ctx->copies_pending = true;
+    if (io->h_in) {
+        // the copy stream starts behind whatever the compute stream has queued so far (buffer growth, earlier readers of the buffer)
+        cudaEvent_t e0 = ctx->io_events[2 * chunks];
+        CU_TRY(cudaEventRecord(e0, ctx->stream));
+        CU_TRY(cudaStreamWaitEvent(ctx->copy_in, e0, 0));
+        for (int64_t c = 0; c < chunks; ++c) {
+            const int64_t n0 = c * CH, n = std::min<int64_t>(CH, N - n0);
+            CU_TRY(cudaMemcpyAsync(io->d_in + n0 * io->in_row, io->h_in + n0 * io->in_row, static_cast<size_t>(n) * io->in_row, cudaMemcpyHostToDevice, ctx->copy_in));
+            CU_TRY(cudaEventRecord(ctx->io_events[c], ctx->copy_in));
+        }
+    }
+    return GANREV_OK;
+}
+static int chunk_io_before(ganrev_ctx* ctx, const ChunkIO* io, int64_t c) {
+    if (io && io->h_in) CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->io_events[c], 0));
+    return GANREV_OK;
+}
+static int chunk_io_after(ganrev_ctx* ctx, const ChunkIO* io, int64_t c, int64_t chunks, int64_t n0, int64_t n) {
+    if (io && io->h_out) {
+        cudaEvent_t e = ctx->io_events[chunks + c];
+        CU_TRY(cudaEventRecord(e, ctx->stream));
+        CU_TRY(cudaStreamWaitEvent(ctx->copy_out, e, 0));
+        CU_TRY(cudaMemcpyAsync(io->h_out + n0 * io->out_row, io->d_out + n0 * io->out_row, static_cast<size_t>(n) * io->out_row, cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+    return GANREV_OK;
+}
+
+static int forward_G_dev(ganrev_ctx* ctx, const float* d_noise, int64_t N, float* d_images, ChunkIO* io = nullptr) {
     GModel& G = ctx->G;
     if (!G.loaded) return fail(ctx, GANREV_ESTATE, "G not loaded");
     const int64_t CH = std::min<int64_t>(chunk_for(ctx, G.H, G.W), std::max<int64_t>(N, 1));
     const size_t per_img = static_cast<size_t>(G.H) * G.W * 128 * 2;   // largest activation (conv2 out); a0/a1 are smaller
     RC_TRY(ensure_arena(ctx, per_img, CH));
     RC_TRY(ensure(ctx, ctx->noise_bf16, static_cast<size_t>(CH) * G.kpad * 2));
+    RC_TRY(chunk_io_begin(ctx, io, N, CH));
+    const int64_t n_chunks = (N + CH - 1) / CH;
     for (int64_t n0 = 0; n0 < N; n0 += CH) {
         const int n = static_cast<int>(std::min<int64_t>(CH, N - n0));
+        RC_TRY(chunk_io_before(ctx, io, n0 / CH));
         {
             ProfScope ps(ctx, "g_noise_to_bf16", 0.0, static_cast<double>(n) * (G.nd * 4.0 + G.kpad * 2.0));
             const long long tot = static_cast<long long>(n) * G.kpad;
@@ -745,11 +804,12 @@ static int forward_G_dev(ganrev_ctx* ctx, const float* d_noise, int64_t N, float
             else          g_conv3_gather_kernel<3><<<blocks, 256, 0, ctx->stream>>>(static_cast<const float*>(ctx->arena[1].p), plane, static_cast<const float*>(G.b3.p), o, G.H, G.W, n);
             CU_TRY(cudaGetLastError());
         }
+        RC_TRY(chunk_io_after(ctx, io, n0 / CH, n_chunks, n0, n));
     }
     return GANREV_OK;
 }
 
-static int forward_R_dev(ganrev_ctx* ctx, int slot, const float* d_images, const uint8_t* d_mask, int64_t N, float* d_attrs) {
+static int forward_R_dev(ganrev_ctx* ctx, int slot, const float* d_images, const uint8_t* d_mask, int64_t N, float* d_attrs, ChunkIO* io = nullptr) {
     if (slot < 0 || slot > 1) return fail(ctx, GANREV_EINVAL, "slot must be 0 or 1");
     RModel& R = ctx->R[slot];
     if (!R.loaded) return fail(ctx, GANREV_ESTATE, "R slot %d not loaded", slot);
@@ -757,8 +817,11 @@ static int forward_R_dev(ganrev_ctx* ctx, int slot, const float* d_images, const
     const size_t per_img = static_cast<size_t>(R.H) * R.W * 64 * 2;   // conv1/conv2 outputs are the largest
     RC_TRY(ensure_arena(ctx, per_img, CH));
     const long long img_elems = static_cast<long long>(R.C) * R.H * R.W;
+    RC_TRY(chunk_io_begin(ctx, io, N, CH));
+    const int64_t n_chunks = (N + CH - 1) / CH;
     for (int64_t n0 = 0; n0 < N; n0 += CH) {
         const int n = static_cast<int>(std::min<int64_t>(CH, N - n0));
+        RC_TRY(chunk_io_before(ctx, io, n0 / CH));
         {
             const long long npix = static_cast<long long>(n) * R.H * R.W;
             ProfScope ps(ctx, "r_conv1", 2.0 * npix * 64 * 9 * R.C, npix * (R.C * (4.0 + (d_mask ? 1.0 : 0.0)) + 128.0));
@@ -799,6 +862,7 @@ static int forward_R_dev(ganrev_ctx* ctx, int slot, const float* d_images, const
         RC_TRY(run_layer(ctx, R.c6, ctx->arena[0].p, ctx->arena[1].p, n, CH));
         RC_TRY(run_layer(ctx, R.l1, ctx->arena[1].p, ctx->arena[0].p, n, CH));
         RC_TRY(run_layer(ctx, R.l2, ctx->arena[0].p, d_attrs + n0 * R.nd, n, CH));
+        RC_TRY(chunk_io_after(ctx, io, n0 / CH, n_chunks, n0, n));
     }
     return GANREV_OK;
 }
@@ -872,6 +936,9 @@ void ganrev_destroy(ganrev_ctx* ctx) {
                       &ctx->mcnt, &ctx->mmean, &ctx->trace})
         release(*b);
     if (ctx->d_err_flag) cudaFree(ctx->d_err_flag);
+    for (auto e : ctx->io_events) cudaEventDestroy(e);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -997,11 +1064,18 @@ int ganrev_forward_G(ganrev_ctx* ctx, const float* noise, int64_t N, float* imag
     if (!ctx || N < 0) return ctx ? fail(ctx, GANREV_EINVAL, "bad forward_G arguments") : GANREV_EINVAL;
     if (!ctx->G.loaded) return fail(ctx, GANREV_ESTATE, "G not loaded");
     CU_TRY(cudaSetDevice(ctx->device));
-    RC_TRY(stage_input(ctx, GANREV_BUF_NOISE, noise, N));
+    ChunkIO io;
+    if (noise) {   // chunk-wise upload beside the kernels instead of one copy in front of them
+        RC_TRY(buf_reserve(ctx, GANREV_BUF_NOISE, N));
+        ctx->buf_rows[GANREV_BUF_NOISE] = N;
+        io.h_in = reinterpret_cast<const uint8_t*>(noise); io.d_in = static_cast<uint8_t*>(ctx->buf[GANREV_BUF_NOISE].p); io.in_row = buf_row_bytes(ctx, GANREV_BUF_NOISE);
+    } else {
+        RC_TRY(stage_input(ctx, GANREV_BUF_NOISE, nullptr, N));
+    }
     RC_TRY(buf_reserve(ctx, GANREV_BUF_IMAGES, N));
-    RC_TRY(forward_G_dev(ctx, static_cast<const float*>(ctx->buf[GANREV_BUF_NOISE].p), N, static_cast<float*>(ctx->buf[GANREV_BUF_IMAGES].p)));
+    if (images) { io.h_out = reinterpret_cast<uint8_t*>(images); io.d_out = static_cast<const uint8_t*>(ctx->buf[GANREV_BUF_IMAGES].p); io.out_row = buf_row_bytes(ctx, GANREV_BUF_IMAGES); }
+    RC_TRY(forward_G_dev(ctx, static_cast<const float*>(ctx->buf[GANREV_BUF_NOISE].p), N, static_cast<float*>(ctx->buf[GANREV_BUF_IMAGES].p), &io));
     ctx->buf_rows[GANREV_BUF_IMAGES] = N;
-    RC_TRY(fetch_output(ctx, GANREV_BUF_IMAGES, images, N));
     return finish(ctx);
 }
 
@@ -1009,7 +1083,14 @@ int ganrev_forward_R(ganrev_ctx* ctx, int slot, const float* images, const uint8
     if (!ctx || N < 0 || slot < 0 || slot > 1) return ctx ? fail(ctx, GANREV_EINVAL, "bad forward_R arguments") : GANREV_EINVAL;
     if (!ctx->R[slot].loaded) return fail(ctx, GANREV_ESTATE, "R slot %d not loaded", slot);
     CU_TRY(cudaSetDevice(ctx->device));
-    RC_TRY(stage_input(ctx, GANREV_BUF_IMAGES, images, N));
+    ChunkIO io;
+    if (images) {
+        RC_TRY(buf_reserve(ctx, GANREV_BUF_IMAGES, N));
+        ctx->buf_rows[GANREV_BUF_IMAGES] = N;
+        io.h_in = reinterpret_cast<const uint8_t*>(images); io.d_in = static_cast<uint8_t*>(ctx->buf[GANREV_BUF_IMAGES].p); io.in_row = buf_row_bytes(ctx, GANREV_BUF_IMAGES);
+    } else {
+        RC_TRY(stage_input(ctx, GANREV_BUF_IMAGES, nullptr, N));
+    }
     const uint8_t* d_mask = nullptr;
     if (mask) {
         RC_TRY(stage_input(ctx, GANREV_BUF_MASK, mask, N));
@@ -1017,9 +1098,9 @@ int ganrev_forward_R(ganrev_ctx* ctx, int slot, const float* images, const uint8
     }
     const int ob = slot == 0 ? GANREV_BUF_ATTRS0 : GANREV_BUF_ATTRS1;
     RC_TRY(buf_reserve(ctx, ob, N));
-    RC_TRY(forward_R_dev(ctx, slot, static_cast<const float*>(ctx->buf[GANREV_BUF_IMAGES].p), d_mask, N, static_cast<float*>(ctx->buf[ob].p)));
+    if (attrs) { io.h_out = reinterpret_cast<uint8_t*>(attrs); io.d_out = static_cast<const uint8_t*>(ctx->buf[ob].p); io.out_row = buf_row_bytes(ctx, ob); }
+    RC_TRY(forward_R_dev(ctx, slot, static_cast<const float*>(ctx->buf[GANREV_BUF_IMAGES].p), d_mask, N, static_cast<float*>(ctx->buf[ob].p), &io));
     ctx->buf_rows[ob] = N;
-    RC_TRY(fetch_output(ctx, ob, attrs, N));
     return finish(ctx);
 }
 
