@@ -36,6 +36,9 @@ _SIGS = {
     "ganrev_fix_l2": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
     "ganrev_l2": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
     "ganrev_nearest_l2": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _vp]),
+    "ganrev_train_R_init": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _sz]),
+    "ganrev_train_R_step": (_i, [_vp, _vp, _i, _vp, _sz, _vp, _vp]),
+    "ganrev_train_R_state": (_i, [_vp, _i, _vp, _sz]),
     "ganrev_anomaly_flags": (_i, [_vp, _vp, _i64, _i64, C.c_double, _vp, C.POINTER(C.c_double)]),
     "ganrev_buffer_put": (_i, [_vp, _i, _vp, _i64]),
     "ganrev_buffer_get": (_i, [_vp, _i, _vp, _i64, _i64]),
@@ -210,6 +213,27 @@ class Context:
             xp = _ptr(np.zeros((1,), np.float32))   # any non-NULL pointer: an EMPTY explicit set, not the resident images
         self._chk(lib().ganrev_nearest_l2(self._h, _ptr(q), Q, xp, N, px, _ptr(ids), _ptr(dist)))
         return ids, dist
+
+    # ---- R training step (train_r.lua:138-170)
+    def train_R_init(self, C, H, W, nd, blob, tanh_out=False, fixer=False):
+        b = _arr(blob, np.float32)
+        self._train_floats = b.size
+        self._chk(lib().ganrev_train_R_init(self._h, C, H, W, nd, int(bool(tanh_out)), int(bool(fixer)), _ptr(b), b.size))
+
+    def train_R_step(self, noise, masks, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, l1=0.0, l2=1e-4, clamp=1.0):
+        """masks: list of uint8 keep-masks in module order (ganrev.h).  Returns (criterion output, f with penalties)."""
+        z = _arr(noise, np.float32)
+        m = np.ascontiguousarray(np.concatenate([np.asarray(a, np.uint8).ravel() for a in masks]))
+        hy = np.array([lr, beta1, beta2, eps, l1, l2, clamp], np.float32)
+        out = np.zeros((2,), np.float64)
+        self._chk(lib().ganrev_train_R_step(self._h, _ptr(z), z.shape[0], _ptr(m), m.size, _ptr(hy), _ptr(out)))
+        return float(out[0]), float(out[1])
+
+    def train_R_state(self, what=0):
+        """0: parameters + running statistics as a weight blob, 1: last gradients (after penalties / clamp), 2 / 3: Adam's m / v."""
+        out = np.empty((self._train_floats,), np.float32)
+        self._chk(lib().ganrev_train_R_state(self._h, what, _ptr(out), out.size))
+        return out
 
     def anomaly_flags(self, l2, n_calc, n_show, quantile):
         l2 = _arr(l2, np.float64)

@@ -17,6 +17,7 @@
 #include "label_tc.cuh"
 #include "stream_tc.cuh"
 #include "nearest_tc.cuh"
+#include "train.cuh"
 #include "kmeans_tc.cuh"
 
 using namespace ganrev;
@@ -66,6 +67,19 @@ struct NcclApi {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// R training state (train.cuh): fp32 parameters in weight-blob layout, Adam moments, step count, activations of one batch
+struct TrainR {
+    bool ready = false;
+    int C = 0, H = 0, W = 0, nd = 0, tanh_out = 0, fixer = 0;
+    size_t n_floats = 0;
+    long long t = 0;
+    DevBuf P, Gd, M, V, flags, work, masks, partial, lossbuf;
+    size_t cw[6], cb[6], cg[6], cbe[6], crm[6], crv[6];   // blob offsets (floats) of conv i: weight, bias, BN gamma, beta, running mean, var
+    size_t l1w, l1b, l1g, l1be, l1rm, l1rv, l2w, l2b;
+    int ci[6], co[6];
+    int B_cap = 0;
+};
 
 struct ganrev_ctx {
     int device = 0, num_sms = 0;
@@ -123,6 +137,7 @@ struct ganrev_ctx {
     DevBuf cen, acc, cnt, total, labels, cosv, tcounts, mids, mcnt, mmean;
     bool assigned = false;
     int assigned_k = 0;
+    TrainR train;
     // nccl
     NcclApi nccl;
     ncclComm_t comm = nullptr;
@@ -928,6 +943,7 @@ void ganrev_destroy(ganrev_ctx* ctx) {
         for (TcLayer* L : {&R.c2, &R.c3, &R.c4, &R.c5, &R.c6, &R.l1, &R.l2}) release_layer(*L);
     }
     for (auto& b : ctx->buf) release(b);
+    for (DevBuf* b : {&ctx->train.P, &ctx->train.Gd, &ctx->train.M, &ctx->train.V, &ctx->train.flags, &ctx->train.work, &ctx->train.masks, &ctx->train.partial, &ctx->train.lossbuf}) release(*b);
     for (DevBuf* b : {&ctx->nn_partial, &ctx->nn_ids, &ctx->nn_dist, &ctx->nn_flag, &ctx->nn_all, &ctx->qsel, &ctx->shard, &ctx->tfs_aux, &ctx->amb, &ctx->pdb, &ctx->pq, &ctx->tc_thr,
                       &ctx->tc_cnt, &ctx->tc_cand, &ctx->tc_pairs, &ctx->tc_keys, &ctx->tc_special, &ctx->tc_flags, &ctx->tc_dump}) release(*b);
     for (DevBuf* b : {&ctx->arena[0], &ctx->arena[1], &ctx->noise_bf16, &ctx->stage_a, &ctx->stage_b, &ctx->l2buf, &ctx->thr, &ctx->flags,
@@ -2258,6 +2274,193 @@ int ganrev_cluster_members(ganrev_ctx* ctx, int k, int m, const float* images, i
 
 // ---------------------------------------------------------------- measurement hooks
 void* ganrev_stream(ganrev_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
+// ---------------------------------------------------------------- R training step (train.cuh; train_r.lua:138-170)
+static size_t train_mask_bytes(const TrainR& T, int B) {
+    const size_t HW = static_cast<size_t>(T.H) * T.W;
+    return (T.fixer ? static_cast<size_t>(B) * T.C * HW : 0) + 2 * static_cast<size_t>(B) * 64 * HW + static_cast<size_t>(B) * 64 * HW / 4 +
+           2 * static_cast<size_t>(B) * 128 * HW / 4 + static_cast<size_t>(B) * 128 + static_cast<size_t>(B) * 512;
+}
+int ganrev_train_R_init(ganrev_ctx* ctx, int C, int H, int W, int noise_dim, int tanh_out, int fixer, const float* blob, size_t n_floats) {
+    if (!ctx || !blob) return ctx ? fail(ctx, GANREV_EINVAL, "bad train_R_init arguments") : GANREV_EINVAL;
+    CU_TRY(cudaSetDevice(ctx->device));
+    RC_TRY(check_geom(ctx, C, H, W, noise_dim));
+    if (ctx->gC != 0 && (ctx->gC != C || ctx->gH != H || ctx->gW != W || ctx->gnd != noise_dim))
+        return fail(ctx, GANREV_EINVAL, "the context holds models of another geometry (%dx%dx%d, nd %d)", ctx->gC, ctx->gH, ctx->gW, ctx->gnd);
+    TrainR& T = ctx->train;
+    T.ready = false;
+    T.C = C; T.H = H; T.W = W; T.nd = noise_dim; T.tanh_out = tanh_out ? 1 : 0; T.fixer = fixer ? 1 : 0;
+    const int chans[7] = {C, 64, 64, 64, 128, 128, 128};
+    size_t o = 0;
+    std::vector<unsigned char> flags;
+    auto take = [&](size_t n, bool param) { const size_t at = o; o += n; flags.insert(flags.end(), n, param ? 1 : 0); return at; };
+    for (int i = 0; i < 6; ++i) {
+        T.ci[i] = chans[i]; T.co[i] = chans[i + 1];
+        T.cw[i] = take(static_cast<size_t>(T.co[i]) * T.ci[i] * 9, true); T.cb[i] = take(T.co[i], true);
+        T.cg[i] = take(T.co[i], true); T.cbe[i] = take(T.co[i], true); T.crm[i] = take(T.co[i], false); T.crv[i] = take(T.co[i], false);
+    }
+    const size_t F = static_cast<size_t>(128) * (H / 4) * (W / 4);
+    T.l1w = take(512 * F, true); T.l1b = take(512, true); T.l1g = take(512, true); T.l1be = take(512, true); T.l1rm = take(512, false); T.l1rv = take(512, false);
+    T.l2w = take(static_cast<size_t>(noise_dim) * 512, true); T.l2b = take(noise_dim, true);
+    if (o != n_floats) return fail(ctx, GANREV_EINVAL, "R blob has %zu floats, this geometry needs %zu", n_floats, o);
+    T.n_floats = o;
+    for (DevBuf* b : {&T.P, &T.Gd, &T.M, &T.V}) RC_TRY(ensure(ctx, *b, sizeof(float) * o));
+    RC_TRY(ensure(ctx, T.flags, o));
+    RC_TRY(ensure(ctx, T.partial, sizeof(double) * 2 * 256));
+    RC_TRY(ensure(ctx, T.lossbuf, sizeof(double) * 4));
+    CU_TRY(cudaMemcpyAsync(T.P.p, blob, sizeof(float) * o, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(T.flags.p, flags.data(), o, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemsetAsync(T.Gd.p, 0, sizeof(float) * o, ctx->stream));
+    CU_TRY(cudaMemsetAsync(T.M.p, 0, sizeof(float) * o, ctx->stream));
+    CU_TRY(cudaMemsetAsync(T.V.p, 0, sizeof(float) * o, ctx->stream));
+    T.t = 0;
+    RC_TRY(finish(ctx));
+    T.ready = true;
+    return GANREV_OK;
+}
+
+int ganrev_train_R_step(ganrev_ctx* ctx, const float* noise, int B, const uint8_t* masks, size_t mask_bytes, const float* hyper7, double* loss2) {
+    if (!ctx || !noise || !masks || !hyper7 || B < 2 || B > 1024) return ctx ? fail(ctx, GANREV_EINVAL, "bad train_R_step arguments (2 <= B <= 1024)") : GANREV_EINVAL;
+    TrainR& T = ctx->train;
+    if (!T.ready) return fail(ctx, GANREV_ESTATE, "call ganrev_train_R_init first");
+    if (!ctx->G.loaded) return fail(ctx, GANREV_ESTATE, "G not loaded (the batch is generated by G, train_r.lua:140-141)");
+    if (mask_bytes != train_mask_bytes(T, B)) return fail(ctx, GANREV_EINVAL, "masks: %zu bytes given, batch of %d needs %zu", mask_bytes, B, train_mask_bytes(T, B));
+    CU_TRY(cudaSetDevice(ctx->device));
+    const int C = T.C, H = T.H, W = T.W, nd = T.nd;
+    const long long HW = static_cast<long long>(H) * W, HW2 = HW / 4, HW4 = HW / 16;
+    const long long F = 128 * HW4;
+    // ---- batch: G(noise) in eval mode through the inference kernels
+    RC_TRY(stage_input(ctx, GANREV_BUF_NOISE, noise, B));
+    RC_TRY(buf_reserve(ctx, GANREV_BUF_IMAGES, B));
+    RC_TRY(forward_G_dev(ctx, static_cast<const float*>(ctx->buf[GANREV_BUF_NOISE].p), B, static_cast<float*>(ctx->buf[GANREV_BUF_IMAGES].p)));
+    ctx->buf_rows[GANREV_BUF_IMAGES] = B;
+    const float* images = static_cast<const float*>(ctx->buf[GANREV_BUF_IMAGES].p);
+    const float* d_noise = static_cast<const float*>(ctx->buf[GANREV_BUF_NOISE].p);
+    RC_TRY(ensure(ctx, T.masks, mask_bytes));
+    CU_TRY(cudaMemcpyAsync(T.masks.p, masks, mask_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    const uint8_t* mk = static_cast<const uint8_t*>(T.masks.p);
+    const uint8_t* m0 = nullptr;
+    if (T.fixer) { m0 = mk; mk += static_cast<size_t>(B) * C * HW; }
+    const uint8_t* md[7];
+    md[0] = mk; mk += static_cast<size_t>(B) * 64 * HW;  md[1] = mk; mk += static_cast<size_t>(B) * 64 * HW;  md[2] = mk; mk += static_cast<size_t>(B) * 64 * HW2;
+    md[3] = mk; mk += static_cast<size_t>(B) * 128 * HW2; md[4] = mk; mk += static_cast<size_t>(B) * 128 * HW2; md[5] = mk; mk += static_cast<size_t>(B) * 128; md[6] = mk;
+    // ---- work space: per layer z (conv output), a (ELU output), in (layer input); pooled tensors; statistics; two gradient buffers
+    const long long res[6] = {HW, HW, HW, HW2, HW2, HW2};
+    size_t need = 0;
+    auto carve = [&](size_t n) { const size_t at = need; need += (n + 63) / 64 * 64; return at; };
+    size_t oz[6], oa[6], oin[6], omean[7], oistd[7];
+    for (int i = 0; i < 6; ++i) { oin[i] = carve(static_cast<size_t>(B) * T.ci[i] * res[i]); oz[i] = carve(static_cast<size_t>(B) * T.co[i] * res[i]); oa[i] = carve(static_cast<size_t>(B) * T.co[i] * res[i]); omean[i] = carve(T.co[i]); oistd[i] = carve(T.co[i]); }
+    omean[6] = carve(512); oistd[6] = carve(512);
+    const size_t op3 = carve(static_cast<size_t>(B) * 64 * HW2), os6 = carve(static_cast<size_t>(B) * 128 * HW2), op6 = carve(static_cast<size_t>(B) * F);
+    const size_t oz7 = carve(static_cast<size_t>(B) * 512), oa7 = carve(static_cast<size_t>(B) * 512), oo7 = carve(static_cast<size_t>(B) * 512), opred = carve(static_cast<size_t>(B) * nd), odpred = carve(static_cast<size_t>(B) * nd);
+    const size_t big = static_cast<size_t>(B) * 128 * HW;       // >= every activation
+    const size_t og0 = carve(big), og1 = carve(big), og2 = carve(big);
+    const size_t oarg3 = carve((static_cast<size_t>(B) * 64 * HW2 + 3) / 4), oarg6 = carve((static_cast<size_t>(B) * F + 3) / 4);
+    RC_TRY(ensure(ctx, T.work, sizeof(float) * need));
+    float* wk = static_cast<float*>(T.work.p);
+    float* Pp = static_cast<float*>(T.P.p);
+    float* Gp = static_cast<float*>(T.Gd.p);
+    uint8_t* arg3 = reinterpret_cast<uint8_t*>(wk + oarg3);
+    uint8_t* arg6 = reinterpret_cast<uint8_t*>(wk + oarg6);
+    auto nb = [](long long n) { return static_cast<unsigned>((n + 255) / 256); };
+    cudaStream_t st = ctx->stream;
+    ProfScope ps(ctx, "train_R_step", 6.0 * B * 174.7e6 * (HW / 1024.0), 0.0);
+    // ---- forward (training mode)
+    if (T.fixer) trn::mask_mul_kernel<<<nb(B * C * HW), 256, 0, st>>>(images, m0, wk + oin[0], B * C * HW);
+    else CU_TRY(cudaMemcpyAsync(wk + oin[0], images, sizeof(float) * B * C * HW, cudaMemcpyDeviceToDevice, st));
+    for (int i = 0; i < 6; ++i) {
+        const int ci = T.ci[i], co = T.co[i], h = i < 3 ? H : H / 2, w = i < 3 ? W : W / 2;
+        const long long hw = res[i], tot = static_cast<long long>(B) * co * hw;
+        trn::conv3x3_kernel<false><<<dim3(static_cast<unsigned>((hw + 127) / 128), (co + 7) / 8, B), 128, 8 * ci * 9 * sizeof(float), st>>>(wk + oin[i], Pp + T.cw[i], Pp + T.cb[i], wk + oz[i], ci, co, h, w);
+        trn::bn_stats_kernel<<<co, 256, 0, st>>>(wk + oz[i], wk + omean[i], wk + oistd[i], Pp + T.crm[i], Pp + T.crv[i], B, co, static_cast<int>(hw));
+        if (i == 2) {          // conv3: ELU -> MaxPool -> Dropout
+            trn::bn_elu_drop_kernel<<<nb(tot), 256, 0, st>>>(wk + oz[i], wk + omean[i], wk + oistd[i], Pp + T.cg[i], Pp + T.cbe[i], nullptr, 0, 1.0f, wk + oa[i], nullptr, tot, co, static_cast<int>(hw));
+            trn::maxpool_fwd_kernel<<<nb(tot / 4), 256, 0, st>>>(wk + oa[i], wk + op3, arg3, tot / 4, h, w);
+            trn::drop_kernel<<<nb(tot / 4), 256, 0, st>>>(wk + op3, md[2], 2.0f, wk + oin[3], tot / 4);
+        } else if (i == 5) {   // conv6: ELU -> SpatialDropout -> MaxPool
+            trn::bn_elu_drop_kernel<<<nb(tot), 256, 0, st>>>(wk + oz[i], wk + omean[i], wk + oistd[i], Pp + T.cg[i], Pp + T.cbe[i], md[5], 1, 1.0f, wk + oa[i], wk + os6, tot, co, static_cast<int>(hw));
+            trn::maxpool_fwd_kernel<<<nb(tot / 4), 256, 0, st>>>(wk + os6, wk + op6, arg6, tot / 4, h, w);
+        } else {
+            trn::bn_elu_drop_kernel<<<nb(tot), 256, 0, st>>>(wk + oz[i], wk + omean[i], wk + oistd[i], Pp + T.cg[i], Pp + T.cbe[i], md[i], 0, 2.0f, wk + oa[i], wk + oin[i + 1], tot, co, static_cast<int>(hw));
+        }
+    }
+    trn::linear_fwd_kernel<<<nb(static_cast<long long>(B) * 512 * 32), 256, 0, st>>>(wk + op6, Pp + T.l1w, Pp + T.l1b, wk + oz7, B, static_cast<int>(F), 512);
+    trn::bn_stats_kernel<<<512, 256, 0, st>>>(wk + oz7, wk + omean[6], wk + oistd[6], Pp + T.l1rm, Pp + T.l1rv, B, 512, 1);
+    trn::bn_elu_drop_kernel<<<nb(B * 512), 256, 0, st>>>(wk + oz7, wk + omean[6], wk + oistd[6], Pp + T.l1g, Pp + T.l1be, md[6], 0, 2.0f, wk + oa7, wk + oo7, B * 512, 512, 1);
+    trn::linear_fwd_kernel<<<nb(static_cast<long long>(B) * nd * 32), 256, 0, st>>>(wk + oo7, Pp + T.l2w, Pp + T.l2b, wk + opred, B, 512, nd);
+    if (T.tanh_out) trn::tanh_fwd_kernel<<<nb(B * nd), 256, 0, st>>>(wk + opred, B * nd);
+    double* lossd = static_cast<double*>(T.lossbuf.p);
+    trn::mse_kernel<<<1, 256, 0, st>>>(wk + opred, d_noise, wk + odpred, lossd, B * nd, T.tanh_out);
+    CU_TRY(cudaGetLastError());
+    // ---- backward
+    trn::linear_bwd_w_kernel<<<nb(static_cast<long long>(nd) * 512), 256, 0, st>>>(wk + odpred, wk + oo7, Gp + T.l2w, Gp + T.l2b, B, 512, nd);
+    trn::linear_bwd_data_kernel<<<nb(B * 512), 256, 0, st>>>(wk + odpred, Pp + T.l2w, wk + og0, B, 512, nd);
+    trn::drop_elu_bwd_kernel<<<nb(B * 512), 256, 0, st>>>(wk + og0, wk + oa7, md[6], 0, 2.0f, wk + og1, B * 512, 1);
+    trn::bn_bwd_reduce_kernel<<<512, 256, 0, st>>>(wk + og1, wk + oz7, wk + omean[6], wk + oistd[6], Gp + T.l1g, Gp + T.l1be, B, 512, 1);
+    trn::bn_bwd_apply_kernel<<<nb(B * 512), 256, 0, st>>>(wk + og1, wk + oz7, wk + omean[6], wk + oistd[6], Pp + T.l1g, Gp + T.l1g, Gp + T.l1be, wk + og0, B * 512, 512, 1, 1.0f / B);
+    trn::linear_bwd_w_kernel<<<nb(512 * F), 256, 0, st>>>(wk + og0, wk + op6, Gp + T.l1w, Gp + T.l1b, B, static_cast<int>(F), 512);
+    trn::linear_bwd_data_kernel<<<nb(B * F), 256, 0, st>>>(wk + og0, Pp + T.l1w, wk + og1, B, static_cast<int>(F), 512);   // d p6
+    float* gcur = wk + og1;     // gradient w.r.t. the OUTPUT of layer i's block (what the next layer consumed)
+    float* gA = wk + og0;
+    float* gB = wk + og2;
+    for (int i = 5; i >= 0; --i) {
+        const int ci = T.ci[i], co = T.co[i], h = i < 3 ? H : H / 2, w = i < 3 ? W : W / 2;
+        const long long hw = res[i], tot = static_cast<long long>(B) * co * hw;
+        // gcur -> gradient w.r.t. the ELU output's consumers, then through dropout / pooling and the ELU: gA = dz
+        if (i == 5) {
+            trn::maxpool_bwd_kernel<<<nb(tot / 4), 256, 0, st>>>(gcur, arg6, gB, tot / 4, h, w);                 // d s6
+            trn::drop_elu_bwd_kernel<<<nb(tot), 256, 0, st>>>(gB, wk + oa[i], md[5], 1, 1.0f, gA, tot, static_cast<int>(hw));
+        } else if (i == 2) {
+            trn::drop_kernel<<<nb(tot / 4), 256, 0, st>>>(gcur, md[2], 2.0f, gA, tot / 4);                       // d p3
+            trn::maxpool_bwd_kernel<<<nb(tot / 4), 256, 0, st>>>(gA, arg3, gB, tot / 4, h, w);                   // d a3
+            trn::drop_elu_bwd_kernel<<<nb(tot), 256, 0, st>>>(gB, wk + oa[i], nullptr, 0, 1.0f, gA, tot, static_cast<int>(hw));
+        } else {
+            trn::drop_elu_bwd_kernel<<<nb(tot), 256, 0, st>>>(gcur, wk + oa[i], md[i], 0, 2.0f, gA, tot, static_cast<int>(hw));
+        }
+        trn::bn_bwd_reduce_kernel<<<co, 256, 0, st>>>(gA, wk + oz[i], wk + omean[i], wk + oistd[i], Gp + T.cg[i], Gp + T.cbe[i], B, co, static_cast<int>(hw));
+        trn::bn_bwd_apply_kernel<<<nb(tot), 256, 0, st>>>(gA, wk + oz[i], wk + omean[i], wk + oistd[i], Pp + T.cg[i], Gp + T.cg[i], Gp + T.cbe[i], gB, tot, co, static_cast<int>(hw), 1.0f / static_cast<float>(B * hw));   // d conv output
+        trn::conv3x3_wgrad_kernel<<<dim3(co, ci), 256, 0, st>>>(wk + oin[i], gB, Gp + T.cw[i], B, ci, co, h, w);
+        trn::channel_sum_kernel<<<co, 256, 0, st>>>(gB, Gp + T.cb[i], B, co, static_cast<int>(hw));
+        if (i > 0) {
+            trn::conv3x3_kernel<true><<<dim3(static_cast<unsigned>((hw + 127) / 128), (ci + 7) / 8, B), 128, 8 * co * 9 * sizeof(float), st>>>(gB, Pp + T.cw[i], nullptr, gA, co, ci, h, w);   // d layer input
+            float* t = gcur; gcur = gA; gA = t;
+        }
+    }
+    CU_TRY(cudaGetLastError());
+    // ---- penalties, clamp, Adam (train_r.lua:150-166; optim.adam)
+    trn::penalty_kernel<<<256, 256, 0, st>>>(Pp, static_cast<const uint8_t*>(T.flags.p), static_cast<long long>(T.n_floats), static_cast<double*>(T.partial.p));
+    T.t += 1;
+    trn::AdamHyper hy{};
+    hy.lr = hyper7[0]; hy.beta1 = hyper7[1]; hy.beta2 = hyper7[2]; hy.eps = hyper7[3]; hy.l1 = hyper7[4]; hy.l2 = hyper7[5]; hy.clamp = hyper7[6];
+    hy.step_size = static_cast<float>(static_cast<double>(hy.lr) * std::sqrt(1.0 - std::pow(static_cast<double>(hy.beta2), static_cast<double>(T.t))) /
+                                      (1.0 - std::pow(static_cast<double>(hy.beta1), static_cast<double>(T.t))));
+    trn::adam_kernel<<<nb(static_cast<long long>(T.n_floats)), 256, 0, st>>>(Pp, Gp, static_cast<float*>(T.M.p), static_cast<float*>(T.V.p), static_cast<const uint8_t*>(T.flags.p), static_cast<long long>(T.n_floats), hy);
+    CU_TRY(cudaGetLastError());
+    ctx->launches += 90;
+    double hl[1];
+    std::vector<double> part(512);
+    CU_TRY(cudaMemcpyAsync(hl, lossd, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(part.data(), T.partial.p, sizeof(double) * 512, cudaMemcpyDeviceToHost, st));
+    RC_TRY(finish(ctx));
+    if (loss2) {
+        double a = 0.0, q = 0.0;
+        for (int k = 0; k < 256; ++k) { a += part[2 * k]; q += part[2 * k + 1]; }
+        loss2[0] = hl[0];
+        loss2[1] = hl[0] + static_cast<double>(hy.l1) * a + static_cast<double>(hy.l2) * q / 2.0;
+    }
+    return GANREV_OK;
+}
+
+int ganrev_train_R_state(ganrev_ctx* ctx, int what, float* out, size_t n_floats) {
+    if (!ctx || !out || what < 0 || what > 3) return ctx ? fail(ctx, GANREV_EINVAL, "bad train_R_state arguments") : GANREV_EINVAL;
+    TrainR& T = ctx->train;
+    if (!T.ready) return fail(ctx, GANREV_ESTATE, "call ganrev_train_R_init first");
+    if (n_floats != T.n_floats) return fail(ctx, GANREV_EINVAL, "state has %zu floats", T.n_floats);
+    CU_TRY(cudaSetDevice(ctx->device));
+    const DevBuf& b = what == 0 ? T.P : (what == 1 ? T.Gd : (what == 2 ? T.M : T.V));
+    CU_TRY(cudaMemcpyAsync(out, b.p, sizeof(float) * n_floats, cudaMemcpyDeviceToHost, ctx->stream));
+    return finish(ctx);
+}
+
 int ganrev_sync(ganrev_ctx* ctx) {
     if (!ctx) return GANREV_EINVAL;
     CU_TRY(cudaSetDevice(ctx->device));

@@ -1,0 +1,320 @@
+// train.cuh -- one optimisation step of R (train_r.lua:138-170): R_default (models.lua:389-464) in TRAINING
+// mode -- batch-norm batch statistics, nn.Dropout / nn.SpatialDropout with the caller's masks -- forward and backward, fp32
+// throughout (the reference trains in FloatTensor arithmetic), NCHW like the reference.  At the reference's batch size (32 faces,
+// 5.6 GMAC forward, 17 GMAC per step) the step is a chain of ~80 small launches, so these are plain CUDA-core kernels written
+// for clarity and determinism (fixed reduction orders, no float atomics): the tensor-core convolution kernels of conv_tc.cuh fold
+// eval-mode batch norm into their weights and cannot serve a pass that needs the batch statistics of the raw convolution output.
+//
+// Upstream semantics restated here (torch/nn, not vendored in the reference):
+//   nn.SpatialConvolution 3x3, stride 1, pad 1;  nn.(Spatial)BatchNormalization: eps 1e-5, momentum 0.1, normalises with the
+//   biased batch variance, running_var takes the unbiased one;  nn.ELU alpha = 1;  nn.Dropout(p) v2: y = x * mask / (1 - p);
+//   nn.Dropout(0.5, true) (the fixer's input layer, v1): y = x * mask;  nn.SpatialDropout(0.25): one Bernoulli(0.75) draw per
+//   (sample, channel), no rescaling in training;  nn.SpatialMaxPooling(2,2): first maximum in row-major window order;
+//   nn.MSECriterion: mean over all elements;  optim.adam: step = lr sqrt(1 - b2^t) / (1 - b1^t), x -= step * m / (sqrt(v) + eps).
+#pragma once
+#include "common.cuh"
+
+namespace ganrev {
+namespace trn {
+
+constexpr float kBnEps = 1.0e-5f;
+constexpr float kBnMomentum = 0.1f;
+
+// ---------------------------------------------------------------- 3x3 convolution, stride 1, pad 1 (forward and backward-data)
+// out[n][o][h][w] = bias[o] + sum_i sum_t in[n][i][h+ty-1][w+tx-1] * Wt(o, i, t).  TR = false: Wt = w[(o*CI + i)*9 + t] (forward);
+// TR = true: Wt = w[(i*CO + o)*9 + (8 - t)] with CO = channels of THIS kernel's output (backward-data: in = dY, out = dX).
+// Block = 128 consecutive pixels of one image x 8 output channels; the 8 x CI x 9 weights are staged in shared memory.
+template <bool TR>
+__global__ void __launch_bounds__(128)
+conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
+               int CI, int CO, int H, int W) {
+    extern __shared__ float ws[];                                  // [8][CI][9]
+    const int o0 = blockIdx.y * 8, n = blockIdx.z;
+    for (int i = threadIdx.x; i < 8 * CI * 9; i += 128) {
+        const int oo = i / (CI * 9), r = i - oo * CI * 9, ci = r / 9, t = r - ci * 9;
+        const int o = o0 + oo;
+        float v = 0.0f;
+        if (o < CO) v = TR ? __ldg(w + (static_cast<size_t>(ci) * CO + o) * 9 + (8 - t)) : __ldg(w + (static_cast<size_t>(o) * CI + ci) * 9 + t);
+        ws[i] = v;
+    }
+    __syncthreads();
+    const int HW = H * W, pix = blockIdx.x * 128 + threadIdx.x;
+    if (pix >= HW) return;
+    const int h = pix / W, x = pix - h * W;
+    float acc[8];
+#pragma unroll
+    for (int oo = 0; oo < 8; ++oo) acc[oo] = (bias != nullptr && o0 + oo < CO) ? __ldg(bias + o0 + oo) : 0.0f;
+    const float* ip = in + static_cast<size_t>(n) * CI * HW;
+    for (int ci = 0; ci < CI; ++ci) {
+        float v[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int hh = h + t / 3 - 1, xx = x + t % 3 - 1;
+            v[t] = (hh >= 0 && hh < H && xx >= 0 && xx < W) ? __ldg(ip + static_cast<size_t>(ci) * HW + hh * W + xx) : 0.0f;
+        }
+#pragma unroll
+        for (int oo = 0; oo < 8; ++oo) {
+            const float* wr = ws + (oo * CI + ci) * 9;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) acc[oo] = fmaf(v[t], wr[t], acc[oo]);
+        }
+    }
+#pragma unroll
+    for (int oo = 0; oo < 8; ++oo)
+        if (o0 + oo < CO) out[(static_cast<size_t>(n) * CO + o0 + oo) * HW + pix] = acc[oo];
+}
+
+// dW[o][i][t] = sum_{n,h,w} dY[n][o][h][w] * X[n][i][h+ty-1][w+tx-1]; one block per (o, i), fixed-order tree reduction.
+__global__ void __launch_bounds__(256)
+conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int B, int CI, int CO, int H, int W) {
+    const int o = blockIdx.x, i = blockIdx.y, HW = H * W;
+    float s[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) s[t] = 0.0f;
+    for (int e = threadIdx.x; e < B * HW; e += 256) {
+        const int n = e / HW, pix = e - n * HW, h = pix / W, xx0 = pix - h * W;
+        const float g = __ldg(dy + (static_cast<size_t>(n) * CO + o) * HW + pix);
+        const float* xp = x + (static_cast<size_t>(n) * CI + i) * HW;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int hh = h + t / 3 - 1, xx = xx0 + t % 3 - 1;
+            if (hh >= 0 && hh < H && xx >= 0 && xx < W) s[t] = fmaf(g, __ldg(xp + hh * W + xx), s[t]);
+        }
+    }
+    __shared__ float red[9][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        float v = s[t];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) red[t][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        float v = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v += red[threadIdx.x][k];
+        dw[(static_cast<size_t>(o) * CI + i) * 9 + threadIdx.x] = v;
+    }
+}
+
+// ---------------------------------------------------------------- per-channel reductions over (n, h, w): one block per channel
+// mode 0: sum(a)  (bias gradient);  mode 1: batch mean and 1/sqrt(var + eps) of a, running statistics updated;
+// mode 2: sum(a) and sum(a * xhat) with xhat = (x - mean) * invstd  (batch-norm backward: dbeta, dgamma)
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int k = 0; k < static_cast<int>(blockDim.x >> 5); ++k) t += red[k];
+    return t;
+}
+__global__ void __launch_bounds__(256)
+channel_sum_kernel(const float* __restrict__ a, float* __restrict__ out, int B, int C, int HW) {
+    __shared__ double red[8];
+    const int c = blockIdx.x;
+    double s = 0.0;
+    for (int e = threadIdx.x; e < B * HW; e += 256) { const int n = e / HW, p = e - n * HW; s += static_cast<double>(__ldg(a + (static_cast<size_t>(n) * C + c) * HW + p)); }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[c] = static_cast<float>(s);
+}
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ run_mean, float* __restrict__ run_var,
+                int B, int C, int HW) {
+    __shared__ double red[8];
+    const int c = blockIdx.x;
+    const double M = static_cast<double>(B) * HW;
+    double s = 0.0;
+    for (int e = threadIdx.x; e < B * HW; e += 256) { const int n = e / HW, p = e - n * HW; s += static_cast<double>(__ldg(x + (static_cast<size_t>(n) * C + c) * HW + p)); }
+    const double mu = block_sum(s, red) / M;
+    double q = 0.0;
+    for (int e = threadIdx.x; e < B * HW; e += 256) { const int n = e / HW, p = e - n * HW; const double dlt = static_cast<double>(__ldg(x + (static_cast<size_t>(n) * C + c) * HW + p)) - mu; q += dlt * dlt; }
+    q = block_sum(q, red);
+    if (threadIdx.x == 0) {
+        const double var = q / M;
+        mean[c] = static_cast<float>(mu);
+        invstd[c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kBnEps)));
+        run_mean[c] = (1.0f - kBnMomentum) * run_mean[c] + kBnMomentum * static_cast<float>(mu);
+        run_var[c] = (1.0f - kBnMomentum) * run_var[c] + kBnMomentum * static_cast<float>(M > 1.0 ? q / (M - 1.0) : var);
+    }
+}
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int C, int HW) {
+    __shared__ double red[8];
+    const int c = blockIdx.x;
+    const float mu = mean[c], is = invstd[c];
+    double s = 0.0, sx = 0.0;
+    for (int e = threadIdx.x; e < B * HW; e += 256) {
+        const int n = e / HW, p = e - n * HW;
+        const size_t idx = (static_cast<size_t>(n) * C + c) * HW + p;
+        const float g = __ldg(dz + idx);
+        s += static_cast<double>(g);
+        sx += static_cast<double>(g * ((__ldg(x + idx) - mu) * is));
+    }
+    s = block_sum(s, red);
+    sx = block_sum(sx, red);
+    if (threadIdx.x == 0) { dbeta[c] = static_cast<float>(s); dgamma[c] = static_cast<float>(sx); }
+}
+
+// ---------------------------------------------------------------- elementwise passes (index e over [B][C][HW])
+// forward: act = ELU(gamma * (x - mean) * invstd + beta); out = act * mask * scale (mask == nullptr: out = act).
+// The mask is indexed per element, or per (n, c) when `spatial` (nn.SpatialDropout).
+__global__ void bn_elu_drop_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const uint8_t* __restrict__ mask, int spatial, float scale, float* __restrict__ act,
+                                   float* __restrict__ out, long long total, int C, int HW) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int c = static_cast<int>((e / HW) % C);
+    const float z = fmaf(gamma[c] * invstd[c], x[e] - mean[c], beta[c]);
+    const float a = z > 0.0f ? z : expm1f(z);
+    act[e] = a;
+    if (out) out[e] = mask ? (mask[spatial ? e / HW : e] ? a * scale : 0.0f) : a;
+}
+// backward through dropout and ELU: dz = dout * mask * scale * (act > 0 ? 1 : act + 1)
+__global__ void drop_elu_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ act, const uint8_t* __restrict__ mask, int spatial, float scale,
+                                    float* __restrict__ dz, long long total, int HW) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    float g = dout[e];
+    if (mask) g = mask[spatial ? e / HW : e] ? g * scale : 0.0f;
+    const float a = act[e];
+    dz[e] = a > 0.0f ? g : g * (a + 1.0f);
+}
+// batch-norm backward (input gradient): dx = gamma * invstd * (dz - dbeta / M - xhat * dgamma / M)
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ dgamma, const float* __restrict__ dbeta, float* __restrict__ dx,
+                                    long long total, int C, int HW, float invM) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int c = static_cast<int>((e / HW) % C);
+    const float xh = (x[e] - mean[c]) * invstd[c];
+    dx[e] = gamma[c] * invstd[c] * (dz[e] - dbeta[c] * invM - xh * dgamma[c] * invM);
+}
+// v1 dropout on the input image (the fixer's nn.Dropout(0.5, true)): y = x * mask
+__global__ void mask_mul_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask, float* __restrict__ y, long long total) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e < total) y[e] = mask[e] ? x[e] : 0.0f;
+}
+// nn.Dropout (v2) on its own (conv3's dropout sits behind the pooling): y = x * mask * scale; the backward pass is the same map
+__global__ void drop_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask, float scale, float* __restrict__ y, long long total) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e < total) y[e] = mask[e] ? x[e] * scale : 0.0f;
+}
+// 2x2 max pooling, stride 2: first maximum in window order (0,0),(0,1),(1,0),(1,1); `arg` keeps its position for the backward pass
+__global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ arg, long long total_out, int H, int W) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= total_out) return;
+    const int Wo = W / 2, Ho = H / 2;
+    const int wo = static_cast<int>(e % Wo), ho = static_cast<int>((e / Wo) % Ho);
+    const long long nc = e / (static_cast<long long>(Wo) * Ho);
+    const float* p = x + nc * H * W + static_cast<long long>(2 * ho) * W + 2 * wo;
+    float best = p[0];
+    int a = 0;
+    if (p[1] > best) { best = p[1]; a = 1; }
+    if (p[W] > best) { best = p[W]; a = 2; }
+    if (p[W + 1] > best) { best = p[W + 1]; a = 3; }
+    y[e] = best;
+    arg[e] = static_cast<uint8_t>(a);
+}
+__global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ arg, float* __restrict__ dx, long long total_out, int H, int W) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= total_out) return;
+    const int Wo = W / 2, Ho = H / 2;
+    const int wo = static_cast<int>(e % Wo), ho = static_cast<int>((e / Wo) % Ho);
+    const long long nc = e / (static_cast<long long>(Wo) * Ho);
+    float* p = dx + nc * H * W + static_cast<long long>(2 * ho) * W + 2 * wo;
+    const int a = arg[e];
+    const float g = dy[e];
+    p[0] = a == 0 ? g : 0.0f; p[1] = a == 1 ? g : 0.0f; p[W] = a == 2 ? g : 0.0f; p[W + 1] = a == 3 ? g : 0.0f;
+}
+
+// ---------------------------------------------------------------- Linear: y[b][o] = bias[o] + sum_k x[b][k] w[o][k]
+__global__ void __launch_bounds__(256)
+linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y, int B, int K, int O) {
+    const int gw = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (gw >= B * O) return;
+    const int b = gw / O, o = gw - b * O;
+    const float* xr = x + static_cast<size_t>(b) * K;
+    const float* wr = w + static_cast<size_t>(o) * K;
+    float s = 0.0f;
+    for (int k = lane; k < K; k += 32) s = fmaf(__ldg(xr + k), __ldg(wr + k), s);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) y[gw] = s + __ldg(bias + o);
+}
+// dx[b][k] = sum_o dy[b][o] w[o][k]
+__global__ void linear_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int B, int K, int O) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= static_cast<long long>(B) * K) return;
+    const int b = static_cast<int>(e / K), k = static_cast<int>(e - static_cast<long long>(b) * K);
+    float s = 0.0f;
+    for (int o = 0; o < O; ++o) s = fmaf(__ldg(dy + static_cast<size_t>(b) * O + o), __ldg(w + static_cast<size_t>(o) * K + k), s);
+    dx[e] = s;
+}
+// dw[o][k] = sum_b dy[b][o] x[b][k];  db[o] = sum_b dy[b][o]  (k == 0 threads)
+__global__ void linear_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw, float* __restrict__ db, int B, int K, int O) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= static_cast<long long>(O) * K) return;
+    const int o = static_cast<int>(e / K), k = static_cast<int>(e - static_cast<long long>(o) * K);
+    float s = 0.0f, sb = 0.0f;
+    for (int b = 0; b < B; ++b) { const float g = __ldg(dy + static_cast<size_t>(b) * O + o); s = fmaf(g, __ldg(x + static_cast<size_t>(b) * K + k), s); sb += g; }
+    dw[e] = s;
+    if (k == 0) db[o] = sb;
+}
+__global__ void tanh_fwd_kernel(float* __restrict__ y, long long total) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e < total) y[e] = tanhf(y[e]);
+}
+
+// ---------------------------------------------------------------- criterion, penalties, Adam
+// nn.MSECriterion: loss = mean((pred - target)^2), dpred = 2 (pred - target) / n (and through Tanh when the net ends in one);
+// one block, fixed-order reduction in double.
+__global__ void __launch_bounds__(256)
+mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, float* __restrict__ dpred, double* __restrict__ loss, int n, int tanh_out) {
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int e = threadIdx.x; e < n; e += 256) {
+        const float df = pred[e] - target[e];
+        s += static_cast<double>(df) * static_cast<double>(df);
+        float g = 2.0f * df / static_cast<float>(n);
+        if (tanh_out) g *= 1.0f - pred[e] * pred[e];
+        dpred[e] = g;
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) loss[0] = s / static_cast<double>(n);
+}
+// L1 / L2 penalty sums over the parameters (loss value only): partial[block] = sum |p|, partial2[block] = sum p^2
+__global__ void __launch_bounds__(256)
+penalty_kernel(const float* __restrict__ p, const uint8_t* __restrict__ is_param, long long n, double* __restrict__ partial) {
+    __shared__ double red[8];
+    double a = 0.0, q = 0.0;
+    for (long long e = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; e < n; e += static_cast<long long>(gridDim.x) * 256)
+        if (is_param[e]) { const double v = p[e]; a += fabs(v); q += v * v; }
+    a = block_sum(a, red);
+    q = block_sum(q, red);
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = a; partial[2 * blockIdx.x + 1] = q; }
+}
+struct AdamHyper { float lr, beta1, beta2, eps, l1, l2, clamp, step_size; };
+// grad += l1 sign(p) + l2 p; clamp; Adam moments and update (train_r.lua:150-166, optim.adam)
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, const uint8_t* __restrict__ is_param,
+                            long long n, AdamHyper h) {
+    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= n || !is_param[e]) return;
+    const float x = p[e];
+    float gr = g[e];
+    if (h.l1 != 0.0f || h.l2 != 0.0f) gr += h.l1 * (x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f)) + h.l2 * x;
+    if (h.clamp != 0.0f) gr = fminf(fmaxf(gr, -h.clamp), h.clamp);
+    g[e] = gr;
+    const float mm = h.beta1 * m[e] + (1.0f - h.beta1) * gr;
+    const float vv = h.beta2 * v[e] + (1.0f - h.beta2) * gr * gr;
+    m[e] = mm; v[e] = vv;
+    p[e] = x - h.step_size * mm / (sqrtf(vv) + h.eps);
+}
+
+}  // namespace trn
+}  // namespace ganrev

@@ -160,6 +160,22 @@ int ganrev_assign_cosine_min(ganrev_ctx* ctx, const float* centroids, int k,
 int ganrev_cluster_members(ganrev_ctx* ctx, int k, int m, const float* images, int px,
                            int64_t* member_ids, int32_t* member_counts, float* mean_images);
 
+/* ---- R training step (train_r.lua:138-170) ------------------------------------------------
+ * One optimisation step of R on a batch generated by the loaded G: images = G(noise) in eval mode (train_r.lua:140-141),
+ * R_default (models.lua:389-464) forward in TRAINING mode (batch-norm batch statistics, running statistics updated with
+ * momentum 0.1), nn.MSECriterion against the noise, backward, L1 / L2 penalties and gradient clamp (train_r.lua:150-163),
+ * optim.adam.  Dropout is never drawn inside the library: `masks` is the concatenation of the uint8 keep-masks (1 = keep)
+ *   [fixer only: B x C x H x W (nn.Dropout(0.5, true), v1: no rescale)] | B x 64 x H x W | B x 64 x H x W | B x 64 x H/2 x W/2 |
+ *   B x 128 x H/2 x W/2 | B x 128 x H/2 x W/2 | B x 128 (nn.SpatialDropout(0.25): per sample and channel) | B x 512,
+ * in module order (nn.Dropout() v2: kept values are scaled by 2).  State (fp32 parameters in weight-blob layout, Adam moments,
+ * step count) lives in the context: train_R_init takes the same blob as ganrev_load_R; train_R_state returns the blob
+ * (what = 0, ready for ganrev_load_R), the last step's gradients after penalties and clamp (1), or Adam's m / v (2 / 3).
+ * hyper7 = {learning rate, beta1, beta2, epsilon, L1, L2, clamp (0 = off)}; optim.adam's defaults are {1e-3, 0.9, 0.999, 1e-8},
+ * train_r.lua's {.., 0, 1e-4, 1}.  loss2[0] = the criterion's output, loss2[1] = with the penalties (feval's f). */
+int ganrev_train_R_init(ganrev_ctx* ctx, int C, int H, int W, int noise_dim, int tanh_out, int fixer, const float* blob, size_t n_floats);
+int ganrev_train_R_step(ganrev_ctx* ctx, const float* noise, int B, const uint8_t* masks, size_t mask_bytes, const float* hyper7, double* loss2);
+int ganrev_train_R_state(ganrev_ctx* ctx, int what, float* out, size_t n_floats);
+
 /* ---- measurement hooks (bench.py) ----------------------------------------------- */
 void*    ganrev_stream(ganrev_ctx* ctx);                 /* cudaStream_t all work runs on */
 int      ganrev_sync(ganrev_ctx* ctx);
