@@ -2354,6 +2354,8 @@ int ganrev_train_R_step(ganrev_ctx* ctx, const float* noise, int B, const uint8_
     const size_t oz7 = carve(static_cast<size_t>(B) * 512), oa7 = carve(static_cast<size_t>(B) * 512), oo7 = carve(static_cast<size_t>(B) * 512), opred = carve(static_cast<size_t>(B) * nd), odpred = carve(static_cast<size_t>(B) * nd);
     const size_t big = static_cast<size_t>(B) * 128 * HW;       // >= every activation
     const size_t og0 = carve(big), og1 = carve(big), og2 = carve(big);
+    constexpr int kWgSlices = 8;
+    const size_t owg = carve(static_cast<size_t>(kWgSlices) * 128 * 128 * 9);
     const size_t oarg3 = carve((static_cast<size_t>(B) * 64 * HW2 + 3) / 4), oarg6 = carve((static_cast<size_t>(B) * F + 3) / 4);
     RC_TRY(ensure(ctx, T.work, sizeof(float) * need));
     float* wk = static_cast<float*>(T.work.p);
@@ -2418,7 +2420,11 @@ int ganrev_train_R_step(ganrev_ctx* ctx, const float* noise, int B, const uint8_
         }
         trn::bn_bwd_reduce_kernel<<<co, 256, 0, st>>>(gA, wk + oz[i], wk + omean[i], wk + oistd[i], Gp + T.cg[i], Gp + T.cbe[i], B, co, static_cast<int>(hw));
         trn::bn_bwd_apply_kernel<<<nb(tot), 256, 0, st>>>(gA, wk + oz[i], wk + omean[i], wk + oistd[i], Pp + T.cg[i], Gp + T.cg[i], Gp + T.cbe[i], gB, tot, co, static_cast<int>(hw), 1.0f / static_cast<float>(B * hw));   // d conv output
-        trn::conv3x3_wgrad_kernel<<<dim3(co, ci), 256, 0, st>>>(wk + oin[i], gB, Gp + T.cw[i], B, ci, co, h, w);
+        {
+            const int nw = co * ci * 9;
+            trn::conv3x3_wgrad_kernel<<<dim3((co + trn::kWgO - 1) / trn::kWgO, (ci + trn::kWgI - 1) / trn::kWgI, kWgSlices), 256, 0, st>>>(wk + oin[i], gB, wk + owg, B, ci, co, h, w);
+            trn::wgrad_sum_kernel<<<nb(nw), 256, 0, st>>>(wk + owg, Gp + T.cw[i], nw, kWgSlices);
+        }
         trn::channel_sum_kernel<<<co, 256, 0, st>>>(gB, Gp + T.cb[i], B, co, static_cast<int>(hw));
         if (i > 0) {
             trn::conv3x3_kernel<true><<<dim3(static_cast<unsigned>((hw + 127) / 128), (ci + 7) / 8, B), 128, 8 * co * 9 * sizeof(float), st>>>(gB, Pp + T.cw[i], nullptr, gA, co, ci, h, w);   // d layer input

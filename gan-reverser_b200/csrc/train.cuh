@@ -64,39 +64,73 @@ conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ w, const 
         if (o0 + oo < CO) out[(static_cast<size_t>(n) * CO + o0 + oo) * HW + pix] = acc[oo];
 }
 
-// dW[o][i][t] = sum_{n,h,w} dY[n][o][h][w] * X[n][i][h+ty-1][w+tx-1]; one block per (o, i), fixed-order tree reduction.
+// dW[o][i][t] = sum_{n,h,w} dY[n][o][h][w] * X[n][i][h+ty-1][w+tx-1].  One block per (4 output channels, 2 input channels): a thread
+// walks positions (n, h, w) with stride 256, loads the 9 taps of its 2 input channels and the 4 gradients once and feeds 72 FMAs
+// (the first version -- one (o, i) pair per block, 10 loads per 9 FMAs -- was 60 % of the step); fixed-order tree reduction.
+constexpr int kWgO = 4, kWgI = 2;
 __global__ void __launch_bounds__(256)
-conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int B, int CI, int CO, int H, int W) {
-    const int o = blockIdx.x, i = blockIdx.y, HW = H * W;
-    float s[9];
+conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw_part, int B, int CI, int CO, int H, int W) {
+    // blockIdx.z = one of gridDim.z slices of the (n, h, w) range; the partial sums of a slice go to dw_part[z] and wgrad_sum_kernel
+    // adds the slices in index order (deterministic, and enough blocks to fill the machine at batch 32)
+    const int o0 = blockIdx.x * kWgO, i0 = blockIdx.y * kWgI, HW = H * W;
+    const int total = B * HW, per = (total + gridDim.z - 1) / gridDim.z;
+    const int e_begin = blockIdx.z * per, e_end = min(total, e_begin + per);
+    float* dw = dw_part + static_cast<size_t>(blockIdx.z) * CO * CI * 9;
+    float s[kWgO][kWgI][9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) s[t] = 0.0f;
-    for (int e = threadIdx.x; e < B * HW; e += 256) {
+    for (int a = 0; a < kWgO; ++a)
+#pragma unroll
+        for (int b = 0; b < kWgI; ++b)
+#pragma unroll
+            for (int t = 0; t < 9; ++t) s[a][b][t] = 0.0f;
+    for (int e = e_begin + threadIdx.x; e < e_end; e += 256) {
         const int n = e / HW, pix = e - n * HW, h = pix / W, xx0 = pix - h * W;
-        const float g = __ldg(dy + (static_cast<size_t>(n) * CO + o) * HW + pix);
-        const float* xp = x + (static_cast<size_t>(n) * CI + i) * HW;
+        float g[kWgO];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const int hh = h + t / 3 - 1, xx = xx0 + t % 3 - 1;
-            if (hh >= 0 && hh < H && xx >= 0 && xx < W) s[t] = fmaf(g, __ldg(xp + hh * W + xx), s[t]);
+        for (int a = 0; a < kWgO; ++a) g[a] = o0 + a < CO ? __ldg(dy + (static_cast<size_t>(n) * CO + o0 + a) * HW + pix) : 0.0f;
+#pragma unroll
+        for (int b = 0; b < kWgI; ++b) {
+            if (i0 + b < CI) {
+                const float* xp = x + (static_cast<size_t>(n) * CI + i0 + b) * HW;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const int hh = h + t / 3 - 1, xx = xx0 + t % 3 - 1;
+                    const float v = (hh >= 0 && hh < H && xx >= 0 && xx < W) ? __ldg(xp + hh * W + xx) : 0.0f;
+#pragma unroll
+                    for (int a = 0; a < kWgO; ++a) s[a][b][t] = fmaf(g[a], v, s[a][b][t]);
+                }
+            }
         }
     }
-    __shared__ float red[9][8];
+    __shared__ float red[kWgO * kWgI * 9][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-        float v = s[t];
+    for (int a = 0; a < kWgO; ++a)
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        if (lane == 0) red[t][warp] = v;
-    }
+        for (int b = 0; b < kWgI; ++b)
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                float v = s[a][b][t];
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                if (lane == 0) red[(a * kWgI + b) * 9 + t][warp] = v;
+            }
     __syncthreads();
-    if (threadIdx.x < 9) {
+    if (threadIdx.x < kWgO * kWgI * 9) {
+        const int a = threadIdx.x / (kWgI * 9), r = threadIdx.x - a * kWgI * 9, b = r / 9, t = r - b * 9;
         float v = 0.0f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) v += red[threadIdx.x][k];
-        dw[(static_cast<size_t>(o) * CI + i) * 9 + threadIdx.x] = v;
+        if (o0 + a < CO && i0 + b < CI) dw[(static_cast<size_t>(o0 + a) * CI + i0 + b) * 9 + t] = v;
     }
+}
+
+__global__ void wgrad_sum_kernel(const float* __restrict__ part, float* __restrict__ dw, int n, int slices) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float v = 0.0f;
+    for (int z = 0; z < slices; ++z) v += part[static_cast<size_t>(z) * n + e];
+    dw[e] = v;
 }
 
 // ---------------------------------------------------------------- per-channel reductions over (n, h, w): one block per channel
