@@ -73,6 +73,10 @@ struct ConvGemm {
     int* err_flag;
     long long* trace;          // optional clock64 timeline of CTA 0 (ganrev_debug_trace), [8 roles][256 events]
     int dbg;                   // timing experiments only: bit0 skip A loads, bit1 skip B loads, bit2 skip epilogue, bit3 skip MMAs
+    // FUSE3 variants (G's Up+Conv 256->128 with the tap products of the last conv, models.lua:132, computed in the epilogue):
+    const float* w3;           // fp32 [9][128] tap-major weights of the 128 -> 1 conv; the activation itself is never stored
+    float* taps;               // fp32 planes P[tap][pixel] (pixel = (n*Hout + oh)*Wout + ow), read by g_conv3_gather_kernel
+    long long taps_plane;      // floats per plane
 };
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2, ACT_TANH = 3, ACT_SIGMOID = 4 };

@@ -318,7 +318,25 @@ __device__ __forceinline__ ItemCoord decode_item(const ConvGemm& p, int item) {
     return c;
 }
 
-template <int NT, int MT, int NDY, bool BRES, int ACT, bool POOL, bool OUT_FP32, int CG>
+// two fp32 FMAs per instruction (FFMA2): the fused tap products below are bound by issue slots, not by the FMA pipe
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    unsigned long long d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+
+// FUSE3 (G's Up+Conv 256->128 + BN + ReLU, models.lua:127-130, C = 1): the layer's activation is consumed where it is
+// produced.  The last conv (128 -> 1, 3x3, models.lua:132) needs, per pixel, the 9 products <act[pixel][0..127], w3[tap]>;
+// each epilogue warp owns one 128-pixel sub-tile (lane = pixel, all 128 channels in two rounds of two 32-column chunks),
+// keeps 9 packed (even, odd channel) fp32 sums per thread and writes them as planes P[tap][pixel] -- 36 B per pixel
+// instead of the 256 B bf16 activation, and the separate tap-product GEMM (a full HBM round trip of that activation)
+// disappears.  The weights sit in shared memory as fp32 (16-byte broadcast loads); the activation is NOT rounded to bf16.
+template <int NT, int MT, int NDY, bool BRES, int ACT, bool POOL, bool OUT_FP32, int CG, bool FUSE3 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvGemm p, const int n_items) {
@@ -527,6 +545,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool run = !(p.dbg & 4) && sub < kPairs;
         const bool no_store = (p.dbg & 16) != 0;
         const int jj = lane & 3;
+        if constexpr (FUSE3) {   // tap weights of the last conv -> shared memory (the store-transpose buffers are unused here)
+            static_assert(NT == 128 && MT == 2 && !POOL && !OUT_FP32 && ACT == ACT_RELU && kEpiWarps == 8, "FUSE3 is G's Up+Conv 256->128");
+            float* w3s = reinterpret_cast<float*>(smem + tail_off + C::kXposeOff);
+            for (int i = etid; i < 9 * 128; i += 32 * kEpiWarps) w3s[i] = __ldg(p.w3 + i);
+            named_bar_sync(1, 32 * kEpiWarps);
+        }
         int it = 0;
         for (int item = unit0; item < n_items; item += ustep, ++it) {
             const ItemCoord c = decode_item(p, item);
@@ -541,6 +565,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int i = etid; i < NT; i += 32 * kEpiWarps) ss[i] = __ldg(p.shift + cbase + i);
                 named_bar_sync(1, 32 * kEpiWarps);
             }
+            if constexpr (FUSE3) {
+                // warp (q, sub) owns sub-tile `sub`: lane = pixel, 4 chunks of 32 channels in two rounds
+                const TileCoord t = decode_tile(p, (c.mgroup * CG + static_cast<int>(rank)) * MT + sub);
+                const int n = t.n0 + n_l, oh = 2 * (t.h0 + h_l) + (c.phase >> 1), ow = 2 * (t.w0 + w_l) + (c.phase & 1);
+                const bool wr = n < p.n_img && !no_store;
+                float* dst = p.taps + (static_cast<long long>(n) * p.Hout + oh) * p.Wout + ow;
+                const ulonglong2* w3v = reinterpret_cast<const ulonglong2*>(smem + tail_off + C::kXposeOff);   // [9][32] x 4 channels
+                if (etid == 0) {
+                    GANREV_TR(7, it);
+                    mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 104);   // the only poller
+                    GANREV_TR(4, it);
+                }
+                named_bar_sync(2, 32 * kEpiWarps);
+                tcgen05_fence_after();
+                const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * MT + sub) * NT);
+                unsigned long long s9[9];
+#pragma unroll
+                for (int tp = 0; tp < 9; ++tp) s9[tp] = 0ull;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    uint32_t ra[32], rb[32];
+                    tmem_ld32(tq + (2 * r) * 32, ra);
+                    tmem_ld32(tq + (2 * r + 1) * 32, rb);
+                    tmem_ld_wait();
+                    if (r == 1) {   // the registers are the third buffer: hand the accumulator stage back at once
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { if (CG == 2) mbar_arrive_cta(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc)); }
+                    }
+                    if (!(p.dbg & 4)) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {     // channels 64*r + 4*j .. +3
+                            const float4 sh = *reinterpret_cast<const float4*>(ss + 64 * r + 4 * j);
+                            const uint32_t* a = j < 8 ? &ra[4 * j] : &rb[4 * (j - 8)];
+                            const unsigned long long v01 = pack_f32x2(fmaxf(__uint_as_float(a[0]) + sh.x, 0.0f), fmaxf(__uint_as_float(a[1]) + sh.y, 0.0f));
+                            const unsigned long long v23 = pack_f32x2(fmaxf(__uint_as_float(a[2]) + sh.z, 0.0f), fmaxf(__uint_as_float(a[3]) + sh.w, 0.0f));
+#pragma unroll
+                            for (int tp = 0; tp < 9; ++tp) {
+                                const ulonglong2 w = w3v[tp * 32 + 16 * r + j];
+                                s9[tp] = ffma2(v01, w.x, s9[tp]);
+                                s9[tp] = ffma2(v23, w.y, s9[tp]);
+                            }
+                        }
+                    }
+                }
+                if (wr) {
+#pragma unroll
+                    for (int tp = 0; tp < 9; ++tp)
+                        __stcg(dst + tp * p.taps_plane, __uint_as_float(static_cast<uint32_t>(s9[tp])) + __uint_as_float(static_cast<uint32_t>(s9[tp] >> 32)));
+                }
+                if (etid == 0) GANREV_TR(5, it);
+            } else {
             // Output offsets of this item's tiles, computed while the MMAs are still running.
             // offs[mt][i]: element offset of pixel (lane>>2) + 8*i of this warp's quarter (the pixel a
             // group of 4 lanes stores after the transpose), -1 = nothing to store.
@@ -709,6 +785,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (lane == 0) { if (CG == 2) mbar_arrive_cta(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc)); }
             }
             if (etid == 0) GANREV_TR(5, it);
+            }   // !FUSE3
         }
     }
 

@@ -79,6 +79,38 @@ def test_R_matches_oracle(pkg, orc, ctx, geom, impl):
     assert rel_l2(got_f, want) > 10 * REL_TOL, "mask must change the result"
 
 
+@pytest.mark.parametrize("pairs", [31, 0], ids=["cta_pairs", "1cta"])
+@pytest.mark.parametrize("geom", [(1, 32, 32, 100, 150), (1, 16, 16, 32, 40), (1, 64, 64, 32, 11)], ids=lambda g: "C%dx%dx%d_nd%d_N%d" % g)
+def test_G_fused_last_conv_matches_two_pass(pkg, orc, ctx, geom, pairs):
+    """C = 1: the last conv's tap products come out of G conv2's epilogue (fuse_conv3 = 1, the default: fp32 FFMA2 on the
+    un-rounded activation, conv_tc.cuh FUSE3) or out of a separate 1x1 tensor-core pass over the bf16 activation
+    (fuse_conv3 = 0).  Both against the oracle (models.lua:127-133), and against each other at bf16-rounding level;
+    several items per persistent CTA and a ragged last chunk."""
+    C, H, W, nd, N = geom
+    gb = pkg.weights.init_G(C, H, W, nd, seed=1, stress=True)
+    noise = np.random.default_rng(3).normal(size=(N, nd)).astype(np.float32)
+    want = orc.forward_G(gb, C, H, W, nd, noise)
+    ctx.set_option("conv_impl", 0)
+    ctx.set_option("cta_pairs", pairs)
+    ctx.set_option("chunk", 64)
+    got = {}
+    try:
+        for fuse in (0, 1):
+            ctx.set_option("fuse_conv3", fuse)
+            ctx.load_G(C, H, W, nd, gb)
+            ctx.profile_reset(); ctx.profile_enable(True)
+            got[fuse] = ctx.forward_G(noise)
+            ctx.profile_enable(False)
+            assert (ctx.profile().get("g_conv3_taps", {"launches": 0})["launches"] > 0) == (fuse == 0), "fuse_conv3 must decide whether the separate pass runs"
+            assert np.abs(got[fuse] - want).max() <= PIX_TOL
+    finally:
+        ctx.set_option("fuse_conv3", 1)
+        ctx.set_option("chunk", 16)
+        ctx.set_option("cta_pairs", 31)
+    assert np.abs(got[1] - want).max() <= np.abs(got[0] - want).max() * 1.5 + 1e-4   # the fused form skips one bf16 rounding
+    assert np.abs(got[0] - got[1]).max() <= 1e-2
+
+
 BENCH_SHAPES = [
     # C, H, W, nd, N, rows checked against the oracle: BASELINE configs[3] and configs[4] geometries at the DEFAULT chunk
     (1, 32, 32, 100, 20000, 1000),
