@@ -74,8 +74,9 @@ struct ConvGemm {
     long long* trace;          // optional clock64 timeline of CTA 0 (ganrev_debug_trace), [8 roles][256 events]
     int dbg;                   // timing experiments only: bit0 skip A loads, bit1 skip B loads, bit2 skip epilogue, bit3 skip MMAs
     // FUSE3 variants (G's Up+Conv 256->128 with the tap products of the last conv, models.lua:132, computed in the epilogue):
-    const float* w3;           // fp32 [9][128] tap-major weights of the 128 -> 1 conv; the activation itself is never stored
-    float* taps;               // fp32 planes P[tap][pixel] (pixel = (n*Hout + oh)*Wout + ow), read by g_conv3_gather_kernel
+    const float* w3;           // fp32 [9*C][128] (tap, output channel)-major weights of the 128 -> C conv; the activation itself is never stored
+    int w3_c;                  // C (1 or 3)
+    float* taps;               // fp32 planes P[tap*C + co][pixel] (pixel = (n*Hout + oh)*Wout + ow), read by g_conv3_gather_kernel
     long long taps_plane;      // floats per plane
 };
 

@@ -330,13 +330,13 @@ __device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
     return d;
 }
 
-// FUSE3 (G's Up+Conv 256->128 + BN + ReLU, models.lua:127-130, C = 1): the layer's activation is consumed where it is
-// produced.  The last conv (128 -> 1, 3x3, models.lua:132) needs, per pixel, the 9 products <act[pixel][0..127], w3[tap]>;
+// FUSE3 = C (G's Up+Conv 256->128 + BN + ReLU, models.lua:127-130): the layer's activation is consumed where it is
+// produced.  The last conv (128 -> C, 3x3, models.lua:132) needs, per pixel, the 9*C products <act[pixel][0..127], w3[tap][co]>;
 // each epilogue warp owns one 128-pixel sub-tile (lane = pixel, all 128 channels in two rounds of two 32-column chunks),
-// keeps 9 packed (even, odd channel) fp32 sums per thread and writes them as planes P[tap][pixel] -- 36 B per pixel
+// keeps 9*C packed (even, odd channel) fp32 sums per thread and writes them as planes P[tap*C + co][pixel] -- 36*C B per pixel
 // instead of the 256 B bf16 activation, and the separate tap-product GEMM (a full HBM round trip of that activation)
 // disappears.  The weights sit in shared memory as fp32 (16-byte broadcast loads); the activation is NOT rounded to bf16.
-template <int NT, int MT, int NDY, bool BRES, int ACT, bool POOL, bool OUT_FP32, int CG, bool FUSE3 = false>
+template <int NT, int MT, int NDY, bool BRES, int ACT, bool POOL, bool OUT_FP32, int CG, int FUSE3 = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvGemm p, const int n_items) {
@@ -545,10 +545,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool run = !(p.dbg & 4) && sub < kPairs;
         const bool no_store = (p.dbg & 16) != 0;
         const int jj = lane & 3;
-        if constexpr (FUSE3) {   // tap weights of the last conv -> shared memory (the store-transpose buffers are unused here)
+        constexpr int kTaps = 9 * FUSE3;
+        if constexpr (FUSE3 != 0) {   // tap weights of the last conv -> shared memory (the store-transpose buffers are unused here)
             static_assert(NT == 128 && MT == 2 && !POOL && !OUT_FP32 && ACT == ACT_RELU && kEpiWarps == 8, "FUSE3 is G's Up+Conv 256->128");
+            static_assert(kTaps * 128 * 4 <= C::kXposeBytes, "tap weights must fit in the store-transpose buffers");
             float* w3s = reinterpret_cast<float*>(smem + tail_off + C::kXposeOff);
-            for (int i = etid; i < 9 * 128; i += 32 * kEpiWarps) w3s[i] = __ldg(p.w3 + i);
+            for (int i = etid; i < kTaps * 128; i += 32 * kEpiWarps) w3s[i] = __ldg(p.w3 + i);
             named_bar_sync(1, 32 * kEpiWarps);
         }
         int it = 0;
@@ -565,13 +567,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int i = etid; i < NT; i += 32 * kEpiWarps) ss[i] = __ldg(p.shift + cbase + i);
                 named_bar_sync(1, 32 * kEpiWarps);
             }
-            if constexpr (FUSE3) {
+            if constexpr (FUSE3 != 0) {
                 // warp (q, sub) owns sub-tile `sub`: lane = pixel, 4 chunks of 32 channels in two rounds
                 const TileCoord t = decode_tile(p, (c.mgroup * CG + static_cast<int>(rank)) * MT + sub);
                 const int n = t.n0 + n_l, oh = 2 * (t.h0 + h_l) + (c.phase >> 1), ow = 2 * (t.w0 + w_l) + (c.phase & 1);
                 const bool wr = n < p.n_img && !no_store;
                 float* dst = p.taps + (static_cast<long long>(n) * p.Hout + oh) * p.Wout + ow;
-                const ulonglong2* w3v = reinterpret_cast<const ulonglong2*>(smem + tail_off + C::kXposeOff);   // [9][32] x 4 channels
+                const ulonglong2* w3v = reinterpret_cast<const ulonglong2*>(smem + tail_off + C::kXposeOff);   // [9*C][32] x 4 channels
                 if (etid == 0) {
                     GANREV_TR(7, it);
                     mbar_wait(tfull_bar(acc), acc_phase, p.err_flag, 104);   // the only poller
@@ -580,9 +582,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 named_bar_sync(2, 32 * kEpiWarps);
                 tcgen05_fence_after();
                 const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((acc * MT + sub) * NT);
-                unsigned long long s9[9];
+                unsigned long long s9[kTaps];
 #pragma unroll
-                for (int tp = 0; tp < 9; ++tp) s9[tp] = 0ull;
+                for (int tp = 0; tp < kTaps; ++tp) s9[tp] = 0ull;
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
                     uint32_t ra[32], rb[32];
@@ -602,7 +604,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const unsigned long long v01 = pack_f32x2(fmaxf(__uint_as_float(a[0]) + sh.x, 0.0f), fmaxf(__uint_as_float(a[1]) + sh.y, 0.0f));
                             const unsigned long long v23 = pack_f32x2(fmaxf(__uint_as_float(a[2]) + sh.z, 0.0f), fmaxf(__uint_as_float(a[3]) + sh.w, 0.0f));
 #pragma unroll
-                            for (int tp = 0; tp < 9; ++tp) {
+                            for (int tp = 0; tp < kTaps; ++tp) {
                                 const ulonglong2 w = w3v[tp * 32 + 16 * r + j];
                                 s9[tp] = ffma2(v01, w.x, s9[tp]);
                                 s9[tp] = ffma2(v23, w.y, s9[tp]);
@@ -612,7 +614,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 if (wr) {
 #pragma unroll
-                    for (int tp = 0; tp < 9; ++tp)
+                    for (int tp = 0; tp < kTaps; ++tp)
                         __stcg(dst + tp * p.taps_plane, __uint_as_float(static_cast<uint32_t>(s9[tp])) + __uint_as_float(static_cast<uint32_t>(s9[tp] >> 32)));
                 }
                 if (etid == 0) GANREV_TR(5, it);

@@ -45,7 +45,7 @@ struct GModel {
     int C = 0, H = 0, W = 0, nd = 0, kpad = 0, F = 0;
     TcLayer lin, c1, c2, c3;   // c3 = pass 1 of the last conv (per-pixel tap products)
     DevBuf b3;
-    DevBuf w3f;                // fp32 [9][128] tap-major weights of the last conv for the fused conv2 epilogue (C = 1)
+    DevBuf w3f;                // fp32 [9][128] tap-major weights of the last conv for the fused conv2 epilogue
     bool fuse3 = false;
 };
 struct RModel {
@@ -92,7 +92,8 @@ struct ganrev_ctx {
     std::string err;
     int64_t chunk = 0;            // images per pipeline chunk; 0 = auto (8192 32x32 faces' worth of pixels, see chunk_for)
     int conv_impl = 0;
-    int fuse_conv3 = 1;           // C = 1: the last conv's tap products are computed in G conv2's epilogue (0 = separate 1x1 GEMM pass; A/B)
+    int fuse_conv3 = 1;           // the last conv's tap products are computed in G conv2's epilogue: 1 = when C == 1 (free there: the epilogue has the
+                                  // slack), 2 = also C == 3 (measured: 27 taps make conv2 epilogue-bound, 8.3 -> 15.3 ms per 4096 64x64 faces), 0 = never
     int tma_store = 1;            // TMA bulk tensor stores in the conv epilogue where the layer allows (0 = st.global everywhere; A/B)
     int search_tc = 1;            // tensor-core candidate filter + exact re-score for many-query searches (0 = fmaf-chain kernels only; A/B)
     uint64_t tc_searches = 0, tc_fallbacks = 0;   // searches served by the tensor-core path / re-run on the fmaf-chain kernels
@@ -425,7 +426,7 @@ static int check_geom(ganrev_ctx* ctx, int C, int H, int W, int nd) {
 // =================================================================================
 // layer launches
 // =================================================================================
-template <int NT, int MT, int NDY, bool BRES, int ACT, bool POOL, bool OUT_FP32, int CG, bool FUSE3 = false>
+template <int NT, int MT, int NDY, bool BRES, int ACT, bool POOL, bool OUT_FP32, int CG, int FUSE3 = 0>
 static int launch_tc(ganrev_ctx* ctx, const TcLayer& L, const CUtensorMap& tmA, const ConvGemm& g, int n_items) {
     auto kern = tc::conv_tc_kernel<NT, MT, NDY, BRES, ACT, POOL, OUT_FP32, CG, FUSE3>;
     static size_t attr_max_dev[kMaxDevices] = {};          // function attributes are per device
@@ -457,10 +458,12 @@ static int dispatch_tc(ganrev_ctx* ctx, const TcLayer& L, const CUtensorMap& tmA
         (g.pool != 0) == POOL_ && (g.out_fp32 != 0) == FP32_ && L.CG == CG_)                                            \
         return launch_tc<NT_, MT_, NDY_, BRES_, ACT_, POOL_, FP32_, CG_>(ctx, L, tmA, g, n_items);
 #define TC_CASE(NT_, MT_, NDY_, BRES_, ACT_, POOL_, FP32_) TC_CASE_CG(NT_, MT_, NDY_, BRES_, ACT_, POOL_, FP32_, 1)
-    if (g.w3 != nullptr) {   // G Up+Conv 256->128 with the last conv's tap products fused into the epilogue (C = 1)
-        if (L.NT == 128 && L.MT == 2 && L.NDY == 2 && L.CG == 2) return launch_tc<128, 2, 2, false, ACT_RELU, false, false, 2, true>(ctx, L, tmA, g, n_items);
-        if (L.NT == 128 && L.MT == 2 && L.NDY == 2 && L.CG == 1) return launch_tc<128, 2, 2, false, ACT_RELU, false, false, 1, true>(ctx, L, tmA, g, n_items);
-        if (L.NT == 128 && L.MT == 2 && L.NDY == 1 && L.CG == 1) return launch_tc<128, 2, 1, false, ACT_RELU, false, false, 1, true>(ctx, L, tmA, g, n_items);
+    if (g.w3 != nullptr) {   // G Up+Conv 256->128 with the last conv's tap products fused into the epilogue
+#define TC_FUSED(NDY_, CG_, C_) \
+        if (L.NT == 128 && L.MT == 2 && L.NDY == NDY_ && L.CG == CG_ && g.w3_c == C_) return launch_tc<128, 2, NDY_, false, ACT_RELU, false, false, CG_, C_>(ctx, L, tmA, g, n_items);
+        TC_FUSED(2, 2, 1) TC_FUSED(2, 1, 1) TC_FUSED(1, 1, 1)
+        TC_FUSED(2, 2, 3) TC_FUSED(2, 1, 3) TC_FUSED(1, 1, 3)
+#undef TC_FUSED
         return fail(ctx, GANREV_EINVAL, "no fused tap-product variant for layer %s", L.name.c_str());
     }
     // CTA-pair (cta_group::2) variants of the halo layers
@@ -517,8 +520,8 @@ static int run_layer(ganrev_ctx* ctx, TcLayer& L, const void* in, void* out, int
     const int mgroups = (g.total_tiles + L.MT * L.CG - 1) / (L.MT * L.CG);
     const int n_items = mgroups * g.nphase * g.n_tiles;
     const double px_out = static_cast<double>(g.Hout) * g.Wout;
-    // fused tap products: + 9 x 128 MACs per output pixel on the FMA pipe, 36 B of planes instead of the 256 B bf16 activation
-    const double fl_img = L.flops_per_img + (g.w3 ? 2.0 * 9 * 128 * px_out : 0.0), by_img = g.w3 ? L.bytes_per_img - 2.0 * 128 * px_out + 36.0 * px_out : L.bytes_per_img;
+    // fused tap products: + 9*C x 128 MACs per output pixel on the FMA pipe, 36*C B of planes instead of the 256 B bf16 activation
+    const double fl_img = L.flops_per_img + (g.w3 ? 2.0 * 9 * g.w3_c * 128 * px_out : 0.0), by_img = g.w3 ? L.bytes_per_img - 2.0 * 128 * px_out + 36.0 * g.w3_c * px_out : L.bytes_per_img;
     ProfScope ps(ctx, L.name, fl_img * n_img, by_img * n_img);
     if (ctx->conv_impl == 1) {
         const long long total = static_cast<long long>(n_img) * g.Hout * g.Wout * g.cout_real;
@@ -640,12 +643,13 @@ static int load_G_impl(ganrev_ctx* ctx, int C, int H, int W, int nd, const float
         const LayerDef d{"g_conv3_taps", KIND_LINEAR, NT3, 1, 1, false, 1, 1, 128, 9 * C, 1, 1, 1, NT3, 0, ACT_NONE, 1.0f, 1, false};
         RC_TRY(build_tc_layer(ctx, G.c3, d, wm.data(), bn));
         RC_TRY(upload(ctx, G.b3, b3, sizeof(float) * C));
-        // fused form (C = 1; conv2 must be one of the MT = 2 variants): tap-major fp32 weights for conv2's epilogue
-        G.fuse3 = ctx->fuse_conv3 && C == 1 && G.c2.NT == 128 && G.c2.MT == 2;
+        // fused form (conv2 must be one of the MT = 2 variants): (tap, channel)-major fp32 weights for conv2's epilogue
+        G.fuse3 = (ctx->fuse_conv3 == 2 || (ctx->fuse_conv3 == 1 && C == 1)) && G.c2.NT == 128 && G.c2.MT == 2;
         if (G.fuse3) {
-            std::vector<float> wt(9 * 128);
+            std::vector<float> wt(static_cast<size_t>(9) * C * 128);
             for (int t = 0; t < 9; ++t)
-                for (int ci = 0; ci < 128; ++ci) wt[t * 128 + ci] = w3[static_cast<size_t>(ci) * 9 + t];
+                for (int co = 0; co < C; ++co)
+                    for (int ci = 0; ci < 128; ++ci) wt[static_cast<size_t>(t * C + co) * 128 + ci] = w3[(static_cast<size_t>(co) * 128 + ci) * 9 + t];
             RC_TRY(upload(ctx, G.w3f, wt.data(), sizeof(float) * wt.size()));
         }
     }
@@ -828,6 +832,7 @@ static int forward_G_dev(ganrev_ctx* ctx, const float* d_noise, int64_t N, float
         const long long plane = static_cast<long long>(CH) * G.H * G.W;
         const bool fused = G.fuse3 && ctx->conv_impl == 0;
         G.c2.g.w3 = fused ? static_cast<const float*>(G.w3f.p) : nullptr;
+        G.c2.g.w3_c = G.C;
         G.c2.g.taps = static_cast<float*>(ctx->arena[0].p);
         G.c2.g.taps_plane = plane;
         RC_TRY(run_layer(ctx, G.c2, ctx->arena[1].p, ctx->arena[0].p, n, CH));      // [n][H][W][128], or (fused) the tap planes
@@ -2679,7 +2684,7 @@ int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "label_tc")) { ctx->label_tc = value != 0; return GANREV_OK; }
     if (!strcmp(name, "stream_tc")) { ctx->stream_tc = value != 0; return GANREV_OK; }
     if (!strcmp(name, "kmeans_tc")) { ctx->kmeans_tc = value != 0; return GANREV_OK; }
-    if (!strcmp(name, "fuse_conv3")) { ctx->fuse_conv3 = value != 0; return GANREV_OK; }   // read by ganrev_load_G
+    if (!strcmp(name, "fuse_conv3")) { ctx->fuse_conv3 = value < 0 ? 0 : (value > 2 ? 2 : static_cast<int>(value)); return GANREV_OK; }   // read by ganrev_load_G
     if (!strcmp(name, "tma_store")) { ctx->tma_store = value < 0 ? 0 : (value > 2 ? 2 : static_cast<int>(value)); return GANREV_OK; }
     if (!strcmp(name, "conv_impl")) {
         if (value != 0 && value != 1) return fail(ctx, GANREV_EINVAL, "conv_impl must be 0 or 1");

@@ -80,9 +80,9 @@ def test_R_matches_oracle(pkg, orc, ctx, geom, impl):
 
 
 @pytest.mark.parametrize("pairs", [31, 0], ids=["cta_pairs", "1cta"])
-@pytest.mark.parametrize("geom", [(1, 32, 32, 100, 150), (1, 16, 16, 32, 40), (1, 64, 64, 32, 11)], ids=lambda g: "C%dx%dx%d_nd%d_N%d" % g)
+@pytest.mark.parametrize("geom", [(1, 32, 32, 100, 150), (1, 16, 16, 32, 40), (1, 64, 64, 32, 11), (3, 32, 32, 64, 70), (3, 64, 64, 256, 9)], ids=lambda g: "C%dx%dx%d_nd%d_N%d" % g)
 def test_G_fused_last_conv_matches_two_pass(pkg, orc, ctx, geom, pairs):
-    """C = 1: the last conv's tap products come out of G conv2's epilogue (fuse_conv3 = 1, the default: fp32 FFMA2 on the
+    """The last conv's tap products come out of G conv2's epilogue (fuse_conv3 = 1, the default: fp32 FFMA2 on the
     un-rounded activation, conv_tc.cuh FUSE3) or out of a separate 1x1 tensor-core pass over the bf16 activation
     (fuse_conv3 = 0).  Both against the oracle (models.lua:127-133), and against each other at bf16-rounding level;
     several items per persistent CTA and a ragged last chunk."""
@@ -96,7 +96,7 @@ def test_G_fused_last_conv_matches_two_pass(pkg, orc, ctx, geom, pairs):
     got = {}
     try:
         for fuse in (0, 1):
-            ctx.set_option("fuse_conv3", fuse)
+            ctx.set_option("fuse_conv3", 2 * fuse)      # 2: also for C = 3 (off by default there: slower, not wrong)
             ctx.load_G(C, H, W, nd, gb)
             ctx.profile_reset(); ctx.profile_enable(True)
             got[fuse] = ctx.forward_G(noise)

@@ -1,12 +1,12 @@
 """A/B a ganrev_set_option knob on one box: per-kernel CUDA-event times of G->R over 32768 faces for each value.
-usage: python tools/ab_option.py tma_store 0 1"""
+usage: [GEOM=C,H,W,nd,N] python tools/ab_option.py tma_store 0 1"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from __graft_entry__ import load_package
 pkg = load_package()
 name, values = sys.argv[1], [int(v) for v in sys.argv[2:]]
-C, H, W, ND, N = 1, 32, 32, 100, 32768
+C, H, W, ND, N = [int(v) for v in os.environ.get("GEOM", "1,32,32,100,32768").split(",")]
 noise = np.random.default_rng(0).normal(size=(N, ND)).astype(np.float32)
 for rep in range(2):
     for v in values:
