@@ -845,10 +845,10 @@ static int forward_G_dev(ganrev_ctx* ctx, const float* d_noise, int64_t N, float
                 RC_TRY(run_layer(ctx, G.c3, ctx->arena[0].p, ctx->arena[1].p, static_cast<int>(npix), CH * G.H * G.W));
             }
             ProfScope ps(ctx, "g_conv3_gather", 9.0 * npix * G.C, npix * (4.0 * 9 * G.C + 4.0 * G.C));
-            const unsigned blocks = static_cast<unsigned>((npix + 255) / 256);
+            const unsigned blocks = static_cast<unsigned>((npix / 4 + 255) / 256);      // a thread per 4 pixels of a row (W >= 16, a power of two)
             float* o = d_images + n0 * G.C * G.H * G.W;
-            if (G.C == 1) g_conv3_gather_kernel<1><<<blocks, 256, 0, ctx->stream>>>(planes, plane, static_cast<const float*>(G.b3.p), o, G.H, G.W, n);
-            else          g_conv3_gather_kernel<3><<<blocks, 256, 0, ctx->stream>>>(planes, plane, static_cast<const float*>(G.b3.p), o, G.H, G.W, n);
+            if (G.C == 1) g_conv3_gather_kernel<1><<<blocks, 256, 0, ctx->stream>>>(planes, plane, static_cast<const float*>(G.b3.p), o, G.H, G.W, ilog2(G.H), ilog2(G.W), n);
+            else          g_conv3_gather_kernel<3><<<blocks, 256, 0, ctx->stream>>>(planes, plane, static_cast<const float*>(G.b3.p), o, G.H, G.W, ilog2(G.H), ilog2(G.W), n);
             CU_TRY(cudaGetLastError());
         }
         RC_TRY(chunk_io_after(ctx, io, n0 / CH, n_chunks, n0, n));

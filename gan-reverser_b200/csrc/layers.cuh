@@ -97,37 +97,56 @@ r_conv1_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mask, 
 // Pass 1 (tensor cores) left P[tap*C + co][n][y][x] = w[co][:, tap] . act[n][y][x][:] (one plane of
 // `plane` floats per tap and output channel) for every INPUT pixel; the 3x3 conv output is the sum of the 9 neighbours' matching tap products
 // (out-of-image neighbours contribute nothing = zero padding), + bias, then Sigmoid
-// (models.lua:132-133).  fp32 NCHW out.  One thread per output pixel and channel.
+// (models.lua:132-133).  fp32 NCHW out.  One thread per FOUR consecutive output pixels of a row (W is a power of two >= 16):
+// each tap plane is read as one aligned 16-byte load plus, for the left / right taps, one edge float -- 15 loads per 4 pixels
+// instead of 36, shifts instead of divisions (the one-pixel version was issue-bound at 2.7 TB/s).  Every pixel still adds its
+// taps in (ky, kx) order.
 template <int COUT>
 __global__ void __launch_bounds__(256)
 g_conv3_gather_kernel(const float* __restrict__ P, long long plane, const float* __restrict__ bias, float* __restrict__ out,
-                      int H, int W, long long n_img) {
-    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long long total = n_img * H * W;
-    if (idx >= total) return;
-    const int x = static_cast<int>(idx % W);
-    const int y = static_cast<int>((idx / W) % H);
-    const long long n = idx / (static_cast<long long>(W) * H);
-    float acc[COUT];
+                      int H, int W, int lgH, int lgW, long long n_img) {
+    const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;     // quad of pixels
+    if (q >= ((n_img << (lgH + lgW)) >> 2)) return;
+    const long long pix = q << 2;                                                          // (n*H + y)*W + x0
+    const int x0 = static_cast<int>(pix) & (W - 1);
+    const int y = static_cast<int>(pix >> lgW) & (H - 1);
+    const long long n = pix >> (lgH + lgW);
+    float acc[COUT][4];
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[co] = __ldg(bias + co);
+    for (int co = 0; co < COUT; ++co) {
+        const float b = __ldg(bias + co);
+        acc[co][0] = acc[co][1] = acc[co][2] = acc[co][3] = b;
+    }
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
         const int yy = y + ky - 1;
         if (yy < 0 || yy >= H) continue;
+        const long long row = pix + static_cast<long long>(ky - 1) * W;                    // pixel (n, yy, x0)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-            const int xx = x + kx - 1;
-            if (xx < 0 || xx >= W) continue;
-            // planar tap products P[tap*COUT + co][pixel]: the 32 lanes of a warp read 32 consecutive floats
-            const float* rec = P + static_cast<long long>((ky * 3 + kx) * COUT) * plane + (n * H + yy) * W + xx;
 #pragma unroll
-            for (int co = 0; co < COUT; ++co) acc[co] += __ldg(rec + co * plane);
+            for (int co = 0; co < COUT; ++co) {
+                const float* pl = P + static_cast<long long>((ky * 3 + kx) * COUT + co) * plane + row;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(pl));
+                if (kx == 0) {          // output x reads input x - 1
+                    if (x0 > 0) acc[co][0] += __ldg(pl - 1);
+                    acc[co][1] += v.x; acc[co][2] += v.y; acc[co][3] += v.z;
+                } else if (kx == 1) {
+                    acc[co][0] += v.x; acc[co][1] += v.y; acc[co][2] += v.z; acc[co][3] += v.w;
+                } else {                // output x reads input x + 1
+                    acc[co][0] += v.y; acc[co][1] += v.z; acc[co][2] += v.w;
+                    if (x0 + 4 < W) acc[co][3] += __ldg(pl + 4);
+                }
+            }
         }
     }
 #pragma unroll
-    for (int co = 0; co < COUT; ++co)
-        out[((n * COUT + co) * H + y) * static_cast<long long>(W) + x] = 1.0f / (1.0f + __expf(-acc[co]));
+    for (int co = 0; co < COUT; ++co) {
+        float4 o;
+        o.x = 1.0f / (1.0f + __expf(-acc[co][0])); o.y = 1.0f / (1.0f + __expf(-acc[co][1]));
+        o.z = 1.0f / (1.0f + __expf(-acc[co][2])); o.w = 1.0f / (1.0f + __expf(-acc[co][3]));
+        *reinterpret_cast<float4*>(out + (((n * COUT + co) << lgH) + y) * static_cast<long long>(W) + x0) = o;
+    }
 }
 
 // ------------------------------------------------------------------ torch.dist, batched
