@@ -126,6 +126,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }   // all but the latest store have read their source
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -531,7 +532,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int pool_row = ((lane >> lg_bw) >> 1) * ((1 << lg_bw) >> 1) + ((lane & ((1 << lg_bw) - 1)) >> 1);
         const int qw0 = (q * 32) & (BW - 1), qh0 = ((q * 32) >> p.lgBW) & ((1 << p.lgBH) - 1), qn0 = (q * 32) >> (p.lgBW + p.lgBH);   // first pixel of this warp's lane quarter
         float* ss_base = reinterpret_cast<float*>(smem + tail_off + C::kBarBytes);
-        uint4* xpose = reinterpret_cast<uint4*>(smem + tail_off + C::kXposeOff) + (warp - 2) * 128;   // 2 KB per warp
+        // 2 KB per warp and buffer; xpose2: two buffers per warp, alternating per TMA store
+        uint4* const xpose0 = reinterpret_cast<uint4*>(smem + tail_off + C::kXposeOff) + (warp - 2) * 128 * (p.xpose2 ? 2 : 1);
+        int xcur = 0;
         constexpr int CW = C::kChunk;
         constexpr int kChunksPerTile = NT / CW;
         constexpr int kPairs = MT * kChunksPerTile;           // (sub-tile, column chunk) pairs per item
@@ -697,7 +700,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     constexpr int kPasses = (OUT_FP32 && NT == 32) ? 2 : 1;
 #pragma unroll
                     for (int hpass = 0; hpass < kPasses; ++hpass) {
-                        if (!OUT_FP32 && p.tma_store) tma_store_wait_read();   // the previous TMA store has read this buffer
+                        uint4* const xpose = xpose0 + xcur * 128;
+                        if (!OUT_FP32 && p.tma_store) { if (p.xpose2) tma_store_wait_read1(); else tma_store_wait_read(); }   // the store that last used this buffer has read it
                         __syncwarp();
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -727,6 +731,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 if (POOL) tma_store_4d(&tmO, smem_u32(xpose), cbase + c0, (tt.w0 + qw0) >> 1, (tt.h0 + qh0) >> 1, tt.n0 + qn0);
                                 else tma_store_4d(&tmO, smem_u32(xpose), cbase + c0, tt.w0 + qw0, tt.h0 + qh0, tt.n0 + qn0);
                             }
+                            if (p.xpose2) xcur ^= 1;
                             continue;
                         }
                         __syncwarp();

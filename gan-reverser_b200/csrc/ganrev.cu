@@ -92,6 +92,7 @@ struct ganrev_ctx {
     std::string err;
     int64_t chunk = 0;            // images per pipeline chunk; 0 = auto (8192 32x32 faces' worth of pixels, see chunk_for)
     int conv_impl = 0;
+    int xpose2 = 1;               // double store-transpose buffers in the TMA-store epilogue (see build_tc_layer); 0 = single (A/B)
     int fuse_conv3 = 1;           // the last conv's tap products are computed in G conv2's epilogue: 1 = when C == 1 (free there: the epilogue has the
                                   // slack), 2 = also C == 3 (measured: 27 taps make conv2 epilogue-bound, 8.3 -> 15.3 ms per 4096 64x64 faces), 0 = never
     int tma_store = 1;            // TMA bulk tensor stores in the conv epilogue where the layer allows (0 = st.global everywhere; A/B)
@@ -393,22 +394,32 @@ static int build_tc_layer(ganrev_ctx* ctx, TcLayer& L, const LayerDef& d, const 
     g.a_unit_bytes = (BH + g.ndy - 1) * BW * BN * 128;
     g.b_kb_bytes = (d.NT / L.CG) * 128;          // this CTA's share of a 64-wide weight tile
     g.dy_stride_bytes = BW * BN * 128;
-    const int tail = ((2 * tc::kMaxStages + 5) * 8 + 24 + 2 * d.NT * 4 + 1023) / 1024 * 1024 + tc::kEpiWarps * 32 * 64;   // barriers, shift (double-buffered), store-transpose buffers
-    const int budget = tc::kSmemBudget - 1024 - tail;
+    // barriers, shift (double-buffered), store-transpose buffers (xp per epilogue warp)
     const size_t wbytes = static_cast<size_t>(g.units) * g.ndy * g.b_kb_bytes;
-    L.bres = d.want_bres && g.nphase == 1 && g.n_tiles == 1 && wbytes + 2 * static_cast<size_t>(L.MT) * g.a_unit_bytes <= static_cast<size_t>(budget);
-    for (;;) {
-        const int res = L.bres ? static_cast<int>(wbytes) : 0;
-        g.unit_bytes = L.MT * g.a_unit_bytes + (L.bres ? 0 : g.ndy * g.b_kb_bytes);
-        const int cyc_unit = L.MT * g.ndy * 4 * std::max(d.NT / 2, 32);          // MMA cycles per unit
-        g.ups = std::max(1, std::min({4, g.units, (512 + cyc_unit - 1) / cyc_unit}));
-        while (g.ups > 1 && (budget - res) / (g.ups * g.unit_bytes) < 3) --g.ups;
-        g.stage_bytes = g.ups * g.unit_bytes;
-        g.stages = std::min(tc::kMaxStages, (budget - res) / g.stage_bytes);
-        if (g.stages >= 2) { L.smem_bytes = static_cast<size_t>(res) + static_cast<size_t>(g.stages) * g.stage_bytes + tail + 1024; break; }
-        if (L.bres) { L.bres = false; continue; }
-        return fail(ctx, GANREV_EINVAL, "layer %s does not fit in shared memory", d.name);
-    }
+    auto plan = [&](int xp) -> bool {
+        const int tail = ((2 * tc::kMaxStages + 5) * 8 + 24 + 2 * d.NT * 4 + 1023) / 1024 * 1024 + xp * tc::kEpiWarps * 32 * 64;
+        const int budget = tc::kSmemBudget - 1024 - tail;
+        L.bres = d.want_bres && g.nphase == 1 && g.n_tiles == 1 && wbytes + 2 * static_cast<size_t>(L.MT) * g.a_unit_bytes <= static_cast<size_t>(budget);
+        for (;;) {
+            const int res = L.bres ? static_cast<int>(wbytes) : 0;
+            g.unit_bytes = L.MT * g.a_unit_bytes + (L.bres ? 0 : g.ndy * g.b_kb_bytes);
+            const int cyc_unit = L.MT * g.ndy * 4 * std::max(d.NT / 2, 32);          // MMA cycles per unit
+            g.ups = std::max(1, std::min({4, g.units, (512 + cyc_unit - 1) / cyc_unit}));
+            while (g.ups > 1 && (budget - res) / (g.ups * g.unit_bytes) < 3) --g.ups;
+            g.stage_bytes = g.ups * g.unit_bytes;
+            g.stages = std::min(tc::kMaxStages, (budget - res) / g.stage_bytes);
+            if (g.stages >= 2) { L.smem_bytes = static_cast<size_t>(res) + static_cast<size_t>(g.stages) * g.stage_bytes + tail + 1024; g.xpose2 = xp == 2; return true; }
+            if (L.bres) { L.bres = false; continue; }
+            return false;
+        }
+    };
+    // Two store-transpose buffers per epilogue warp let a TMA store's shared-memory read overlap the next chunk's math (with one
+    // buffer every chunk waits for the previous store).  Measured per layer (tools/ab_option.py xpose2 0 1 2, 32768 faces): G's Linear
+    // (K = 128, store-bound) 2.33 -> 2.00 ms; R conv2 +5 % and R Linear1 +13 % (the 16 KB cost them a pipeline stage), R conv4 / conv5
+    // unchanged.  xpose2 = 1 (default): G's Linear only; 2: every plain bf16 layer (A/B); 0: nowhere.
+    const bool plain = !d.pool && !d.out_fp32 && d.kind != KIND_UPCONV3 && !d.nchw && d.cout_real == g.cout_pad && d.NT % 32 == 0;
+    const bool want2 = plain && (ctx->xpose2 == 2 || (ctx->xpose2 == 1 && !strcmp(d.name, "g_linear")));
+    if (!(want2 && plan(2)) && !plan(1)) return fail(ctx, GANREV_EINVAL, "layer %s does not fit in shared memory", d.name);
     const double px_in = static_cast<double>(d.Hin) * d.Win;
     L.flops_per_img = 2.0 * px_in * g.nphase * (d.out_fp32 ? d.cout_real : g.cout_pad) * L.Ktot;   // zero-padded output lanes are not work
     L.bytes_per_img = 2.0 * px_in * d.Cin + (d.out_fp32 ? 4.0 : 2.0) * d.Hout * d.Wout * d.cout_real;
@@ -2684,6 +2695,7 @@ int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "label_tc")) { ctx->label_tc = value != 0; return GANREV_OK; }
     if (!strcmp(name, "stream_tc")) { ctx->stream_tc = value != 0; return GANREV_OK; }
     if (!strcmp(name, "kmeans_tc")) { ctx->kmeans_tc = value != 0; return GANREV_OK; }
+    if (!strcmp(name, "xpose2")) { ctx->xpose2 = value < 0 ? 0 : (value > 2 ? 2 : static_cast<int>(value)); return GANREV_OK; }   // read at load time
     if (!strcmp(name, "fuse_conv3")) { ctx->fuse_conv3 = value < 0 ? 0 : (value > 2 ? 2 : static_cast<int>(value)); return GANREV_OK; }   // read by ganrev_load_G
     if (!strcmp(name, "tma_store")) { ctx->tma_store = value < 0 ? 0 : (value > 2 ? 2 : static_cast<int>(value)); return GANREV_OK; }
     if (!strcmp(name, "conv_impl")) {
