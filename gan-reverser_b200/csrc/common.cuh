@@ -64,6 +64,7 @@ struct ConvGemm {
     long long out_sN;          // output strides (elements): image,
     int out_sP, out_sC;        //   pixel (row-major oh*Wout+ow), channel.  bf16 NHWC: (H*W*C, C, 1); fp32 NCHW: (C*H*W, 1, H*W)
     int Hout, Wout, up, pool, act, out_fp32;
+    int tma_hybrid;            // TMA-store epilogue: first chunk of each round by st.global, second by TMA (no wait on the staging buffer)
     int xpose2;                // two store-transpose buffers per epilogue warp (TMA-store epilogue: one store may still be reading)
     int tma_store;             // bf16 NHWC output written by TMA bulk tensor stores (plain convs / linears); else st.global
     float post_scale;

@@ -679,7 +679,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < CW; ++j) v[j] = act_fn<ACT>(v[j], p.act);
             };
-            auto store = [&](const int pair, const int mt, const float (&v)[32]) {
+            auto store = [&](const int pair, const int mt, const float (&v)[32], const bool use_tma) {
                 const int c0 = (pair % kChunksPerTile) * CW;
                 long long o4[4] = {-1, -1, -1, -1};
                 size_t po = 0;
@@ -701,7 +701,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int hpass = 0; hpass < kPasses; ++hpass) {
                         uint4* const xpose = xpose0 + xcur * 128;
-                        if (!OUT_FP32 && p.tma_store) { if (p.xpose2) tma_store_wait_read1(); else tma_store_wait_read(); }   // the store that last used this buffer has read it
+                        if (!OUT_FP32 && p.tma_store) { if (p.xpose2) tma_store_wait_read1(); else tma_store_wait_read(); }   // the store that last used this buffer has read it (no-op when none is pending)
                         __syncwarp();
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -715,13 +715,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 pk.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
                                 pk.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
                             }
-                            if (POOL && !OUT_FP32 && p.tma_store) {   // pooled: only the even-(h, w) lanes hold a result; pack them densely
+                            if (POOL && !OUT_FP32 && use_tma) {   // pooled: only the even-(h, w) lanes hold a result; pack them densely
                                 if (pool_writer) xpose[pool_row * 4 + (j ^ ((pool_row >> 1) & 3))] = pk;
                             } else {
                                 xpose[lane * 4 + (j ^ ((lane >> 1) & 3))] = pk;
                             }
                         }
-                        if (!OUT_FP32 && p.tma_store) {
+                        if (!OUT_FP32 && use_tma) {
                             // The buffer is exactly a [32 pixels][32 channels] bf16 box in TMA's 64B-swizzle layout: one
                             // bulk tensor store per chunk replaces the read-back, the address math and the predicated STGs
                             // (pixels past the end of the batch are clipped by the tensor map).
@@ -780,9 +780,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     math(pa, ra, va);
                     if (two) math(pb, rb, vb);
                     GANREV_TRE(1, it * 4 + i0);
-                    store(pa, mta < MT ? mta : 0, va);
+                    // tma_hybrid: the first chunk of a round leaves through the read-back / st.global path (its buffer is free at once),
+                    // the second through a TMA store whose shared-memory read then has a whole round to complete -- no chunk waits
+                    store(pa, mta < MT ? mta : 0, va, p.tma_store && !(p.tma_hybrid && two));
                     GANREV_TRE(2, it * 4 + i0);
-                    if (two) store(pb, mtb < MT ? mtb : 0, vb);
+                    if (two) store(pb, mtb < MT ? mtb : 0, vb, p.tma_store != 0);
                     GANREV_TRE(3, it * 4 + i0);
                 }
             }

@@ -92,6 +92,7 @@ struct ganrev_ctx {
     std::string err;
     int64_t chunk = 0;            // images per pipeline chunk; 0 = auto (8192 32x32 faces' worth of pixels, see chunk_for)
     int conv_impl = 0;
+    int tma_hybrid = 0;           // see ConvGemm::tma_hybrid (A/B)
     int xpose2 = 1;               // double store-transpose buffers in the TMA-store epilogue (see build_tc_layer); 0 = single (A/B)
     int fuse_conv3 = 1;           // the last conv's tap products are computed in G conv2's epilogue: 1 = when C == 1 (free there: the epilogue has the
                                   // slack), 2 = also C == 3 (measured: 27 taps make conv2 epilogue-bound, 8.3 -> 15.3 ms per 4096 64x64 faces), 0 = never
@@ -555,6 +556,7 @@ static int run_layer(ganrev_ctx* ctx, TcLayer& L, const void* in, void* out, int
     // quarter's 32 pixels are one box {32 ch, bw, bh, bn} of the [n][Hout][Wout][channels] tensor; rows past n_img are clipped.
     // (pooled layers can use it too -- the epilogue packs the writer lanes densely -- but measured 1.5-4 % slower there: option value 2)
     g.tma_store = (ctx->tma_store && (!g.pool || ctx->tma_store == 2) && !g.out_fp32 && g.up == 1 && g.out_sC == 1 && g.cout_real == g.cout_pad && L.NT % 32 == 0) ? 1 : 0;
+    g.tma_hybrid = (g.tma_store && !g.xpose2 && !g.pool) ? ctx->tma_hybrid : 0;
     L.tmO = tmA;
     {
         const int BW = 1 << g.lgBW, BH = 1 << g.lgBH;
@@ -2695,6 +2697,7 @@ int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "label_tc")) { ctx->label_tc = value != 0; return GANREV_OK; }
     if (!strcmp(name, "stream_tc")) { ctx->stream_tc = value != 0; return GANREV_OK; }
     if (!strcmp(name, "kmeans_tc")) { ctx->kmeans_tc = value != 0; return GANREV_OK; }
+    if (!strcmp(name, "tma_hybrid")) { ctx->tma_hybrid = value != 0; return GANREV_OK; }
     if (!strcmp(name, "xpose2")) { ctx->xpose2 = value < 0 ? 0 : (value > 2 ? 2 : static_cast<int>(value)); return GANREV_OK; }   // read at load time
     if (!strcmp(name, "fuse_conv3")) { ctx->fuse_conv3 = value < 0 ? 0 : (value > 2 ? 2 : static_cast<int>(value)); return GANREV_OK; }   // read by ganrev_load_G
     if (!strcmp(name, "tma_store")) { ctx->tma_store = value < 0 ? 0 : (value > 2 ? 2 : static_cast<int>(value)); return GANREV_OK; }
