@@ -236,6 +236,43 @@ def hbm_kernels(ctx, pkg, peak_gbs):
     return out
 
 
+def train_leg(ctx, pkg, geom, fp32_tf, cpu=True, B=32, steps=20):
+    """one optimisation step of R (train_r.lua:138-170: G forward of the batch, R forward in training mode,
+    MSE, backward, L2 penalty, clamp, Adam) at the reference's batch size, timed on the device with the library's CUDA events;
+    beside it the same step (without the optimiser) in PyTorch-CPU autograd, the stand-in for Torch7 nn on the host cores."""
+    Cc, Hh, Ww, nd = geom
+    rng = np.random.default_rng(5)
+    rb = pkg.weights.init_R(Cc, Hh, Ww, nd, seed=2)
+    ctx.train_R_init(Cc, Hh, Ww, nd, rb)
+    noise = rng.standard_normal(size=(B, nd)).astype(np.float32)
+    from oracle.torch_cpu import train_masks, train_R_step
+    masks = train_masks(rng, B, Cc, Hh, Ww, False)
+    for _ in range(3):
+        ctx.train_R_step(noise, masks)
+    ctx.profile_reset(); ctx.profile_enable(True)
+    for _ in range(steps):
+        ctx.train_R_step(noise, masks)
+    ctx.profile_enable(False)
+    pr = ctx.profile()
+    ms = pr["train_R_step"]["ms"] / steps
+    g_ms = sum(v["ms"] for k, v in pr.items() if k.startswith("g_")) / steps
+    r_flops = 3.0 * flops_for(Cc, Hh, Ww, nd)[1] * B                                  # forward + backward-data + backward-weights of every contraction
+    tf = r_flops / (ms * 1e-3) * 1e-12
+    out = {"batch": B, "ms_per_step": ms, "g_forward_ms": g_ms, "faces_per_sec": B / ((ms + g_ms) * 1e-3), "dtype": "f32",
+           "fp32_tflops": tf, "frac_of_fp32_fma_peak": (tf / fp32_tf) if fp32_tf else None,
+           "kernels": "fp32 CUDA-core kernels (csrc/train.cuh): conv fwd / dgrad / wgrad, batch-norm statistics, ELU, dropout, Adam"}
+    if cpu:
+        import torch
+        torch.set_num_threads(host_threads())
+        images = ctx.forward_G(noise)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            train_R_step(pkg, rb, Cc, Hh, Ww, nd, images, noise, masks, False, False, 0.0, 1e-4, 1.0)
+        out["cpu_torch_ms_per_step"] = (time.perf_counter() - t0) / 3 * 1e3
+        out["cpu_torch_threads"] = torch.get_num_threads()
+    return out
+
+
 def fp32_peak(ctx):
     """Measured fp32 FMA roof at the clocks this run sees (MEASURED_PEAKS.json has no fp32 figure)."""
     try:
@@ -599,6 +636,11 @@ def main():
         line["config5"] = cfg5
     if world == 1 and not args.no_hbm_kernels:
         line["hbm_kernels"] = hbm_kernels(ctx, pkg, peak_gbs)
+    if world == 1 and not args.no_hbm_kernels:
+        try:
+            line["train_leg"] = train_leg(ctx, pkg, geom, fp32_tf, cpu=not args.no_cpu_baseline)
+        except Exception as ex:
+            line["train_leg"] = {"unavailable": repr(ex)[:200]}
     if world == 1 and not args.no_cpu_baseline:
         ips, qps, cores, sample, _, _ = cpu_port(args.cpu_images, 20000, 64, geom=geom)
         line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample,

@@ -2418,7 +2418,10 @@ int ganrev_train_R_step(ganrev_ctx* ctx, const float* noise, int B, const uint8_
     for (int i = 0; i < 6; ++i) {
         const int ci = T.ci[i], co = T.co[i], h = i < 3 ? H : H / 2, w = i < 3 ? W : W / 2;
         const long long hw = res[i], tot = static_cast<long long>(B) * co * hw;
-        trn::conv3x3_kernel<false><<<dim3(static_cast<unsigned>((hw + 127) / 128), (co + 7) / 8, B), 128, 8 * ci * 9 * sizeof(float), st>>>(wk + oin[i], Pp + T.cw[i], Pp + T.cb[i], wk + oz[i], ci, co, h, w);
+        {
+            const unsigned cthreads = static_cast<unsigned>(std::min<long long>(128, hw / 4));      // a thread per 4 pixels of a row
+            trn::conv3x3_kernel<false><<<dim3(static_cast<unsigned>((hw / 4 + cthreads - 1) / cthreads), (co + 7) / 8, B), cthreads, 8 * ci * 9 * sizeof(float), st>>>(wk + oin[i], Pp + T.cw[i], Pp + T.cb[i], wk + oz[i], ci, co, h, w);
+        }
         trn::bn_stats_kernel<<<co, 256, 0, st>>>(wk + oz[i], wk + omean[i], wk + oistd[i], Pp + T.crm[i], Pp + T.crv[i], B, co, static_cast<int>(hw));
         if (i == 2) {          // conv3: ELU -> MaxPool -> Dropout
             trn::bn_elu_drop_kernel<<<nb(tot), 256, 0, st>>>(wk + oz[i], wk + omean[i], wk + oistd[i], Pp + T.cg[i], Pp + T.cbe[i], nullptr, 0, 1.0f, wk + oa[i], nullptr, tot, co, static_cast<int>(hw));
@@ -2468,12 +2471,13 @@ int ganrev_train_R_step(ganrev_ctx* ctx, const float* noise, int B, const uint8_
         trn::bn_bwd_apply_kernel<<<nb(tot), 256, 0, st>>>(gA, wk + oz[i], wk + omean[i], wk + oistd[i], Pp + T.cg[i], Gp + T.cg[i], Gp + T.cbe[i], gB, tot, co, static_cast<int>(hw), 1.0f / static_cast<float>(B * hw));   // d conv output
         {
             const int nw = co * ci * 9;
-            trn::conv3x3_wgrad_kernel<<<dim3((co + trn::kWgO - 1) / trn::kWgO, (ci + trn::kWgI - 1) / trn::kWgI, kWgSlices), 256, 0, st>>>(wk + oin[i], gB, wk + owg, B, ci, co, h, w);
+            trn::conv3x3_wgrad_kernel<<<dim3((co + trn::kWgO - 1) / trn::kWgO, (ci + trn::kWgI - 1) / trn::kWgI, kWgSlices), 256, trn::wgrad_smem_bytes(h, w), st>>>(wk + oin[i], gB, wk + owg, B, ci, co, h, w);
             trn::wgrad_sum_kernel<<<nb(nw), 256, 0, st>>>(wk + owg, Gp + T.cw[i], nw, kWgSlices);
         }
         trn::channel_sum_kernel<<<co, 256, 0, st>>>(gB, Gp + T.cb[i], B, co, static_cast<int>(hw));
         if (i > 0) {
-            trn::conv3x3_kernel<true><<<dim3(static_cast<unsigned>((hw + 127) / 128), (ci + 7) / 8, B), 128, 8 * co * 9 * sizeof(float), st>>>(gB, Pp + T.cw[i], nullptr, gA, co, ci, h, w);   // d layer input
+            const unsigned cthreads = static_cast<unsigned>(std::min<long long>(128, hw / 4));
+            trn::conv3x3_kernel<true><<<dim3(static_cast<unsigned>((hw / 4 + cthreads - 1) / cthreads), (ci + 7) / 8, B), cthreads, 8 * co * 9 * sizeof(float), st>>>(gB, Pp + T.cw[i], nullptr, gA, co, ci, h, w);   // d layer input
             float* t = gcur; gcur = gA; gA = t;
         }
     }

@@ -23,106 +23,160 @@ constexpr float kBnMomentum = 0.1f;
 // ---------------------------------------------------------------- 3x3 convolution, stride 1, pad 1 (forward and backward-data)
 // out[n][o][h][w] = bias[o] + sum_i sum_t in[n][i][h+ty-1][w+tx-1] * Wt(o, i, t).  TR = false: Wt = w[(o*CI + i)*9 + t] (forward);
 // TR = true: Wt = w[(i*CO + o)*9 + (8 - t)] with CO = channels of THIS kernel's output (backward-data: in = dY, out = dX).
-// Block = 128 consecutive pixels of one image x 8 output channels; the 8 x CI x 9 weights are staged in shared memory.
+// A thread owns 4 consecutive pixels of a row x 8 output channels: per input channel 3 rows of (one aligned 16-byte load + two edge
+// floats) and 18 16-byte broadcast loads of the staged weights [ci][tap][8] feed 288 FMAs (the first version -- one pixel per
+// thread, one scalar shared load per FMA -- was shared-load bound).  Each output still adds its products in (ci, tap) order.
+// W is a multiple of 4 (H, W are powers of two >= 8 here).
+constexpr int kCvO = 8;
 template <bool TR>
 __global__ void __launch_bounds__(128)
 conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
                int CI, int CO, int H, int W) {
-    extern __shared__ float ws[];                                  // [8][CI][9]
-    const int o0 = blockIdx.y * 8, n = blockIdx.z;
-    for (int i = threadIdx.x; i < 8 * CI * 9; i += 128) {
-        const int oo = i / (CI * 9), r = i - oo * CI * 9, ci = r / 9, t = r - ci * 9;
+    extern __shared__ float4 ws4[];                                // [CI][9][8]
+    float* ws = reinterpret_cast<float*>(ws4);
+    const int o0 = blockIdx.y * kCvO, n = blockIdx.z;
+    for (int i = threadIdx.x; i < kCvO * CI * 9; i += blockDim.x) {
+        const int oo = i & 7, r = i >> 3, ci = r / 9, t = r - ci * 9;
         const int o = o0 + oo;
         float v = 0.0f;
         if (o < CO) v = TR ? __ldg(w + (static_cast<size_t>(ci) * CO + o) * 9 + (8 - t)) : __ldg(w + (static_cast<size_t>(o) * CI + ci) * 9 + t);
         ws[i] = v;
     }
     __syncthreads();
-    const int HW = H * W, pix = blockIdx.x * 128 + threadIdx.x;
+    const int HW = H * W, pix = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (pix >= HW) return;
-    const int h = pix / W, x = pix - h * W;
-    float acc[8];
+    const int h = pix / W, x0 = pix - h * W;
+    float acc[kCvO][4];
 #pragma unroll
-    for (int oo = 0; oo < 8; ++oo) acc[oo] = (bias != nullptr && o0 + oo < CO) ? __ldg(bias + o0 + oo) : 0.0f;
-    const float* ip = in + static_cast<size_t>(n) * CI * HW;
-    for (int ci = 0; ci < CI; ++ci) {
-        float v[9];
+    for (int oo = 0; oo < kCvO; ++oo) {
+        const float b = (bias != nullptr && o0 + oo < CO) ? __ldg(bias + o0 + oo) : 0.0f;
+        acc[oo][0] = acc[oo][1] = acc[oo][2] = acc[oo][3] = b;
+    }
+    const float* ip = in + static_cast<size_t>(n) * CI * HW + pix;
+    for (int ci = 0; ci < CI; ++ci, ip += HW) {
+        float v[3][6];                                             // rows h-1..h+1, columns x0-1..x0+4
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int hh = h + r - 1;
+            if (hh >= 0 && hh < H) {
+                const float* rp = ip + (r - 1) * W;
+                const float4 m = __ldg(reinterpret_cast<const float4*>(rp));
+                v[r][0] = x0 > 0 ? __ldg(rp - 1) : 0.0f;
+                v[r][1] = m.x; v[r][2] = m.y; v[r][3] = m.z; v[r][4] = m.w;
+                v[r][5] = x0 + 4 < W ? __ldg(rp + 4) : 0.0f;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) v[r][c] = 0.0f;
+            }
+        }
+        const float4* wr = ws4 + ci * 18;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-            const int hh = h + t / 3 - 1, xx = x + t % 3 - 1;
-            v[t] = (hh >= 0 && hh < H && xx >= 0 && xx < W) ? __ldg(ip + static_cast<size_t>(ci) * HW + hh * W + xx) : 0.0f;
-        }
+            const float4 wa = wr[2 * t], wb = wr[2 * t + 1];
+            const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-        for (int oo = 0; oo < 8; ++oo) {
-            const float* wr = ws + (oo * CI + ci) * 9;
+            for (int oo = 0; oo < kCvO; ++oo)
 #pragma unroll
-            for (int t = 0; t < 9; ++t) acc[oo] = fmaf(v[t], wr[t], acc[oo]);
+                for (int px = 0; px < 4; ++px) acc[oo][px] = fmaf(v[t / 3][t % 3 + px], wv[oo], acc[oo][px]);
         }
     }
 #pragma unroll
-    for (int oo = 0; oo < 8; ++oo)
-        if (o0 + oo < CO) out[(static_cast<size_t>(n) * CO + o0 + oo) * HW + pix] = acc[oo];
+    for (int oo = 0; oo < kCvO; ++oo)
+        if (o0 + oo < CO)
+            *reinterpret_cast<float4*>(out + (static_cast<size_t>(n) * CO + o0 + oo) * HW + pix) = make_float4(acc[oo][0], acc[oo][1], acc[oo][2], acc[oo][3]);
 }
 
-// dW[o][i][t] = sum_{n,h,w} dY[n][o][h][w] * X[n][i][h+ty-1][w+tx-1].  One block per (4 output channels, 2 input channels): a thread
-// walks positions (n, h, w) with stride 256, loads the 9 taps of its 2 input channels and the 4 gradients once and feeds 72 FMAs
-// (the first version -- one (o, i) pair per block, 10 loads per 9 FMAs -- was 60 % of the step); fixed-order tree reduction.
-constexpr int kWgO = 4, kWgI = 2;
+// dW[o][i][t] = sum_{n,h,w} dY[n][o][h][w] * X[n][i][h+ty-1][w+tx-1].  Block = 16 output x 8 input channels x 9 taps over one slice
+// (blockIdx.z of gridDim.z) of the images; the partial sums of a slice go to dw_part[z] and wgrad_sum_kernel adds the slices in
+// index order (deterministic, and enough blocks to fill the machine at batch 32).  Per chunk of <= 256 pixels (whole rows of one
+// image) the block stages dY[16][chunk] and X[8][rows + 2][W + 8] (zero halo, rows 16-byte aligned) in shared memory; thread
+// (pixel lane 0..15, o-group of 4, i-pair) walks the chunk's pixel quads: 4 + 18 shared loads feed 288 FMAs into its 4 x 2 x 9
+// register tile (the first version -- positions strided over threads, every operand from L1/L2 -- was 46-60 % of the step).  The 16
+// pixel lanes of a tile are the lanes of a half-warp: fixed-order xor-shuffle reduction at the end.
+constexpr int kWgO = 16, kWgI = 8, kWgChunk = 256;
 __global__ void __launch_bounds__(256)
 conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw_part, int B, int CI, int CO, int H, int W) {
-    // blockIdx.z = one of gridDim.z slices of the (n, h, w) range; the partial sums of a slice go to dw_part[z] and wgrad_sum_kernel
-    // adds the slices in index order (deterministic, and enough blocks to fill the machine at batch 32)
-    const int o0 = blockIdx.x * kWgO, i0 = blockIdx.y * kWgI, HW = H * W;
-    const int total = B * HW, per = (total + gridDim.z - 1) / gridDim.z;
-    const int e_begin = blockIdx.z * per, e_end = min(total, e_begin + per);
-    float* dw = dw_part + static_cast<size_t>(blockIdx.z) * CO * CI * 9;
-    float s[kWgO][kWgI][9];
+    extern __shared__ float4 wg_smem4[];
+    float* sdy = reinterpret_cast<float*>(wg_smem4);               // [16][chunk]
+    const int HW = H * W, chunk = min(kWgChunk, HW), rows = chunk / W, XS = W + 8, xplane = (rows + 2) * XS;
+    float* sx = sdy + kWgO * kWgChunk;                             // [8][rows + 2][XS]; pixel (r, c) of the chunk at [r + 1][c + 4]
+    const int o0 = blockIdx.x * kWgO, i0 = blockIdx.y * kWgI;
+    const int per = (B + gridDim.z - 1) / gridDim.z, n_begin = blockIdx.z * per, n_end = min(B, n_begin + per);
+    const int tid = threadIdx.x, pl = tid & 15, og = (tid >> 4) & 3, ip = tid >> 6;     // pixel lane, o-group (4 channels), i-pair
+    float s[4][2][9];
 #pragma unroll
-    for (int a = 0; a < kWgO; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < kWgI; ++b)
+        for (int b = 0; b < 2; ++b)
 #pragma unroll
             for (int t = 0; t < 9; ++t) s[a][b][t] = 0.0f;
-    for (int e = e_begin + threadIdx.x; e < e_end; e += 256) {
-        const int n = e / HW, pix = e - n * HW, h = pix / W, xx0 = pix - h * W;
-        float g[kWgO];
+    const int chunks_per_img = HW / chunk, qpr = W >> 2, nquads = chunk >> 2;
+    for (int n = n_begin; n < n_end; ++n) {
+        for (int c = 0; c < chunks_per_img; ++c) {
+            const int h0 = c * rows;
+            __syncthreads();                                       // the previous chunk has been consumed
+            for (int e = tid; e < kWgO * nquads; e += 256) {       // dY tile, 16-byte loads
+                const int o = e / nquads, q = e - o * nquads;
+                float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (o0 + o < CO) v = __ldg(reinterpret_cast<const float4*>(dy + (static_cast<size_t>(n) * CO + o0 + o) * HW + h0 * W) + q);
+                reinterpret_cast<float4*>(sdy + o * kWgChunk)[q] = v;
+            }
+            const int xq = XS >> 2;                                // 16-byte groups per staged row: [halo group][W/4 groups][halo group]
+            for (int e = tid; e < kWgI * (rows + 2) * xq; e += 256) {
+                const int i = e / ((rows + 2) * xq), r2 = e - i * (rows + 2) * xq, r = r2 / xq, g = r2 - r * xq;
+                const int hh = h0 + r - 1;
+                float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (i0 + i < CI && hh >= 0 && hh < H && g >= 1 && g <= qpr)
+                    v = __ldg(reinterpret_cast<const float4*>(x + (static_cast<size_t>(n) * CI + i0 + i) * HW + hh * W) + (g - 1));
+                reinterpret_cast<float4*>(sx + i * xplane + r * XS)[g] = v;
+            }
+            __syncthreads();
+            for (int q = pl; q < nquads; q += 16) {
+                const int r = q / qpr, c4 = (q - r * qpr) << 2;    // quad = pixels (r, c4 .. c4+3) of the chunk
+                float4 g4[4];
 #pragma unroll
-        for (int a = 0; a < kWgO; ++a) g[a] = o0 + a < CO ? __ldg(dy + (static_cast<size_t>(n) * CO + o0 + a) * HW + pix) : 0.0f;
+                for (int a = 0; a < 4; ++a) g4[a] = reinterpret_cast<const float4*>(sdy + (og * 4 + a) * kWgChunk)[q];
 #pragma unroll
-        for (int b = 0; b < kWgI; ++b) {
-            if (i0 + b < CI) {
-                const float* xp = x + (static_cast<size_t>(n) * CI + i0 + b) * HW;
+                for (int b = 0; b < 2; ++b) {
+                    const float* xp = sx + (ip * 2 + b) * xplane + r * XS + c4 + 3;      // -> pixel (r - 1, c4 - 1)
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const int hh = h + t / 3 - 1, xx = xx0 + t % 3 - 1;
-                    const float v = (hh >= 0 && hh < H && xx >= 0 && xx < W) ? __ldg(xp + hh * W + xx) : 0.0f;
+                    for (int ty = 0; ty < 3; ++ty) {
+                        const float* rp = xp + ty * XS;
+                        const float4 m = *reinterpret_cast<const float4*>(rp + 1);
+                        const float v[6] = {rp[0], m.x, m.y, m.z, m.w, rp[5]};
 #pragma unroll
-                    for (int a = 0; a < kWgO; ++a) s[a][b][t] = fmaf(g[a], v, s[a][b][t]);
+                        for (int tx = 0; tx < 3; ++tx)
+#pragma unroll
+                            for (int a = 0; a < 4; ++a) {
+                                float acc = s[a][b][ty * 3 + tx];
+                                acc = fmaf(g4[a].x, v[tx], acc);
+                                acc = fmaf(g4[a].y, v[tx + 1], acc);
+                                acc = fmaf(g4[a].z, v[tx + 2], acc);
+                                acc = fmaf(g4[a].w, v[tx + 3], acc);
+                                s[a][b][ty * 3 + tx] = acc;
+                            }
+                    }
                 }
             }
         }
     }
-    __shared__ float red[kWgO * kWgI * 9][8];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* dw = dw_part + static_cast<size_t>(blockIdx.z) * CO * CI * 9;
 #pragma unroll
-    for (int a = 0; a < kWgO; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < kWgI; ++b)
+        for (int b = 0; b < 2; ++b)
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
                 float v = s[a][b][t];
 #pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                if (lane == 0) red[(a * kWgI + b) * 9 + t][warp] = v;
+                for (int off = 8; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                const int o = o0 + og * 4 + a, i = i0 + ip * 2 + b;
+                if (pl == 0 && o < CO && i < CI) dw[(static_cast<size_t>(o) * CI + i) * 9 + t] = v;
             }
-    __syncthreads();
-    if (threadIdx.x < kWgO * kWgI * 9) {
-        const int a = threadIdx.x / (kWgI * 9), r = threadIdx.x - a * kWgI * 9, b = r / 9, t = r - b * 9;
-        float v = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v += red[threadIdx.x][k];
-        if (o0 + a < CO && i0 + b < CI) dw[(static_cast<size_t>(o0 + a) * CI + i0 + b) * 9 + t] = v;
-    }
+}
+inline size_t wgrad_smem_bytes(int H, int W) {
+    const int chunk = H * W < kWgChunk ? H * W : kWgChunk, rows = chunk / W;
+    return sizeof(float) * (static_cast<size_t>(kWgO) * kWgChunk + static_cast<size_t>(kWgI) * (rows + 2) * (W + 8));
 }
 
 __global__ void wgrad_sum_kernel(const float* __restrict__ part, float* __restrict__ dw, int n, int slices) {

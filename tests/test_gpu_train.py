@@ -10,55 +10,7 @@ torch = pytest.importorskip("torch")
 F = torch.nn.functional
 
 
-def _masks(rng, B, C, H, W, fixer):
-    shapes = ([(B, C, H, W)] if fixer else []) + [(B, 64, H, W), (B, 64, H, W), (B, 64, H // 2, W // 2), (B, 128, H // 2, W // 2), (B, 128, H // 2, W // 2)]
-    out = [(rng.random(s) >= 0.5).astype(np.uint8) for s in shapes]
-    out.append((rng.random((B, 128)) >= 0.25).astype(np.uint8))          # nn.SpatialDropout(0.25): keep with probability 0.75
-    out.append((rng.random((B, 512)) >= 0.5).astype(np.uint8))
-    return out
-
-
-def _torch_step(pkg, blob, C, H, W, nd, images, noise, masks, fixer, tanh_out, l1, l2, clamp):
-    """Returns (loss, f, grads as a blob-shaped vector incl. penalties + clamp, new running statistics dict)."""
-    lay = pkg.weights.r_layout(C, H, W, nd)
-    p = {k: torch.tensor(v.copy(), dtype=torch.float32, requires_grad=not (k.endswith(".m") or k.endswith(".v"))) for k, v in pkg.weights.unpack(blob, lay).items()}
-    x = torch.tensor(images)
-    mk = [torch.tensor(m.astype(np.float32)) for m in masks]
-    if fixer:
-        x = x * mk.pop(0)                                                 # nn.Dropout(0.5, true): v1, no rescale
-    run = {}
-
-    def bn(z, i):
-        rm, rv = p[f"bn{i}.m"].detach().clone(), p[f"bn{i}.v"].detach().clone()
-        y = F.batch_norm(z, rm, rv, p[f"bn{i}.g"], p[f"bn{i}.b"], training=True, momentum=0.1, eps=1e-5)
-        run[f"bn{i}.m"], run[f"bn{i}.v"] = rm.numpy(), rv.numpy()
-        return y
-
-    for i in range(1, 7):
-        x = F.elu(bn(F.conv2d(x, p[f"c{i}.w"], p[f"c{i}.b"], padding=1), i))
-        if i == 3:
-            x = F.max_pool2d(x, 2) * mk[2] * 2.0
-        elif i == 6:
-            x = F.max_pool2d(x * mk[5][:, :, None, None], 2)
-        else:
-            x = x * mk[i - 1] * 2.0
-    x = x.reshape(x.shape[0], -1)
-    x = F.elu(bn(F.linear(x, p["l1.w"], p["l1.b"]), 7)) * mk[6] * 2.0
-    pred = F.linear(x, p["l2.w"], p["l2.b"])
-    if tanh_out:
-        pred = torch.tanh(pred)
-    loss = F.mse_loss(pred, torch.tensor(noise))
-    loss.backward()
-    f = float(loss.detach())
-    grads = {}
-    for k, v in p.items():
-        if v.requires_grad:
-            g = v.grad + l1 * torch.sign(v.detach()) + l2 * v.detach()
-            f += l1 * float(v.detach().abs().sum()) + l2 * float((v.detach() ** 2).sum()) / 2.0
-            grads[k] = (g.clamp(-clamp, clamp) if clamp else g).numpy()
-        else:
-            grads[k] = np.zeros(v.shape, np.float32)
-    return float(loss.detach()), f, pkg.weights.pack(grads, lay), run
+from oracle.torch_cpu import train_masks as _masks, train_R_step as _torch_step   # the PyTorch-CPU restatement (also bench.py's train_leg baseline)
 
 
 @pytest.mark.parametrize("C,H,W,nd,B,fixer,tanh_out", [(1, 32, 32, 32, 8, False, False), (3, 16, 16, 20, 6, True, True), (1, 32, 32, 100, 32, False, False)])
