@@ -42,6 +42,9 @@ int ganrev_search_rows(ganrev_ctx* ctx, const int64_t* rows, int Q, int k, int64
 int ganrev_kmeans(ganrev_ctx* ctx, int k, int niter, const float* init_centroids, float* centroids, float* total_counts, int32_t* last_labels);
 int ganrev_assign_cosine_min(ganrev_ctx* ctx, const float* centroids, int k, int32_t* cluster, float* cosv);
 int ganrev_cluster_members(ganrev_ctx* ctx, int k, int m, const float* images, int px, int64_t* member_ids, int32_t* member_counts, float* mean_images);
+int ganrev_train_R_init(ganrev_ctx* ctx, int C, int H, int W, int noise_dim, int tanh_out, int fixer, const float* blob, size_t n_floats);
+int ganrev_train_R_step(ganrev_ctx* ctx, const float* noise, int B, const uint8_t* masks, size_t mask_bytes, const float* hyper7, double* loss2);
+int ganrev_train_R_state(ganrev_ctx* ctx, int what, float* out, size_t n_floats);
 int ganrev_sync(ganrev_ctx* ctx);
 int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value);
 ]]
@@ -303,6 +306,40 @@ function M.findClosestNeighboursOf(ctx, images, trainingSet)
         table.insert(result, {images[i], ts[ids[i] + 1]:clone(), dist[i]})
     end
     return result
+end
+
+-- train_r.lua:129-170.  trainer = ganrev.train_R(ctx, dimensions, noiseDim, noiseMethod, fixer, blob): the optimiser state (Adam's
+-- m / v, step count) lives in the context; G must be loaded (train_r.lua:96-98).  trainer.step(noise, masks, hyper) replaces
+--   optim.adam(fevalR, PARAMETERS_R, OPTSTATE.adam.R)   train_r.lua:165
+-- noise = NN_UTILS.createNoiseInputs(OPT.batchSize); masks = list of ByteTensors in module order (include/ganrev.h), drawn by the
+-- caller with torch.bernoulli so Torch's generator keeps owning the randomness; hyper = {learningRate, beta1, beta2, epsilon,
+-- R_L1, R_L2, R_clamp} (defaults: optim.adam's + train_r.lua:22-24).  Returns the criterion's loss and feval's f (with penalties).
+function M.train_R(ctx, dimensions, noiseDim, noiseMethod, fixer, blob)
+    blob = (blob or M.init_blob_R(dimensions, noiseDim)):float():contiguous()
+    check(ctx, lib.ganrev_train_R_init(ctx, dimensions[1], dimensions[2], dimensions[3], noiseDim,
+                                       noiseMethod ~= 'normal' and 1 or 0, fixer and 1 or 0, blob:data(), blob:nElement()))
+    local n_floats = blob:nElement()
+    local T = {}
+    function T.step(noise, masks, hyper)
+        local z = noise:float():contiguous()
+        local total = 0
+        for _, m in ipairs(masks) do total = total + m:nElement() end
+        local mk = torch.ByteTensor(total)
+        local at = 1
+        for _, m in ipairs(masks) do mk:narrow(1, at, m:nElement()):copy(m:byte():view(-1)); at = at + m:nElement() end
+        local hy = torch.FloatTensor(hyper or {1e-3, 0.9, 0.999, 1e-8, 0, 1e-4, 1})
+        local out = ffi.new('double[2]')
+        check(ctx, lib.ganrev_train_R_step(ctx, z:data(), z:size(1), mk:data(), total, hy:data(), out))
+        return tonumber(out[0]), tonumber(out[1])
+    end
+    -- what: 0 parameters + running statistics (the blob create_R / ganrev_load_R take, what train_r.lua:228-235 saves),
+    -- 1 last gradients, 2 / 3 Adam's m / v
+    function T.state(what)
+        local out = torch.FloatTensor(n_floats)
+        check(ctx, lib.ganrev_train_R_state(ctx, what or 0, out:data(), n_floats))
+        return out
+    end
+    return T
 end
 
 return M

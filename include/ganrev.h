@@ -206,6 +206,10 @@ int ganrev_debug_trace_read(ganrev_ctx* ctx, int64_t* out);
  *   "chunk"     images per pipeline chunk; 0 = default = 8192 32x32 faces' worth of pixels
  *   "conv_impl" 0 = tcgen05 implicit GEMM (default), 1 = plain CUDA-core kernels kept for on-device A/B checks
  *   "cta_pairs" bit mask of the conv layers that run as tcgen05 cta_group::2 CTA pairs (default all; read at ganrev_load_*)
+ *   "fuse_conv3" 1 = C == 1: the tap products of G's last conv come out of conv2's epilogue (default), 2 = also C == 3 (measured
+ *               slower), 0 = separate 1x1 tensor-core pass over the stored activation; read at ganrev_load_G
+ *   "xpose2"    1 = second store-transpose buffer per epilogue warp for G's Linear (default), 2 = every plain bf16 layer, 0 = none;
+ *               read at ganrev_load_*.  "tma_hybrid" 1 = first chunk of an epilogue round by st.global, second by TMA store (default 0)
  *   "tma_store" 1 = TMA bulk tensor stores in the conv epilogue of the plain layers (default), 2 = also the pooled layers, 0 = st.global everywhere
  *   "search_tc" 1 = many-query searches (Q >= 48, >= 8192 rows per rank) run as tensor-core candidate filter + exact re-score (default;
  *               results are bit-identical), 0 = fmaf-chain kernels only
