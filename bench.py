@@ -68,12 +68,18 @@ class ClockSampler:
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.gpu, self.proc, self.lines, self.t_mark = gpu_index, None, [], None
+
+    def mark(self):
+        """The timed region starts now: only samples that arrive from here on are reported (nvidia-smi takes ~1 s to
+        deliver its first line, so it is started before the warm-up; a timed region shorter than the sampling period
+        -- 1M faces over 8 GPUs is 0.3 s -- falls back to the warm-up + timed window and says so)."""
+        self.t_mark = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -82,7 +88,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -93,7 +99,9 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        timed_only = [ln for t, ln in self.lines if self.t_mark is not None and t >= self.t_mark]
+        window = "timed region" if len(timed_only) >= 2 else "warm-up + timed region (timed region shorter than two sampling periods)"
+        for ln in (timed_only if len(timed_only) >= 2 else [ln for _, ln in self.lines]):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -105,7 +113,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
@@ -483,10 +491,12 @@ def main():
         return ms, ctx.launch_count() - l0, out
 
     ctx.buffer_put(pkg._lib.BUF_NOISE, noise)
-    for _ in range(args.warmup):
-        step_resident()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler.mark()
     ms_res, launches, _ = timed(step_resident, args.steps)          # headline: per-kernel profiling OFF
     clocks = sampler.stop()
     # per-kernel profile: the same step, CUDA events around every launch of the library (separate pass)
