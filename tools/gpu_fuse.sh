@@ -1,3 +1,4 @@
-mkdir -p gpurun_out
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv --log-file gpurun_out/train_launches.csv python tools/exp_train.py 32 > gpurun_out/train_ncu.log 2>&1; echo "ncu exit $?"
-python tools/launch_list.py gpurun_out/train_launches.csv | head -24
+for rep in 1 2 3; do
+echo "--- store_early=1 (default lib)"; timeout 300 python tools/ab_option.py tma_store 1 2>&1 | tail -1
+echo "--- store_early=0"; GANREV_CUDA_LIB=$PWD/gan-reverser_b200/libganrev_cuda_trace.so timeout 300 python tools/ab_option.py tma_store 1 2>&1 | tail -1
+done
