@@ -109,7 +109,7 @@ r_conv1_tc_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mas
     auto build_and_issue = [&](const int b) {
         uint4* A = sA + b * (C::kABytes / 16);
         // hi = the tap truncated to its top 16 bits (a bf16 value, exactly), lo = tap - hi (exact in fp32,
-        // rounded to bf16 when packed): tap = hi + lo to 2^-16.  Integer ops + one pack per pair -- the
+        // truncated to bf16 when packed): tap = hi + lo to 2^-16.  Integer ops + one pack per pair -- the
         // conversion unit is this kernel's scarcest pipe (64 ex2 per pixel already go through it).
         float f[C::KP];
 #pragma unroll
@@ -121,13 +121,16 @@ r_conv1_tc_kernel(const float* __restrict__ img, const uint8_t* __restrict__ mas
             f[k] = hi;
             f[C::K9 + k] = xv - hi;
         }
+        // Packing by byte permute (integer pipe), not by cvt (the conversion unit is the bottleneck here): the hi halves ARE bf16 values;
+        // the lo halves are truncated instead of rounded (2^-8 of lo = 2^-16 of the tap, the same order as the split itself).
+        auto hi2 = [](float a, float b) { return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632); };
 #pragma unroll
         for (int c = 0; c < C::kChunks; ++c) {
             uint4 pk;
-            pk.x = pack_bf16x2(f[8 * c + 0], f[8 * c + 1]);
-            pk.y = pack_bf16x2(f[8 * c + 2], f[8 * c + 3]);
-            pk.z = pack_bf16x2(f[8 * c + 4], f[8 * c + 5]);
-            pk.w = pack_bf16x2(f[8 * c + 6], f[8 * c + 7]);
+            pk.x = hi2(f[8 * c + 0], f[8 * c + 1]);
+            pk.y = hi2(f[8 * c + 2], f[8 * c + 3]);
+            pk.z = hi2(f[8 * c + 4], f[8 * c + 5]);
+            pk.w = hi2(f[8 * c + 6], f[8 * c + 7]);
             A[t * 8 + (c ^ (t & 7))] = pk;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core

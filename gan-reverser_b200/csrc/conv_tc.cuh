@@ -42,6 +42,9 @@
 #ifndef GANREV_STORE_EARLY
 #define GANREV_STORE_EARLY 1
 #endif
+#ifndef GANREV_POOL_DIRECT
+#define GANREV_POOL_DIRECT 1
+#endif
 
 namespace ganrev {
 namespace tc {
@@ -558,6 +561,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // the pooled / fp32 layers keep both chunks' math in one basic block
         // (measured, same box: R conv2 7.62 -> 7.13 ms, R conv4 3.28 -> 2.98 ms per 32768 faces; G's Linear, which has two staging
         // buffers and cheap ReLU math, is 7 % faster with the interleaved order and keeps it)
+        // pooled bf16 layers: the four lanes of a 2x2 window split the chunk's 32 channels between them WHILE pooling (each exchange
+        // keeps half of the channels: 24 shuffles instead of 64), so each lane ends with 8 pooled channels: shift + ELU on 8 values
+        // instead of 32 (the pooled epilogue was bound by 32 ex2 per lane and chunk of which 24 were thrown away) and one 16-byte
+        // st.global per lane -- a window's four lanes write its 64 contiguous bytes, no shared-memory transpose
+        constexpr bool kPoolDirect = GANREV_POOL_DIRECT && POOL && !OUT_FP32 && C::kChunk == 32;
         constexpr bool kStoreEarly = GANREV_STORE_EARLY && !POOL && !OUT_FP32 && ACT == ACT_ELU;
         if constexpr (FUSE3 != 0) {   // tap weights of the last conv -> shared memory (the store-transpose buffers are unused here)
             static_assert(NT == 128 && MT == 2 && !POOL && !OUT_FP32 && ACT == ACT_RELU && kEpiWarps == 8, "FUSE3 is G's Up+Conv 256->128");
@@ -637,13 +645,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // group of 4 lanes stores after the transpose), -1 = nothing to store.
             long long offs[MT][4];
             size_t pix_off[MT];
-            bool writer[MT];
+            bool writer[MT], live[MT];
             TileCoord tco[MT];
-            const bool by_tma = !OUT_FP32 && p.tma_store && !p.tma_hybrid;   // TMA stores address by tile coordinates: no per-pixel offsets needed
+            const bool by_tma = !OUT_FP32 && !kPoolDirect && p.tma_store && !p.tma_hybrid;   // TMA stores address by tile coordinates: no per-pixel offsets needed
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 const TileCoord t = decode_tile(p, (c.mgroup * CG + static_cast<int>(rank)) * MT + mt);
                 tco[mt] = t;
+                live[mt] = false;
                 if (by_tma) {
                     pix_off[mt] = 0; writer[mt] = false;
 #pragma unroll
@@ -653,6 +662,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int n = t.n0 + n_l, h = t.h0 + h_l, w = t.w0 + w_l;
                 int oh = h, ow = w;
                 writer[mt] = n < p.n_img;
+                live[mt] = writer[mt] && !no_store;
                 if (POOL) {
                     oh = h >> 1; ow = w >> 1;
                     writer[mt] = writer[mt] && !(h & 1) && !(w & 1);
@@ -662,7 +672,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 pix_off[mt] = static_cast<size_t>(n) * p.out_sN + (static_cast<size_t>(oh) * p.Wout + ow) * p.out_sP;
                 const long long my_off = (writer[mt] && !no_store) ? static_cast<long long>(pix_off[mt]) : -1ll;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) offs[mt][i] = xposed ? __shfl_sync(0xffffffffu, my_off, (lane >> 2) + 8 * i) : -1ll;
+                for (int i = 0; i < 4; ++i) offs[mt][i] = (xposed && !kPoolDirect) ? __shfl_sync(0xffffffffu, my_off, (lane >> 2) + 8 * i) : -1ll;
             }
             if (etid == 0) {
                 GANREV_TR(7, it);
@@ -792,6 +802,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tcgen05_fence_before();
                         __syncwarp();
                         if (lane == 0) { if (CG == 2) mbar_arrive_cta(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc)); }
+                    }
+                    if constexpr (kPoolDirect) {
+                        const bool wodd = (lane & 1) != 0, hodd = (lane & BW) != 0;
+                        auto pool_store = [&](const int pair, const int mt, const uint32_t (&a)[32]) {
+                            float m16[16], m8[8];
+#pragma unroll
+                            for (int k = 0; k < 16; ++k) {          // across w: the even lane keeps channels 0..15, the odd lane 16..31
+                                const float lo = __uint_as_float(a[k]), hi = __uint_as_float(a[16 + k]);
+                                const float recv = __shfl_xor_sync(0xffffffffu, wodd ? lo : hi, 1);
+                                m16[k] = fmaxf(wodd ? hi : lo, recv);
+                            }
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {           // across h: the even row keeps the first 8 of those, the odd row the last 8
+                                const float recv = __shfl_xor_sync(0xffffffffu, hodd ? m16[k] : m16[8 + k], BW);
+                                m8[k] = fmaxf(hodd ? m16[8 + k] : m16[k], recv);
+                            }
+                            const int cs = (pair % kChunksPerTile) * CW + (wodd ? 16 : 0) + (hodd ? 8 : 0);
+                            const float4 s0 = *reinterpret_cast<const float4*>(ss + cs), s1 = *reinterpret_cast<const float4*>(ss + cs + 4);
+                            const float sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) m8[k] = act_fn<ACT>(m8[k] + sh[k], p.act);   // max(a, b) + s == max(a + s, b + s)
+                            uint4 pk;
+                            pk.x = pack_bf16x2(m8[0], m8[1]); pk.y = pack_bf16x2(m8[2], m8[3]);
+                            pk.z = pack_bf16x2(m8[4], m8[5]); pk.w = pack_bf16x2(m8[6], m8[7]);
+                            size_t po = 0;
+                            bool lv = false;
+#pragma unroll
+                            for (int m2 = 0; m2 < MT; ++m2)
+                                if (m2 == mt) { po = pix_off[m2]; lv = live[m2]; }
+                            if (lv) __stcg(reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + po + cbase + cs), pk);
+                        };
+                        pool_store(pa, mta < MT ? mta : 0, ra);
+                        if (two) pool_store(pb, mtb < MT ? mtb : 0, rb);
+                        GANREV_TRE(3, it * 4 + i0);
+                        continue;
                     }
                     float va[32], vb[32];
                     math(pa, ra, va);
