@@ -2410,6 +2410,8 @@ int ganrev_train_R_step(ganrev_ctx* ctx, const float* noise, int B, const uint8_
     uint8_t* arg3 = reinterpret_cast<uint8_t*>(wk + oarg3);
     uint8_t* arg6 = reinterpret_cast<uint8_t*>(wk + oarg6);
     auto nb = [](long long n) { return static_cast<unsigned>((n + 255) / 256); };
+    // per-channel reductions: one block per channel, as many threads as the channel has 16-byte quads (256 .. 1024)
+    auto red_threads = [](long long per_channel) { return static_cast<unsigned>(std::min<long long>(trn::kRedThreads, std::max<long long>(256, (per_channel / 4 + 31) / 32 * 32))); };
     cudaStream_t st = ctx->stream;
     ProfScope ps(ctx, "train_R_step", 6.0 * B * 174.7e6 * (HW / 1024.0), 0.0);
     // ---- forward (training mode)
@@ -2422,7 +2424,7 @@ int ganrev_train_R_step(ganrev_ctx* ctx, const float* noise, int B, const uint8_
             const unsigned cthreads = static_cast<unsigned>(std::min<long long>(128, hw / 4));      // a thread per 4 pixels of a row
             trn::conv3x3_kernel<false><<<dim3(static_cast<unsigned>((hw / 4 + cthreads - 1) / cthreads), (co + 7) / 8, B), cthreads, 8 * ci * 9 * sizeof(float), st>>>(wk + oin[i], Pp + T.cw[i], Pp + T.cb[i], wk + oz[i], ci, co, h, w);
         }
-        trn::bn_stats_kernel<<<co, 256, 0, st>>>(wk + oz[i], wk + omean[i], wk + oistd[i], Pp + T.crm[i], Pp + T.crv[i], B, co, static_cast<int>(hw));
+        trn::bn_stats_kernel<<<co, red_threads(B * hw), 0, st>>>(wk + oz[i], wk + omean[i], wk + oistd[i], Pp + T.crm[i], Pp + T.crv[i], B, co, static_cast<int>(hw));
         if (i == 2) {          // conv3: ELU -> MaxPool -> Dropout
             trn::bn_elu_drop_kernel<<<nb(tot), 256, 0, st>>>(wk + oz[i], wk + omean[i], wk + oistd[i], Pp + T.cg[i], Pp + T.cbe[i], nullptr, 0, 1.0f, wk + oa[i], nullptr, tot, co, static_cast<int>(hw));
             trn::maxpool_fwd_kernel<<<nb(tot / 4), 256, 0, st>>>(wk + oa[i], wk + op3, arg3, tot / 4, h, w);
@@ -2435,7 +2437,7 @@ int ganrev_train_R_step(ganrev_ctx* ctx, const float* noise, int B, const uint8_
         }
     }
     trn::linear_fwd_kernel<<<nb(static_cast<long long>(B) * 512 * 32), 256, 0, st>>>(wk + op6, Pp + T.l1w, Pp + T.l1b, wk + oz7, B, static_cast<int>(F), 512);
-    trn::bn_stats_kernel<<<512, 256, 0, st>>>(wk + oz7, wk + omean[6], wk + oistd[6], Pp + T.l1rm, Pp + T.l1rv, B, 512, 1);
+    trn::bn_stats_kernel<<<512, red_threads(B), 0, st>>>(wk + oz7, wk + omean[6], wk + oistd[6], Pp + T.l1rm, Pp + T.l1rv, B, 512, 1);
     trn::bn_elu_drop_kernel<<<nb(B * 512), 256, 0, st>>>(wk + oz7, wk + omean[6], wk + oistd[6], Pp + T.l1g, Pp + T.l1be, md[6], 0, 2.0f, wk + oa7, wk + oo7, B * 512, 512, 1);
     trn::linear_fwd_kernel<<<nb(static_cast<long long>(B) * nd * 32), 256, 0, st>>>(wk + oo7, Pp + T.l2w, Pp + T.l2b, wk + opred, B, 512, nd);
     if (T.tanh_out) trn::tanh_fwd_kernel<<<nb(B * nd), 256, 0, st>>>(wk + opred, B * nd);
@@ -2444,12 +2446,12 @@ int ganrev_train_R_step(ganrev_ctx* ctx, const float* noise, int B, const uint8_
     CU_TRY(cudaGetLastError());
     // ---- backward
     trn::linear_bwd_w_kernel<<<nb(static_cast<long long>(nd) * 512), 256, 0, st>>>(wk + odpred, wk + oo7, Gp + T.l2w, Gp + T.l2b, B, 512, nd);
-    trn::linear_bwd_data_kernel<<<nb(B * 512), 256, 0, st>>>(wk + odpred, Pp + T.l2w, wk + og0, B, 512, nd);
+    trn::linear_bwd_data_kernel<<<dim3((512 + trn::kLbK - 1) / trn::kLbK, (B + trn::kLbB - 1) / trn::kLbB), trn::kLbK * trn::kLbS, 0, st>>>(wk + odpred, Pp + T.l2w, wk + og0, B, 512, nd);
     trn::drop_elu_bwd_kernel<<<nb(B * 512), 256, 0, st>>>(wk + og0, wk + oa7, md[6], 0, 2.0f, wk + og1, B * 512, 1);
-    trn::bn_bwd_reduce_kernel<<<512, 256, 0, st>>>(wk + og1, wk + oz7, wk + omean[6], wk + oistd[6], Gp + T.l1g, Gp + T.l1be, B, 512, 1);
+    trn::bn_bwd_reduce_kernel<<<512, red_threads(B), 0, st>>>(wk + og1, wk + oz7, wk + omean[6], wk + oistd[6], Gp + T.l1g, Gp + T.l1be, B, 512, 1);
     trn::bn_bwd_apply_kernel<<<nb(B * 512), 256, 0, st>>>(wk + og1, wk + oz7, wk + omean[6], wk + oistd[6], Pp + T.l1g, Gp + T.l1g, Gp + T.l1be, wk + og0, B * 512, 512, 1, 1.0f / B);
     trn::linear_bwd_w_kernel<<<nb(512 * F), 256, 0, st>>>(wk + og0, wk + op6, Gp + T.l1w, Gp + T.l1b, B, static_cast<int>(F), 512);
-    trn::linear_bwd_data_kernel<<<nb(B * F), 256, 0, st>>>(wk + og0, Pp + T.l1w, wk + og1, B, static_cast<int>(F), 512);   // d p6
+    trn::linear_bwd_data_kernel<<<dim3(static_cast<unsigned>((F + trn::kLbK - 1) / trn::kLbK), (B + trn::kLbB - 1) / trn::kLbB), trn::kLbK * trn::kLbS, 0, st>>>(wk + og0, Pp + T.l1w, wk + og1, B, static_cast<int>(F), 512);   // d p6
     float* gcur = wk + og1;     // gradient w.r.t. the OUTPUT of layer i's block (what the next layer consumed)
     float* gA = wk + og0;
     float* gB = wk + og2;
@@ -2467,14 +2469,14 @@ int ganrev_train_R_step(ganrev_ctx* ctx, const float* noise, int B, const uint8_
         } else {
             trn::drop_elu_bwd_kernel<<<nb(tot), 256, 0, st>>>(gcur, wk + oa[i], md[i], 0, 2.0f, gA, tot, static_cast<int>(hw));
         }
-        trn::bn_bwd_reduce_kernel<<<co, 256, 0, st>>>(gA, wk + oz[i], wk + omean[i], wk + oistd[i], Gp + T.cg[i], Gp + T.cbe[i], B, co, static_cast<int>(hw));
+        trn::bn_bwd_reduce_kernel<<<co, red_threads(B * hw), 0, st>>>(gA, wk + oz[i], wk + omean[i], wk + oistd[i], Gp + T.cg[i], Gp + T.cbe[i], B, co, static_cast<int>(hw));
         trn::bn_bwd_apply_kernel<<<nb(tot), 256, 0, st>>>(gA, wk + oz[i], wk + omean[i], wk + oistd[i], Pp + T.cg[i], Gp + T.cg[i], Gp + T.cbe[i], gB, tot, co, static_cast<int>(hw), 1.0f / static_cast<float>(B * hw));   // d conv output
         {
             const int nw = co * ci * 9;
             trn::conv3x3_wgrad_kernel<<<dim3((co + trn::kWgO - 1) / trn::kWgO, (ci + trn::kWgI - 1) / trn::kWgI, kWgSlices), 256, trn::wgrad_smem_bytes(h, w), st>>>(wk + oin[i], gB, wk + owg, B, ci, co, h, w);
             trn::wgrad_sum_kernel<<<nb(nw), 256, 0, st>>>(wk + owg, Gp + T.cw[i], nw, kWgSlices);
         }
-        trn::channel_sum_kernel<<<co, 256, 0, st>>>(gB, Gp + T.cb[i], B, co, static_cast<int>(hw));
+        trn::channel_sum_kernel<<<co, red_threads(B * hw), 0, st>>>(gB, Gp + T.cb[i], B, co, static_cast<int>(hw));
         if (i > 0) {
             const unsigned cthreads = static_cast<unsigned>(std::min<long long>(128, hw / 4));
             trn::conv3x3_kernel<true><<<dim3(static_cast<unsigned>((hw / 4 + cthreads - 1) / cthreads), (ci + 7) / 8, B), cthreads, 8 * co * 9 * sizeof(float), st>>>(gB, Pp + T.cw[i], nullptr, gA, co, ci, h, w);   // d layer input

@@ -53,6 +53,7 @@ conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ w, const 
         acc[oo][0] = acc[oo][1] = acc[oo][2] = acc[oo][3] = b;
     }
     const float* ip = in + static_cast<size_t>(n) * CI * HW + pix;
+#pragma unroll 2
     for (int ci = 0; ci < CI; ++ci, ip += HW) {
         float v[3][6];                                             // rows h-1..h+1, columns x0-1..x0+4
 #pragma unroll
@@ -201,26 +202,48 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     for (int k = 0; k < static_cast<int>(blockDim.x >> 5); ++k) t += red[k];
     return t;
 }
-__global__ void __launch_bounds__(256)
+// Blocks of up to 1024 threads (kRedThreads at the launch sites); 16-byte loads when HW % 4 == 0.  visit(v) sees every element of
+// channel c once, in a fixed per-thread order.
+constexpr int kRedThreads = 1024;
+template <typename F>
+__device__ __forceinline__ void for_channel(const float* __restrict__ a, int c, int B, int C, int HW, F visit) {
+    if ((HW & 3) == 0) {
+        const int q = HW >> 2;
+        for (int e = threadIdx.x; e < B * q; e += blockDim.x) {
+            const int n = e / q, p = e - n * q;
+            const size_t idx = (static_cast<size_t>(n) * C + c) * HW + 4 * p;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(a + idx));
+            visit(idx, v.x); visit(idx + 1, v.y); visit(idx + 2, v.z); visit(idx + 3, v.w);
+        }
+    } else {
+        for (int e = threadIdx.x; e < B * HW; e += blockDim.x) {
+            const int n = e / HW, p = e - n * HW;
+            const size_t idx = (static_cast<size_t>(n) * C + c) * HW + p;
+            visit(idx, __ldg(a + idx));
+        }
+    }
+}
+__global__ void __launch_bounds__(kRedThreads)
 channel_sum_kernel(const float* __restrict__ a, float* __restrict__ out, int B, int C, int HW) {
-    __shared__ double red[8];
+    __shared__ double red[32];
     const int c = blockIdx.x;
     double s = 0.0;
-    for (int e = threadIdx.x; e < B * HW; e += 256) { const int n = e / HW, p = e - n * HW; s += static_cast<double>(__ldg(a + (static_cast<size_t>(n) * C + c) * HW + p)); }
+    for_channel(a, c, B, C, HW, [&](size_t, float v) { s += static_cast<double>(v); });
     s = block_sum(s, red);
     if (threadIdx.x == 0) out[c] = static_cast<float>(s);
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kRedThreads)
 bn_stats_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ run_mean, float* __restrict__ run_var,
                 int B, int C, int HW) {
-    __shared__ double red[8];
+    __shared__ double red[32];
     const int c = blockIdx.x;
     const double M = static_cast<double>(B) * HW;
     double s = 0.0;
-    for (int e = threadIdx.x; e < B * HW; e += 256) { const int n = e / HW, p = e - n * HW; s += static_cast<double>(__ldg(x + (static_cast<size_t>(n) * C + c) * HW + p)); }
+    for_channel(x, c, B, C, HW, [&](size_t, float v) { s += static_cast<double>(v); });
     const double mu = block_sum(s, red) / M;
+    __syncthreads();                                               // red[] is reused
     double q = 0.0;
-    for (int e = threadIdx.x; e < B * HW; e += 256) { const int n = e / HW, p = e - n * HW; const double dlt = static_cast<double>(__ldg(x + (static_cast<size_t>(n) * C + c) * HW + p)) - mu; q += dlt * dlt; }
+    for_channel(x, c, B, C, HW, [&](size_t, float v) { const double dlt = static_cast<double>(v) - mu; q += dlt * dlt; });
     q = block_sum(q, red);
     if (threadIdx.x == 0) {
         const double var = q / M;
@@ -230,21 +253,35 @@ bn_stats_kernel(const float* __restrict__ x, float* __restrict__ mean, float* __
         run_var[c] = (1.0f - kBnMomentum) * run_var[c] + kBnMomentum * static_cast<float>(M > 1.0 ? q / (M - 1.0) : var);
     }
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kRedThreads)
 bn_bwd_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ invstd,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int C, int HW) {
-    __shared__ double red[8];
+    __shared__ double red[32];
     const int c = blockIdx.x;
     const float mu = mean[c], is = invstd[c];
     double s = 0.0, sx = 0.0;
-    for (int e = threadIdx.x; e < B * HW; e += 256) {
-        const int n = e / HW, p = e - n * HW;
-        const size_t idx = (static_cast<size_t>(n) * C + c) * HW + p;
-        const float g = __ldg(dz + idx);
-        s += static_cast<double>(g);
-        sx += static_cast<double>(g * ((__ldg(x + idx) - mu) * is));
+    if ((HW & 3) == 0) {
+        const int q = HW >> 2;
+        for (int e = threadIdx.x; e < B * q; e += blockDim.x) {
+            const int n = e / q, p = e - n * q;
+            const size_t idx = (static_cast<size_t>(n) * C + c) * HW + 4 * p;
+            const float4 g = __ldg(reinterpret_cast<const float4*>(dz + idx)), v = __ldg(reinterpret_cast<const float4*>(x + idx));
+            s += static_cast<double>(g.x); sx += static_cast<double>(g.x * ((v.x - mu) * is));
+            s += static_cast<double>(g.y); sx += static_cast<double>(g.y * ((v.y - mu) * is));
+            s += static_cast<double>(g.z); sx += static_cast<double>(g.z * ((v.z - mu) * is));
+            s += static_cast<double>(g.w); sx += static_cast<double>(g.w * ((v.w - mu) * is));
+        }
+    } else {
+        for (int e = threadIdx.x; e < B * HW; e += blockDim.x) {
+            const int n = e / HW, p = e - n * HW;
+            const size_t idx = (static_cast<size_t>(n) * C + c) * HW + p;
+            const float g = __ldg(dz + idx);
+            s += static_cast<double>(g);
+            sx += static_cast<double>(g * ((__ldg(x + idx) - mu) * is));
+        }
     }
     s = block_sum(s, red);
+    __syncthreads();
     sx = block_sum(sx, red);
     if (threadIdx.x == 0) { dbeta[c] = static_cast<float>(s); dgamma[c] = static_cast<float>(sx); }
 }
@@ -335,14 +372,52 @@ linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
     for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     if (lane == 0) y[gw] = s + __ldg(bias + o);
 }
-// dx[b][k] = sum_o dy[b][o] w[o][k]
-__global__ void linear_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int B, int K, int O) {
-    const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= static_cast<long long>(B) * K) return;
-    const int b = static_cast<int>(e / K), k = static_cast<int>(e - static_cast<long long>(b) * K);
-    float s = 0.0f;
-    for (int o = 0; o < O; ++o) s = fmaf(__ldg(dy + static_cast<size_t>(b) * O + o), __ldg(w + static_cast<size_t>(o) * K + k), s);
-    dx[e] = s;
+// dx[b][k] = sum_o dy[b][o] w[o][k].  Block = 64 columns k x 32 batch rows (blockIdx.y) x 4 slices of the o range: thread
+// (k, slice) keeps the 32 rows' sums in registers, reads each weight ONCE (coalesced over k) and the dy values of a 32 x 32 chunk as
+// 16-byte broadcasts from shared memory; the four slices are added in index order through shared memory.  (The first version -- a
+// thread per (b, k) -- read the 16 MB weight matrix of the 8192 -> 512 layer once per batch row.)
+constexpr int kLbK = 64, kLbS = 4, kLbOC = 32, kLbB = 32;
+__global__ void __launch_bounds__(kLbK * kLbS)
+linear_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int B, int K, int O) {
+    __shared__ float4 sm4[kLbS * kLbB * kLbK / 4];                 // 32 KB: the dy chunks [slice][o][32 rows] (16 KB), then the slices' sums
+    float* sm = reinterpret_cast<float*>(sm4);
+    const int kk = threadIdx.x & (kLbK - 1), sl = threadIdx.x / kLbK;
+    const int k = blockIdx.x * kLbK + kk, b0 = blockIdx.y * kLbB;
+    const int per = (O + kLbS - 1) / kLbS, o_begin = sl * per, o_end = min(O, o_begin + per);
+    float acc[kLbB];
+#pragma unroll
+    for (int r = 0; r < kLbB; ++r) acc[r] = 0.0f;
+    float* sdy = sm + sl * kLbOC * kLbB;
+    for (int oc = 0; oc < per; oc += kLbOC) {
+        __syncthreads();
+        for (int e = kk; e < kLbOC * kLbB; e += kLbK) {            // this slice's chunk: o fastest in the global reads
+            const int oo = e & (kLbOC - 1), bb = e / kLbOC, o = o_begin + oc + oo;
+            sdy[oo * kLbB + bb] = (o < o_end && b0 + bb < B) ? __ldg(dy + static_cast<size_t>(b0 + bb) * O + o) : 0.0f;
+        }
+        __syncthreads();
+        for (int oo = 0; oo < kLbOC; ++oo) {
+            const int o = o_begin + oc + oo;
+            if (o >= o_end) break;
+            const float wv = k < K ? __ldg(w + static_cast<size_t>(o) * K + k) : 0.0f;
+            const float4* row = reinterpret_cast<const float4*>(sdy + oo * kLbB);
+#pragma unroll
+            for (int r4 = 0; r4 < kLbB / 4; ++r4) {
+                const float4 g = row[r4];
+                acc[4 * r4 + 0] = fmaf(g.x, wv, acc[4 * r4 + 0]); acc[4 * r4 + 1] = fmaf(g.y, wv, acc[4 * r4 + 1]);
+                acc[4 * r4 + 2] = fmaf(g.z, wv, acc[4 * r4 + 2]); acc[4 * r4 + 3] = fmaf(g.w, wv, acc[4 * r4 + 3]);
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kLbB; ++r) sm[(sl * kLbB + r) * kLbK + kk] = acc[r];
+    __syncthreads();
+    for (int r = sl; r < kLbB; r += kLbS) {                         // slice sl finishes rows sl, sl + 4, ...
+        float v = 0.0f;
+#pragma unroll
+        for (int z = 0; z < kLbS; ++z) v += sm[(z * kLbB + r) * kLbK + kk];
+        if (k < K && b0 + r < B) dx[static_cast<size_t>(b0 + r) * K + k] = v;
+    }
 }
 // dw[o][k] = sum_b dy[b][o] x[b][k];  db[o] = sum_b dy[b][o]  (k == 0 threads)
 __global__ void linear_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw, float* __restrict__ db, int B, int K, int O) {
