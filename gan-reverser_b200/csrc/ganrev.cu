@@ -2421,8 +2421,9 @@ int ganrev_train_R_step(ganrev_ctx* ctx, const float* noise, int B, const uint8_
         const int ci = T.ci[i], co = T.co[i], h = i < 3 ? H : H / 2, w = i < 3 ? W : W / 2;
         const long long hw = res[i], tot = static_cast<long long>(B) * co * hw;
         {
-            const unsigned cthreads = static_cast<unsigned>(std::min<long long>(128, hw / 4));      // a thread per 4 pixels of a row
-            trn::conv3x3_kernel<false><<<dim3(static_cast<unsigned>((hw / 4 + cthreads - 1) / cthreads), (co + 7) / 8, B), cthreads, 8 * ci * 9 * sizeof(float), st>>>(wk + oin[i], Pp + T.cw[i], Pp + T.cb[i], wk + oz[i], ci, co, h, w);
+            // a thread per 4 pixels of a row; 128 threads = 512 pixels of one image, or several whole images of the small layers
+            const unsigned ipb = static_cast<unsigned>(std::max<long long>(1, 128 / (hw / 4)));
+            trn::conv3x3_kernel<false><<<dim3(static_cast<unsigned>(ipb > 1 ? 1 : (hw / 4 + 127) / 128), (co + 7) / 8, (B + ipb - 1) / ipb), 128, 8 * ci * 9 * sizeof(float), st>>>(wk + oin[i], Pp + T.cw[i], Pp + T.cb[i], wk + oz[i], B, ci, co, h, w);
         }
         trn::bn_stats_kernel<<<co, red_threads(B * hw), 0, st>>>(wk + oz[i], wk + omean[i], wk + oistd[i], Pp + T.crm[i], Pp + T.crv[i], B, co, static_cast<int>(hw));
         if (i == 2) {          // conv3: ELU -> MaxPool -> Dropout
@@ -2478,8 +2479,8 @@ int ganrev_train_R_step(ganrev_ctx* ctx, const float* noise, int B, const uint8_
         }
         trn::channel_sum_kernel<<<co, red_threads(B * hw), 0, st>>>(gB, Gp + T.cb[i], B, co, static_cast<int>(hw));
         if (i > 0) {
-            const unsigned cthreads = static_cast<unsigned>(std::min<long long>(128, hw / 4));
-            trn::conv3x3_kernel<true><<<dim3(static_cast<unsigned>((hw / 4 + cthreads - 1) / cthreads), (ci + 7) / 8, B), cthreads, 8 * co * 9 * sizeof(float), st>>>(gB, Pp + T.cw[i], nullptr, gA, co, ci, h, w);   // d layer input
+            const unsigned ipb = static_cast<unsigned>(std::max<long long>(1, 128 / (hw / 4)));
+            trn::conv3x3_kernel<true><<<dim3(static_cast<unsigned>(ipb > 1 ? 1 : (hw / 4 + 127) / 128), (ci + 7) / 8, (B + ipb - 1) / ipb), 128, 8 * co * 9 * sizeof(float), st>>>(gB, Pp + T.cw[i], nullptr, gA, B, co, ci, h, w);   // d layer input
             float* t = gcur; gcur = gA; gA = t;
         }
     }

@@ -31,10 +31,10 @@ constexpr int kCvO = 8;
 template <bool TR>
 __global__ void __launch_bounds__(128)
 conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
-               int CI, int CO, int H, int W) {
+               int NB, int CI, int CO, int H, int W) {
     extern __shared__ float4 ws4[];                                // [CI][9][8]
     float* ws = reinterpret_cast<float*>(ws4);
-    const int o0 = blockIdx.y * kCvO, n = blockIdx.z;
+    const int o0 = blockIdx.y * kCvO;
     for (int i = threadIdx.x; i < kCvO * CI * 9; i += blockDim.x) {
         const int oo = i & 7, r = i >> 3, ci = r / 9, t = r - ci * 9;
         const int o = o0 + oo;
@@ -43,8 +43,11 @@ conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ w, const 
         ws[i] = v;
     }
     __syncthreads();
-    const int HW = H * W, pix = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (pix >= HW) return;
+    // blockIdx.z covers `ipb` images when an image has fewer quads than the block has threads (the 16x16 / 8x8 layers: more warps
+    // per staged weight tile), else one image whose quads are split over blockIdx.x
+    const int HW = H * W, qpi = HW >> 2, ipb = max(1, static_cast<int>(blockDim.x) / qpi);
+    const int g = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.z * ipb + (ipb > 1 ? g / qpi : 0), pix = (ipb > 1 ? g % qpi : g) * 4;
+    if (pix >= HW || n >= NB) return;
     const int h = pix / W, x0 = pix - h * W;
     float acc[kCvO][4];
 #pragma unroll
