@@ -56,14 +56,14 @@ conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ w, const 
         acc[oo][0] = acc[oo][1] = acc[oo][2] = acc[oo][3] = b;
     }
     const float* ip = in + static_cast<size_t>(n) * CI * HW + pix;
-#pragma unroll 2
-    for (int ci = 0; ci < CI; ++ci, ip += HW) {
-        float v[3][6];                                             // rows h-1..h+1, columns x0-1..x0+4
+    // rows h-1..h+1, columns x0-1..x0+4 of one input channel; the NEXT channel's window is requested before the current one's
+    // 288 FMAs so that its L1 / L2 latency hides behind them
+    auto window = [&](const float* cp, float (&v)[3][6]) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             const int hh = h + r - 1;
             if (hh >= 0 && hh < H) {
-                const float* rp = ip + (r - 1) * W;
+                const float* rp = cp + (r - 1) * W;
                 const float4 m = __ldg(reinterpret_cast<const float4*>(rp));
                 v[r][0] = x0 > 0 ? __ldg(rp - 1) : 0.0f;
                 v[r][1] = m.x; v[r][2] = m.y; v[r][3] = m.z; v[r][4] = m.w;
@@ -73,6 +73,17 @@ conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ w, const 
                 for (int c = 0; c < 6; ++c) v[r][c] = 0.0f;
             }
         }
+    };
+    float vn[3][6];
+    window(ip, vn);
+    for (int ci = 0; ci < CI; ++ci) {
+        float v[3][6];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) v[r][c] = vn[r][c];
+        ip += HW;
+        if (ci + 1 < CI) window(ip, vn);
         const float4* wr = ws4 + ci * 18;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
