@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_train.py -m gpu -q --timeout=300 -x -p no:cacheprovider > gpurun_out/train.log 2>&1; echo "train tests exit $?"; tail -5 gpurun_out/train.log
-timeout 300 python tools/exp_train.py 32 2>&1 | tail -2
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 77 python -m pytest tests/test_gpu_train.py -m gpu -q --timeout=800 -x -p no:cacheprovider -k "matches_torch and 8-False" > gpurun_out/racecheck_train.log 2>&1; echo "racecheck train exit $?"; grep -E "RACECHECK SUMMARY|hazard|passed|failed" gpurun_out/racecheck_train.log | head -10
