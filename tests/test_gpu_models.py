@@ -111,6 +111,35 @@ def test_G_fused_last_conv_matches_two_pass(pkg, orc, ctx, geom, pairs):
     assert np.abs(got[0] - got[1]).max() <= 1e-2
 
 
+@pytest.mark.parametrize("opts", [{"xpose2": 2}, {"xpose2": 0}, {"tma_hybrid": 1}, {"tma_store": 0}, {"tma_store": 2}], ids=lambda o: "_".join(f"{k}{v}" for k, v in o.items()))
+def test_epilogue_store_variants_match_oracle(pkg, orc, ctx, opts):
+    """The A/B knobs of the conv epilogue's store path (ganrev.h: xpose2, tma_hybrid, tma_store) select different code in the shipped
+    library: each must give the same G / R results within tolerance (several items per CTA, ragged last chunk)."""
+    C, H, W, nd, N = 1, 32, 32, 32, 150
+    defaults = {"xpose2": 1, "tma_hybrid": 0, "tma_store": 1}
+    gb = pkg.weights.init_G(C, H, W, nd, seed=1, stress=True)
+    rb = pkg.weights.init_R(C, H, W, nd, seed=2, stress=True)
+    noise = np.random.default_rng(3).normal(size=(N, nd)).astype(np.float32)
+    want_img = orc.forward_G(gb, C, H, W, nd, noise)
+    want_att = orc.forward_R(rb, C, H, W, nd, want_img)
+    ctx.set_option("conv_impl", 0)
+    ctx.set_option("cta_pairs", 31)
+    ctx.set_option("chunk", 64)
+    try:
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        ctx.load_G(C, H, W, nd, gb)
+        ctx.load_R(0, C, H, W, nd, rb)
+        assert np.abs(ctx.forward_G(noise) - want_img).max() <= PIX_TOL
+        got = ctx.forward_R(0, want_img)
+        assert row_cosine(got, want_att).min() >= COS_TOL
+        assert rel_l2(got, want_att) <= REL_TOL
+    finally:
+        for k, v in defaults.items():
+            ctx.set_option(k, v)
+        ctx.set_option("chunk", 16)
+
+
 BENCH_SHAPES = [
     # C, H, W, nd, N, rows checked against the oracle: BASELINE configs[3] and configs[4] geometries at the DEFAULT chunk
     (1, 32, 32, 100, 20000, 1000),

@@ -172,3 +172,56 @@ def test_file_unique_id_handoff(pkg, tmp_path):
     assert got["r1"] == bytes(range(128)) and not os.path.exists(path + ".tmp")
     with pytest.raises(TimeoutError):
         pkg.dist.file_unique_id(None, 2, 1, str(tmp_path / "never"), timeout_s=0.1)
+
+
+def test_train_r_host_loop_and_torch_restatement(pkg):
+    """train_r.py (mirror of train_r.lua:129-170) against a recording stand-in for the context: one init, nbBatches steps, masks
+    in the module order include/ganrev.h documents, hyper-parameters passed through; and the PyTorch-CPU restatement used as
+    the GPU tests' checker (oracle/torch_cpu.py) agrees with a finite difference of its own loss."""
+    torch = pytest.importorskip("torch")
+    C, H, W, nd, B = 1, 16, 16, 8, 4
+
+    class Rec:
+        def __init__(self):
+            self.calls = []
+
+        def train_R_init(self, *a, **k):
+            self.calls.append(("init", a, k))
+
+        def train_R_step(self, noise, masks, **k):
+            self.calls.append(("step", noise.shape, [m.shape for m in masks], [m.dtype for m in masks], k))
+            return 1.0 / len(self.calls), 0.0
+
+        def train_R_state(self, what):
+            return np.zeros(3, np.float32)
+
+    rec = Rec()
+    blob, losses = pkg.train_r.train(rec, (C, H, W), nd, nbBatches=3, batchSize=B, fixer=True, R_L2=2e-4, learningRate=5e-4)
+    assert [c[0] for c in rec.calls] == ["init", "step", "step", "step"] and len(losses) == 3
+    assert rec.calls[0][2] == {"tanh_out": False, "fixer": True}
+    _, nshape, mshapes, mdtypes, hyper = rec.calls[1]
+    assert nshape == (B, nd) and hyper == {"lr": 5e-4, "l1": 0.0, "l2": 2e-4, "clamp": 1.0}
+    assert mshapes == [(B, C, H, W), (B, 64, H, W), (B, 64, H, W), (B, 64, H // 2, W // 2), (B, 128, H // 2, W // 2),
+                       (B, 128, H // 2, W // 2), (B, 128), (B, 512)]
+    assert all(d == np.uint8 for d in mdtypes)
+    # the checker itself: d loss / d (one bias) by central differences
+    from oracle.torch_cpu import train_masks, train_R_step
+    rng = np.random.default_rng(0)
+    rb = pkg.weights.init_R(C, H, W, nd, seed=2, stress=True)
+    lay = pkg.weights.r_layout(C, H, W, nd)
+    images = rng.random((B, C, H, W)).astype(np.float32)
+    noise = rng.standard_normal((B, nd)).astype(np.float32)
+    masks = train_masks(rng, B, C, H, W, False)
+    loss, f, grads, _ = train_R_step(pkg, rb, C, H, W, nd, images, noise, masks, False, False, 0.0, 0.0, 0.0)
+    assert f == pytest.approx(loss)
+    off = 0
+    for k, shp in lay:
+        if k == "l2.b":
+            break
+        off += int(np.prod(shp))
+    eps = 1e-2
+    up, dn = rb.copy(), rb.copy()
+    up[off] += eps; dn[off] -= eps
+    lu = train_R_step(pkg, up, C, H, W, nd, images, noise, masks, False, False, 0.0, 0.0, 0.0)[0]
+    ld = train_R_step(pkg, dn, C, H, W, nd, images, noise, masks, False, False, 0.0, 0.0, 0.0)[0]
+    assert grads[off] == pytest.approx((lu - ld) / (2 * eps), rel=2e-2, abs=1e-5)
