@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 77 python -m pytest tests/test_gpu_train.py -m gpu -q --timeout=800 -x -p no:cacheprovider -k "matches_torch and 8-False" > gpurun_out/racecheck_train.log 2>&1; echo "racecheck train exit $?"; grep -E "RACECHECK SUMMARY|hazard|passed|failed" gpurun_out/racecheck_train.log | head -10
+timeout 600 python -m pytest tests/test_gpu_models.py -m gpu -q --timeout=300 -x -p no:cacheprovider -k "R_matches or benchmark or resident" > gpurun_out/models.log 2>&1; echo "exit $?"; tail -3 gpurun_out/models.log
+for rep in 1 2 3; do timeout 300 python tools/ab_option.py tma_store 1 2>&1 | tail -1; done
