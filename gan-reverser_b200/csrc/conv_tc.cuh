@@ -350,6 +350,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ ConvGemm p, const int n_items) {
     using C = Cfg<NT, MT, CG>;
     constexpr int NACC = C::kNAcc;
+    // Programmatic dependent launch: the NEXT kernel of the stream may become resident as soon as this grid's CTAs leave their SMs
+    // (its barrier init / TMEM allocation / descriptor prefetch / resident-weight loads then overlap this grid's tail); it waits
+    // for this grid's completion itself (griddepcontrol.wait below) before it touches an activation.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;          // CG == 2: rank 0 is the leader (issues the MMAs)
     const int unit0 = static_cast<int>(blockIdx.x) / CG;             // persistent loop over items, one CTA pair (or CTA) each
     const int ustep = static_cast<int>(gridDim.x) / CG;
@@ -407,6 +411,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (threadIdx.x == 32) mbar_wait(bres_bar, 0u, p.err_flag, 105);
         cluster_sync_all();
     }
+
+    // everything above touched only this kernel's own shared memory / TMEM and the (constant) weights; from here on the producer
+    // reads the previous kernel's output and the epilogue overwrites what the previous kernel may still be reading
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (one elected thread)

@@ -93,6 +93,8 @@ struct ganrev_ctx {
     int64_t chunk = 0;            // images per pipeline chunk; 0 = auto (8192 32x32 faces' worth of pixels, see chunk_for)
     int conv_impl = 0;
     int tma_hybrid = 0;           // see ConvGemm::tma_hybrid (A/B)
+    int pdl = 0;                  // conv layers launched with programmatic stream serialization (prologue overlaps the previous kernel's tail);
+                                  // measured +0.4 % on the resident G->R chain (tools/ab_total.py pdl 0 1: within noise), so off by default
     int xpose2 = 1;               // double store-transpose buffers in the TMA-store epilogue (see build_tc_layer); 0 = single (A/B)
     int fuse_conv3 = 1;           // the last conv's tap products are computed in G conv2's epilogue: 1 = when C == 1 (free there: the epilogue has the
                                   // slack), 2 = also C == 3 (measured: 27 taps make conv2 epilogue-bound, 8.3 -> 15.3 ms per 4096 64x64 faces), 0 = never
@@ -454,11 +456,20 @@ static int launch_tc(ganrev_ctx* ctx, const TcLayer& L, const CUtensorMap& tmA, 
     cfg.blockDim = dim3(tc::kThreads);
     cfg.dynamicSmemBytes = L.smem_bytes;
     cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CG == 2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = CG; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (ctx->pdl) {   // programmatic dependent launch: this kernel's prologue may overlap the previous kernel's tail (conv_tc.cuh)
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = CG == 2 ? 1 : 0;
+    cfg.numAttrs = na;
     CU_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, L.tmB, L.tmO, g, n_items));
     return GANREV_OK;
 }
@@ -2705,6 +2716,7 @@ int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "stream_tc")) { ctx->stream_tc = value != 0; return GANREV_OK; }
     if (!strcmp(name, "kmeans_tc")) { ctx->kmeans_tc = value != 0; return GANREV_OK; }
     if (!strcmp(name, "tma_hybrid")) { ctx->tma_hybrid = value != 0; return GANREV_OK; }
+    if (!strcmp(name, "pdl")) { ctx->pdl = value != 0; return GANREV_OK; }
     if (!strcmp(name, "xpose2")) { ctx->xpose2 = value < 0 ? 0 : (value > 2 ? 2 : static_cast<int>(value)); return GANREV_OK; }   // read at load time
     if (!strcmp(name, "fuse_conv3")) { ctx->fuse_conv3 = value < 0 ? 0 : (value > 2 ? 2 : static_cast<int>(value)); return GANREV_OK; }   // read by ganrev_load_G
     if (!strcmp(name, "tma_store")) { ctx->tma_store = value < 0 ? 0 : (value > 2 ? 2 : static_cast<int>(value)); return GANREV_OK; }
