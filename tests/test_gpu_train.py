@@ -13,7 +13,8 @@ F = torch.nn.functional
 from oracle.torch_cpu import train_masks as _masks, train_R_step as _torch_step   # the PyTorch-CPU restatement (also bench.py's train_leg baseline)
 
 
-@pytest.mark.parametrize("C,H,W,nd,B,fixer,tanh_out", [(1, 32, 32, 32, 8, False, False), (3, 16, 16, 20, 6, True, True), (1, 32, 32, 100, 32, False, False)])
+@pytest.mark.parametrize("C,H,W,nd,B,fixer,tanh_out", [(1, 32, 32, 32, 8, False, False), (3, 16, 16, 20, 6, True, True), (1, 32, 32, 100, 32, False, False),
+                                                       (3, 64, 64, 24, 3, True, False), (1, 16, 16, 12, 37, False, True)])
 def test_train_step_matches_torch_autograd(pkg, C, H, W, nd, B, fixer, tanh_out):
     rng = np.random.default_rng(B + nd)
     ctx = pkg.Context(0)
