@@ -2485,6 +2485,14 @@ int ganrev_train_R_step(ganrev_ctx* ctx, const float* noise, int B, const uint8_
         trn::bn_bwd_apply_kernel<<<nb(tot), 256, 0, st>>>(gA, wk + oz[i], wk + omean[i], wk + oistd[i], Pp + T.cg[i], Gp + T.cg[i], Gp + T.cbe[i], gB, tot, co, static_cast<int>(hw), 1.0f / static_cast<float>(B * hw));   // d conv output
         {
             const int nw = co * ci * 9;
+            {   // two cp.async stages exceed the 48 KB default of dynamic shared memory
+                static size_t wg_attr_dev[kMaxDevices] = {};
+                const size_t need_smem = trn::wgrad_smem_bytes(h, w);
+                if (need_smem > wg_attr_dev[ctx->device]) {
+                    CU_TRY(cudaFuncSetAttribute(trn::conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(need_smem)));
+                    wg_attr_dev[ctx->device] = need_smem;
+                }
+            }
             trn::conv3x3_wgrad_kernel<<<dim3((co + trn::kWgO - 1) / trn::kWgO, (ci + trn::kWgI - 1) / trn::kWgI, kWgSlices), 256, trn::wgrad_smem_bytes(h, w), st>>>(wk + oin[i], gB, wk + owg, B, ci, co, h, w);
             trn::wgrad_sum_kernel<<<nb(nw), 256, 0, st>>>(wk + owg, Gp + T.cw[i], nw, kWgSlices);
         }

@@ -104,17 +104,22 @@ conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ w, const 
 // dW[o][i][t] = sum_{n,h,w} dY[n][o][h][w] * X[n][i][h+ty-1][w+tx-1].  Block = 16 output x 8 input channels x 9 taps over one slice
 // (blockIdx.z of gridDim.z) of the images; the partial sums of a slice go to dw_part[z] and wgrad_sum_kernel adds the slices in
 // index order (deterministic, and enough blocks to fill the machine at batch 32).  Per chunk of <= 256 pixels (whole rows of one
-// image) the block stages dY[16][chunk] and X[8][rows + 2][W + 8] (zero halo, rows 16-byte aligned) in shared memory; thread
+// image) the block stages dY[16][chunk] and X[8][rows + 2][W + 8] (zero halo, rows 16-byte aligned) in shared memory -- by cp.async,
+// double-buffered, so the next chunk's loads run under this chunk's FMAs; thread
 // (pixel lane 0..15, o-group of 4, i-pair) walks the chunk's pixel quads: 4 + 18 shared loads feed 288 FMAs into its 4 x 2 x 9
 // register tile (the first version -- positions strided over threads, every operand from L1/L2 -- was 46-60 % of the step).  The 16
 // pixel lanes of a tile are the lanes of a half-warp: fixed-order xor-shuffle reduction at the end.
 constexpr int kWgO = 16, kWgI = 8, kWgChunk = 256;
+__device__ __forceinline__ void wg_cp16(void* smem_dst, const void* gsrc, bool valid) {   // 16-byte cp.async, zero-filled when !valid
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc), "r"(n) : "memory");
+}
 __global__ void __launch_bounds__(256)
 conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw_part, int B, int CI, int CO, int H, int W) {
     extern __shared__ float4 wg_smem4[];
-    float* sdy = reinterpret_cast<float*>(wg_smem4);               // [16][chunk]
     const int HW = H * W, chunk = min(kWgChunk, HW), rows = chunk / W, XS = W + 8, xplane = (rows + 2) * XS;
-    float* sx = sdy + kWgO * kWgChunk;                             // [8][rows + 2][XS]; pixel (r, c) of the chunk at [r + 1][c + 4]
+    const int stage_floats = kWgO * kWgChunk + kWgI * xplane;      // one stage: dY [16][chunk] then X [8][rows + 2][XS] (pixel (r, c) at [r + 1][c + 4])
+    float* smem = reinterpret_cast<float*>(wg_smem4);              // two stages: the next chunk arrives by cp.async while this one is consumed
     const int o0 = blockIdx.x * kWgO, i0 = blockIdx.y * kWgI;
     const int per = (B + gridDim.z - 1) / gridDim.z, n_begin = blockIdx.z * per, n_end = min(B, n_begin + per);
     const int tid = threadIdx.x, pl = tid & 15, og = (tid >> 4) & 3, ip = tid >> 6;     // pixel lane, o-group (4 channels), i-pair
@@ -125,55 +130,60 @@ conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
         for (int b = 0; b < 2; ++b)
 #pragma unroll
             for (int t = 0; t < 9; ++t) s[a][b][t] = 0.0f;
-    const int chunks_per_img = HW / chunk, qpr = W >> 2, nquads = chunk >> 2;
-    for (int n = n_begin; n < n_end; ++n) {
-        for (int c = 0; c < chunks_per_img; ++c) {
-            const int h0 = c * rows;
-            __syncthreads();                                       // the previous chunk has been consumed
-            for (int e = tid; e < kWgO * nquads; e += 256) {       // dY tile, 16-byte loads
-                const int o = e / nquads, q = e - o * nquads;
-                float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (o0 + o < CO) v = __ldg(reinterpret_cast<const float4*>(dy + (static_cast<size_t>(n) * CO + o0 + o) * HW + h0 * W) + q);
-                reinterpret_cast<float4*>(sdy + o * kWgChunk)[q] = v;
-            }
-            const int xq = XS >> 2;                                // 16-byte groups per staged row: [halo group][W/4 groups][halo group]
-            for (int e = tid; e < kWgI * (rows + 2) * xq; e += 256) {
-                const int i = e / ((rows + 2) * xq), r2 = e - i * (rows + 2) * xq, r = r2 / xq, g = r2 - r * xq;
-                const int hh = h0 + r - 1;
-                float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (i0 + i < CI && hh >= 0 && hh < H && g >= 1 && g <= qpr)
-                    v = __ldg(reinterpret_cast<const float4*>(x + (static_cast<size_t>(n) * CI + i0 + i) * HW + hh * W) + (g - 1));
-                reinterpret_cast<float4*>(sx + i * xplane + r * XS)[g] = v;
-            }
-            __syncthreads();
-            for (int q = pl; q < nquads; q += 16) {
-                const int r = q / qpr, c4 = (q - r * qpr) << 2;    // quad = pixels (r, c4 .. c4+3) of the chunk
-                float4 g4[4];
+    const int chunks_per_img = HW / chunk, qpr = W >> 2, nquads = chunk >> 2, xq = XS >> 2;   // xq 16-byte groups per staged row: [halo][W/4][halo]
+    const int n_chunks = max(0, n_end - n_begin) * chunks_per_img;
+    auto issue = [&](int j) {                                       // chunk j of this block -> stage j & 1
+        const int n = n_begin + j / chunks_per_img, h0 = (j % chunks_per_img) * rows;
+        float* sdy = smem + (j & 1) * stage_floats;
+        float* sx = sdy + kWgO * kWgChunk;
+        for (int e = tid; e < kWgO * nquads; e += 256) {
+            const int o = e / nquads, q = e - o * nquads;
+            const bool ok = o0 + o < CO;
+            wg_cp16(sdy + o * kWgChunk + 4 * q, dy + (static_cast<size_t>(n) * CO + (ok ? o0 + o : 0)) * HW + h0 * W + 4 * q, ok);
+        }
+        for (int e = tid; e < kWgI * (rows + 2) * xq; e += 256) {
+            const int i = e / ((rows + 2) * xq), r2 = e - i * (rows + 2) * xq, r = r2 / xq, g = r2 - r * xq;
+            const int hh = h0 + r - 1;
+            const bool ok = i0 + i < CI && hh >= 0 && hh < H && g >= 1 && g <= qpr;
+            wg_cp16(sx + i * xplane + r * XS + 4 * g, x + (static_cast<size_t>(n) * CI + (ok ? i0 + i : 0)) * HW + (ok ? hh * W + 4 * (g - 1) : 0), ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (n_chunks > 0) issue(0);
+    for (int j = 0; j < n_chunks; ++j) {
+        if (j + 1 < n_chunks) { issue(j + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                           // chunk j has landed for every thread
+        const float* sdy = smem + (j & 1) * stage_floats;
+        const float* sx = sdy + kWgO * kWgChunk;
+        for (int q = pl; q < nquads; q += 16) {
+            const int r = q / qpr, c4 = (q - r * qpr) << 2;        // quad = pixels (r, c4 .. c4+3) of the chunk
+            float4 g4[4];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) g4[a] = reinterpret_cast<const float4*>(sdy + (og * 4 + a) * kWgChunk)[q];
+            for (int a = 0; a < 4; ++a) g4[a] = reinterpret_cast<const float4*>(sdy + (og * 4 + a) * kWgChunk)[q];
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    const float* xp = sx + (ip * 2 + b) * xplane + r * XS + c4 + 3;      // -> pixel (r - 1, c4 - 1)
+            for (int b = 0; b < 2; ++b) {
+                const float* xp = sx + (ip * 2 + b) * xplane + r * XS + c4 + 3;      // -> pixel (r - 1, c4 - 1)
 #pragma unroll
-                    for (int ty = 0; ty < 3; ++ty) {
-                        const float* rp = xp + ty * XS;
-                        const float4 m = *reinterpret_cast<const float4*>(rp + 1);
-                        const float v[6] = {rp[0], m.x, m.y, m.z, m.w, rp[5]};
+                for (int ty = 0; ty < 3; ++ty) {
+                    const float* rp = xp + ty * XS;
+                    const float4 m = *reinterpret_cast<const float4*>(rp + 1);
+                    const float v[6] = {rp[0], m.x, m.y, m.z, m.w, rp[5]};
 #pragma unroll
-                        for (int tx = 0; tx < 3; ++tx)
+                    for (int tx = 0; tx < 3; ++tx)
 #pragma unroll
-                            for (int a = 0; a < 4; ++a) {
-                                float acc = s[a][b][ty * 3 + tx];
-                                acc = fmaf(g4[a].x, v[tx], acc);
-                                acc = fmaf(g4[a].y, v[tx + 1], acc);
-                                acc = fmaf(g4[a].z, v[tx + 2], acc);
-                                acc = fmaf(g4[a].w, v[tx + 3], acc);
-                                s[a][b][ty * 3 + tx] = acc;
-                            }
-                    }
+                        for (int a = 0; a < 4; ++a) {
+                            float acc = s[a][b][ty * 3 + tx];
+                            acc = fmaf(g4[a].x, v[tx], acc);
+                            acc = fmaf(g4[a].y, v[tx + 1], acc);
+                            acc = fmaf(g4[a].z, v[tx + 2], acc);
+                            acc = fmaf(g4[a].w, v[tx + 3], acc);
+                            s[a][b][ty * 3 + tx] = acc;
+                        }
                 }
             }
         }
+        __syncthreads();                                           // stage j & 1 may be refilled (by issue(j + 2) in the next iteration)
     }
     float* dw = dw_part + static_cast<size_t>(blockIdx.z) * CO * CI * 9;
 #pragma unroll
@@ -191,7 +201,7 @@ conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
 }
 inline size_t wgrad_smem_bytes(int H, int W) {
     const int chunk = H * W < kWgChunk ? H * W : kWgChunk, rows = chunk / W;
-    return sizeof(float) * (static_cast<size_t>(kWgO) * kWgChunk + static_cast<size_t>(kWgI) * (rows + 2) * (W + 8));
+    return 2 * sizeof(float) * (static_cast<size_t>(kWgO) * kWgChunk + static_cast<size_t>(kWgI) * (rows + 2) * (W + 8));   // two stages
 }
 
 __global__ void wgrad_sum_kernel(const float* __restrict__ part, float* __restrict__ dw, int n, int slices) {
