@@ -1,3 +1,7 @@
-mkdir -p gpurun_out
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 77 python -m pytest tests/test_gpu_train.py -m gpu -q --timeout=800 -x -p no:cacheprovider -k "matches_torch and 8-False" > gpurun_out/racecheck_train.log 2>&1; echo "racecheck train exit $?"; grep -E "RACECHECK SUMMARY|passed|failed" gpurun_out/racecheck_train.log | head -5; grep -c "trn::" gpurun_out/racecheck_train.log
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 77 python -m pytest tests/test_gpu_train.py -m gpu -q --timeout=800 -x -p no:cacheprovider -k "matches_torch" > gpurun_out/memcheck_train.log 2>&1; echo "memcheck train exit $?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/memcheck_train.log | head -5
+mkdir -p gpurun_out/final
+timeout 900 python bench.py --config 5 > gpurun_out/final/bench_cfg5.json 2> gpurun_out/final/bench_cfg5.err; echo "cfg5 exit $?"; tail -c 300 gpurun_out/final/bench_cfg5.err
+python - <<'PY'
+import json
+d = json.loads([l for l in open('gpurun_out/final/bench_cfg5.json').read().splitlines() if l.startswith('{"')][-1])
+print({k: d.get(k) for k in ('value','ms_per_step','verified','clocks')}); print('e2e', d['e2e']['value']); print('kmeans', json.dumps(d['config5']['kmeans'])); print('search ms', d['config5']['search']['ms'])
+PY
