@@ -31,7 +31,35 @@ def toRgb(images, colorSpace):
         return images
     if colorSpace == "y":
         return np.tile(images, (1, 3, 1, 1))                 # torch.repeatTensor(images, 1, 3, 1, 1)
-    raise ValueError(f"colour space '{colorSpace}' needs image.hsl2rgb / image.yuv2rgb, which are out of scope")
+    if colorSpace == "hsl":
+        return np.stack([hsl2rgb(im) for im in images]) if len(images) else images
+    if colorSpace == "yuv":
+        return np.stack([yuv2rgb(im) for im in images]) if len(images) else images
+    raise ValueError(f"Unknown color space <from>: '{colorSpace}'")   # nn_utils.lua:165
+
+
+def hsl2rgb(image):
+    """image.hsl2rgb [upstream torch/image, not vendored: restated from its published algorithm -- the CSS3 / "hue2rgb"
+    conversion with h, s, l in [0, 1]; s == 0 gives grey]: 3 x H x W -> 3 x H x W."""
+    h, s, l = (np.asarray(image[c], np.float32) for c in range(3))
+    q = np.where(l < 0.5, l * (1.0 + s), l + s - l * s)
+    p = 2.0 * l - q
+
+    def hue2rgb(t):
+        t = np.where(t < 0.0, t + 1.0, t)
+        t = np.where(t > 1.0, t - 1.0, t)
+        return np.where(t < 1.0 / 6.0, p + (q - p) * 6.0 * t,
+                        np.where(t < 0.5, q, np.where(t < 2.0 / 3.0, p + (q - p) * (2.0 / 3.0 - t) * 6.0, p)))
+
+    rgb = np.stack([hue2rgb(h + 1.0 / 3.0), hue2rgb(h), hue2rgb(h - 1.0 / 3.0)])
+    return np.where(s[None] == 0.0, np.stack([l, l, l]), rgb).astype(np.float32)
+
+
+def yuv2rgb(image):
+    """image.yuv2rgb [upstream torch/image, not vendored: restated from its published coefficients, the inverse of
+    y = 0.299 r + 0.587 g + 0.114 b, u = -0.14713 r - 0.28886 g + 0.436 b, v = 0.615 r - 0.51499 g - 0.10001 b]."""
+    y, u, v = (np.asarray(image[c], np.float32) for c in range(3))
+    return np.stack([y + 1.13983 * v, y - 0.39465 * u - 0.58060 * v, y + 2.03211 * u]).astype(np.float32)
 
 
 def toRgbSingle(image, colorSpace):

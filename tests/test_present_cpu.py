@@ -43,7 +43,23 @@ def test_toRgb(pr):
     assert pr.toRgb(rgb, "rgb") is rgb or np.array_equal(pr.toRgb(rgb, "rgb"), rgb)
     assert pr.toRgbSingle(y[0], "y").shape == (3, 3, 3)
     with pytest.raises(ValueError):
-        pr.toRgb(rgb, "hsl")
+        pr.toRgb(rgb, "lab")                                  # nn_utils.lua:165: unknown colour space
+
+
+def test_toRgb_hsl_yuv_known_answers(pr):
+    """image.hsl2rgb / image.yuv2rgb behind NN_UTILS.toRgb (nn_utils.lua:152-163): primaries, greys and the analytic inverse."""
+    hsl = np.zeros((1, 3, 1, 6), np.float32)
+    #            red      green     blue     grey(s=0)  dark red   light cyan
+    hsl[0, 0] = [0.0, 1.0 / 3.0, 2.0 / 3.0, 0.7,       0.0,       0.5]
+    hsl[0, 1] = [1.0, 1.0,       1.0,       0.0,       1.0,       1.0]
+    hsl[0, 2] = [0.5, 0.5,       0.5,       0.25,      0.25,      0.75]
+    want = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [0.25, 0.25, 0.25], [0.5, 0, 0], [0.5, 1, 1]], np.float32).T
+    np.testing.assert_allclose(pr.toRgb(hsl, "hsl")[0, :, 0, :], want, atol=1e-6)
+    rgb = np.random.default_rng(2).random((3, 3, 4, 5)).astype(np.float32)
+    r, g, b = rgb[:, 0], rgb[:, 1], rgb[:, 2]
+    yuv = np.stack([0.299 * r + 0.587 * g + 0.114 * b, -0.14713 * r - 0.28886 * g + 0.436 * b, 0.615 * r - 0.51499 * g - 0.10001 * b], axis=1)
+    np.testing.assert_allclose(pr.toRgb(yuv.astype(np.float32), "yuv"), rgb, atol=2e-4)
+    assert pr.toRgbSingle(yuv[0].astype(np.float32), "yuv").shape == (3, 4, 5)
 
 
 def test_apply_r_artefacts(pr, tmp_path):
