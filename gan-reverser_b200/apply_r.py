@@ -126,6 +126,7 @@ def main(G=None, R=None, R_fixer=None, writeTo="r_results", seed=1, dimensions=(
     for i in range(noiseDim):
         noise[i * nbSteps:(i + 1) * nbSteps, i] = steps
     out["variations"] = nn_utils.forwardBatched(model_G, noise)
+    out["variation_noise"] = noise
 
     noise = nn_utils.createNoiseInputs(nbImages, noiseDim, noiseMethod, rng=rng)                  # :143
     images = nn_utils.forwardBatched(model_G, noise)                                              # :144

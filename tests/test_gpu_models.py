@@ -320,6 +320,20 @@ def test_apply_r_main_end_to_end(pkg, tmp_path):
     ctx = pkg.Context(0)
     try:
         out = pkg.apply_r.main(writeTo=str(tmp_path), nbImages=1200, ctx=ctx)
+        # component variations (apply_r.lua:111-136): row i*16 + j is the base vector with component i set to steps[j] ...
+        vn, steps = out["variation_noise"], np.linspace(-3, 3, 16).astype(np.float32)
+        assert vn.shape == (100 * 16, 100)
+        for i in (0, 37, 99):
+            blk = vn[i * 16:(i + 1) * 16]
+            np.testing.assert_allclose(blk[:, i], steps, rtol=1e-6)
+            others = np.delete(blk, i, axis=1)
+            assert (others == others[0]).all()
+        base = vn[16].copy(); base[1] = vn[0][1]                  # the base vector: any row with its varied component restored
+        assert np.array_equal(np.delete(vn[0], 0), np.delete(base, 0))
+        # ... and the images are G of exactly those rows (each image is computed independently of its batch position)
+        rows = np.array([0, 15, 16, 600, 1599])
+        np.testing.assert_array_equal(ctx.forward_G(vn[rows]), out["variations"][rows])
+        assert np.abs(out["variations"][0] - out["variations"][15]).max() > 0   # varying a component changes the face
     finally:
         ctx.close()
     names = sorted(os.path.basename(f) for f in out["files"])
