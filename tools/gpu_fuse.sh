@@ -1,2 +1,3 @@
-mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_models.py -m gpu -q --timeout=300 -x -p no:cacheprovider -k "apply_r_main" > gpurun_out/models.log 2>&1; echo "exit $?"; tail -12 gpurun_out/models.log
+mkdir -p gpurun_out/final
+timeout 1500 python -m pytest tests -m gpu -q --timeout=600 -p no:cacheprovider > gpurun_out/final/pytest_gpu.log 2>&1; echo "pytest gpu exit $?"; tail -3 gpurun_out/final/pytest_gpu.log
+timeout 300 python __graft_entry__.py smoke > gpurun_out/final/smoke.log 2>&1; echo "smoke exit $?"; tail -1 gpurun_out/final/smoke.log
