@@ -93,6 +93,7 @@ struct ganrev_ctx {
     int64_t chunk = 0;            // images per pipeline chunk; 0 = auto (8192 32x32 faces' worth of pixels, see chunk_for)
     int conv_impl = 0;
     int tma_hybrid = 0;           // see ConvGemm::tma_hybrid (A/B)
+    int ups_cycles = 512;         // a pipeline stage carries enough units for this many MMA cycles (one mbarrier round trip per stage); read at load time
     int pdl = 0;                  // conv layers launched with programmatic stream serialization (prologue overlaps the previous kernel's tail);
                                   // measured +0.4 % on the resident G->R chain (tools/ab_total.py pdl 0 1: within noise), so off by default
     int xpose2 = 1;               // double store-transpose buffers in the TMA-store epilogue (see build_tc_layer); 0 = single (A/B)
@@ -407,7 +408,11 @@ static int build_tc_layer(ganrev_ctx* ctx, TcLayer& L, const LayerDef& d, const 
             const int res = L.bres ? static_cast<int>(wbytes) : 0;
             g.unit_bytes = L.MT * g.a_unit_bytes + (L.bres ? 0 : g.ndy * g.b_kb_bytes);
             const int cyc_unit = L.MT * g.ndy * 4 * std::max(d.NT / 2, 32);          // MMA cycles per unit
-            g.ups = std::max(1, std::min({4, g.units, (512 + cyc_unit - 1) / cyc_unit}));
+            // units per stage: one mbarrier round trip per >= ups_cycles MMA cycles.  G's Up+Conv 512->256 (N = 256: 548 MMA cycles per unit,
+            // 32 units per item) measured 5 % faster with two units per stage (same-box A/B against conv2, tools/ab_option.py ups_cycles
+            // 512 1024); the Linear layers measured 2 % slower with it, the others do not change
+            const int tgt = (d.kind == KIND_UPCONV3 && d.NT == 256) ? std::max(ctx->ups_cycles, 1024) : ctx->ups_cycles;
+            g.ups = std::max(1, std::min({4, g.units, (tgt + cyc_unit - 1) / cyc_unit}));
             while (g.ups > 1 && (budget - res) / (g.ups * g.unit_bytes) < 3) --g.ups;
             g.stage_bytes = g.ups * g.unit_bytes;
             g.stages = std::min(tc::kMaxStages, (budget - res) / g.stage_bytes);
@@ -2724,6 +2729,7 @@ int ganrev_set_option(ganrev_ctx* ctx, const char* name, int64_t value) {
     if (!strcmp(name, "stream_tc")) { ctx->stream_tc = value != 0; return GANREV_OK; }
     if (!strcmp(name, "kmeans_tc")) { ctx->kmeans_tc = value != 0; return GANREV_OK; }
     if (!strcmp(name, "tma_hybrid")) { ctx->tma_hybrid = value != 0; return GANREV_OK; }
+    if (!strcmp(name, "ups_cycles")) { ctx->ups_cycles = value < 1 ? 1 : static_cast<int>(value); return GANREV_OK; }
     if (!strcmp(name, "pdl")) { ctx->pdl = value != 0; return GANREV_OK; }
     if (!strcmp(name, "xpose2")) { ctx->xpose2 = value < 0 ? 0 : (value > 2 ? 2 : static_cast<int>(value)); return GANREV_OK; }   // read at load time
     if (!strcmp(name, "fuse_conv3")) { ctx->fuse_conv3 = value < 0 ? 0 : (value > 2 ? 2 : static_cast<int>(value)); return GANREV_OK; }   // read by ganrev_load_G

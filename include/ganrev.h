@@ -210,6 +210,7 @@ int ganrev_debug_trace_read(ganrev_ctx* ctx, int64_t* out);
  *               slower), 0 = separate 1x1 tensor-core pass over the stored activation; read at ganrev_load_G
  *   "xpose2"    1 = second store-transpose buffer per epilogue warp for G's Linear (default), 2 = every plain bf16 layer, 0 = none;
  *               read at ganrev_load_*.  "tma_hybrid" 1 = first chunk of an epilogue round by st.global, second by TMA store (default 0)
+ *   "ups_cycles" MMA cycles a conv pipeline stage should carry (units per stage; default 512, G's first Up+Conv uses >= 1024); read at load time
  *   "pdl"       1 = conv layers launched with programmatic stream serialization (griddepcontrol: the next layer's prologue overlaps
  *               this layer's tail; measured +0.4 %, within noise), 0 = plain stream order (default)
  *   "tma_store" 1 = TMA bulk tensor stores in the conv epilogue of the plain layers (default), 2 = also the pooled layers, 0 = st.global everywhere
